@@ -1,0 +1,159 @@
+/* movi_gpu.h -- C ABI of the B200 (sm_100a) implementation of Movi's query hot path.
+ *
+ * Movi (the reference) has no plugin / FFI interface; its in-process seam for this path is
+ *     MoveStructure::query_pml(MoveQuery&)                      include/move_structure.hpp:150
+ *     MoveStructure::query_zml(MoveQuery&)                      include/move_structure.hpp:151
+ *     MoveStructure::query_backward_search(MoveQuery&, int32&)  include/move_structure.hpp:89
+ * called per read from query() (src/movi.cpp:221-400) through handle_pml_zml / handle_count
+ * (src/movi.cpp:23-76), or per batch from ReadProcessor::process_latency_hiding
+ * (include/read_processor.hpp:62, src/read_processor.cpp:641-730).  The entry points below are what
+ * a binding at that seam calls instead: whole batches of reads in, the same per-base / per-read
+ * results out, bit for bit.  INTEGRATION.md shows the reference-side call sites.
+ *
+ * Conventions
+ *   - plain C, no exceptions: every call returns MOVI_GPU_OK or an error code; the text of the last
+ *     error of a context is available from movi_gpu_last_error().
+ *   - one context per GPU; a context is not thread safe (use one host thread per context, like the
+ *     reference uses one ReadProcessor strand set per OpenMP thread).
+ *   - the host owns every host buffer; device buffers belong to the context.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Read batches are passed concatenated: read i is bases[read_offsets[i] .. read_offsets[i+1]).
+ * Matching lengths come back at the same offsets in the reference's storage order, i.e. for every
+ * read, element 0 belongs to the LAST base (MoveQuery::add_ml appends while the read is walked
+ * right to left: include/move_query.hpp:26-38; BPF files store them in this order, src/utils.cpp:202-246).
+ */
+#ifndef MOVI_GPU_H
+#define MOVI_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOVI_GPU_ABI_VERSION 1
+
+enum {
+    MOVI_GPU_OK = 0,
+    MOVI_GPU_ERR_ARG = 1,        /* bad argument */
+    MOVI_GPU_ERR_CUDA = 2,       /* CUDA runtime failure, or no device */
+    MOVI_GPU_ERR_INDEX = 3,      /* unsupported / inconsistent index description */
+    MOVI_GPU_ERR_QUERY = 4,      /* a read drove the walk into a state where the reference throws
+                                    ("This should not happen": src/move_structure_query.cpp:348,582-598,
+                                    src/move_structure.cpp:63-65) */
+    MOVI_GPU_ERR_NOMEM = 5
+};
+
+/* Index modes = the reference's compile-time MODE (include/utils.hpp:133-147). */
+#define MOVI_MODE_REGULAR_THRESHOLDS 6   /* 8-byte rows  */
+#define MOVI_MODE_SAMPLED_THRESHOLDS 7   /* 3-byte rows + id checkpoints ("tally") */
+#define MOVI_MODE_BLOCKED_THRESHOLDS 8   /* 6-byte rows + id_blocks */
+
+/* What MoveStructure holds after deserialize() (include/move_structure.hpp:328-380), by pointer.
+ * All pointers are HOST pointers; they only need to stay valid during movi_gpu_upload_index(). */
+typedef struct MoviGpuIndexDesc {
+    int32_t  mode;                       /* MOVI_MODE_* (MoviHeader.type, include/utils.hpp:32-61) */
+    uint32_t sigma;                      /* alphabet.size(): 4, or 5 with separators ("%ACGT") */
+    uint64_t length;                     /* n, BWT length */
+    uint64_t r;                          /* number of move rows */
+    uint64_t end_bwt_idx;                /* row of '$' */
+    const void* rows;                    /* rlbwt.data(): r packed MoveRow (8 / 6 / 3 bytes each, include/move_row.hpp:104-154) */
+    uint8_t  alphabet[8];                /* alphabet[i] */
+    const uint64_t* alphamap;            /* 256 entries, 256 == not in the alphabet (src/move_structure_build.cpp:428-447) */
+    uint64_t end_bwt_idx_thresholds[4];  /* src/move_structure_io.cpp:147 */
+    uint64_t first_runs[8], first_offsets[8], last_runs[8], last_offsets[8];   /* sigma+1 used; io.cpp:269-287 */
+    /* MODE 8 (src/move_structure_io.cpp:305-324) */
+    const uint32_t* id_blocks;           /* sigma * id_blocks_size, character major */
+    uint64_t id_blocks_size;
+    uint64_t block_size;
+    /* MODE 7 (src/move_structure_io.cpp:338-349) */
+    const void* tally_ids;               /* sigma * tally_len MoveTally {u32 right; u8 left}, 5 bytes each */
+    uint64_t tally_len;
+    uint32_t tally_checkpoints;
+    uint32_t reserved0;
+    /* separators (src/move_structure_io.cpp:415-433); zero / NULL when the index has none */
+    const uint16_t* separators_thresholds;   /* sep_count * 4 (ThresholdsRow) */
+    uint64_t sep_count;
+    const uint64_t* separators_map;          /* sep_map_size pairs (row, slot) in any order */
+    uint64_t sep_map_size;
+} MoviGpuIndexDesc;
+
+typedef struct movi_gpu_ctx movi_gpu_ctx;
+
+/* Query flags */
+#define MOVI_GPU_FLAG_NONE 0u
+
+/* Device-resident row layouts (chosen at upload). */
+#define MOVI_GPU_LAYOUT_AUTO     0   /* EXPANDED8 when it fits, else the compact layout of the mode */
+#define MOVI_GPU_LAYOUT_EXPANDED8 1  /* every mode re-laid out as 8-byte rows with the full id resolved:
+                                        one 32-byte sector holds 4 rows, one sector fetch per LF step */
+
+int  movi_gpu_abi_version(void);
+int  movi_gpu_device_count(void);
+
+/* replaces: MoveStructure construction per process (src/movi.cpp:661-667); one ctx per GPU */
+int  movi_gpu_create(int device, movi_gpu_ctx** ctx);
+int  movi_gpu_destroy(movi_gpu_ctx* ctx);
+const char* movi_gpu_last_error(const movi_gpu_ctx* ctx);   /* ctx may be NULL: last create() error */
+
+/* replaces: MoveStructure::deserialize() filling rlbwt & side tables (src/move_structure_io.cpp:471-511).
+ * Copies the row table and side tables into HBM once (re-laid out, see MOVI_GPU_LAYOUT_*). */
+int  movi_gpu_upload_index(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* desc, int layout);
+/* bytes of HBM held by the uploaded index */
+uint64_t movi_gpu_index_device_bytes(const movi_gpu_ctx* ctx);
+
+/* replaces: MoveStructure::query_pml, one call per batch instead of per read (src/move_structure_query.cpp:234-474).
+ * HOST buffers.  out_ml has read_offsets[n_reads] entries.  Copies in, runs, copies out (pipelined). */
+int  movi_gpu_query_pml(movi_gpu_ctx* ctx, const char* bases, const uint64_t* read_offsets, uint64_t n_reads,
+                        uint32_t flags, uint16_t* out_ml);
+/* replaces: MoveStructure::query_zml (src/move_structure_query.cpp:690-786) */
+int  movi_gpu_query_zml(movi_gpu_ctx* ctx, const char* bases, const uint64_t* read_offsets, uint64_t n_reads,
+                        uint32_t flags, uint16_t* out_ml);
+/* replaces: MoveStructure::query_backward_search + MoveInterval::count (src/move_structure_search.cpp:340-352,
+ * include/move_intervals.hpp:47-58).  out_pos_on_r[i] is pos_on_r as the reference leaves it (the text
+ * output prints len - pos_on_r, src/utils.cpp:248-256). */
+int  movi_gpu_query_count(movi_gpu_ctx* ctx, const char* bases, const uint64_t* read_offsets, uint64_t n_reads,
+                          uint32_t flags, uint64_t* out_count, int32_t* out_pos_on_r);
+
+/* Same queries on DEVICE buffers (already resident in HBM), enqueued on `cuda_stream` (a cudaStream_t,
+ * NULL = default stream) without synchronising: for callers that pipeline their own copies.
+ * d_bases must be 8-byte aligned and readable up to the next multiple of 8 bytes; read_offsets are
+ * relative to d_bases; total bases per call < 2^32.  d_out_ml has read_offsets[n_reads] entries. */
+int  movi_gpu_query_pml_device(movi_gpu_ctx* ctx, const char* d_bases, const uint64_t* d_read_offsets, uint64_t n_reads,
+                               uint32_t flags, uint16_t* d_out_ml, void* cuda_stream);
+int  movi_gpu_query_zml_device(movi_gpu_ctx* ctx, const char* d_bases, const uint64_t* d_read_offsets, uint64_t n_reads,
+                               uint32_t flags, uint16_t* d_out_ml, void* cuda_stream);
+int  movi_gpu_query_count_device(movi_gpu_ctx* ctx, const char* d_bases, const uint64_t* d_read_offsets, uint64_t n_reads,
+                                 uint32_t flags, uint64_t* d_out_count, int32_t* d_out_pos_on_r, void* cuda_stream);
+/* After a *_device call has completed (caller synchronised the stream): MOVI_GPU_OK, or
+ * MOVI_GPU_ERR_QUERY if any read hit a "should not happen" state.  Clears the flag. */
+int  movi_gpu_check_device_status(movi_gpu_ctx* ctx);
+
+/* Binary classification on the device from PMLs already in HBM (Classifier::classify, src/classifier.cpp:99-143):
+ * per read bins_above / bins_below / sum of bin maxima; found = above/(above+below) > 0.5. */
+int  movi_gpu_classify_device(movi_gpu_ctx* ctx, const uint16_t* d_ml, const uint64_t* d_read_offsets, uint64_t n_reads,
+                              uint32_t bin_width, uint32_t max_value_thr,
+                              uint32_t* d_bins_above, uint32_t* d_bins_below, uint64_t* d_sum_max, void* cuda_stream);
+
+/* Introspection for benchmarks: kernels launched by this context so far, name and time of the last one. */
+uint64_t movi_gpu_launch_count(const movi_gpu_ctx* ctx);
+/* Tuning knobs (benchmarks / profiling): "pml_variant", "blocks_per_sm", "threads_per_block", "batch_bases". */
+int  movi_gpu_set_option(movi_gpu_ctx* ctx, const char* key, int64_t value);
+int64_t movi_gpu_get_option(const movi_gpu_ctx* ctx, const char* key);
+
+/* Pinned host memory for callers that want DMA-speed copies through the host-buffer entry points. */
+int  movi_gpu_host_alloc(void** p, uint64_t bytes);
+int  movi_gpu_host_free(void* p);
+
+/* Random-access roofline probe: `n_threads` independent chains of `steps` dependent (or independent)
+ * 8- or 32-byte loads at pseudo-random row addresses of the uploaded table (or a scratch table of
+ * table_bytes when no index is uploaded).  Returns seconds of device time in *seconds. */
+int  movi_gpu_gather_probe(movi_gpu_ctx* ctx, uint64_t table_bytes, uint32_t load_bytes, uint32_t dependent,
+                           uint32_t steps, uint32_t blocks_per_sm, uint32_t threads_per_block, double* seconds,
+                           uint64_t* loads_done);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOVI_GPU_H */

@@ -1,0 +1,60 @@
+/* movi_host.h -- C ABI of the host-side helpers around the GPU query path (pure C++ inside, no CUDA).
+ *
+ * These restate the reference's host code either side of the hot path so that a caller can go from
+ * Movi's on-disk files to movi_gpu_* calls and back to Movi's output files:
+ *   index.movi reader        MoveStructure::deserialize            src/move_structure_io.cpp:471-511
+ *   FASTA / FASTQ batches    BatchLoader::loadBatch / grabNextRead  src/batch_loader.cpp:26-143
+ *   .bpf / count / stdout    output_base_stats / output_counts      src/utils.cpp:202-256, 319-384
+ *   binary classification    Classifier                              src/classifier.cpp:24-143
+ */
+#ifndef MOVI_HOST_H
+#define MOVI_HOST_H
+
+#include <stdint.h>
+#include "movi_gpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct movi_host_index movi_host_index;
+typedef struct movi_host_reads movi_host_reads;
+
+const char* movi_host_last_error(void);
+
+/* index.movi (path may be the index directory or the file).  The file is memory-mapped; the
+ * descriptor's pointers stay valid until movi_host_index_close(). */
+int  movi_host_index_open(const char* path, movi_host_index** out);
+int  movi_host_index_desc(const movi_host_index* ix, MoviGpuIndexDesc* out);
+uint64_t movi_host_index_original_r(const movi_host_index* ix);
+const char* movi_host_index_type_name(const movi_host_index* ix);   /* "regular-thresholds", ... (src/utils.cpp:10-45) */
+void movi_host_index_close(movi_host_index* ix);
+
+/* Whole read file (FASTA, possibly multi-line, or 4-line FASTQ; "-" = stdin) into one concatenated batch.
+ * Read ids follow the reference: header from its 2nd character through AND INCLUDING the first
+ * blank / tab / CR (src/batch_loader.cpp:117-119).  reverse != 0 reverses every read (--reverse). */
+int  movi_host_reads_load(const char* path, int reverse, movi_host_reads** out);
+uint64_t movi_host_reads_count(const movi_host_reads* rd);
+const char* movi_host_reads_bases(const movi_host_reads* rd);          /* concatenated */
+const uint64_t* movi_host_reads_offsets(const movi_host_reads* rd);    /* count + 1 */
+const char* movi_host_reads_id(const movi_host_reads* rd, uint64_t i, uint32_t* len);
+void movi_host_reads_free(movi_host_reads* rd);
+
+/* movi.<q>.nulldb -> Classifier::initialize_report_file's threshold: max(percentile, 3) + 1
+ * (src/classifier.cpp:24-32, src/emperical_null_database.cpp:106-126) */
+int  movi_host_nulldb_threshold(const char* index_dir, const char* query_type, uint64_t* max_value_thr);
+
+/* Writers.  `ml` holds the matching lengths of read i at offsets[i]..offsets[i+1] in storage order
+ * (element 0 = last base), exactly what movi_gpu_query_pml / _zml return. */
+int  movi_host_write_bpf(const char* file, const movi_host_reads* rd, const uint16_t* ml);          /* src/utils.cpp:202-246 + BPFHeader */
+int  movi_host_write_ml_text(int fd, const movi_host_reads* rd, const uint16_t* ml);                /* --stdout form */
+int  movi_host_write_counts(int fd, const movi_host_reads* rd, const uint64_t* counts, const int32_t* pos_on_r);   /* src/utils.cpp:248-256 */
+/* Classification report / filter (src/classifier.cpp:99-143, src/movi.cpp:36-47).
+ * mode: 0 = report (with header) to fd, 1 = filter: print FOUND reads, 2 = filter --invert. found_out may be NULL. */
+int  movi_host_classify(int fd, int mode, const movi_host_reads* rd, const uint16_t* ml, uint64_t bin_width,
+                        uint64_t max_value_thr, uint8_t* found_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOVI_HOST_H */

@@ -1,0 +1,202 @@
+"""Thin object layer over the C ABIs; every compute call goes through libmovi_gpu.so."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _native as N
+
+LAYOUT_AUTO, LAYOUT_EXPANDED8 = 0, 1
+
+
+class MoviGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("movi_gpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+def device_count():
+    return N.gpu_lib().movi_gpu_device_count()
+
+
+class HostIndex:
+    """index.movi opened on the host (MoveStructure::deserialize, reference src/move_structure_io.cpp:471-511)."""
+
+    def __init__(self, path):
+        self._h = C.c_void_p()
+        L = N.host_lib()
+        if L.movi_host_index_open(os.fsencode(path), C.byref(self._h)) != 0:
+            raise RuntimeError(L.movi_host_last_error().decode())
+        self.desc = N.MoviGpuIndexDesc()
+        L.movi_host_index_desc(self._h, C.byref(self.desc))
+        self.type_name = L.movi_host_index_type_name(self._h).decode()
+        self.original_r = L.movi_host_index_original_r(self._h)
+        self.path = path
+
+    mode = property(lambda s: s.desc.mode)
+    r = property(lambda s: s.desc.r)
+    n = property(lambda s: s.desc.length)
+    end_bwt_idx = property(lambda s: s.desc.end_bwt_idx)
+    alphabet = property(lambda s: bytes(s.desc.alphabet[: s.desc.sigma]))
+
+    def close(self):
+        if self._h:
+            N.host_lib().movi_host_index_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Reads:
+    """A FASTA / FASTQ file parsed like the reference's BatchLoader (src/batch_loader.cpp:26-143)."""
+
+    def __init__(self, path, reverse=False):
+        self._h = C.c_void_p()
+        L = N.host_lib()
+        if L.movi_host_reads_load(os.fsencode(path), int(reverse), C.byref(self._h)) != 0:
+            raise RuntimeError(L.movi_host_last_error().decode())
+        self.count = L.movi_host_reads_count(self._h)
+        off = L.movi_host_reads_offsets(self._h)
+        self.offsets = np.ctypeslib.as_array(C.cast(off, N.u64p), shape=(self.count + 1,)).copy()
+        total = int(self.offsets[-1])
+        b = L.movi_host_reads_bases(self._h)
+        self.bases = np.ctypeslib.as_array(C.cast(b, N.u8p), shape=(total,)).copy() if total else np.zeros(0, np.uint8)
+
+    def id(self, i):
+        n = C.c_uint32()
+        p = N.host_lib().movi_host_reads_id(self._h, i, C.byref(n))
+        return C.string_at(p, n.value).decode()
+
+    def ids(self):
+        return [self.id(i) for i in range(self.count)]
+
+    def read(self, i):
+        return self.bases[int(self.offsets[i]):int(self.offsets[i + 1])].tobytes().decode()
+
+    def close(self):
+        if self._h:
+            N.host_lib().movi_host_reads_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _ptr(a):
+    return a.ctypes.data if isinstance(a, np.ndarray) else int(a)
+
+
+class MoveStructure:
+    """The move structure resident in one GPU's HBM + the three queries of the hot path.
+
+    Mirrors the reference's MoveStructure for this path: deserialize() -> upload, query_pml / query_zml /
+    query_backward_search on whole batches (numpy host arrays), *_device variants on raw device pointers
+    (e.g. torch tensors' data_ptr()).
+    """
+
+    def __init__(self, index, device=0, layout=LAYOUT_AUTO):
+        self._L = N.gpu_lib()
+        self._ctx = C.c_void_p()
+        rc = self._L.movi_gpu_create(device, C.byref(self._ctx))
+        if rc != 0:
+            raise MoviGpuError(rc, self._L.movi_gpu_last_error(None).decode())
+        self.device = device
+        self.host_index = index if isinstance(index, HostIndex) else HostIndex(index)
+        rc = self._L.movi_gpu_upload_index(self._ctx, C.byref(self.host_index.desc), layout)
+        self._check(rc)
+        self.r = self.host_index.r
+        self.mode = self.host_index.mode
+
+    def _check(self, rc):
+        if rc != 0:
+            raise MoviGpuError(rc, self._L.movi_gpu_last_error(self._ctx).decode())
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._L.movi_gpu_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- options / introspection
+    def set_option(self, key, value):
+        self._check(self._L.movi_gpu_set_option(self._ctx, key.encode(), int(value)))
+
+    def get_option(self, key):
+        return self._L.movi_gpu_get_option(self._ctx, key.encode())
+
+    @property
+    def launch_count(self):
+        return self._L.movi_gpu_launch_count(self._ctx)
+
+    @property
+    def index_device_bytes(self):
+        return self._L.movi_gpu_index_device_bytes(self._ctx)
+
+    # ---- host-buffer queries (copies inside)
+    @staticmethod
+    def _prep(bases, offsets):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        return bases, offsets, len(offsets) - 1
+
+    def query_pml(self, bases, offsets, out=None):
+        bases, offsets, n = self._prep(bases, offsets)
+        if out is None:
+            out = np.empty(int(offsets[-1]) if n >= 0 and len(offsets) else 0, dtype=np.uint16)
+        self._check(self._L.movi_gpu_query_pml(self._ctx, _ptr(bases), _ptr(offsets), max(n, 0), 0, _ptr(out)))
+        return out
+
+    def query_zml(self, bases, offsets, out=None):
+        bases, offsets, n = self._prep(bases, offsets)
+        if out is None:
+            out = np.empty(int(offsets[-1]) if len(offsets) else 0, dtype=np.uint16)
+        self._check(self._L.movi_gpu_query_zml(self._ctx, _ptr(bases), _ptr(offsets), max(n, 0), 0, _ptr(out)))
+        return out
+
+    def query_backward_search(self, bases, offsets):
+        """count query -> (counts uint64[n], pos_on_r int32[n])"""
+        bases, offsets, n = self._prep(bases, offsets)
+        counts = np.zeros(max(n, 0), dtype=np.uint64)
+        pos = np.zeros(max(n, 0), dtype=np.int32)
+        self._check(self._L.movi_gpu_query_count(self._ctx, _ptr(bases), _ptr(offsets), max(n, 0), 0, _ptr(counts), _ptr(pos)))
+        return counts, pos
+
+    query_count = query_backward_search
+
+    # ---- raw pointer forms (host pinned or device pointers as ints)
+    def query_pml_ptr(self, bases_ptr, offsets_ptr, n_reads, out_ptr):
+        self._check(self._L.movi_gpu_query_pml(self._ctx, bases_ptr, offsets_ptr, n_reads, 0, out_ptr))
+
+    def query_pml_device(self, d_bases, d_offsets, n_reads, d_out, stream=0):
+        self._check(self._L.movi_gpu_query_pml_device(self._ctx, d_bases, d_offsets, n_reads, 0, d_out, stream))
+
+    def query_zml_device(self, d_bases, d_offsets, n_reads, d_out, stream=0):
+        self._check(self._L.movi_gpu_query_zml_device(self._ctx, d_bases, d_offsets, n_reads, 0, d_out, stream))
+
+    def query_count_device(self, d_bases, d_offsets, n_reads, d_counts, d_pos, stream=0):
+        self._check(self._L.movi_gpu_query_count_device(self._ctx, d_bases, d_offsets, n_reads, 0, d_counts, d_pos, stream))
+
+    def check_device_status(self):
+        self._check(self._L.movi_gpu_check_device_status(self._ctx))
+
+    def classify_device(self, d_ml, d_offsets, n_reads, bin_width, max_value_thr, d_above, d_below, d_sum, stream=0):
+        self._check(self._L.movi_gpu_classify_device(self._ctx, d_ml, d_offsets, n_reads, bin_width, max_value_thr,
+                                                     d_above, d_below, d_sum, stream))
+
+    def gather_probe(self, table_bytes, load_bytes=8, dependent=True, steps=256, blocks_per_sm=8, threads_per_block=256):
+        sec, loads = C.c_double(), C.c_uint64()
+        self._check(self._L.movi_gpu_gather_probe(self._ctx, table_bytes, load_bytes, int(dependent), steps, blocks_per_sm,
+                                                  threads_per_block, C.byref(sec), C.byref(loads)))
+        return sec.value, loads.value

@@ -1,0 +1,159 @@
+// convert.cuh -- upload-time re-layout kernels: packed on-disk rows -> R8 device rows.
+//
+// Each kernel decodes one on-disk layout exactly as the reference's per-MODE getters do and resolves
+// MoveStructure::get_id (src/move_structure.cpp:91-286) ONCE per row:
+//   blocked-thresholds (MODE 8): id22 + id_blocks[c][idx / block_size] + first_runs[c + 1]   (:95-102)
+//   sampled-thresholds (MODE 7): forward scan to the next id checkpoint + backward walk        (:103-219)
+// so that the query kernels do one 8-byte row fetch per LF step whatever the on-disk layout was.
+#pragma once
+#include "dev_index.cuh"
+
+namespace movi {
+
+// ---- MODE 8: 6-byte rows {u16 id; u16 n; u16 offset} (include/move_row.hpp:128-130,139-142;
+//      bit fields include/move_row_configs.hpp:76-104)
+__global__ void convert_blocked_kernel(const uint16_t* __restrict__ raw, uint2* __restrict__ out,
+                                       unsigned long long r, unsigned long long end_idx,
+                                       const uint32_t* __restrict__ id_blocks, unsigned long long id_blocks_size,
+                                       unsigned long long block_size, const unsigned long long* __restrict__ first_runs) {
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (; i < r; i += stride) {
+        const uint32_t f_id = raw[3 * i], f_n = raw[3 * i + 1], f_off = raw[3 * i + 2];
+        const uint32_t n = f_n & 0x3FFu;
+        const uint32_t off = f_off & 0x3FFu;
+        const uint32_t c = (f_off >> 10) & 7u;
+        const uint32_t thr = (f_off >> 13) & 7u;                       // thresholds #0..#2 = offset bits 13..15
+        unsigned long long id = (unsigned long long)f_id | ((unsigned long long)((f_n >> 10) & 0x3Fu) << 16);
+        if (i != end_idx) id += (unsigned long long)id_blocks[c * id_blocks_size + i / block_size] + first_runs[c + 1];
+        out[i] = make_r8(id, n, off, c, thr);
+    }
+}
+
+// ---- MODE 7: 3-byte rows {u8 n; u8 offset; u8 c} (include/move_row.hpp:122-126; bit fields
+//      include/move_row_configs.hpp:120-136), MoveTally = {u32 right; u8 left} (include/move_row.hpp:13-39)
+struct Raw3 {
+    const uint8_t* p;
+    unsigned long long end_idx;
+    __device__ __forceinline__ uint32_t n(unsigned long long i) const { return (uint32_t)p[3 * i] | (((uint32_t)p[3 * i + 2] >> 1) & 1u) << 8; }
+    __device__ __forceinline__ uint32_t off(unsigned long long i) const { return (uint32_t)p[3 * i + 1] | ((uint32_t)p[3 * i + 2] & 1u) << 8; }
+    __device__ __forceinline__ uint32_t c(unsigned long long i) const { return ((uint32_t)p[3 * i + 2] >> 2) & 7u; }
+    __device__ __forceinline__ uint32_t thr(unsigned long long i) const { return ((uint32_t)p[3 * i + 2] >> 5) & 7u; }
+    // get_char (src/move_structure.cpp:288-293): '$' (here 8) for the end row
+    __device__ __forceinline__ uint32_t ch(unsigned long long i) const { return i == end_idx ? 8u : c(i); }
+};
+
+__device__ __forceinline__ unsigned long long tally_get(const uint8_t* tally, unsigned long long tally_len, uint32_t c, unsigned long long k) {
+    const uint8_t* q = tally + (c * tally_len + k) * 5;
+    return (unsigned long long)q[0] | ((unsigned long long)q[1] << 8) | ((unsigned long long)q[2] << 16) |
+           ((unsigned long long)q[3] << 24) | ((unsigned long long)q[4] << 32);
+}
+
+__global__ void convert_sampled_kernel(const uint8_t* __restrict__ raw, uint2* __restrict__ out,
+                                       unsigned long long r, unsigned long long end_idx,
+                                       const uint8_t* __restrict__ tally, unsigned long long tally_len, uint32_t cp,
+                                       unsigned int* __restrict__ status) {
+    const Raw3 R{raw, end_idx};
+    unsigned long long idx = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (; idx < r; idx += stride) {
+        unsigned long long id;
+        const uint32_t ci = R.c(idx);
+        if (idx == end_idx) {
+            id = 0;                                                           // :106-108
+        } else if (idx == r - 1) {
+            id = tally_get(tally, tally_len, ci, tally_len - 1);              // :114-117
+        } else if (idx % cp == 0) {
+            id = tally_get(tally, tally_len, ci, idx / cp);                   // :121-124
+        } else {
+            const unsigned long long tally_b = idx / cp + 1;
+            unsigned long long next_cp = tally_b * cp;
+            if (next_cp >= r) next_cp = r - 1;                                // :135-139
+            id = tally_get(tally, tally_len, ci, tally_b);
+            unsigned long long rows_until = 0, last_id = r;
+            const uint32_t my_ch = R.ch(idx);
+            for (unsigned long long i = idx; i < next_cp; i++)                // :165-171
+                if (R.ch(i) == my_ch) { rows_until += R.n(i); last_id = i; }
+            const bool same_as_cp = (my_ch == R.ch(next_cp));
+            if (!(last_id == idx && !same_as_cp)) {                           // :175-177
+                uint32_t off = R.off(next_cp);
+                if (!same_as_cp) { rows_until -= R.n(last_id); off = R.off(last_id); }   // :190-193
+                if (id >= r || off >= R.n(id)) { atomicOr(status, 2u); }      // :196-199 (reference throws)
+                else if (off < rows_until) {                                  // :200-215
+                    rows_until -= (off + 1);
+                    id -= 1;
+                    while (rows_until != 0) {
+                        const uint32_t nn = R.n(id);
+                        if (rows_until >= nn) { rows_until -= nn; id -= 1; } else rows_until = 0;
+                    }
+                }
+            }
+        }
+        out[idx] = make_r8(id, R.n(idx), R.off(idx), ci, R.thr(idx));
+    }
+}
+
+// ---- sampled prefix sums of run lengths (for MoveInterval::count in O(1): include/move_intervals.hpp:47-58)
+// pass 1: group sums (one u32 per 2^PREFIX_SHIFT rows) and per-block totals
+constexpr int SCAN_BLOCK = 1024;
+__global__ void prefix_group_sums_kernel(const uint2* __restrict__ rows, unsigned long long r,
+                                         unsigned long long n_groups, unsigned long long* __restrict__ group_sum,
+                                         unsigned long long* __restrict__ block_sum) {
+    __shared__ unsigned long long s[SCAN_BLOCK / 32];
+    const unsigned long long g = blockIdx.x * (unsigned long long)SCAN_BLOCK + threadIdx.x;
+    unsigned long long sum = 0;
+    if (g < n_groups) {
+        const unsigned long long b = g << PREFIX_SHIFT;
+        for (int k = 0; k < (1 << PREFIX_SHIFT); k++) if (b + k < r) sum += row_n(rows[b + k].y);
+        group_sum[g] = sum;
+    }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned long long v = threadIdx.x < SCAN_BLOCK / 32 ? s[threadIdx.x] : 0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) block_sum[blockIdx.x] = v;
+    }
+}
+// pass 2: exclusive scan of the block totals by a single block (n_blocks is r / 16384: small)
+__global__ void prefix_scan_blocks_kernel(unsigned long long* __restrict__ block_sum, unsigned long long n_blocks) {
+    __shared__ unsigned long long s[SCAN_BLOCK];
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (unsigned long long base = 0; base < n_blocks; base += SCAN_BLOCK) {
+        const unsigned long long i = base + threadIdx.x;
+        const unsigned long long v = i < n_blocks ? block_sum[i] : 0;
+        s[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < SCAN_BLOCK; o <<= 1) {
+            unsigned long long t = threadIdx.x >= o ? s[threadIdx.x - o] : 0;
+            __syncthreads();
+            s[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < n_blocks) block_sum[i] = carry + s[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == SCAN_BLOCK - 1) carry += s[threadIdx.x];
+        __syncthreads();
+    }
+}
+// pass 3: exclusive scan inside each block + block offset, in place (group_sum -> prefix)
+__global__ void prefix_finish_kernel(unsigned long long* __restrict__ group_sum, unsigned long long n_groups,
+                                     const unsigned long long* __restrict__ block_off) {
+    __shared__ unsigned long long s[SCAN_BLOCK];
+    const unsigned long long g = blockIdx.x * (unsigned long long)SCAN_BLOCK + threadIdx.x;
+    const unsigned long long v = g < n_groups ? group_sum[g] : 0;
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < SCAN_BLOCK; o <<= 1) {
+        unsigned long long t = threadIdx.x >= o ? s[threadIdx.x - o] : 0;
+        __syncthreads();
+        s[threadIdx.x] += t;
+        __syncthreads();
+    }
+    if (g < n_groups) group_sum[g] = block_off[blockIdx.x] + s[threadIdx.x] - v;
+}
+
+}  // namespace movi

@@ -1,0 +1,75 @@
+// dev_index.cuh -- device-resident form of a Movi index and the row decode.
+//
+// Device row format "R8" (one 64-bit word per move row, 4 rows per 32-byte HBM sector).  It is bit
+// for bit the reference's regular-thresholds MoveRow (include/move_row.hpp:131-142 with
+// include/move_row_configs.hpp:34-51), so a MODE 6 table is uploaded with a plain copy:
+//     x (low 32)  : id bits 0..31
+//     y bits 0..10: n (run length, <= 2047)        y bit 11 : threshold #1     y bit 12 : threshold #2
+//     y bits13..15: c (alphabet index)             y bits 16..26: offset       y bit 27 : threshold #0
+//     y bits28..31: id bits 32..35
+// blocked-thresholds (6-byte rows + id_blocks) and sampled-thresholds (3-byte rows + id checkpoints)
+// tables are re-laid out into R8 on the device at upload time (convert.cuh), resolving the full
+// destination id once per row instead of once per LF step.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace movi {
+
+struct DevIndex {
+    const uint2* rows;            // R8 rows
+    unsigned long long r;
+    unsigned long long end_idx;   // row of '$'
+    uint32_t n_last;              // n(r-1)
+    uint32_t sep;                 // 1: alphabet is "%ACGT" (codes 1..4 legal), 0: codes 0..sigma-1
+    uint32_t sigma;
+    uint32_t sep_cnt;
+    uint32_t end_thr[4];          // end_bwt_idx_thresholds, saturated to 32 bits
+    const unsigned long long* sep_keys;   // sorted rows holding '%' (separators_thresholds_map keys)
+    const uint16_t* sep_vals;             // 4 x u16 per key (ThresholdsRow), same order as sep_keys, + 1 entry = slot 0
+    // backward-search seeds, index k = code + 1 (src/move_structure_search.cpp:285-292)
+    unsigned long long first_runs[8], last_runs[8];
+    uint32_t first_offsets[8], last_offsets[8];
+    const unsigned long long* prefix;     // sampled run-length prefix sums: prefix[k] = sum_{j < k*PREFIX_STRIDE} n(j)
+    uint8_t code_of[256];         // byte -> alphabet index, 0xFF = not a legal query character
+};
+
+constexpr int PREFIX_SHIFT = 4;   // one u64 prefix per 16 rows (0.5 B/row)
+constexpr uint32_t CODE_ILLEGAL = 0xFFu;
+
+__device__ __forceinline__ uint32_t row_n(uint32_t y) { return y & 0x7FFu; }
+__device__ __forceinline__ uint32_t row_c(uint32_t y) { return (y >> 13) & 7u; }
+__device__ __forceinline__ uint32_t row_off(uint32_t y) { return (y >> 16) & 0x7FFu; }
+// thresholds #0..#2 gathered into bits 0..2
+__device__ __forceinline__ uint32_t row_thr_bits(uint32_t y) { return ((y >> 27) & 1u) | ((y >> 10) & 6u); }
+template <typename IdxT>
+__device__ __forceinline__ IdxT row_id(uint2 v) {
+    if constexpr (sizeof(IdxT) == 8) return (IdxT)v.x | ((IdxT)(v.y >> 28) << 32);
+    else return (IdxT)v.x;
+}
+__host__ __device__ __forceinline__ uint2 make_r8(unsigned long long id, uint32_t n, uint32_t off, uint32_t c, uint32_t thr_bits) {
+    uint2 v;
+    v.x = (uint32_t)(id & 0xFFFFFFFFull);
+    v.y = (n & 0x7FFu) | (((thr_bits >> 1) & 1u) << 11) | (((thr_bits >> 2) & 1u) << 12) | ((c & 7u) << 13) |
+          ((off & 0x7FFu) << 16) | ((thr_bits & 1u) << 27) | ((uint32_t)((id >> 32) & 0xFull) << 28);
+    return v;
+}
+
+__device__ __forceinline__ uint2 ldg64(const uint2* p) { return __ldg(p); }
+
+// alphamap_3 (src/utils.cpp:5-8): slot of read character b among the three thresholds of a row with character a
+__device__ __forceinline__ uint32_t thr_slot(uint32_t a, uint32_t b) { return b - (b > a ? 1u : 0u); }
+
+// threshold value of a '%' row (separators_thresholds[separators_thresholds_map[idx]].values[ai],
+// src/move_structure_query.cpp:540-541); rows missing from the map read slot 0 like unordered_map::operator[]
+__device__ __forceinline__ uint32_t sep_threshold(const DevIndex& ix, unsigned long long idx, uint32_t ai) {
+    uint32_t lo = 0, hi = ix.sep_cnt;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (ix.sep_keys[mid] < idx) lo = mid + 1; else hi = mid;
+    }
+    if (lo < ix.sep_cnt && ix.sep_keys[lo] == idx) return ix.sep_vals[lo * 4 + ai];
+    return ix.sep_vals[ix.sep_cnt * 4 + ai];   // entry sep_cnt mirrors slot 0 (set at upload)
+}
+
+}  // namespace movi

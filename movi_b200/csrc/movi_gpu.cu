@@ -1,0 +1,585 @@
+// movi_gpu.cu -- C ABI (include/movi_gpu.h) over the sm_100a query kernels.
+//
+// Owns: the device context, the upload / re-layout of an index into HBM, the pipelined host-buffer
+// entry points (H2D copy -> kernel -> D2H copy over three streams) and the device-buffer entry points.
+// There is deliberately no CPU fallback anywhere in this file.
+#include "../../include/movi_gpu.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bs_kernel.cuh"
+#include "convert.cuh"
+#include "dev_index.cuh"
+#include "misc_kernels.cuh"
+#include "pml_kernel.cuh"
+
+using namespace movi;
+
+namespace {
+
+constexpr int NBUF = 3;                       // pipeline depth of the host-buffer entry points
+std::string g_create_error;
+
+struct Staging {                              // one pipeline slot
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    uint8_t* d_bases = nullptr; size_t bases_cap = 0;
+    unsigned long long* d_offsets = nullptr; size_t offsets_cap = 0;   // in elements
+    uint16_t* d_ml = nullptr; size_t ml_cap = 0;                        // in elements
+    unsigned long long* d_count = nullptr; int32_t* d_pos = nullptr; size_t count_cap = 0;
+    unsigned long long* d_counter = nullptr;
+    bool busy = false;
+};
+
+}  // namespace
+
+struct movi_gpu_ctx {
+    int device = 0;
+    int num_sms = 0;
+    std::string err;
+    // index
+    bool has_index = false;
+    DevIndex ix{};
+    uint2* d_rows = nullptr;
+    unsigned long long* d_sep_keys = nullptr; uint16_t* d_sep_vals = nullptr;
+    unsigned long long* d_prefix = nullptr;
+    uint64_t index_bytes = 0;
+    int mode = 0;
+    // query plumbing
+    unsigned int* d_status = nullptr;
+    unsigned long long* d_counters = nullptr;        // ring of work-queue heads for the *_device calls
+    uint32_t counter_slot = 0;
+    Staging slot[NBUF];
+    uint64_t launches = 0;
+    // options
+    int64_t pml_variant = 1;          // 0: 2-byte stores, 1: register-buffered 16-byte stores
+    int64_t blocks_per_sm = 0;        // 0: occupancy query
+    int64_t threads_per_block = 256;
+    int64_t batch_bases = 48ll << 20; // bases per pipeline slot in the host-buffer entry points
+    // gather probe scratch
+    uint2* d_probe = nullptr; uint64_t probe_bytes = 0;
+};
+
+namespace {
+
+int fail(movi_gpu_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, MOVI_GPU_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+template <typename K>
+int blocks_for(movi_gpu_ctx* ctx, K kernel, int threads) {
+    int per_sm = 0;
+    if (ctx->blocks_per_sm > 0) per_sm = (int)ctx->blocks_per_sm;
+    else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return per_sm * ctx->num_sms;
+}
+
+void free_index(movi_gpu_ctx* ctx) {
+    cudaFree(ctx->d_rows); ctx->d_rows = nullptr;
+    cudaFree(ctx->d_sep_keys); ctx->d_sep_keys = nullptr;
+    cudaFree(ctx->d_sep_vals); ctx->d_sep_vals = nullptr;
+    cudaFree(ctx->d_prefix); ctx->d_prefix = nullptr;
+    ctx->has_index = false; ctx->index_bytes = 0;
+}
+
+int ensure_prefix(movi_gpu_ctx* ctx, cudaStream_t st) {
+    if (ctx->d_prefix) return MOVI_GPU_OK;
+    const unsigned long long r = ctx->ix.r;
+    const unsigned long long n_groups = (r >> PREFIX_SHIFT) + 2;
+    const unsigned long long n_blocks = (n_groups + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    unsigned long long* d_block = nullptr;
+    CU(cudaMalloc(&ctx->d_prefix, n_groups * sizeof(unsigned long long)));
+    CU(cudaMalloc(&d_block, n_blocks * sizeof(unsigned long long)));
+    prefix_group_sums_kernel<<<(unsigned)n_blocks, SCAN_BLOCK, 0, st>>>(ctx->d_rows, r, n_groups, ctx->d_prefix, d_block);
+    prefix_scan_blocks_kernel<<<1, SCAN_BLOCK, 0, st>>>(d_block, n_blocks);
+    prefix_finish_kernel<<<(unsigned)n_blocks, SCAN_BLOCK, 0, st>>>(ctx->d_prefix, n_groups, d_block);
+    ctx->launches += 3;
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    cudaFree(d_block);
+    ctx->ix.prefix = ctx->d_prefix;
+    ctx->index_bytes += n_groups * sizeof(unsigned long long);
+    return MOVI_GPU_OK;
+}
+
+enum Kind { Q_PML = 0, Q_ZML = 1, Q_COUNT = 2 };
+
+// enqueue one query kernel on `st` (device pointers)
+int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t st) {
+    const int threads = (int)ctx->threads_per_block;
+    const bool wide = ctx->ix.r > 0xFFFFFFF0ull;
+#define LAUNCH(KERNEL)                                                            \
+    do {                                                                          \
+        auto k_ = KERNEL;                                                         \
+        const int blocks_ = blocks_for(ctx, k_, threads);                         \
+        k_<<<blocks_, threads, 0, st>>>(ctx->ix, qa);                             \
+    } while (0)
+    if (kind == Q_PML) {
+        if (ctx->pml_variant == 0) { if (wide) LAUNCH((movi_pml_kernel<unsigned long long, 0>)); else LAUNCH((movi_pml_kernel<uint32_t, 0>)); }
+        else                       { if (wide) LAUNCH((movi_pml_kernel<unsigned long long, 1>)); else LAUNCH((movi_pml_kernel<uint32_t, 1>)); }
+    } else if (kind == Q_ZML) {
+        if (wide) LAUNCH((movi_bs_kernel<unsigned long long, KIND_ZML>)); else LAUNCH((movi_bs_kernel<uint32_t, KIND_ZML>));
+    } else {
+        if (wide) LAUNCH((movi_bs_kernel<unsigned long long, KIND_COUNT>)); else LAUNCH((movi_bs_kernel<uint32_t, KIND_COUNT>));
+    }
+#undef LAUNCH
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    return MOVI_GPU_OK;
+}
+
+int check_query_ready(movi_gpu_ctx* ctx, Kind kind, uint64_t n_reads) {
+    if (!ctx) return MOVI_GPU_ERR_ARG;
+    if (!ctx->has_index) return fail(ctx, MOVI_GPU_ERR_INDEX, "no index uploaded");
+    if (n_reads >= 0xFFFFFFF0ull) return fail(ctx, MOVI_GPU_ERR_ARG, "too many reads in one device call (limit 2^32 - 16)");
+    if (kind != Q_PML && ctx->mode == MOVI_MODE_SAMPLED_THRESHOLDS)
+        // reference src/movi.cpp:228-233
+        return fail(ctx, MOVI_GPU_ERR_INDEX, "This query type is not suppported by the sampled modes yet.");
+    return MOVI_GPU_OK;
+}
+
+int device_query(movi_gpu_ctx* ctx, Kind kind, const char* d_bases, const uint64_t* d_offsets, uint64_t origin,
+                 uint64_t n_reads, uint16_t* d_ml, uint64_t* d_count, int32_t* d_pos, unsigned long long* d_counter,
+                 cudaStream_t st) {
+    if (n_reads == 0) return MOVI_GPU_OK;
+    if (reinterpret_cast<uintptr_t>(d_bases) & 7u) return fail(ctx, MOVI_GPU_ERR_ARG, "d_bases must be 8-byte aligned");
+    if (kind == Q_COUNT) { int rc = ensure_prefix(ctx, st); if (rc) return rc; }
+    CU(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st));
+    QueryArgs qa{};
+    qa.bases = reinterpret_cast<const uint8_t*>(d_bases);
+    qa.offsets = reinterpret_cast<const unsigned long long*>(d_offsets);
+    qa.origin = origin;
+    qa.n_reads = (uint32_t)n_reads;
+    qa.out_ml = d_ml;
+    qa.out_count = reinterpret_cast<unsigned long long*>(d_count);
+    qa.out_pos = d_pos;
+    qa.counter = d_counter;
+    qa.status = ctx->d_status;
+    return launch_query(ctx, kind, qa, st);
+}
+
+template <typename T>
+int grow(movi_gpu_ctx* ctx, T*& p, size_t& cap, size_t need) {
+    if (need <= cap) return MOVI_GPU_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = need + need / 8 + 64;
+    CU(cudaMalloc(&p, want * sizeof(T)));
+    cap = want;
+    return MOVI_GPU_OK;
+}
+
+// Host-buffer entry point: split the batch into slices of ~batch_bases, run them through a 3-deep
+// pipeline (H2D on slot stream, kernel, D2H), results land directly in the caller's buffers.
+int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* offsets, uint64_t n_reads,
+               uint16_t* out_ml, uint64_t* out_count, int32_t* out_pos) {
+    int rc = check_query_ready(ctx, kind, 0);
+    if (rc) return rc;
+    if (n_reads == 0) return MOVI_GPU_OK;
+    if (!bases || !offsets) return fail(ctx, MOVI_GPU_ERR_ARG, "null input buffer");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemset(ctx->d_status, 0, sizeof(unsigned int)));
+    if (kind == Q_COUNT) { rc = ensure_prefix(ctx, ctx->slot[0].stream); if (rc) return rc; }
+
+    uint64_t i0 = 0;
+    int s = 0;
+    const uint64_t max_bases = (uint64_t)std::max<int64_t>(ctx->batch_bases, 1 << 16);
+    while (i0 < n_reads) {
+        // slice [i0, i1): at least one read, at most max_bases bases (a single longer read gets its own slice)
+        uint64_t i1 = i0 + 1;
+        {
+            const uint64_t limit = offsets[i0] + max_bases;
+            // offsets is non-decreasing: binary search the last read that still fits
+            uint64_t lo = i0 + 1, hi = std::min<uint64_t>(n_reads, i0 + 0x7FFFFFF0ull);
+            while (lo < hi) { uint64_t mid = (lo + hi + 1) / 2; if (offsets[mid] <= limit) lo = mid; else hi = mid - 1; }
+            i1 = std::max(i1, lo);
+        }
+        const uint64_t o0 = offsets[i0], o1 = offsets[i1];
+        const uint64_t nb = o1 - o0, nr = i1 - i0;
+        if (nb >= 0xFFFFFFF0ull) return fail(ctx, MOVI_GPU_ERR_ARG, "a single read longer than 2^32 bases is not supported");
+        Staging& S = ctx->slot[s];
+        if (S.busy) { CU(cudaEventSynchronize(S.done)); S.busy = false; }
+        // host address of the first base may be unaligned: shift the copy so that device bases stay 8-byte aligned
+        const uint64_t shift = o0 & 7u;
+        if ((rc = grow(ctx, S.d_bases, S.bases_cap, nb + shift + 16))) return rc;
+        if ((rc = grow(ctx, S.d_offsets, S.offsets_cap, nr + 1))) return rc;
+        if (kind == Q_COUNT) {
+            size_t cap2 = S.count_cap;
+            if ((rc = grow(ctx, S.d_count, S.count_cap, nr))) return rc;
+            if ((rc = grow(ctx, S.d_pos, cap2, nr))) return rc;
+        } else {
+            if ((rc = grow(ctx, S.d_ml, S.ml_cap, nb + shift + 16))) return rc;
+        }
+        CU(cudaMemcpyAsync(S.d_bases + shift, bases + o0, nb, cudaMemcpyHostToDevice, S.stream));
+        CU(cudaMemcpyAsync(S.d_offsets, offsets + i0, (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, S.stream));
+        rc = device_query(ctx, kind, reinterpret_cast<const char*>(S.d_bases), reinterpret_cast<const uint64_t*>(S.d_offsets),
+                          o0 - shift, nr, S.d_ml, reinterpret_cast<uint64_t*>(S.d_count), S.d_pos, S.d_counter, S.stream);
+        if (rc) return rc;
+        if (kind == Q_COUNT) {
+            CU(cudaMemcpyAsync(out_count + i0, S.d_count, nr * sizeof(uint64_t), cudaMemcpyDeviceToHost, S.stream));
+            CU(cudaMemcpyAsync(out_pos + i0, S.d_pos, nr * sizeof(int32_t), cudaMemcpyDeviceToHost, S.stream));
+        } else {
+            CU(cudaMemcpyAsync(out_ml + o0, S.d_ml + shift, nb * sizeof(uint16_t), cudaMemcpyDeviceToHost, S.stream));
+        }
+        CU(cudaEventRecord(S.done, S.stream));
+        S.busy = true;
+        s = (s + 1) % NBUF;
+        i0 = i1;
+    }
+    for (int k = 0; k < NBUF; k++)
+        if (ctx->slot[k].busy) { CU(cudaEventSynchronize(ctx->slot[k].done)); ctx->slot[k].busy = false; }
+    return movi_gpu_check_device_status(ctx);
+}
+
+}  // namespace
+
+extern "C" {
+
+int movi_gpu_abi_version(void) { return MOVI_GPU_ABI_VERSION; }
+
+int movi_gpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* movi_gpu_last_error(const movi_gpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int movi_gpu_create(int device, movi_gpu_ctx** out) {
+    movi_gpu_ctx* ctx = nullptr;   // for the CU macro: errors go to g_create_error
+    if (!out) return MOVI_GPU_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, MOVI_GPU_ERR_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                    "); this library has no CPU fallback");
+    if (device < 0 || device >= n) return fail(nullptr, MOVI_GPU_ERR_ARG, "device ordinal out of range");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    movi_gpu_ctx* c = new movi_gpu_ctx();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    ctx = c;
+    cudaError_t e2 = cudaMalloc(&c->d_status, sizeof(unsigned int));
+    if (e2 == cudaSuccess) e2 = cudaMemset(c->d_status, 0, sizeof(unsigned int));
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&c->d_counters, 64 * sizeof(unsigned long long));
+    for (int k = 0; k < NBUF && e2 == cudaSuccess; k++) {
+        e2 = cudaStreamCreateWithFlags(&c->slot[k].stream, cudaStreamNonBlocking);
+        if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&c->slot[k].done, cudaEventDisableTiming);
+        if (e2 == cudaSuccess) e2 = cudaMalloc(&c->slot[k].d_counter, sizeof(unsigned long long));
+    }
+    if (e2 != cudaSuccess) {
+        g_create_error = std::string("context setup failed: ") + cudaGetErrorString(e2);
+        movi_gpu_destroy(c);
+        return MOVI_GPU_ERR_CUDA;
+    }
+    *out = c;
+    return MOVI_GPU_OK;
+}
+
+int movi_gpu_destroy(movi_gpu_ctx* ctx) {
+    if (!ctx) return MOVI_GPU_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    free_index(ctx);
+    for (int k = 0; k < NBUF; k++) {
+        Staging& S = ctx->slot[k];
+        cudaFree(S.d_bases); cudaFree(S.d_offsets); cudaFree(S.d_ml); cudaFree(S.d_count); cudaFree(S.d_pos); cudaFree(S.d_counter);
+        if (S.done) cudaEventDestroy(S.done);
+        if (S.stream) cudaStreamDestroy(S.stream);
+    }
+    cudaFree(ctx->d_status); cudaFree(ctx->d_counters); cudaFree(ctx->d_probe);
+    delete ctx;
+    return MOVI_GPU_OK;
+}
+
+uint64_t movi_gpu_index_device_bytes(const movi_gpu_ctx* ctx) { return ctx ? ctx->index_bytes : 0; }
+uint64_t movi_gpu_launch_count(const movi_gpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int movi_gpu_set_option(movi_gpu_ctx* ctx, const char* key, int64_t value) {
+    if (!ctx || !key) return MOVI_GPU_ERR_ARG;
+    const std::string k(key);
+    if (k == "pml_variant") { if (value < 0 || value > 1) return fail(ctx, MOVI_GPU_ERR_ARG, "pml_variant: 0 or 1"); ctx->pml_variant = value; }
+    else if (k == "blocks_per_sm") { if (value < 0 || value > 32) return fail(ctx, MOVI_GPU_ERR_ARG, "blocks_per_sm: 0..32"); ctx->blocks_per_sm = value; }
+    else if (k == "threads_per_block") {
+        if (value < 32 || value > 256 || value % 32) return fail(ctx, MOVI_GPU_ERR_ARG, "threads_per_block: multiple of 32 in [32, 256]");
+        ctx->threads_per_block = value;
+    }
+    else if (k == "batch_bases") { if (value < (1 << 16)) return fail(ctx, MOVI_GPU_ERR_ARG, "batch_bases: >= 65536"); ctx->batch_bases = value; }
+    else return fail(ctx, MOVI_GPU_ERR_ARG, "unknown option " + k);
+    return MOVI_GPU_OK;
+}
+int64_t movi_gpu_get_option(const movi_gpu_ctx* ctx, const char* key) {
+    if (!ctx || !key) return -1;
+    const std::string k(key);
+    if (k == "pml_variant") return ctx->pml_variant;
+    if (k == "blocks_per_sm") return ctx->blocks_per_sm;
+    if (k == "threads_per_block") return ctx->threads_per_block;
+    if (k == "batch_bases") return ctx->batch_bases;
+    if (k == "num_sms") return ctx->num_sms;
+    return -1;
+}
+
+int movi_gpu_upload_index(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout) {
+    if (!ctx || !d) return MOVI_GPU_ERR_ARG;
+    if (layout != MOVI_GPU_LAYOUT_AUTO && layout != MOVI_GPU_LAYOUT_EXPANDED8)
+        return fail(ctx, MOVI_GPU_ERR_ARG, "unknown device layout");
+    if (d->mode != MOVI_MODE_REGULAR_THRESHOLDS && d->mode != MOVI_MODE_BLOCKED_THRESHOLDS && d->mode != MOVI_MODE_SAMPLED_THRESHOLDS)
+        return fail(ctx, MOVI_GPU_ERR_INDEX, "unsupported index mode " + std::to_string(d->mode) +
+                    " (regular-thresholds 6, blocked-thresholds 8, sampled-thresholds 7)");
+    if (!d->rows || !d->alphamap || d->r == 0) return fail(ctx, MOVI_GPU_ERR_INDEX, "empty index description");
+    if (d->r >= (1ull << 36)) return fail(ctx, MOVI_GPU_ERR_INDEX, "more than 2^36 rows");
+    if (d->end_bwt_idx >= d->r) return fail(ctx, MOVI_GPU_ERR_INDEX, "end_bwt_idx out of range");
+    const bool sep = (d->sigma == 5 && d->alphabet[0] == '%');       // use_separator(), src/move_structure.cpp:547-552
+    if (!sep && (d->sigma < 1 || d->sigma > 4))
+        return fail(ctx, MOVI_GPU_ERR_INDEX, "alphabet must have at most 4 characters, or be \"%ACGT\" with separators");
+    if (d->mode == MOVI_MODE_BLOCKED_THRESHOLDS && (!d->id_blocks || d->block_size == 0 || d->id_blocks_size < (d->r + d->block_size - 1) / d->block_size))
+        return fail(ctx, MOVI_GPU_ERR_INDEX, "blocked-thresholds index without a consistent id_blocks table");
+    if (d->mode == MOVI_MODE_SAMPLED_THRESHOLDS && (!d->tally_ids || d->tally_checkpoints == 0 || d->tally_len < d->r / d->tally_checkpoints + 1))
+        return fail(ctx, MOVI_GPU_ERR_INDEX, "sampled-thresholds index without a consistent id checkpoint table");
+    if (sep && d->sep_count && (!d->separators_thresholds || (d->sep_map_size && !d->separators_map)))
+        return fail(ctx, MOVI_GPU_ERR_INDEX, "separators index without its thresholds table");
+
+    CU(cudaSetDevice(ctx->device));
+    free_index(ctx);
+    cudaStream_t st = ctx->slot[0].stream;
+    const unsigned long long r = d->r;
+    CU(cudaMalloc(&ctx->d_rows, (r + 4) * sizeof(uint2)));
+    CU(cudaMemsetAsync(ctx->d_rows + r, 0, 4 * sizeof(uint2), st));
+    ctx->index_bytes = (r + 4) * sizeof(uint2);
+
+    if (d->mode == MOVI_MODE_REGULAR_THRESHOLDS) {
+        // the on-disk row IS the device row: one copy
+        CU(cudaMemcpyAsync(ctx->d_rows, d->rows, r * sizeof(uint2), cudaMemcpyHostToDevice, st));
+    } else if (d->mode == MOVI_MODE_BLOCKED_THRESHOLDS) {
+        uint16_t* d_raw = nullptr; uint32_t* d_blocks = nullptr; unsigned long long* d_first = nullptr;
+        CU(cudaMalloc(&d_raw, r * 6 + 8));
+        CU(cudaMalloc(&d_blocks, (size_t)d->sigma * d->id_blocks_size * sizeof(uint32_t)));
+        CU(cudaMalloc(&d_first, 8 * sizeof(unsigned long long)));
+        CU(cudaMemcpyAsync(d_raw, d->rows, r * 6, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_blocks, d->id_blocks, (size_t)d->sigma * d->id_blocks_size * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_first, d->first_runs, 8 * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+        convert_blocked_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(d_raw, ctx->d_rows, r, d->end_bwt_idx, d_blocks, d->id_blocks_size,
+                                                               d->block_size, d_first);
+        ctx->launches += 1;
+        CU(cudaStreamSynchronize(st));
+        CU(cudaGetLastError());
+        cudaFree(d_raw); cudaFree(d_blocks); cudaFree(d_first);
+    } else {
+        uint8_t* d_raw = nullptr; uint8_t* d_tally = nullptr;
+        const size_t tally_bytes = (size_t)d->sigma * d->tally_len * 5;
+        CU(cudaMalloc(&d_raw, r * 3 + 8));
+        CU(cudaMalloc(&d_tally, tally_bytes + 8));
+        CU(cudaMemcpyAsync(d_raw, d->rows, r * 3, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_tally, d->tally_ids, tally_bytes, cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(ctx->d_status, 0, sizeof(unsigned int), st));
+        convert_sampled_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(d_raw, ctx->d_rows, r, d->end_bwt_idx, d_tally, d->tally_len,
+                                                               d->tally_checkpoints, ctx->d_status);
+        ctx->launches += 1;
+        unsigned int status = 0;
+        CU(cudaMemcpyAsync(&status, ctx->d_status, sizeof(status), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        CU(cudaGetLastError());
+        cudaFree(d_raw); cudaFree(d_tally);
+        if (status) {
+            CU(cudaMemset(ctx->d_status, 0, sizeof(unsigned int)));
+            free_index(ctx);
+            return fail(ctx, MOVI_GPU_ERR_INDEX, "[get id - tally mode] The offset in the destination run should be always smaller than the length of that run.");
+        }
+    }
+
+    DevIndex& ix = ctx->ix;
+    std::memset(&ix, 0, sizeof(ix));
+    ix.rows = ctx->d_rows;
+    ix.r = r;
+    ix.end_idx = d->end_bwt_idx;
+    ix.sep = sep ? 1u : 0u;
+    ix.sigma = d->sigma;
+    for (int k = 0; k < 4; k++) ix.end_thr[k] = (uint32_t)std::min<uint64_t>(d->end_bwt_idx_thresholds[k], 0xFFFFFFFFull);
+    for (int k = 0; k < 8; k++) {
+        ix.first_runs[k] = d->first_runs[k]; ix.last_runs[k] = d->last_runs[k];
+        ix.first_offsets[k] = (uint32_t)d->first_offsets[k]; ix.last_offsets[k] = (uint32_t)d->last_offsets[k];
+    }
+    for (int b = 0; b < 256; b++) {
+        // check_alphabet, src/move_structure.cpp:383-397: '%' is never a legal query character with separators
+        const uint64_t a = d->alphamap[b];
+        ix.code_of[b] = (a < d->sigma && !(sep && b == '%')) ? (uint8_t)a : (uint8_t)CODE_ILLEGAL;
+    }
+    {   // n(r-1) for the start state of query_pml
+        uint2 last;
+        CU(cudaMemcpy(&last, ctx->d_rows + (r - 1), sizeof(last), cudaMemcpyDeviceToHost));
+        ix.n_last = last.y & 0x7FFu;
+        if (ix.n_last == 0) { free_index(ctx); return fail(ctx, MOVI_GPU_ERR_INDEX, "last row has length 0"); }
+    }
+    if (sep) {
+        // separators_thresholds_map: row -> slot; keep it as a sorted key array + thresholds in key order,
+        // plus one trailing entry that mirrors slot 0 (what unordered_map::operator[] would yield for a miss)
+        std::vector<std::pair<uint64_t, uint64_t>> kv(d->sep_map_size);
+        for (uint64_t i = 0; i < d->sep_map_size; i++) kv[i] = {d->separators_map[2 * i], d->separators_map[2 * i + 1]};
+        std::sort(kv.begin(), kv.end());
+        std::vector<unsigned long long> keys(kv.size() + 1, 0);
+        std::vector<uint16_t> vals((kv.size() + 1) * 4, 0);
+        for (size_t i = 0; i < kv.size(); i++) {
+            keys[i] = kv[i].first;
+            if (kv[i].second >= d->sep_count) { free_index(ctx); return fail(ctx, MOVI_GPU_ERR_INDEX, "separators map points outside the thresholds table"); }
+            for (int k = 0; k < 4; k++) vals[i * 4 + k] = d->separators_thresholds[kv[i].second * 4 + k];
+        }
+        if (d->sep_count) for (int k = 0; k < 4; k++) vals[kv.size() * 4 + k] = d->separators_thresholds[k];
+        CU(cudaMalloc(&ctx->d_sep_keys, keys.size() * sizeof(unsigned long long)));
+        CU(cudaMalloc(&ctx->d_sep_vals, vals.size() * sizeof(uint16_t)));
+        CU(cudaMemcpy(ctx->d_sep_keys, keys.data(), keys.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(ctx->d_sep_vals, vals.data(), vals.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        ix.sep_keys = ctx->d_sep_keys; ix.sep_vals = ctx->d_sep_vals; ix.sep_cnt = (uint32_t)kv.size();
+        ctx->index_bytes += keys.size() * 8 + vals.size() * 2;
+    }
+    CU(cudaStreamSynchronize(st));
+    ctx->mode = d->mode;
+    ctx->has_index = true;
+    return MOVI_GPU_OK;
+}
+
+int movi_gpu_query_pml(movi_gpu_ctx* ctx, const char* bases, const uint64_t* read_offsets, uint64_t n_reads,
+                       uint32_t, uint16_t* out_ml) {
+    if (!ctx) return MOVI_GPU_ERR_ARG;
+    if (n_reads && !out_ml) return fail(ctx, MOVI_GPU_ERR_ARG, "null output buffer");
+    return host_query(ctx, Q_PML, bases, read_offsets, n_reads, out_ml, nullptr, nullptr);
+}
+int movi_gpu_query_zml(movi_gpu_ctx* ctx, const char* bases, const uint64_t* read_offsets, uint64_t n_reads,
+                       uint32_t, uint16_t* out_ml) {
+    if (!ctx) return MOVI_GPU_ERR_ARG;
+    if (n_reads && !out_ml) return fail(ctx, MOVI_GPU_ERR_ARG, "null output buffer");
+    int rc = check_query_ready(ctx, Q_ZML, 0);
+    if (rc) return rc;
+    return host_query(ctx, Q_ZML, bases, read_offsets, n_reads, out_ml, nullptr, nullptr);
+}
+int movi_gpu_query_count(movi_gpu_ctx* ctx, const char* bases, const uint64_t* read_offsets, uint64_t n_reads,
+                         uint32_t, uint64_t* out_count, int32_t* out_pos_on_r) {
+    if (!ctx) return MOVI_GPU_ERR_ARG;
+    if (n_reads && (!out_count || !out_pos_on_r)) return fail(ctx, MOVI_GPU_ERR_ARG, "null output buffer");
+    int rc = check_query_ready(ctx, Q_COUNT, 0);
+    if (rc) return rc;
+    return host_query(ctx, Q_COUNT, bases, read_offsets, n_reads, nullptr, out_count, out_pos_on_r);
+}
+
+static unsigned long long* next_counter(movi_gpu_ctx* ctx) {
+    unsigned long long* p = ctx->d_counters + (ctx->counter_slot & 63u);
+    ctx->counter_slot++;
+    return p;
+}
+
+int movi_gpu_query_pml_device(movi_gpu_ctx* ctx, const char* d_bases, const uint64_t* d_read_offsets, uint64_t n_reads,
+                              uint32_t, uint16_t* d_out_ml, void* stream) {
+    int rc = check_query_ready(ctx, Q_PML, n_reads);
+    if (rc) return rc;
+    return device_query(ctx, Q_PML, d_bases, d_read_offsets, 0, n_reads, d_out_ml, nullptr, nullptr, next_counter(ctx), (cudaStream_t)stream);
+}
+int movi_gpu_query_zml_device(movi_gpu_ctx* ctx, const char* d_bases, const uint64_t* d_read_offsets, uint64_t n_reads,
+                              uint32_t, uint16_t* d_out_ml, void* stream) {
+    int rc = check_query_ready(ctx, Q_ZML, n_reads);
+    if (rc) return rc;
+    return device_query(ctx, Q_ZML, d_bases, d_read_offsets, 0, n_reads, d_out_ml, nullptr, nullptr, next_counter(ctx), (cudaStream_t)stream);
+}
+int movi_gpu_query_count_device(movi_gpu_ctx* ctx, const char* d_bases, const uint64_t* d_read_offsets, uint64_t n_reads,
+                                uint32_t, uint64_t* d_out_count, int32_t* d_out_pos_on_r, void* stream) {
+    int rc = check_query_ready(ctx, Q_COUNT, n_reads);
+    if (rc) return rc;
+    return device_query(ctx, Q_COUNT, d_bases, d_read_offsets, 0, n_reads, nullptr, d_out_count, d_out_pos_on_r, next_counter(ctx), (cudaStream_t)stream);
+}
+
+int movi_gpu_check_device_status(movi_gpu_ctx* ctx) {
+    if (!ctx) return MOVI_GPU_ERR_ARG;
+    unsigned int status = 0;
+    CU(cudaMemcpy(&status, ctx->d_status, sizeof(status), cudaMemcpyDeviceToHost));
+    if (status) {
+        CU(cudaMemset(ctx->d_status, 0, sizeof(unsigned int)));
+        return fail(ctx, MOVI_GPU_ERR_QUERY, "[reposition thresholds] no row with the read's character in the threshold direction: "
+                    "This should not happen! (the reference throws here, src/move_structure_query.cpp:348,582-598)");
+    }
+    return MOVI_GPU_OK;
+}
+
+int movi_gpu_classify_device(movi_gpu_ctx* ctx, const uint16_t* d_ml, const uint64_t* d_read_offsets, uint64_t n_reads,
+                             uint32_t bin_width, uint32_t max_value_thr, uint32_t* d_above, uint32_t* d_below,
+                             uint64_t* d_sum_max, void* stream) {
+    if (!ctx) return MOVI_GPU_ERR_ARG;
+    if (bin_width == 0) return fail(ctx, MOVI_GPU_ERR_ARG, "bin_width must be positive");
+    if (n_reads == 0) return MOVI_GPU_OK;
+    const int threads = 256;
+    const uint64_t warps = n_reads;
+    const unsigned blocks = (unsigned)std::min<uint64_t>((warps * 32 + threads - 1) / threads, (uint64_t)ctx->num_sms * 16);
+    classify_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(d_ml, reinterpret_cast<const unsigned long long*>(d_read_offsets), n_reads,
+                                                                  bin_width, max_value_thr, d_above, d_below,
+                                                                  reinterpret_cast<unsigned long long*>(d_sum_max));
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    return MOVI_GPU_OK;
+}
+
+int movi_gpu_host_alloc(void** p, uint64_t bytes) {
+    if (!p) return MOVI_GPU_ERR_ARG;
+    cudaError_t e = cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); *p = nullptr; return MOVI_GPU_ERR_NOMEM; }
+    return MOVI_GPU_OK;
+}
+int movi_gpu_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? MOVI_GPU_OK : MOVI_GPU_ERR_CUDA; }
+
+int movi_gpu_gather_probe(movi_gpu_ctx* ctx, uint64_t table_bytes, uint32_t load_bytes, uint32_t dependent, uint32_t steps,
+                          uint32_t blocks_per_sm, uint32_t threads_per_block, double* seconds, uint64_t* loads_done) {
+    if (!ctx || !seconds) return MOVI_GPU_ERR_ARG;
+    if (load_bytes != 8 && load_bytes != 16 && load_bytes != 32) return fail(ctx, MOVI_GPU_ERR_ARG, "load_bytes: 8, 16 or 32");
+    if (threads_per_block == 0 || threads_per_block > 1024 || blocks_per_sm == 0) return fail(ctx, MOVI_GPU_ERR_ARG, "bad launch shape");
+    CU(cudaSetDevice(ctx->device));
+    const uint2* table; uint64_t n_rows;
+    if (table_bytes == 0) {
+        if (!ctx->has_index) return fail(ctx, MOVI_GPU_ERR_ARG, "no index uploaded and table_bytes == 0");
+        table = ctx->d_rows; n_rows = ctx->ix.r & ~3ull;
+    } else {
+        table_bytes &= ~255ull;
+        if (ctx->probe_bytes != table_bytes) {
+            cudaFree(ctx->d_probe); ctx->d_probe = nullptr; ctx->probe_bytes = 0;
+            CU(cudaMalloc(&ctx->d_probe, table_bytes));
+            ctx->probe_bytes = table_bytes;
+            probe_fill_kernel<<<ctx->num_sms * 8, 256>>>(ctx->d_probe, table_bytes / 8);
+            CU(cudaDeviceSynchronize());
+        }
+        table = ctx->d_probe; n_rows = table_bytes / 8;
+    }
+    unsigned long long* d_sink = nullptr;
+    CU(cudaMalloc(&d_sink, sizeof(unsigned long long)));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    const unsigned blocks = blocks_per_sm * ctx->num_sms;
+    auto run = [&](uint32_t nsteps) {
+        if (load_bytes == 8) { if (dependent) gather_probe_kernel<8, true><<<blocks, threads_per_block>>>(table, n_rows, nsteps, d_sink); else gather_probe_kernel<8, false><<<blocks, threads_per_block>>>(table, n_rows, nsteps, d_sink); }
+        else if (load_bytes == 16) { if (dependent) gather_probe_kernel<16, true><<<blocks, threads_per_block>>>(table, n_rows, nsteps, d_sink); else gather_probe_kernel<16, false><<<blocks, threads_per_block>>>(table, n_rows, nsteps, d_sink); }
+        else { if (dependent) gather_probe_kernel<32, true><<<blocks, threads_per_block>>>(table, n_rows, nsteps, d_sink); else gather_probe_kernel<32, false><<<blocks, threads_per_block>>>(table, n_rows, nsteps, d_sink); }
+    };
+    run(std::max(1u, steps / 8));     // warm-up
+    CU(cudaEventRecord(e0));
+    run(steps);
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    CU(cudaGetLastError());
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    ctx->launches += 2;
+    *seconds = ms * 1e-3;
+    if (loads_done) *loads_done = (uint64_t)blocks * threads_per_block * steps;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_sink);
+    return MOVI_GPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,392 @@
+// movi_host.cpp -- host-side helpers either side of the GPU query path (include/movi_host.h).
+// Pure C++ (no CUDA): index.movi reader, FASTA/FASTQ reader, .bpf / text / count writers, classifier.
+#include "../../include/movi_host.h"
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+int fail(const std::string& m) { g_err = m; return 1; }
+
+constexpr uint32_t MOVI_MAGIC = 0x4D4F5649u;   // reference include/utils.hpp:29
+constexpr uint32_t BPF_MAGIC = 0x42504600u;    // reference include/utils.hpp:26
+
+}  // namespace
+
+struct movi_host_index {
+    int fd = -1;
+    const uint8_t* map = nullptr;
+    size_t size = 0;
+    MoviGpuIndexDesc d{};
+    uint64_t original_r = 0;
+    std::vector<uint64_t> alphamap;
+    std::vector<uint16_t> sep_thr;
+    std::vector<uint64_t> sep_map;
+    std::vector<uint32_t> id_blocks;      // aligned copy
+    std::string type_name;
+};
+
+struct movi_host_reads {
+    std::string bases;
+    std::vector<uint64_t> offsets{0};
+    std::string ids;                      // concatenated ids
+    std::vector<uint64_t> id_offsets{0};
+};
+
+namespace {
+
+struct Cursor {
+    const uint8_t* p; size_t size; size_t pos = 0; bool ok = true;
+    bool need(size_t n) { if (!ok || pos + n > size || pos + n < pos) { ok = false; return false; } return true; }
+    template <typename T> T get() { T v{}; if (need(sizeof(T))) { std::memcpy(&v, p + pos, sizeof(T)); pos += sizeof(T); } return v; }
+    const uint8_t* take(size_t n) { if (!need(n)) return nullptr; const uint8_t* q = p + pos; pos += n; return q; }
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* movi_host_last_error(void) { return g_err.c_str(); }
+
+// MoveStructure::deserialize, reference src/move_structure_io.cpp:471-511 (modern header only)
+int movi_host_index_open(const char* path, movi_host_index** out) {
+    if (!path || !out) return fail("null argument");
+    *out = nullptr;
+    std::string file(path);
+    struct stat sb;
+    if (stat(file.c_str(), &sb) == 0 && S_ISDIR(sb.st_mode)) file += "/index.movi";     // io.cpp:16-22
+    int fd = open(file.c_str(), O_RDONLY);
+    if (fd < 0) return fail("[deserialize index] Failed to open the index file at: " + std::string(path));
+    if (fstat(fd, &sb) != 0 || sb.st_size < 64) { close(fd); return fail("index file too small: " + file); }
+    void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (m == MAP_FAILED) { close(fd); return fail("mmap failed for " + file); }
+    movi_host_index* ix = new movi_host_index();
+    ix->fd = fd; ix->map = static_cast<const uint8_t*>(m); ix->size = (size_t)sb.st_size;
+    Cursor c{ix->map, ix->size};
+    MoviGpuIndexDesc& d = ix->d;
+    auto bad = [&](const std::string& why) { movi_host_index_close(ix); return fail("[deserialize index] " + why); };
+
+    // MoviHeader, include/utils.hpp:32-61: u32 magic; u8 version[3]; char type; u8 reserved; pad; 4 x u64
+    const uint8_t* h = c.take(48);
+    if (!h) return bad("truncated header");
+    uint32_t magic; std::memcpy(&magic, h, 4);
+    if (magic != MOVI_MAGIC) return bad("Invalid magic number in header. Not a valid Movi 2.0 index file.");
+    d.mode = (int32_t)(int8_t)h[7];
+    std::memcpy(&d.length, h + 16, 8); std::memcpy(&d.r, h + 24, 8);
+    std::memcpy(&ix->original_r, h + 32, 8); std::memcpy(&d.end_bwt_idx, h + 40, 8);
+    size_t row_bytes;
+    switch (d.mode) {
+        case MOVI_MODE_REGULAR_THRESHOLDS: row_bytes = 8; ix->type_name = "regular-thresholds"; break;
+        case MOVI_MODE_BLOCKED_THRESHOLDS: row_bytes = 6; ix->type_name = "blocked-thresholds"; break;
+        case MOVI_MODE_SAMPLED_THRESHOLDS: row_bytes = 3; ix->type_name = "sampled-thresholds"; break;
+        default: return bad("Index mode " + std::to_string(d.mode) + " is not supported by the GPU query path "
+                            "(regular-thresholds, blocked-thresholds, sampled-thresholds only)");
+    }
+    // read_basic_index_data, io.cpp:145-184
+    for (int k = 0; k < 4; k++) d.end_bwt_idx_thresholds[k] = c.get<uint64_t>();
+    c.take(64);                                          // end_bwt_idx_next_down / next_up (constant mode only)
+    const uint64_t alphamap_size = c.get<uint64_t>();
+    if (!c.ok || alphamap_size != 256) return bad("unexpected alphamap size");
+    ix->alphamap.resize(256);
+    for (auto& a : ix->alphamap) a = c.get<uint64_t>();
+    d.alphamap = ix->alphamap.data();
+    const uint64_t sigma = c.get<uint64_t>();
+    if (!c.ok || sigma == 0 || sigma > 7) return bad("unexpected alphabet size");
+    d.sigma = (uint32_t)sigma;
+    const uint8_t* al = c.take(sigma);
+    if (!al) return bad("truncated alphabet");
+    std::memcpy(d.alphabet, al, sigma);
+    c.take(3);                                           // u16 nt_splitting; u8 constant
+    // read_main_table, io.cpp:361-397
+    d.rows = c.take(d.r * row_bytes);
+    if (!d.rows) return bad("truncated row table");
+    // read_tally_table, io.cpp:338-349
+    if (d.mode == MOVI_MODE_SAMPLED_THRESHOLDS) {
+        d.tally_checkpoints = c.get<uint32_t>();
+        d.tally_len = c.get<uint64_t>();
+        d.tally_ids = c.take((size_t)sigma * d.tally_len * 5);
+        if (!d.tally_ids) return bad("truncated id checkpoint table");
+    }
+    // read_overflow_tables, io.cpp:219-237
+    uint64_t sz = c.get<uint64_t>(); c.take(sz * 8);
+    sz = c.get<uint64_t>(); c.take(sz * 8);
+    sz = c.get<uint64_t>(); c.take(sz * 8 * (sigma - 1));
+    // read_counts_data, io.cpp:269-287
+    sz = c.get<uint64_t>();
+    if (!c.ok || sz != sigma) return bad("unexpected counts size");
+    c.take(sz * 8);
+    const uint64_t k1 = c.get<uint64_t>();
+    if (!c.ok || k1 != sigma + 1 || k1 > 8) return bad("unexpected first/last runs size");
+    for (uint64_t k = 0; k < k1; k++) d.last_runs[k] = c.get<uint64_t>();
+    for (uint64_t k = 0; k < k1; k++) d.last_offsets[k] = c.get<uint64_t>();
+    for (uint64_t k = 0; k < k1; k++) d.first_runs[k] = c.get<uint64_t>();
+    for (uint64_t k = 0; k < k1; k++) d.first_offsets[k] = c.get<uint64_t>();
+    // read_id_blocks, io.cpp:305-324
+    if (d.mode == MOVI_MODE_BLOCKED_THRESHOLDS) {
+        d.id_blocks_size = c.get<uint64_t>();
+        const uint8_t* b = c.take((size_t)sigma * d.id_blocks_size * 4);
+        if (!b && d.id_blocks_size) return bad("truncated id_blocks");
+        ix->id_blocks.resize((size_t)sigma * d.id_blocks_size);
+        if (b) std::memcpy(ix->id_blocks.data(), b, ix->id_blocks.size() * 4);
+        d.id_blocks = ix->id_blocks.data();
+        d.block_size = c.get<uint64_t>();
+    }
+    if (!c.ok) return bad("truncated index file");
+    // read_separators_thresholds, io.cpp:415-433 (present iff use_separator(), move_structure.cpp:547-552)
+    if (sigma == 5 && d.alphabet[0] == '%') {
+        d.sep_count = c.get<uint64_t>();
+        const uint8_t* t = c.take(d.sep_count * 8);
+        if (!c.ok) return bad("truncated separators thresholds");
+        ix->sep_thr.resize(d.sep_count * 4);
+        if (t) std::memcpy(ix->sep_thr.data(), t, d.sep_count * 8);
+        d.sep_map_size = c.get<uint64_t>();
+        const uint8_t* mp = c.take(d.sep_map_size * 16);
+        if (!c.ok) return bad("truncated separators map");
+        ix->sep_map.resize(d.sep_map_size * 2);
+        if (mp) std::memcpy(ix->sep_map.data(), mp, d.sep_map_size * 16);
+        d.separators_thresholds = ix->sep_thr.data();
+        d.separators_map = ix->sep_map.data();
+    }
+    *out = ix;
+    return 0;
+}
+
+int movi_host_index_desc(const movi_host_index* ix, MoviGpuIndexDesc* out) {
+    if (!ix || !out) return fail("null argument");
+    *out = ix->d;
+    return 0;
+}
+uint64_t movi_host_index_original_r(const movi_host_index* ix) { return ix ? ix->original_r : 0; }
+const char* movi_host_index_type_name(const movi_host_index* ix) { return ix ? ix->type_name.c_str() : ""; }
+
+void movi_host_index_close(movi_host_index* ix) {
+    if (!ix) return;
+    if (ix->map) munmap(const_cast<uint8_t*>(ix->map), ix->size);
+    if (ix->fd >= 0) close(ix->fd);
+    delete ix;
+}
+
+// BatchLoader::loadBatch + grabNextRead (reference src/batch_loader.cpp:26-143) over the whole input.
+int movi_host_reads_load(const char* path, int reverse, movi_host_reads** out) {
+    if (!path || !out) return fail("null argument");
+    *out = nullptr;
+    std::ifstream file;
+    std::istream* in = &std::cin;
+    if (std::string(path) != "-") {                     // "-" = stdin, reference src/movi.cpp:106-118
+        file.open(path);
+        if (!file) return fail("The input file " + std::string(path) + " does not exist.");
+        in = &file;
+    }
+    movi_host_reads* rd = new movi_host_reads();
+    const int first = in->peek();
+    if (first == EOF) { *out = rd; return 0; }
+    bool fastq;
+    if (first == '>') fastq = false;
+    else if (first == '@') fastq = true;
+    else { delete rd; return fail("unrecognized input query file type - expects FASTA or FASTQ."); }
+
+    std::string line, seq;
+    auto rtrim = [](std::string& s) { while (!s.empty() && std::isspace(static_cast<unsigned char>(s.back()))) s.pop_back(); };
+    auto add = [&](const std::string& header, std::string& s) {
+        // id: header[1 .. first whitespace] INCLUDING that whitespace character (batch_loader.cpp:117-119)
+        size_t idl = header.find_first_of(" \t\r", 1);
+        idl = (idl == std::string::npos) ? header.size() : idl;
+        rd->ids.append(header.substr(1, idl));
+        rd->id_offsets.push_back(rd->ids.size());
+        if (reverse) std::reverse(s.begin(), s.end());   // read_processor.cpp:49-51, movi.cpp:351-352
+        rd->bases.append(s);
+        rd->offsets.push_back(rd->bases.size());
+    };
+    bool have_line = static_cast<bool>(std::getline(*in, line));
+    while (have_line) {
+        if (line.empty()) break;                         // grabNextRead: an empty line ends the batch
+        if (fastq ? line[0] != '@' : line[0] != '>') {
+            delete rd;
+            return fail(std::string("Incorrect ") + (fastq ? "FASTQ entry, it should start with '@'" : "FASTA entry, it should start with '>'"));
+        }
+        if (line.size() <= 2) { delete rd; return fail("header line is missing an id. invalid query cannot be processed."); }
+        const std::string header = line;
+        seq.clear();
+        if (fastq) {
+            if (!std::getline(*in, seq)) break;
+            rtrim(seq);
+            std::string plus, qual;
+            if (!std::getline(*in, plus)) break;
+            if (!std::getline(*in, qual)) break;
+            add(header, seq);
+            have_line = static_cast<bool>(std::getline(*in, line));
+        } else {
+            have_line = false;
+            while (std::getline(*in, line)) {
+                if (!line.empty() && line[0] == '>') { have_line = true; break; }
+                rtrim(line);
+                seq.append(line);
+            }
+            add(header, seq);
+        }
+    }
+    *out = rd;
+    return 0;
+}
+
+uint64_t movi_host_reads_count(const movi_host_reads* rd) { return rd ? rd->offsets.size() - 1 : 0; }
+const char* movi_host_reads_bases(const movi_host_reads* rd) { return rd ? rd->bases.data() : nullptr; }
+const uint64_t* movi_host_reads_offsets(const movi_host_reads* rd) { return rd ? rd->offsets.data() : nullptr; }
+const char* movi_host_reads_id(const movi_host_reads* rd, uint64_t i, uint32_t* len) {
+    if (!rd || i + 1 >= rd->id_offsets.size()) { if (len) *len = 0; return nullptr; }
+    if (len) *len = (uint32_t)(rd->id_offsets[i + 1] - rd->id_offsets[i]);
+    return rd->ids.data() + rd->id_offsets[i];
+}
+void movi_host_reads_free(movi_host_reads* rd) { delete rd; }
+
+// Classifier::initialize_report_file :24-32 + EmpNullDatabase::deserialize (emperical_null_database.cpp:106-126)
+int movi_host_nulldb_threshold(const char* index_dir, const char* query_type, uint64_t* max_value_thr) {
+    if (!index_dir || !query_type || !max_value_thr) return fail("null argument");
+    const std::string name = std::string(index_dir) + "/movi." + query_type + ".nulldb";
+    std::ifstream f(name, std::ios::binary);
+    if (!f) return fail("cannot open null database " + name);
+    uint64_t num = 0, percentile = 0; double mean = 0;
+    f.read(reinterpret_cast<char*>(&num), 8); f.read(reinterpret_cast<char*>(&mean), 8); f.read(reinterpret_cast<char*>(&percentile), 8);
+    if (!f) return fail("truncated null database " + name);
+    // max_value_thr is a uint16_t member in the reference (include/classifier.hpp:30)
+    *max_value_thr = (uint16_t)(std::max<uint64_t>(percentile, 3) + 1);   // MIN_MATCHING_LENGTH = 3, include/utils.hpp:152
+    return 0;
+}
+
+namespace {
+struct FdWriter {
+    int fd; std::string buf;
+    explicit FdWriter(int f) : fd(f) { buf.reserve(1 << 20); }
+    bool flush() {
+        size_t o = 0;
+        while (o < buf.size()) { ssize_t w = ::write(fd, buf.data() + o, buf.size() - o); if (w <= 0) return false; o += (size_t)w; }
+        buf.clear(); return true;
+    }
+    bool put(const char* p, size_t n) { buf.append(p, n); return buf.size() < (1 << 20) || flush(); }
+    bool put(const std::string& s) { return put(s.data(), s.size()); }
+};
+}  // namespace
+
+// output_base_stats (binary branch) + BPFHeader, reference src/utils.cpp:202-246, include/utils.hpp:64-86
+int movi_host_write_bpf(const char* file, const movi_host_reads* rd, const uint16_t* ml) {
+    if (!file || !rd || (!ml && !rd->bases.empty())) return fail("null argument");
+    FILE* f = std::fopen(file, "wb");
+    if (!f) return fail(std::string("cannot open ") + file);
+    uint8_t header[12] = {0};
+    std::memcpy(header, &BPF_MAGIC, 4);
+    header[4] = 1; header[5] = 0; header[6] = 0;         // BPF_VERSION 1.0.0, include/version.hpp:13-15
+    header[7] = 16;                                      // entry size in bits
+    std::fwrite(header, 1, 12, f);
+    const uint64_t n = rd->offsets.size() - 1;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint16_t idl = (uint16_t)(rd->id_offsets[i + 1] - rd->id_offsets[i]);
+        std::fwrite(&idl, 2, 1, f);
+        std::fwrite(rd->ids.data() + rd->id_offsets[i], 1, idl, f);
+        const uint64_t len = rd->offsets[i + 1] - rd->offsets[i];
+        std::fwrite(&len, 8, 1, f);
+        std::fwrite(ml + rd->offsets[i], 2, len, f);
+    }
+    const bool ok = std::fclose(f) == 0;
+    return ok ? 0 : fail(std::string("write failed: ") + file);
+}
+
+// output_base_stats (--stdout branch), reference src/utils.cpp:204-209 with MoveQuery::add_ml's string
+// (include/move_query.hpp:33-37): values in read order, each followed by one blank
+int movi_host_write_ml_text(int fd, const movi_host_reads* rd, const uint16_t* ml) {
+    if (!rd || (!ml && !rd->bases.empty())) return fail("null argument");
+    FdWriter w(fd);
+    const uint64_t n = rd->offsets.size() - 1;
+    char num[8];
+    for (uint64_t i = 0; i < n; i++) {
+        w.put(">", 1);
+        w.put(rd->ids.data() + rd->id_offsets[i], rd->id_offsets[i + 1] - rd->id_offsets[i]);
+        w.put("\n", 1);
+        const uint64_t s = rd->offsets[i], e = rd->offsets[i + 1];
+        for (uint64_t k = e; k > s; k--) {
+            unsigned v = ml[k - 1];
+            int l = 0; char tmp[6];
+            do { tmp[l++] = (char)('0' + v % 10); v /= 10; } while (v);
+            for (int j = 0; j < l; j++) num[j] = tmp[l - 1 - j];
+            num[l] = ' ';
+            w.put(num, (size_t)l + 1);
+        }
+        w.put("\n", 1);
+    }
+    return w.flush() ? 0 : fail("write failed");
+}
+
+// output_counts, reference src/utils.cpp:248-256
+int movi_host_write_counts(int fd, const movi_host_reads* rd, const uint64_t* counts, const int32_t* pos_on_r) {
+    if (!rd || !counts || !pos_on_r) return fail("null argument");
+    FdWriter w(fd);
+    const uint64_t n = rd->offsets.size() - 1;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t len = rd->offsets[i + 1] - rd->offsets[i];
+        w.put(rd->ids.data() + rd->id_offsets[i], rd->id_offsets[i + 1] - rd->id_offsets[i]);
+        w.put("\t" + std::to_string(len - (uint64_t)(int64_t)pos_on_r[i]) + "/" + std::to_string(len) + "\t" + std::to_string(counts[i]) + "\n");
+    }
+    return w.flush() ? 0 : fail("write failed");
+}
+
+// Classifier::initialize_report_file (header) + classify (rows), reference src/classifier.cpp:49-60, 99-143;
+// filter output = output_read, src/utils.cpp:291-294 via src/movi.cpp:41-47
+int movi_host_classify(int fd, int mode, const movi_host_reads* rd, const uint16_t* ml, uint64_t bin_width,
+                       uint64_t max_value_thr, uint8_t* found_out) {
+    if (!rd || (!ml && !rd->bases.empty()) || bin_width == 0) return fail("bad argument");
+    FdWriter w(fd);
+    std::ostringstream out;
+    const uint16_t thr = (uint16_t)max_value_thr;
+    if (mode == 0) {
+        out.precision(4);
+        out << std::setw(30) << std::left << "read id:" << std::setw(15) << std::left << "status:"
+            << std::setw(19) << std::left << "avg max-value (thr=" << std::setw(2) << std::left << thr
+            << std::setw(5) << std::left << "):" << std::setw(12) << std::left << "above thr:"
+            << std::setw(12) << std::left << "below thr:" << std::endl;
+    }
+    const uint64_t n = rd->offsets.size() - 1;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint16_t* v = ml + rd->offsets[i];
+        const size_t len = rd->offsets[i + 1] - rd->offsets[i];
+        size_t above = 0, below = 0, sum = 0, nbins = 0, start = 0, end = 0;
+        while (start < len) {
+            end = (start + bin_width < len) ? start + bin_width : len;
+            if (len - end < bin_width) end = len;
+            const uint16_t mx = *std::max_element(v + start, v + end);
+            if (mx >= thr) above++; else below++;
+            sum += mx; nbins++;
+            start += (end - start);
+        }
+        const bool found = (above / (above + below + 0.0) > 0.50);
+        if (found_out) found_out[i] = found ? 1 : 0;
+        const std::string id(rd->ids.data() + rd->id_offsets[i], rd->id_offsets[i + 1] - rd->id_offsets[i]);
+        if (mode == 0) {
+            out.precision(3);
+            out << std::setw(30) << std::left << id << std::setw(15) << std::left << (found ? "FOUND" : "NOT_PRESENT")
+                << std::setw(26) << std::left << (sum + 0.0) / nbins << std::setw(12) << std::left << above
+                << std::setw(12) << std::left << below << "\n";
+        } else if ((mode == 1 && found) || (mode == 2 && !found)) {
+            out << ">" << id << "\n";
+            out.write(rd->bases.data() + rd->offsets[i], (std::streamsize)len);
+            out << "\n";
+        }
+        if (out.tellp() > (1 << 20)) { w.put(out.str()); out.str(""); }
+    }
+    w.put(out.str());
+    return w.flush() ? 0 : fail("write failed");
+}
+
+}  // extern "C"

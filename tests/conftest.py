@@ -1,0 +1,62 @@
+import lzma
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+TYPES = ["regular-thresholds", "blocked-thresholds", "sampled-thresholds"]
+READ_SETS = ["sample.fastq", "sample.fasta", "long6.fasta", "synth300.fasta", "edge.fasta"]
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    # GPU tests are selected with `-m gpu`; if someone runs everything on a CPU box, skip instead of failing
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def index_dirs(tmp_path_factory):
+    """{(type, sep): directory holding index.movi + frozen nulldbs}, unpacked from tests/golden/c1."""
+    base = tmp_path_factory.mktemp("c1")
+    out = {}
+    for typ in TYPES:
+        for sep in (False, True):
+            tag = typ + (".sep" if sep else "")
+            d = base / tag
+            d.mkdir()
+            with lzma.open(os.path.join(GOLD, "c1", tag, "index.movi.xz")) as f:
+                (d / "index.movi").write_bytes(f.read())
+            nd = os.path.join(GOLD, "c1", "regular-thresholds" + (".sep" if sep else ""))
+            for q in ("pml", "zml"):
+                with lzma.open(os.path.join(nd, "movi.%s.nulldb.xz" % q)) as f:
+                    (d / ("movi.%s.nulldb" % q)).write_bytes(f.read())
+            out[(typ, sep)] = str(d)
+    return out
+
+
+def expected_text(read_set, query, sep=False):
+    name = "%s%s.%s.txt.xz" % (read_set, ".sep" if sep else "", query)
+    with lzma.open(os.path.join(GOLD, "expected", name)) as f:
+        return f.read().decode()
+
+
+def reads_path(read_set):
+    return os.path.join(GOLD, "reads", read_set)

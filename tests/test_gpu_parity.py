@@ -1,0 +1,175 @@
+"""Parity of the CUDA path (through the C ABI) with the reference outputs and with the CPU oracle.
+Bit-exact: PML / ZML are uint16 per base, counts are uint64 per read."""
+import numpy as np
+import pytest
+
+from conftest import READ_SETS, TYPES, expected_text, reads_path
+from _fmt import count_text, ml_text
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def structures(index_dirs):
+    from movi_b200 import MoveStructure
+    ms = {k: MoveStructure(v) for k, v in index_dirs.items()}
+    yield ms
+    for m in ms.values():
+        m.close()
+
+
+@pytest.fixture(scope="module")
+def read_sets():
+    from movi_b200 import Reads
+    return {s: Reads(reads_path(s)) for s in READ_SETS}
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("sep", [False, True])
+@pytest.mark.parametrize("typ", TYPES)
+@pytest.mark.parametrize("read_set", READ_SETS)
+def test_pml_matches_reference(structures, read_sets, typ, read_set, sep, variant):
+    rd = read_sets[read_set]
+    ms = structures[(typ, sep)]
+    ms.set_option("pml_variant", variant)
+    ml = ms.query_pml(rd.bases, rd.offsets)
+    assert ml_text(rd.ids(), rd.offsets, ml) == expected_text(read_set, "pml", sep)
+
+
+@pytest.mark.parametrize("sep", [False, True])
+@pytest.mark.parametrize("typ", TYPES[:2])
+@pytest.mark.parametrize("read_set", READ_SETS)
+def test_zml_matches_reference(structures, read_sets, typ, read_set, sep):
+    rd = read_sets[read_set]
+    ml = structures[(typ, sep)].query_zml(rd.bases, rd.offsets)
+    assert ml_text(rd.ids(), rd.offsets, ml) == expected_text(read_set, "zml", sep)
+
+
+@pytest.mark.parametrize("sep", [False, True])
+@pytest.mark.parametrize("typ", TYPES[:2])
+@pytest.mark.parametrize("read_set", READ_SETS)
+def test_count_matches_reference(structures, read_sets, typ, read_set, sep):
+    rd = read_sets[read_set]
+    counts, pos = structures[(typ, sep)].query_backward_search(rd.bases, rd.offsets)
+    assert count_text(rd.ids(), rd.offsets, counts, pos) == expected_text(read_set, "count", sep)
+
+
+def test_sampled_rejects_zml_and_count(structures, read_sets):
+    """reference src/movi.cpp:228-233"""
+    from movi_b200 import MoviGpuError
+    rd = read_sets["sample.fasta"]
+    ms = structures[("sampled-thresholds", False)]
+    with pytest.raises(MoviGpuError, match="not suppported by the sampled modes"):
+        ms.query_zml(rd.bases, rd.offsets)
+    with pytest.raises(MoviGpuError, match="not suppported by the sampled modes"):
+        ms.query_backward_search(rd.bases, rd.offsets)
+
+
+def _random_reads(seed, n_reads, max_len, ref_seq, p_illegal=0.01):
+    rng = np.random.default_rng(seed)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    both = ref_seq + ref_seq.translate(comp)[::-1]
+    reads = []
+    for i in range(n_reads):
+        L = int(rng.integers(0 if i % 97 == 0 else 1, max_len + 1))
+        if rng.random() < 0.15:
+            s = bytearray(rng.choice(np.frombuffer(b"ACGT", np.uint8), L).tobytes())
+        else:
+            p = int(rng.integers(0, len(both) - L))
+            s = bytearray(both[p:p + L])
+            for j in np.nonzero(rng.random(L) < 0.02)[0]:
+                s[j] = b"ACGT"[int(rng.integers(0, 4))]
+        for j in np.nonzero(rng.random(L) < p_illegal)[0]:
+            s[j] = b"NnRa%$"[int(rng.integers(0, 6))]
+        reads.append(bytes(s))
+    return reads
+
+
+@pytest.fixture(scope="module")
+def ref_seq():
+    import lzma, os
+    from conftest import GOLD
+    txt = lzma.open(os.path.join(GOLD, "ref.fasta.xz")).read().decode()
+    return "".join(l.strip() for l in txt.split("\n") if not l.startswith(">")).upper().encode()
+
+
+@pytest.mark.parametrize("sep", [False, True])
+@pytest.mark.parametrize("typ", TYPES)
+def test_random_reads_vs_oracle(structures, index_dirs, ref_seq, typ, sep):
+    """20k ragged reads (empty, 1-base, illegal characters, up to 600 bases) -- every value must equal the oracle's."""
+    from oracle.port import OracleIndex, pack_reads
+    reads = _random_reads(7, 20000, 600, ref_seq)
+    bases, offsets = pack_reads(reads)
+    orc = OracleIndex(index_dirs[(typ, sep)])
+    ms = structures[(typ, sep)]
+    for variant in (0, 1):
+        ms.set_option("pml_variant", variant)
+        assert np.array_equal(ms.query_pml(bases, offsets), orc.query_pml(bases, offsets, threads=0))
+    if typ != "sampled-thresholds":
+        # reads of length 0 are outside the reference's domain for zml/count (it indexes R[-1]); compare the rest
+        assert np.array_equal(ms.query_zml(bases, offsets), orc.query_zml(bases, offsets, threads=0))
+        c1, p1 = ms.query_backward_search(bases, offsets)
+        c2, p2 = orc.query_count(bases, offsets, threads=0)
+        assert np.array_equal(c1, c2) and np.array_equal(p1, p2)
+
+
+def test_small_pipeline_slices(structures, index_dirs, ref_seq):
+    """The host entry point slices big batches; force many tiny slices and compare with one big slice."""
+    from oracle.port import pack_reads
+    reads = _random_reads(11, 5000, 300, ref_seq)
+    bases, offsets = pack_reads(reads)
+    ms = structures[("regular-thresholds", False)]
+    big = ms.query_pml(bases, offsets)
+    old = ms.get_option("batch_bases")
+    ms.set_option("batch_bases", 65536)
+    try:
+        small = ms.query_pml(bases, offsets)
+        z_small = ms.query_zml(bases, offsets)
+        c_small = ms.query_backward_search(bases, offsets)
+    finally:
+        ms.set_option("batch_bases", old)
+    assert np.array_equal(big, small)
+    assert np.array_equal(z_small, ms.query_zml(bases, offsets))
+    c_big = ms.query_backward_search(bases, offsets)
+    assert np.array_equal(c_small[0], c_big[0]) and np.array_equal(c_small[1], c_big[1])
+
+
+def test_device_entry_points_with_torch(structures, index_dirs, ref_seq):
+    """The *_device entry points on torch-owned HBM buffers, plus device-side classification."""
+    import torch
+    from oracle.port import OracleIndex, pack_reads, classify
+    reads = [r for r in _random_reads(13, 4000, 500, ref_seq) if len(r) > 0]
+    bases, offsets = pack_reads(reads)
+    ms = structures[("regular-thresholds", False)]
+    orc = OracleIndex(index_dirs[("regular-thresholds", False)])
+    dev = torch.device("cuda:0")
+    pad = (-len(bases)) % 16 + 16
+    d_bases = torch.from_numpy(np.concatenate([bases, np.zeros(pad, np.uint8)])).to(dev)
+    d_off = torch.from_numpy(offsets.astype(np.int64)).to(dev)
+    d_out = torch.zeros(len(bases) + 16, dtype=torch.int16, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    ms.query_pml_device(d_bases.data_ptr(), d_off.data_ptr(), len(reads), d_out.data_ptr(), stream)
+    torch.cuda.synchronize()
+    ms.check_device_status()
+    got = d_out.cpu().numpy().view(np.uint16)[: len(bases)]
+    want = orc.query_pml(bases, offsets, threads=0)
+    assert np.array_equal(got, want)
+    n = len(reads)
+    d_above = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_below = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_sum = torch.zeros(n, dtype=torch.int64, device=dev)
+    ms.classify_device(d_out.data_ptr(), d_off.data_ptr(), n, 150, 7, d_above.data_ptr(), d_below.data_ptr(), d_sum.data_ptr(), stream)
+    torch.cuda.synchronize()
+    a, b, s = d_above.cpu().numpy(), d_below.cpu().numpy(), d_sum.cpu().numpy()
+    for i in range(0, n, 37):
+        f, ea, eb, es, _ = classify(want[int(offsets[i]):int(offsets[i + 1])], 150, 7)
+        assert (a[i], b[i], s[i]) == (ea, eb, es)
+    d_cnt = torch.zeros(n, dtype=torch.int64, device=dev)
+    d_pos = torch.zeros(n, dtype=torch.int32, device=dev)
+    ms.query_count_device(d_bases.data_ptr(), d_off.data_ptr(), n, d_cnt.data_ptr(), d_pos.data_ptr(), stream)
+    ms.query_zml_device(d_bases.data_ptr(), d_off.data_ptr(), n, d_out.data_ptr(), stream)
+    torch.cuda.synchronize()
+    ms.check_device_status()
+    c2, p2 = orc.query_count(bases, offsets, threads=0)
+    assert np.array_equal(d_cnt.cpu().numpy().view(np.uint64), c2) and np.array_equal(d_pos.cpu().numpy(), p2)
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint16)[: len(bases)], orc.query_zml(bases, offsets, threads=0))
