@@ -1,0 +1,245 @@
+// movi_cli.cpp -- `movi-b200 query ...`: the reference's `movi query` command line over the GPU query path.
+//
+// Mirrors the query action of the reference (flags: src/movi_parser.cpp:132-162; driver: query() in
+// src/movi.cpp:221-400; output routing: include/movi_options.hpp:70-71, src/utils.cpp:319-384,
+// src/classifier.cpp:24-63).  Reads are loaded on the host, sharded over --gpus GPUs (index replicated,
+// one host thread + one context per GPU), results are written in read order (= reference --no-prefetch -t1).
+// `movi-b200 view --bpf F` prints a .bpf file like the reference's view action (src/movi.cpp:402-503).
+#include <unistd.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/movi_gpu.h"
+#include "../../include/movi_host.h"
+
+namespace {
+
+struct Options {
+    std::string action, index_dir, read_file, out_file, bpf_file;
+    std::string query = "pml";
+    bool classify = false, filter = false, invert = false, to_stdout = false, no_output = false, reverse = false, verbose = false;
+    int ignore_illegal = 0, gpus = 1, device = 0, threads = 1, strands = 16;
+    uint64_t bin_width = 150;     // include/movi_options.hpp default
+    bool write_output_allowed() const { return !no_output && !filter; }          // movi_options.hpp:70
+    bool write_stdout_enabled() const { return to_stdout && !classify; }         // movi_options.hpp:71
+};
+
+[[noreturn]] void usage_error(const std::string& m) {
+    fprintf(stderr, "\033[31m\n\n[ERROR] %s\n\033[0m\n", m.c_str());
+    fprintf(stderr, "usage: movi-b200 query -i <index dir> -r <reads.fa|fq|-> [--pml|--zml|--count] [--classify|--filter [-v]]\n"
+                    "                       [--stdout] [-o prefix] [--no-output] [--reverse] [--ignore-illegal-chars 1|2]\n"
+                    "                       [--bin-width N] [--gpus N] [--device D] [-t N] [-s N] [-n]\n"
+                    "       movi-b200 view --bpf <file.bpf>\n");
+    exit(1);
+}
+
+// cxxopts semantics used by the reference's tests: "-t1", "-t 1", "--threads 1", "--threads=1"
+bool take_value(int argc, char** argv, int& i, const char* shortf, const char* longf, std::string& out) {
+    const std::string a = argv[i];
+    if (shortf && a.rfind(shortf, 0) == 0 && a.size() > 2 && a[1] != '-') { out = a.substr(2); return true; }
+    if ((shortf && a == shortf) || a == longf) {
+        if (i + 1 >= argc) usage_error("missing value for " + a);
+        out = argv[++i]; return true;
+    }
+    const std::string eq = std::string(longf) + "=";
+    if (a.rfind(eq, 0) == 0) { out = a.substr(eq.size()); return true; }
+    return false;
+}
+
+Options parse(int argc, char** argv) {
+    Options o;
+    if (argc < 2) usage_error("no action given");
+    o.action = argv[1];
+    std::string v;
+    for (int i = 2; i < argc; i++) {
+        const std::string a = argv[i];
+        if (take_value(argc, argv, i, "-i", "--index", v)) o.index_dir = v;
+        else if (take_value(argc, argv, i, "-r", "--read", v)) o.read_file = v;
+        else if (take_value(argc, argv, i, "-o", "--out-file", v)) o.out_file = v;
+        else if (take_value(argc, argv, i, "-t", "--threads", v)) o.threads = atoi(v.c_str());
+        else if (take_value(argc, argv, i, "-s", "--strands", v)) o.strands = atoi(v.c_str());
+        else if (take_value(argc, argv, i, nullptr, "--bin-width", v)) o.bin_width = strtoull(v.c_str(), nullptr, 10);
+        else if (take_value(argc, argv, i, nullptr, "--ignore-illegal-chars", v)) o.ignore_illegal = atoi(v.c_str());
+        else if (take_value(argc, argv, i, nullptr, "--gpus", v)) o.gpus = atoi(v.c_str());
+        else if (take_value(argc, argv, i, nullptr, "--device", v)) o.device = atoi(v.c_str());
+        else if (take_value(argc, argv, i, nullptr, "--bpf", v)) o.bpf_file = v;
+        else if (a == "--pml") o.query = "pml";
+        else if (a == "--zml") o.query = "zml";
+        else if (a == "--count") o.query = "count";
+        else if (a == "--classify") o.classify = true;
+        else if (a == "--filter") { o.filter = true; o.classify = true; }      // movi_options.hpp:122-125
+        else if (a == "-v" || a == "--invert") o.invert = true;
+        else if (a == "--stdout") o.to_stdout = true;
+        else if (a == "--no-output") o.no_output = true;
+        else if (a == "--reverse") o.reverse = true;
+        else if (a == "-n" || a == "--no-prefetch") { /* latency hiding is the GPU's job here */ }
+        else if (a == "--verbose") o.verbose = true;
+        else if (a == "--separators" || a == "--mmap") { /* detected from the index / not applicable */ }
+        else usage_error("unknown option " + a);
+    }
+    return o;
+}
+
+int view_bpf(const std::string& file) {   // reference src/movi.cpp:402-503 (16-bit entries)
+    FILE* f = fopen(file.c_str(), "rb");
+    if (!f) { fprintf(stderr, "cannot open %s\n", file.c_str()); return 1; }
+    uint8_t h[12];
+    uint32_t magic = 0;
+    if (fread(h, 1, 12, f) != 12 || (memcpy(&magic, h, 4), magic != 0x42504600u) || h[7] != 16) {
+        fprintf(stderr, "not a 16-bit BPF file: %s\n", file.c_str()); fclose(f); return 1;
+    }
+    for (;;) {
+        uint16_t idl;
+        if (fread(&idl, 2, 1, f) != 1) break;
+        std::string id(idl, '\0');
+        uint64_t n = 0;
+        if (fread(&id[0], 1, idl, f) != idl || fread(&n, 8, 1, f) != 1) break;
+        std::vector<uint16_t> v(n);
+        if (n && fread(v.data(), 2, n, f) != n) break;
+        printf(">%s\n", id.c_str());
+        for (uint64_t k = n; k > 0; k--) printf("%u ", (unsigned)v[k - 1]);
+        printf("\n");
+    }
+    fclose(f);
+    return 0;
+}
+
+struct ShardResult { int rc = 0; std::string err; };
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    Options o = parse(argc, argv);
+    if (o.action == "view") { if (o.bpf_file.empty()) usage_error("view needs --bpf"); return view_bpf(o.bpf_file); }
+    if (o.action != "query") usage_error("only the query (and view) actions exist in the GPU build; use the reference for " + o.action);
+    if (o.index_dir.empty() || o.read_file.empty()) usage_error("query needs --index and --read");
+
+    auto t_load0 = std::chrono::steady_clock::now();
+    movi_host_index* hix = nullptr;
+    if (movi_host_index_open(o.index_dir.c_str(), &hix)) { fprintf(stderr, "\033[31m\n\n[ERROR] %s\n\033[0m", movi_host_last_error()); return 1; }
+    MoviGpuIndexDesc desc;
+    movi_host_index_desc(hix, &desc);
+    const std::string type = movi_host_index_type_name(hix);
+    if (desc.mode == MOVI_MODE_SAMPLED_THRESHOLDS && o.query != "pml") {   // src/movi.cpp:228-233
+        fprintf(stderr, "\033[31m\n\n[ERROR] This query type is not suppported by the sampled modes yet.\n\033[0m");
+        return 1;
+    }
+    movi_host_reads* rd = nullptr;
+    if (movi_host_reads_load(o.read_file.c_str(), o.reverse ? 1 : 0, &rd)) { fprintf(stderr, "\033[31m\n\n[ERROR] %s\n\033[0m", movi_host_last_error()); return 1; }
+    const uint64_t n_reads = movi_host_reads_count(rd);
+    const uint64_t* offsets = movi_host_reads_offsets(rd);
+    char* bases = const_cast<char*>(movi_host_reads_bases(rd));
+    const uint64_t n_bases = n_reads ? offsets[n_reads] : 0;
+
+    if (o.ignore_illegal > 0) {   // check_alphabet's in-place substitution, src/move_structure.cpp:389-395
+        std::mt19937 gen{std::random_device{}()};
+        std::uniform_int_distribution<int> dist(1, 100);
+        const bool sep = (desc.sigma == 5 && desc.alphabet[0] == '%');
+        for (uint64_t i = 0; i < n_bases; i++) {
+            const unsigned char c = (unsigned char)bases[i];
+            if (sep && c == '%') continue;
+            if (desc.alphamap[c] == 256) bases[i] = o.ignore_illegal == 1 ? 'A' : (char)desc.alphabet[dist(gen) % desc.sigma];
+        }
+    }
+
+    int n_dev = movi_gpu_device_count();
+    if (n_dev <= 0) { fprintf(stderr, "\033[31m\n\n[ERROR] no CUDA device: movi-b200 has no CPU path (use the reference binaries on CPU-only hosts)\n\033[0m"); return 1; }
+    const int gpus = std::max(1, std::min(o.gpus, n_dev));
+
+    uint64_t max_value_thr = 0;
+    if (o.classify) {
+        if (movi_host_nulldb_threshold(o.index_dir.c_str(), o.query.c_str(), &max_value_thr)) {
+            fprintf(stderr, "\033[31m\n\n[ERROR] %s\n\033[0m", movi_host_last_error()); return 1;
+        }
+    }
+
+    std::vector<uint16_t> ml; std::vector<uint64_t> counts; std::vector<int32_t> pos;
+    if (o.query == "count") { counts.resize(n_reads); pos.resize(n_reads); } else ml.resize(n_bases);
+
+    // contiguous shards balanced by bases (same decomposition as the reference's OpenMP batches, movi.cpp:274-301)
+    std::vector<uint64_t> cut(gpus + 1, n_reads);
+    cut[0] = 0;
+    for (int g = 1; g < gpus; g++) {
+        const uint64_t target = n_bases / gpus * g;
+        uint64_t i = cut[g - 1];
+        while (i < n_reads && offsets[i] < target) i++;
+        cut[g] = i;
+    }
+    std::vector<ShardResult> res(gpus);
+    auto t_q0 = std::chrono::steady_clock::now();
+    auto worker = [&](int g) {
+        movi_gpu_ctx* ctx = nullptr;
+        int rc = movi_gpu_create(o.device + g, &ctx);
+        if (rc) { res[g] = {rc, movi_gpu_last_error(nullptr)}; return; }
+        rc = movi_gpu_upload_index(ctx, &desc, MOVI_GPU_LAYOUT_AUTO);
+        if (!rc && cut[g + 1] > cut[g]) {
+            const uint64_t i0 = cut[g], nr = cut[g + 1] - cut[g];
+            // offsets stay absolute: the entry points index bases / outputs by them
+            if (o.query == "pml") rc = movi_gpu_query_pml(ctx, bases, offsets + i0, nr, 0, ml.data());
+            else if (o.query == "zml") rc = movi_gpu_query_zml(ctx, bases, offsets + i0, nr, 0, ml.data());
+            else rc = movi_gpu_query_count(ctx, bases, offsets + i0, nr, 0, counts.data() + i0, pos.data() + i0);
+        }
+        if (rc) res[g] = {rc, movi_gpu_last_error(ctx)};
+        movi_gpu_destroy(ctx);
+    };
+    std::vector<std::thread> th;
+    for (int g = 0; g < gpus; g++) th.emplace_back(worker, g);
+    for (auto& t : th) t.join();
+    for (int g = 0; g < gpus; g++)
+        if (res[g].rc) { fprintf(stderr, "\033[31m\n\n[ERROR] GPU %d: %s\n\033[0m", o.device + g, res[g].err.c_str()); return 1; }
+    auto t_q1 = std::chrono::steady_clock::now();
+    if (o.verbose)
+        fprintf(stderr, "[INFO] index + reads loaded in %.3f s; index upload + query on %d GPU(s): %.3f s for %llu reads / %llu bases\n",
+                std::chrono::duration<double>(t_q0 - t_load0).count(), gpus, std::chrono::duration<double>(t_q1 - t_q0).count(),
+                (unsigned long long)n_reads, (unsigned long long)n_bases);
+
+    // ---- outputs, in the order of handle_pml_zml / handle_count (src/movi.cpp:23-76)
+    const std::string prefix = (o.out_file.empty() ? o.read_file + "." + type : o.out_file) + "." + o.query;   // utils.cpp:348-351
+    int rc = 0;
+    if (o.query == "count") {
+        if (o.write_output_allowed()) {
+            if (o.write_stdout_enabled()) rc = movi_host_write_counts(STDOUT_FILENO, rd, counts.data(), pos.data());
+            else {
+                FILE* f = fopen((prefix + ".matches").c_str(), "w");
+                if (!f) { fprintf(stderr, "cannot open %s.matches\n", prefix.c_str()); return 1; }
+                fflush(f);
+                rc = movi_host_write_counts(fileno(f), rd, counts.data(), pos.data());
+                fclose(f);
+            }
+        }
+    } else {
+        if (o.classify) {
+            if (!o.filter) {
+                // report: stdout with --stdout, else <reads>.<type>.<q>.report (classifier.cpp:39-60)
+                FILE* f = nullptr; int fd = STDOUT_FILENO;
+                if (!o.to_stdout) {
+                    f = fopen((o.read_file + "." + type + "." + o.query + ".report").c_str(), "w");
+                    if (!f) { fprintf(stderr, "cannot open the report file\n"); return 1; }
+                    fd = fileno(f);
+                }
+                // with --no-output the reference still prints the header but no rows (write_output_allowed)
+                movi_host_reads* none = nullptr;
+                if (o.no_output) { movi_host_reads_load("/dev/null", 0, &none); rc = movi_host_classify(fd, 0, none, nullptr, o.bin_width, max_value_thr, nullptr); movi_host_reads_free(none); }
+                else rc = movi_host_classify(fd, 0, rd, ml.data(), o.bin_width, max_value_thr, nullptr);
+                if (f) fclose(f);
+            } else if (!o.no_output) {
+                rc = movi_host_classify(STDOUT_FILENO, o.invert ? 2 : 1, rd, ml.data(), o.bin_width, max_value_thr, nullptr);
+            }
+        }
+        if (!rc && o.write_output_allowed()) {
+            if (o.write_stdout_enabled()) rc = movi_host_write_ml_text(STDOUT_FILENO, rd, ml.data());
+            else rc = movi_host_write_bpf((prefix + ".bpf").c_str(), rd, ml.data());
+        }
+    }
+    if (rc) { fprintf(stderr, "\033[31m\n\n[ERROR] %s\n\033[0m", movi_host_last_error()); return 1; }
+    movi_host_reads_free(rd);
+    movi_host_index_close(hix);
+    return 0;
+}
