@@ -118,8 +118,9 @@ int  movi_gpu_query_count(movi_gpu_ctx* ctx, const char* bases, const uint64_t* 
 
 /* Same queries on DEVICE buffers (already resident in HBM), enqueued on `cuda_stream` (a cudaStream_t,
  * NULL = default stream) without synchronising: for callers that pipeline their own copies.
- * d_bases must be 8-byte aligned and readable up to the next multiple of 8 bytes; read_offsets are
- * relative to d_bases; total bases per call < 2^32.  d_out_ml has read_offsets[n_reads] entries. */
+ * d_bases and d_out_ml must be 32-byte aligned and d_bases readable up to the next multiple of 32 bytes (the
+ * kernels move whole aligned 32-byte sectors); read_offsets are relative to d_bases; total bases per call < 2^32.
+ * d_out_ml has read_offsets[n_reads] entries. */
 int  movi_gpu_query_pml_device(movi_gpu_ctx* ctx, const char* d_bases, const uint64_t* d_read_offsets, uint64_t n_reads,
                                uint32_t flags, uint16_t* d_out_ml, void* cuda_stream);
 int  movi_gpu_query_zml_device(movi_gpu_ctx* ctx, const char* d_bases, const uint64_t* d_read_offsets, uint64_t n_reads,

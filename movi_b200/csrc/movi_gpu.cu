@@ -16,12 +16,14 @@
 #include "dev_index.cuh"
 #include "misc_kernels.cuh"
 #include "pml_kernel.cuh"
+#include "pml_kernel2.cuh"
+#include "pml_kernel3.cuh"
 
 using namespace movi;
 
 namespace {
 
-constexpr int NBUF = 3;                       // pipeline depth of the host-buffer entry points
+constexpr int NBUF = 4;                       // pipeline depth of the host-buffer entry points
 std::string g_create_error;
 
 struct Staging {                              // one pipeline slot
@@ -40,6 +42,7 @@ struct Staging {                              // one pipeline slot
 struct movi_gpu_ctx {
     int device = 0;
     int num_sms = 0;
+    int64_t max_persist_bytes = 0, max_window_bytes = 0;
     std::string err;
     // index
     bool has_index = false;
@@ -56,10 +59,14 @@ struct movi_gpu_ctx {
     Staging slot[NBUF];
     uint64_t launches = 0;
     // options
-    int64_t pml_variant = 1;          // 0: 2-byte stores, 1: register-buffered 16-byte stores
+    int64_t pml_variant = 4;          // 0/1: branchy kernel (2-byte / 16-byte stores); 2/3: convergent kernel (+/- L2 hints); 4: convergent + sector staging in smem
+    int64_t l2_persist_mb = 0;        // > 0: mark the row table persisting in L2 (access policy window) for query launches
+    int64_t l2_fetch_granularity = 0; // 0: leave the device default; 32 / 64 / 128: cudaLimitMaxL2FetchGranularity
+    int64_t row_ld_mode = 0;          // cache recipe of the row fetch (pml_kernel2.cuh: ld_row)
     int64_t blocks_per_sm = 0;        // 0: occupancy query
     int64_t threads_per_block = 256;
-    int64_t batch_bases = 48ll << 20; // bases per pipeline slot in the host-buffer entry points
+    int64_t batch_bases = 16ll << 20; // bases per pipeline slot in the host-buffer entry points (D2H of the results is the
+                                      // bottleneck of the host path: small slices keep the pipeline ramp short)
     // gather probe scratch
     uint2* d_probe = nullptr; uint64_t probe_bytes = 0;
 };
@@ -119,15 +126,37 @@ enum Kind { Q_PML = 0, Q_ZML = 1, Q_COUNT = 2 };
 int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t st) {
     const int threads = (int)ctx->threads_per_block;
     const bool wide = ctx->ix.r > 0xFFFFFFF0ull;
+    // optional: keep the row table persisting in L2 (launch attribute; the carve-out is set in set_option)
+    cudaLaunchAttribute attr[1];
+    int n_attr = 0;
+    if (ctx->l2_persist_mb > 0) {
+        const size_t table = (size_t)ctx->ix.r * sizeof(uint2);
+        const size_t win = std::min<size_t>(table, (size_t)ctx->max_window_bytes);
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = (void*)ctx->d_rows;
+        attr[0].val.accessPolicyWindow.num_bytes = win;
+        attr[0].val.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)(ctx->l2_persist_mb << 20) / (double)win);
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        n_attr = 1;
+    }
 #define LAUNCH(KERNEL)                                                            \
     do {                                                                          \
         auto k_ = KERNEL;                                                         \
-        const int blocks_ = blocks_for(ctx, k_, threads);                         \
-        k_<<<blocks_, threads, 0, st>>>(ctx->ix, qa);                             \
+        cudaLaunchConfig_t cfg_ = {};                                             \
+        cfg_.gridDim = dim3((unsigned)blocks_for(ctx, k_, threads));              \
+        cfg_.blockDim = dim3((unsigned)threads);                                  \
+        cfg_.stream = st;                                                         \
+        cfg_.attrs = attr; cfg_.numAttrs = n_attr;                                \
+        CU(cudaLaunchKernelEx(&cfg_, k_, ctx->ix, qa));                           \
     } while (0)
     if (kind == Q_PML) {
         if (ctx->pml_variant == 0) { if (wide) LAUNCH((movi_pml_kernel<unsigned long long, 0>)); else LAUNCH((movi_pml_kernel<uint32_t, 0>)); }
-        else                       { if (wide) LAUNCH((movi_pml_kernel<unsigned long long, 1>)); else LAUNCH((movi_pml_kernel<uint32_t, 1>)); }
+        else if (ctx->pml_variant == 1) { if (wide) LAUNCH((movi_pml_kernel<unsigned long long, 1>)); else LAUNCH((movi_pml_kernel<uint32_t, 1>)); }
+        else if (ctx->pml_variant == 2) { if (wide) LAUNCH((movi_pml_kernel2<unsigned long long, true>)); else LAUNCH((movi_pml_kernel2<uint32_t, true>)); }
+        else if (ctx->pml_variant == 3) { if (wide) LAUNCH((movi_pml_kernel2<unsigned long long, false>)); else LAUNCH((movi_pml_kernel2<uint32_t, false>)); }
+        else if (ctx->ix.sep) { if (wide) LAUNCH((movi_pml_kernel3<unsigned long long, true>)); else LAUNCH((movi_pml_kernel3<uint32_t, true>)); }
+        else { if (wide) LAUNCH((movi_pml_kernel3<unsigned long long, false>)); else LAUNCH((movi_pml_kernel3<uint32_t, false>)); }
     } else if (kind == Q_ZML) {
         if (wide) LAUNCH((movi_bs_kernel<unsigned long long, KIND_ZML>)); else LAUNCH((movi_bs_kernel<uint32_t, KIND_ZML>));
     } else {
@@ -153,7 +182,8 @@ int device_query(movi_gpu_ctx* ctx, Kind kind, const char* d_bases, const uint64
                  uint64_t n_reads, uint16_t* d_ml, uint64_t* d_count, int32_t* d_pos, unsigned long long* d_counter,
                  cudaStream_t st) {
     if (n_reads == 0) return MOVI_GPU_OK;
-    if (reinterpret_cast<uintptr_t>(d_bases) & 7u) return fail(ctx, MOVI_GPU_ERR_ARG, "d_bases must be 8-byte aligned");
+    if (reinterpret_cast<uintptr_t>(d_bases) & 31u) return fail(ctx, MOVI_GPU_ERR_ARG, "d_bases must be 32-byte aligned");
+    if (reinterpret_cast<uintptr_t>(d_ml) & 31u) return fail(ctx, MOVI_GPU_ERR_ARG, "d_out_ml must be 32-byte aligned");
     if (kind == Q_COUNT) { int rc = ensure_prefix(ctx, st); if (rc) return rc; }
     CU(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st));
     QueryArgs qa{};
@@ -166,6 +196,7 @@ int device_query(movi_gpu_ctx* ctx, Kind kind, const char* d_bases, const uint64
     qa.out_pos = d_pos;
     qa.counter = d_counter;
     qa.status = ctx->d_status;
+    qa.ld_mode = (uint32_t)ctx->row_ld_mode;
     return launch_query(ctx, kind, qa, st);
 }
 
@@ -210,16 +241,16 @@ int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* 
         if (nb >= 0xFFFFFFF0ull) return fail(ctx, MOVI_GPU_ERR_ARG, "a single read longer than 2^32 bases is not supported");
         Staging& S = ctx->slot[s];
         if (S.busy) { CU(cudaEventSynchronize(S.done)); S.busy = false; }
-        // host address of the first base may be unaligned: shift the copy so that device bases stay 8-byte aligned
-        const uint64_t shift = o0 & 7u;
-        if ((rc = grow(ctx, S.d_bases, S.bases_cap, nb + shift + 16))) return rc;
+        // keep the device copy congruent to the host offsets modulo 32: the kernels stage whole aligned 32-byte sectors
+        const uint64_t shift = o0 & 31u;
+        if ((rc = grow(ctx, S.d_bases, S.bases_cap, nb + shift + 64))) return rc;
         if ((rc = grow(ctx, S.d_offsets, S.offsets_cap, nr + 1))) return rc;
         if (kind == Q_COUNT) {
             size_t cap2 = S.count_cap;
             if ((rc = grow(ctx, S.d_count, S.count_cap, nr))) return rc;
             if ((rc = grow(ctx, S.d_pos, cap2, nr))) return rc;
         } else {
-            if ((rc = grow(ctx, S.d_ml, S.ml_cap, nb + shift + 16))) return rc;
+            if ((rc = grow(ctx, S.d_ml, S.ml_cap, nb + shift + 64))) return rc;
         }
         CU(cudaMemcpyAsync(S.d_bases + shift, bases + o0, nb, cudaMemcpyHostToDevice, S.stream));
         CU(cudaMemcpyAsync(S.d_offsets, offsets + i0, (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, S.stream));
@@ -272,6 +303,8 @@ int movi_gpu_create(int device, movi_gpu_ctx** out) {
     movi_gpu_ctx* c = new movi_gpu_ctx();
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
+    c->max_persist_bytes = prop.persistingL2CacheMaxSize;
+    c->max_window_bytes = prop.accessPolicyMaxWindowSize;
     ctx = c;
     cudaError_t e2 = cudaMalloc(&c->d_status, sizeof(unsigned int));
     if (e2 == cudaSuccess) e2 = cudaMemset(c->d_status, 0, sizeof(unsigned int));
@@ -312,7 +345,22 @@ uint64_t movi_gpu_launch_count(const movi_gpu_ctx* ctx) { return ctx ? ctx->laun
 int movi_gpu_set_option(movi_gpu_ctx* ctx, const char* key, int64_t value) {
     if (!ctx || !key) return MOVI_GPU_ERR_ARG;
     const std::string k(key);
-    if (k == "pml_variant") { if (value < 0 || value > 1) return fail(ctx, MOVI_GPU_ERR_ARG, "pml_variant: 0 or 1"); ctx->pml_variant = value; }
+    if (k == "pml_variant") { if (value < 0 || value > 4) return fail(ctx, MOVI_GPU_ERR_ARG, "pml_variant: 0..4"); ctx->pml_variant = value; }
+    else if (k == "row_ld_mode") { if (value < 0 || value > 7) return fail(ctx, MOVI_GPU_ERR_ARG, "row_ld_mode: 0..7"); ctx->row_ld_mode = value; }
+    else if (k == "l2_persist_mb") {
+        if (value < 0) return fail(ctx, MOVI_GPU_ERR_ARG, "l2_persist_mb: >= 0");
+        CU(cudaSetDevice(ctx->device));
+        const int64_t capped = std::min<int64_t>(value, ctx->max_persist_bytes >> 20);
+        CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)capped << 20));
+        if (capped == 0) cudaCtxResetPersistingL2Cache();
+        ctx->l2_persist_mb = capped;
+    }
+    else if (k == "l2_fetch_granularity") {
+        if (value != 32 && value != 64 && value != 128) return fail(ctx, MOVI_GPU_ERR_ARG, "l2_fetch_granularity: 32, 64 or 128");
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
+        ctx->l2_fetch_granularity = value;
+    }
     else if (k == "blocks_per_sm") { if (value < 0 || value > 32) return fail(ctx, MOVI_GPU_ERR_ARG, "blocks_per_sm: 0..32"); ctx->blocks_per_sm = value; }
     else if (k == "threads_per_block") {
         if (value < 32 || value > 256 || value % 32) return fail(ctx, MOVI_GPU_ERR_ARG, "threads_per_block: multiple of 32 in [32, 256]");
@@ -330,6 +378,14 @@ int64_t movi_gpu_get_option(const movi_gpu_ctx* ctx, const char* key) {
     if (k == "threads_per_block") return ctx->threads_per_block;
     if (k == "batch_bases") return ctx->batch_bases;
     if (k == "num_sms") return ctx->num_sms;
+    if (k == "row_ld_mode") return ctx->row_ld_mode;
+    if (k == "l2_persist_mb") return ctx->l2_persist_mb;
+    if (k == "l2_persist_max_mb") return ctx->max_persist_bytes >> 20;
+    if (k == "l2_fetch_granularity") {
+        size_t v = 0;
+        if (cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity) != cudaSuccess) { cudaGetLastError(); return -1; }
+        return (int64_t)v;
+    }
     return -1;
 }
 
@@ -418,6 +474,7 @@ int movi_gpu_upload_index(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layo
         const uint64_t a = d->alphamap[b];
         ix.code_of[b] = (a < d->sigma && !(sep && b == '%')) ? (uint8_t)a : (uint8_t)CODE_ILLEGAL;
     }
+    CU(cudaStreamSynchronize(st));   // the table copy / conversion ran on a non-blocking stream
     {   // n(r-1) for the start state of query_pml
         uint2 last;
         CU(cudaMemcpy(&last, ctx->d_rows + (r - 1), sizeof(last), cudaMemcpyDeviceToHost));

@@ -32,10 +32,11 @@ struct QueryArgs {
     int32_t* out_pos;                     // count query
     unsigned long long* counter;          // work-queue head (zeroed before launch)
     unsigned int* status;                 // sticky error bits
+    uint32_t ld_mode;                     // row fetch cache recipe (pml_kernel2.cuh: ld_row)
 };
 
 constexpr uint32_t ST_IDLE = 0, ST_NEW = 1, ST_FF = 2, ST_UP = 3, ST_DOWN = 4;
-constexpr uint32_t QUEUE_CHUNK = 64;      // reads taken from the global counter per warp refill
+constexpr uint32_t QUEUE_CHUNK = 32;      // reads taken from the global counter per warp refill (small: short tail)
 constexpr unsigned FULL = 0xffffffffu;
 
 // Register-buffered output (OUTV == 1): the last `pend` (< 8) pushed values sit in the top `pend`

@@ -521,3 +521,22 @@ int movi_oracle_classify(const uint16_t* ml, uint64_t len, uint64_t bin_width, u
     *bins_above = above; *bins_below = below; *sum_max = sum; *n_bins = nb;
     return (double)above / ((double)(above + below) + 0.0) > 0.50;
 }
+
+/* Analysis hook (not part of any parity check): rows[k] = the row the k-th LF step of query_pml starts from,
+ * i.e. the one random row fetch of that base.  Used by tools/ to study the access distribution of a workload. */
+int movi_oracle_trace_pml_rows(const movi_oracle_index* ix, const char* read, int64_t len, uint64_t* rows) {
+    int64_t pos = len - 1;
+    uint64_t idx = ix->r - 1, offset = row_n(ix, idx) - 1, k = 0;
+    while (pos > -1) {
+        unsigned char rc = (unsigned char)read[pos];
+        if (check_alphabet(ix, rc) && raw_char(ix, idx) != (int)rc) {
+            int up = reposition_thresholds(ix, &idx, offset, rc);
+            if (up < 0) return -1;
+            offset = up ? row_n(ix, idx) - 1 : 0;
+        }
+        rows[k++] = idx;
+        pos -= 1;
+        if (lf_move(ix, &offset, &idx) < 0) return -1;
+    }
+    return 0;
+}
