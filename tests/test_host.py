@@ -1,0 +1,149 @@
+"""Host-side helpers (libmovi_host.so, pure C++) against the oracle and the reference outputs -- CPU only.
+Also: both native libraries load and export every symbol their headers declare."""
+import lzma
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLD, READ_SETS, ROOT, TYPES, expected_text, reads_path
+from movi_b200 import HostIndex, Reads
+from movi_b200 import _native as N
+from oracle.port import OracleIndex
+
+
+def _declared(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    return sorted(set(re.findall(r"\b(movi_(?:gpu|host)_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_gpu_library_exports_every_declared_symbol():
+    """The C ABI library loads without a GPU and exports all of include/movi_gpu.h (no compute calls here)."""
+    lib = N.gpu_lib()
+    names = _declared("movi_gpu.h")
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), n
+        assert n in N.GPU_SYMBOLS, "ctypes signature missing for " + n
+    assert lib.movi_gpu_abi_version() == 1
+
+
+def test_host_library_exports_every_declared_symbol():
+    lib = N.host_lib()
+    for n in _declared("movi_host.h"):
+        assert hasattr(lib, n), n
+        assert n in N.HOST_SYMBOLS, n
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a CUDA device the product must fail loudly instead of computing on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from movi_b200 import MoveStructure, MoviGpuError
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "index.movi"), "wb").write(lzma.open(os.path.join(GOLD, "c1", "regular-thresholds", "index.movi.xz")).read())
+        with pytest.raises(MoviGpuError, match="no CUDA device"):
+            MoveStructure(td)
+
+
+@pytest.mark.parametrize("sep", [False, True])
+@pytest.mark.parametrize("typ", TYPES)
+def test_index_reader_matches_oracle_reader(index_dirs, typ, sep):
+    d = index_dirs[(typ, sep)]
+    h, o = HostIndex(d), OracleIndex(d)
+    assert (h.mode, h.r, h.n, h.end_bwt_idx) == (o.mode, o.r, o.n, o.end_bwt_idx)
+    assert h.type_name == typ
+    assert h.alphabet == (b"%ACGT" if sep else b"ACGT")
+    assert (h.desc.sep_count > 0) == sep
+    if typ == "blocked-thresholds":
+        assert h.desc.block_size == 1048576 and h.desc.id_blocks_size == 1
+    if typ == "sampled-thresholds":
+        assert h.desc.tally_checkpoints == 20 and h.desc.tally_len == h.r // 20 + 2
+
+
+def test_index_reader_rejects_garbage(tmp_path):
+    p = tmp_path / "index.movi"
+    p.write_bytes(b"\0" * 4096)
+    with pytest.raises(RuntimeError, match="magic"):
+        HostIndex(str(tmp_path))
+    with pytest.raises(RuntimeError, match="Failed to open"):
+        HostIndex(str(tmp_path / "nope"))
+
+
+def test_reads_loader_ids_and_sequences():
+    """id = header from its 2nd character through and including the first blank/tab (src/batch_loader.cpp:117-119)."""
+    rd = Reads(reads_path("synth300.fasta"))
+    assert rd.count == 300
+    assert rd.id(0) == "syn.0 " and rd.id(1) == "syn.1\t" and rd.id(2) == "syn.2"
+    # multi-line FASTA is concatenated
+    txt = open(reads_path("synth300.fasta")).read().split(">")[1:]
+    for i in (0, 1, 2, 150, 299):
+        assert rd.read(i) == "".join(txt[i].split("\n")[1:])
+    fq = Reads(reads_path("sample.fastq"))
+    assert fq.count == 25 and fq.id(0) == "simulated.1" and len(fq.read(0)) == 150
+    rev = Reads(reads_path("sample.fastq"), reverse=True)
+    assert rev.read(3) == fq.read(3)[::-1]
+
+
+def _write_via(fn, *args):
+    import tempfile
+    with tempfile.TemporaryFile() as f:
+        assert fn(f.fileno(), *args) == 0, N.host_lib().movi_host_last_error()
+        f.seek(0)
+        return f.read().decode()
+
+
+@pytest.mark.parametrize("read_set", READ_SETS)
+def test_text_writers_reproduce_reference_stdout(index_dirs, read_set):
+    """oracle values -> host writers == the reference's --stdout bytes (src/utils.cpp:204-209, 248-256)."""
+    L = N.host_lib()
+    rd = Reads(reads_path(read_set))
+    orc = OracleIndex(index_dirs[("regular-thresholds", False)])
+    pml = orc.query_pml(rd.bases, rd.offsets)
+    assert _write_via(L.movi_host_write_ml_text, rd._h, pml.ctypes.data) == expected_text(read_set, "pml")
+    counts, pos = orc.query_count(rd.bases, rd.offsets)
+    assert _write_via(L.movi_host_write_counts, rd._h, counts.ctypes.data, pos.ctypes.data) == expected_text(read_set, "count")
+
+
+def test_bpf_writer_is_byte_identical_to_reference(index_dirs, tmp_path):
+    """<reads>.regular-thresholds.pml.bpf written by the reference for sample.fasta (header padding bytes excepted: 10, 11)."""
+    L = N.host_lib()
+    rd = Reads(reads_path("sample.fasta"))
+    pml = OracleIndex(index_dirs[("regular-thresholds", False)]).query_pml(rd.bases, rd.offsets)
+    out = tmp_path / "x.bpf"
+    assert L.movi_host_write_bpf(str(out).encode(), rd._h, pml.ctypes.data) == 0
+    got = out.read_bytes()
+    want = lzma.open(os.path.join(GOLD, "expected", "sample.fasta.pml.bpf.xz")).read()
+    assert len(got) == len(want) and got[:10] == want[:10] and got[12:] == want[12:]
+
+
+@pytest.mark.parametrize("read_set", ["long6.fasta", "sample.fasta", "synth300.fasta"])
+def test_classifier_report_and_filter_match_reference(index_dirs, read_set):
+    """--classify report (incl. header and number formatting) and --filter / --filter -v outputs."""
+    L = N.host_lib()
+    d = index_dirs[("regular-thresholds", False)]
+    thr = N.C.c_uint64()
+    assert L.movi_host_nulldb_threshold(d.encode(), b"pml", N.C.byref(thr)) == 0
+    assert thr.value == 7                        # "thr=7", tests_data/reads.fasta.pmls.report.sorted
+    rd = Reads(reads_path(read_set))
+    pml = OracleIndex(d).query_pml(rd.bases, rd.offsets)
+    report = _write_via(L.movi_host_classify, 0, rd._h, pml.ctypes.data, 150, thr.value, None)
+    assert report == open(os.path.join(GOLD, "expected", read_set + ".pml.report")).read()
+    for mode, name in ((1, "filtered"), (2, "filtered_notfound")):
+        got = _write_via(L.movi_host_classify, mode, rd._h, pml.ctypes.data, 150, thr.value, None)
+        assert got == lzma.open(os.path.join(GOLD, "expected", "%s.pml.%s.xz" % (read_set, name))).read().decode()
+
+
+def test_cli_fails_loudly_without_gpu(index_dirs):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from movi_b200 import build
+    build.build_host()
+    r = subprocess.run([build.CLI, "query", "-i", index_dirs[("regular-thresholds", False)], "-r", reads_path("sample.fastq"), "--pml", "--stdout"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr and r.stdout == ""
