@@ -1,0 +1,99 @@
+"""`movi-b200 query ...` end to end on the GPU against the reference's own stdout / files (tests/golden/expected)."""
+import lzma
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from conftest import GOLD, READ_SETS, TYPES, expected_text, reads_path
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cli():
+    from movi_b200 import build
+    build.build_host()
+    return build.CLI
+
+
+def run(cli, *args, cwd=None):
+    r = subprocess.run([cli] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, cwd=cwd)
+    assert r.returncode == 0, r.stderr.decode()[-1000:]
+    return r.stdout.decode()
+
+
+@pytest.mark.parametrize("typ", TYPES)
+@pytest.mark.parametrize("read_set", READ_SETS)
+def test_pml_stdout(cli, index_dirs, typ, read_set):
+    # attached short-flag values as in the reference's tests (tests/test_pml.cpp:59-86)
+    out = run(cli, "query", "--index", index_dirs[(typ, False)], "--read", reads_path(read_set), "--pml", "--no-prefetch", "-t1", "--stdout")
+    assert out == expected_text(read_set, "pml")
+
+
+@pytest.mark.parametrize("q", ["zml", "count"])
+@pytest.mark.parametrize("sep", [False, True])
+def test_zml_count_stdout(cli, index_dirs, q, sep):
+    for read_set in ("edge.fasta", "synth300.fasta"):
+        out = run(cli, "query", "-i", index_dirs[("blocked-thresholds", sep)], "-r", reads_path(read_set), "--" + q, "-s16", "-t", "4", "--stdout")
+        assert out == expected_text(read_set, q, sep)
+
+
+def test_sampled_rejects_count(cli, index_dirs):
+    r = subprocess.run([cli, "query", "-i", index_dirs[("sampled-thresholds", False)], "-r", reads_path("sample.fasta"), "--count", "--stdout"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 1 and b"not suppported by the sampled modes" in r.stderr
+
+
+def test_classify_report_filter_and_bpf(cli, index_dirs, tmp_path):
+    d = index_dirs[("regular-thresholds", False)]
+    for read_set in ("long6.fasta", "sample.fasta"):
+        reads = tmp_path / read_set
+        shutil.copy(reads_path(read_set), reads)
+        # --classify --stdout: report on stdout AND the .bpf file next to the reads
+        out = run(cli, "query", "-i", d, "-r", str(reads), "--pml", "--classify", "--stdout")
+        assert out == open(os.path.join(GOLD, "expected", read_set + ".pml.report")).read()
+        bpf = str(reads) + ".regular-thresholds.pml.bpf"
+        assert os.path.exists(bpf)
+        if read_set == "sample.fasta":
+            got = open(bpf, "rb").read()
+            want = lzma.open(os.path.join(GOLD, "expected", "sample.fasta.pml.bpf.xz")).read()
+            assert got[:10] == want[:10] and got[12:] == want[12:]
+            # view prints the lengths back in read order
+            assert run(cli, "view", "--bpf", bpf) == expected_text(read_set, "pml")
+        os.remove(bpf)
+        # --classify without --stdout: report file, named after the reads and the index type
+        run(cli, "query", "-i", d, "-r", str(reads), "--pml", "--classify")
+        rep = str(reads) + ".regular-thresholds.pml.report"
+        assert open(rep).read() == open(os.path.join(GOLD, "expected", read_set + ".pml.report")).read()
+        for inv, name in ((False, "filtered"), (True, "filtered_notfound")):
+            out = run(cli, "query", "-i", d, "-r", str(reads), "--pml", "--filter", *(["-v"] if inv else []))
+            assert out == lzma.open(os.path.join(GOLD, "expected", "%s.pml.%s.xz" % (read_set, name))).read().decode()
+
+
+def test_out_prefix_count_file_and_stdin(cli, index_dirs, tmp_path):
+    d = index_dirs[("regular-thresholds", False)]
+    prefix = str(tmp_path / "res")
+    run(cli, "query", "-i", d, "-r", reads_path("synth300.fasta"), "--count", "-o", prefix)
+    assert open(prefix + ".count.matches").read() == expected_text("synth300.fasta", "count")
+    r = subprocess.run([cli, "query", "-i", d, "-r", "-", "--zml", "--stdout"], input=open(reads_path("sample.fastq"), "rb").read(),
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0 and r.stdout.decode() == expected_text("sample.fastq", "zml")
+
+
+def test_reverse_and_ignore_illegal(cli, index_dirs):
+    """--reverse reverses (not complements) each read; --ignore-illegal-chars 1 substitutes 'A' before the walk."""
+    import numpy as np
+    from movi_b200 import Reads
+    from oracle.port import OracleIndex, pack_reads
+    from _fmt import ml_text
+    d = index_dirs[("regular-thresholds", False)]
+    rd = Reads(reads_path("edge.fasta"))
+    orc = OracleIndex(d)
+    rev = [rd.read(i)[::-1] for i in range(rd.count)]
+    b, o = pack_reads(rev)
+    assert run(cli, "query", "-i", d, "-r", reads_path("edge.fasta"), "--pml", "--reverse", "--stdout") == ml_text(rd.ids(), o, orc.query_pml(b, o))
+    sub = ["".join(c if c in "ACGT" else "A" for c in rd.read(i)) for i in range(rd.count)]
+    b, o = pack_reads(sub)
+    assert run(cli, "query", "-i", d, "-r", reads_path("edge.fasta"), "--pml", "--ignore-illegal-chars", "1", "--stdout") == ml_text(rd.ids(), o, orc.query_pml(b, o))
