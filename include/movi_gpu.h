@@ -139,7 +139,8 @@ int  movi_gpu_classify_device(movi_gpu_ctx* ctx, const uint16_t* d_ml, const uin
 
 /* Introspection for benchmarks: kernels launched by this context so far, name and time of the last one. */
 uint64_t movi_gpu_launch_count(const movi_gpu_ctx* ctx);
-/* Tuning knobs (benchmarks / profiling): "pml_variant", "blocks_per_sm", "threads_per_block", "batch_bases". */
+/* Tuning knobs (benchmarks / profiling / tests): "pml_variant", "blocks_per_sm", "threads_per_block", "batch_bases",
+ * "force_wide" (64-bit row indices on small tables), "row_ld_mode", "l2_persist_mb", "l2_fetch_granularity". */
 int  movi_gpu_set_option(movi_gpu_ctx* ctx, const char* key, int64_t value);
 int64_t movi_gpu_get_option(const movi_gpu_ctx* ctx, const char* key);
 

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "bs_kernel.cuh"
+#include "bs_kernel2.cuh"
 #include "convert.cuh"
 #include "dev_index.cuh"
 #include "misc_kernels.cuh"
@@ -62,6 +63,8 @@ struct movi_gpu_ctx {
     int64_t pml_variant = 4;          // 0/1: branchy kernel (2-byte / 16-byte stores); 2/3: convergent kernel (+/- L2 hints); 4: convergent + sector staging in smem
     int64_t l2_persist_mb = 0;        // > 0: mark the row table persisting in L2 (access policy window) for query launches
     int64_t l2_fetch_granularity = 0; // 0: leave the device default; 32 / 64 / 128: cudaLimitMaxL2FetchGranularity
+    int64_t bs_variant = 1;           // count / ZML kernel: 0 = branch-per-state (bs_kernel.cuh), 1 = convergent + sector staging
+    int64_t force_wide = 0;           // tests: run the 64-bit-index instantiations on a small table
     int64_t row_ld_mode = 0;          // cache recipe of the row fetch (pml_kernel2.cuh: ld_row)
     int64_t blocks_per_sm = 0;        // 0: occupancy query
     int64_t threads_per_block = 256;
@@ -125,7 +128,7 @@ enum Kind { Q_PML = 0, Q_ZML = 1, Q_COUNT = 2 };
 // enqueue one query kernel on `st` (device pointers)
 int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t st) {
     const int threads = (int)ctx->threads_per_block;
-    const bool wide = ctx->ix.r > 0xFFFFFFF0ull;
+    const bool wide = ctx->ix.r > 0xFFFFFFF0ull || ctx->force_wide;   // 64-bit row indices (tables beyond 2^32 rows = 34 GB)
     // optional: keep the row table persisting in L2 (launch attribute; the carve-out is set in set_option)
     cudaLaunchAttribute attr[1];
     int n_attr = 0;
@@ -158,9 +161,11 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
         else if (ctx->ix.sep) { if (wide) LAUNCH((movi_pml_kernel3<unsigned long long, true>)); else LAUNCH((movi_pml_kernel3<uint32_t, true>)); }
         else { if (wide) LAUNCH((movi_pml_kernel3<unsigned long long, false>)); else LAUNCH((movi_pml_kernel3<uint32_t, false>)); }
     } else if (kind == Q_ZML) {
-        if (wide) LAUNCH((movi_bs_kernel<unsigned long long, KIND_ZML>)); else LAUNCH((movi_bs_kernel<uint32_t, KIND_ZML>));
+        if (ctx->bs_variant == 0) { if (wide) LAUNCH((movi_bs_kernel<unsigned long long, KIND_ZML>)); else LAUNCH((movi_bs_kernel<uint32_t, KIND_ZML>)); }
+        else { if (wide) LAUNCH((movi_bs_kernel2<unsigned long long, KIND_ZML>)); else LAUNCH((movi_bs_kernel2<uint32_t, KIND_ZML>)); }
     } else {
-        if (wide) LAUNCH((movi_bs_kernel<unsigned long long, KIND_COUNT>)); else LAUNCH((movi_bs_kernel<uint32_t, KIND_COUNT>));
+        if (ctx->bs_variant == 0) { if (wide) LAUNCH((movi_bs_kernel<unsigned long long, KIND_COUNT>)); else LAUNCH((movi_bs_kernel<uint32_t, KIND_COUNT>)); }
+        else { if (wide) LAUNCH((movi_bs_kernel2<unsigned long long, KIND_COUNT>)); else LAUNCH((movi_bs_kernel2<uint32_t, KIND_COUNT>)); }
     }
 #undef LAUNCH
     ctx->launches += 1;
@@ -183,7 +188,7 @@ int device_query(movi_gpu_ctx* ctx, Kind kind, const char* d_bases, const uint64
                  cudaStream_t st) {
     if (n_reads == 0) return MOVI_GPU_OK;
     if (reinterpret_cast<uintptr_t>(d_bases) & 31u) return fail(ctx, MOVI_GPU_ERR_ARG, "d_bases must be 32-byte aligned");
-    if (reinterpret_cast<uintptr_t>(d_ml) & 31u) return fail(ctx, MOVI_GPU_ERR_ARG, "d_out_ml must be 32-byte aligned");
+    if (d_ml && (reinterpret_cast<uintptr_t>(d_ml) & 31u)) return fail(ctx, MOVI_GPU_ERR_ARG, "d_out_ml must be 32-byte aligned");
     if (kind == Q_COUNT) { int rc = ensure_prefix(ctx, st); if (rc) return rc; }
     CU(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st));
     QueryArgs qa{};
@@ -346,6 +351,8 @@ int movi_gpu_set_option(movi_gpu_ctx* ctx, const char* key, int64_t value) {
     if (!ctx || !key) return MOVI_GPU_ERR_ARG;
     const std::string k(key);
     if (k == "pml_variant") { if (value < 0 || value > 4) return fail(ctx, MOVI_GPU_ERR_ARG, "pml_variant: 0..4"); ctx->pml_variant = value; }
+    else if (k == "bs_variant") { if (value < 0 || value > 1) return fail(ctx, MOVI_GPU_ERR_ARG, "bs_variant: 0 or 1"); ctx->bs_variant = value; }
+    else if (k == "force_wide") { ctx->force_wide = value ? 1 : 0; }
     else if (k == "row_ld_mode") { if (value < 0 || value > 7) return fail(ctx, MOVI_GPU_ERR_ARG, "row_ld_mode: 0..7"); ctx->row_ld_mode = value; }
     else if (k == "l2_persist_mb") {
         if (value < 0) return fail(ctx, MOVI_GPU_ERR_ARG, "l2_persist_mb: >= 0");
@@ -379,6 +386,8 @@ int64_t movi_gpu_get_option(const movi_gpu_ctx* ctx, const char* key) {
     if (k == "batch_bases") return ctx->batch_bases;
     if (k == "num_sms") return ctx->num_sms;
     if (k == "row_ld_mode") return ctx->row_ld_mode;
+    if (k == "force_wide") return ctx->force_wide;
+    if (k == "bs_variant") return ctx->bs_variant;
     if (k == "l2_persist_mb") return ctx->l2_persist_mb;
     if (k == "l2_persist_max_mb") return ctx->max_persist_bytes >> 20;
     if (k == "l2_fetch_granularity") {

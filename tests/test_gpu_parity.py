@@ -106,11 +106,14 @@ def test_random_reads_vs_oracle(structures, index_dirs, ref_seq, typ, sep):
         ms.set_option("pml_variant", variant)
         assert np.array_equal(ms.query_pml(bases, offsets), orc.query_pml(bases, offsets, threads=0))
     if typ != "sampled-thresholds":
-        # reads of length 0 are outside the reference's domain for zml/count (it indexes R[-1]); compare the rest
-        assert np.array_equal(ms.query_zml(bases, offsets), orc.query_zml(bases, offsets, threads=0))
-        c1, p1 = ms.query_backward_search(bases, offsets)
+        # (reads of length 0 are outside the reference's domain for zml/count -- it indexes R[-1]; both sides emit nothing / 0)
+        want_z = orc.query_zml(bases, offsets, threads=0)
         c2, p2 = orc.query_count(bases, offsets, threads=0)
-        assert np.array_equal(c1, c2) and np.array_equal(p1, p2)
+        for bs_variant in (0, 1):
+            ms.set_option("bs_variant", bs_variant)
+            assert np.array_equal(ms.query_zml(bases, offsets), want_z)
+            c1, p1 = ms.query_backward_search(bases, offsets)
+            assert np.array_equal(c1, c2) and np.array_equal(p1, p2)
 
 
 def test_small_pipeline_slices(structures, index_dirs, ref_seq):

@@ -23,7 +23,9 @@ def main():
     d_cnt = torch.zeros(n_reads, dtype=torch.int64, device=dev)
     d_pos = torch.zeros(n_reads, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
-    for bps in [int(x) for x in (sys.argv[2:] or ["0"])]:
+    for spec in (sys.argv[2:] or ["1:0"]):
+        variant, bps = [int(x) for x in spec.split(":")]
+        ms.set_option("bs_variant", variant)
         ms.set_option("blocks_per_sm", bps)
         for kind in ("zml", "count"):
             def go():
@@ -44,7 +46,7 @@ def main():
             if kind == "count":
                 pos = d_pos.cpu().numpy()
                 extra = {"mean_matched_suffix": float((150 - pos).mean())}
-            print(json.dumps({"kind": kind + "_" + name, "blocks_per_sm": bps, "ms": round(t, 3), "Gbases_per_s": round(n_bases / t / 1e6, 2), **extra}), flush=True)
+            print(json.dumps({"kind": kind + "_" + name, "variant": variant, "blocks_per_sm": bps, "ms": round(t, 3), "Gbases_per_s": round(n_bases / t / 1e6, 2), **extra}), flush=True)
 
 
 if __name__ == "__main__":
