@@ -67,9 +67,26 @@ def build_host(force=False):
     return HOST_LIB
 
 
+SYNTH_LIB = os.path.join(LIBDIR, "libmovi_synth.so")
+
+
+def build_synth(force=False):
+    """Bench data generator: synthetic human-scale tables built directly in HBM (datagen/synth_gpu.cu)."""
+    src = os.path.join(HERE, "datagen", "synth_gpu.cu")
+    if force or _newer(SYNTH_LIB, [src, GPU_LIB]):
+        cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--compiler-options", "-fPIC",
+               "-shared", src, "-L" + LIBDIR, "-lmovi_gpu", "-Xlinker", "-rpath=$ORIGIN", "-o", SYNTH_LIB]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode:
+            sys.stderr.write(r.stdout)
+            raise RuntimeError("nvcc failed (synth_gpu.cu)")
+    return SYNTH_LIB
+
+
 def build_all(force=False, verbose=False):
     build_gpu(force, verbose)
     build_host(force)
+    build_synth(force)
     subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "datagen")])
 
 

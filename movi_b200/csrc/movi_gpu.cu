@@ -5,6 +5,8 @@
 // There is deliberately no CPU fallback anywhere in this file.
 #include "../../include/movi_gpu.h"
 
+#include <cuda.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -72,6 +74,8 @@ struct movi_gpu_ctx {
                                       // bottleneck of the host path: small slices keep the pipeline ramp short)
     // gather probe scratch
     uint2* d_probe = nullptr; uint64_t probe_bytes = 0;
+    int64_t probe_vmm_align_mb = 0;   // > 0: allocate the probe table through the VMM API at this alignment
+    unsigned long long probe_vmm[3] = {0, 0, 0};   // VmmBlock {ptr, size, handle} of the probe table
 };
 
 namespace {
@@ -86,6 +90,56 @@ int fail(movi_gpu_ctx* c, int code, const std::string& msg) {
         if (e_ != cudaSuccess)                                                                     \
             return fail(ctx, MOVI_GPU_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
+
+// Device memory through the virtual-memory-management driver API (entry points resolved at run time, so the
+// library does not link against libcuda): lets the row table be mapped at a large alignment, which the driver may back
+// with larger page-table entries than cudaMalloc's 2 MB pages -- the reach of the GPU TLBs is what bounds random row
+// fetches on tables beyond ~1 GB (profiles/r01_summary.md).
+struct VmmBlock { CUdeviceptr ptr = 0; size_t size = 0; CUmemGenericAllocationHandle handle = 0; };
+
+template <typename F> bool drv(const char* name, F* fn) {
+    void* p = nullptr; cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) { cudaGetLastError(); return false; }
+    *fn = reinterpret_cast<F>(p);
+    return true;
+}
+
+bool vmm_alloc(int device, size_t bytes, size_t align, VmmBlock* out) {
+    CUresult (*memCreate)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+    CUresult (*addrReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*memMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*setAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+    CUresult (*getGran)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+    if (!drv("cuMemCreate", &memCreate) || !drv("cuMemAddressReserve", &addrReserve) || !drv("cuMemMap", &memMap) ||
+        !drv("cuMemSetAccess", &setAccess) || !drv("cuMemGetAllocationGranularity", &getGran)) return false;
+    CUmemAllocationProp prop = {};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = device;
+    size_t gran = 0;
+    if (getGran(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || gran == 0) return false;
+    const size_t unit = std::max(gran, align);
+    const size_t size = (bytes + unit - 1) / unit * unit;
+    CUmemGenericAllocationHandle h;
+    if (memCreate(&h, size, &prop, 0) != CUDA_SUCCESS) return false;
+    CUdeviceptr ptr = 0;
+    if (addrReserve(&ptr, size, align, 0, 0) != CUDA_SUCCESS) return false;
+    if (memMap(ptr, size, 0, h, 0) != CUDA_SUCCESS) return false;
+    CUmemAccessDesc acc = {};
+    acc.location = prop.location; acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    if (setAccess(ptr, size, &acc, 1) != CUDA_SUCCESS) return false;
+    out->ptr = ptr; out->size = size; out->handle = h;
+    return true;
+}
+void vmm_free(VmmBlock* b) {
+    if (!b->ptr) return;
+    CUresult (*unmap)(CUdeviceptr, size_t) = nullptr; CUresult (*release)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*addrFree)(CUdeviceptr, size_t) = nullptr;
+    if (drv("cuMemUnmap", &unmap) && drv("cuMemRelease", &release) && drv("cuMemAddressFree", &addrFree)) {
+        unmap(b->ptr, b->size); release(b->handle); addrFree(b->ptr, b->size);
+    }
+    *b = VmmBlock{};
+}
 
 template <typename K>
 int blocks_for(movi_gpu_ctx* ctx, K kernel, int threads) {
@@ -339,18 +393,22 @@ int movi_gpu_destroy(movi_gpu_ctx* ctx) {
         if (S.done) cudaEventDestroy(S.done);
         if (S.stream) cudaStreamDestroy(S.stream);
     }
-    cudaFree(ctx->d_status); cudaFree(ctx->d_counters); cudaFree(ctx->d_probe);
+    cudaFree(ctx->d_status); cudaFree(ctx->d_counters);
+    if (ctx->probe_vmm[0]) { VmmBlock b; b.ptr = ctx->probe_vmm[0]; b.size = ctx->probe_vmm[1]; b.handle = ctx->probe_vmm[2]; vmm_free(&b); }
+    else cudaFree(ctx->d_probe);
     delete ctx;
     return MOVI_GPU_OK;
 }
 
 uint64_t movi_gpu_index_device_bytes(const movi_gpu_ctx* ctx) { return ctx ? ctx->index_bytes : 0; }
+const void* movi_gpu_index_device_rows(const movi_gpu_ctx* ctx) { return ctx && ctx->has_index ? ctx->d_rows : nullptr; }
 uint64_t movi_gpu_launch_count(const movi_gpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int movi_gpu_set_option(movi_gpu_ctx* ctx, const char* key, int64_t value) {
     if (!ctx || !key) return MOVI_GPU_ERR_ARG;
     const std::string k(key);
     if (k == "pml_variant") { if (value < 0 || value > 4) return fail(ctx, MOVI_GPU_ERR_ARG, "pml_variant: 0..4"); ctx->pml_variant = value; }
+    else if (k == "probe_vmm_align_mb") { if (value < 0 || value > 4096) return fail(ctx, MOVI_GPU_ERR_ARG, "probe_vmm_align_mb: 0..4096"); ctx->probe_vmm_align_mb = value; }
     else if (k == "bs_variant") { if (value < 0 || value > 1) return fail(ctx, MOVI_GPU_ERR_ARG, "bs_variant: 0 or 1"); ctx->bs_variant = value; }
     else if (k == "force_wide") { ctx->force_wide = value ? 1 : 0; }
     else if (k == "row_ld_mode") { if (value < 0 || value > 7) return fail(ctx, MOVI_GPU_ERR_ARG, "row_ld_mode: 0..7"); ctx->row_ld_mode = value; }
@@ -398,14 +456,27 @@ int64_t movi_gpu_get_option(const movi_gpu_ctx* ctx, const char* key) {
     return -1;
 }
 
+static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout, uint2* adopt_rows);
+
 int movi_gpu_upload_index(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout) {
+    return upload_impl(ctx, d, layout, nullptr);
+}
+
+int movi_gpu_adopt_device_rows(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, void* d_rows) {
+    if (!d_rows) return ctx ? fail(ctx, MOVI_GPU_ERR_ARG, "null device row table") : MOVI_GPU_ERR_ARG;
+    if (d && d->mode != MOVI_MODE_REGULAR_THRESHOLDS)
+        return fail(ctx, MOVI_GPU_ERR_INDEX, "an adopted device table must already be in the 8-byte regular-thresholds row format");
+    return upload_impl(ctx, d, MOVI_GPU_LAYOUT_EXPANDED8, static_cast<uint2*>(d_rows));
+}
+
+static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout, uint2* adopt_rows) {
     if (!ctx || !d) return MOVI_GPU_ERR_ARG;
     if (layout != MOVI_GPU_LAYOUT_AUTO && layout != MOVI_GPU_LAYOUT_EXPANDED8)
         return fail(ctx, MOVI_GPU_ERR_ARG, "unknown device layout");
     if (d->mode != MOVI_MODE_REGULAR_THRESHOLDS && d->mode != MOVI_MODE_BLOCKED_THRESHOLDS && d->mode != MOVI_MODE_SAMPLED_THRESHOLDS)
         return fail(ctx, MOVI_GPU_ERR_INDEX, "unsupported index mode " + std::to_string(d->mode) +
                     " (regular-thresholds 6, blocked-thresholds 8, sampled-thresholds 7)");
-    if (!d->rows || !d->alphamap || d->r == 0) return fail(ctx, MOVI_GPU_ERR_INDEX, "empty index description");
+    if ((!d->rows && !adopt_rows) || !d->alphamap || d->r == 0) return fail(ctx, MOVI_GPU_ERR_INDEX, "empty index description");
     if (d->r >= (1ull << 36)) return fail(ctx, MOVI_GPU_ERR_INDEX, "more than 2^36 rows");
     if (d->end_bwt_idx >= d->r) return fail(ctx, MOVI_GPU_ERR_INDEX, "end_bwt_idx out of range");
     const bool sep = (d->sigma == 5 && d->alphabet[0] == '%');       // use_separator(), src/move_structure.cpp:547-552
@@ -422,11 +493,14 @@ int movi_gpu_upload_index(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layo
     free_index(ctx);
     cudaStream_t st = ctx->slot[0].stream;
     const unsigned long long r = d->r;
-    CU(cudaMalloc(&ctx->d_rows, (r + 4) * sizeof(uint2)));
+    if (adopt_rows) ctx->d_rows = adopt_rows;        // already resident (r + 4 rows, 8-byte format); ownership moves to the context
+    else CU(cudaMalloc(&ctx->d_rows, (r + 4) * sizeof(uint2)));
     CU(cudaMemsetAsync(ctx->d_rows + r, 0, 4 * sizeof(uint2), st));
     ctx->index_bytes = (r + 4) * sizeof(uint2);
 
-    if (d->mode == MOVI_MODE_REGULAR_THRESHOLDS) {
+    if (adopt_rows) {
+        // nothing to copy
+    } else if (d->mode == MOVI_MODE_REGULAR_THRESHOLDS) {
         // the on-disk row IS the device row: one copy
         CU(cudaMemcpyAsync(ctx->d_rows, d->rows, r * sizeof(uint2), cudaMemcpyHostToDevice, st));
     } else if (d->mode == MOVI_MODE_BLOCKED_THRESHOLDS) {
@@ -614,8 +688,16 @@ int movi_gpu_gather_probe(movi_gpu_ctx* ctx, uint64_t table_bytes, uint32_t load
         table = ctx->d_rows; n_rows = ctx->ix.r & ~3ull;
     } else {
         table_bytes &= ~255ull;
-        if (ctx->probe_bytes != table_bytes) {
-            cudaFree(ctx->d_probe); ctx->d_probe = nullptr; ctx->probe_bytes = 0;
+        if (ctx->probe_bytes != table_bytes || (ctx->probe_vmm_align_mb > 0) != (ctx->probe_vmm[0] != 0)) {
+            if (ctx->probe_vmm[0]) { VmmBlock b; b.ptr = ctx->probe_vmm[0]; b.size = ctx->probe_vmm[1]; b.handle = ctx->probe_vmm[2]; vmm_free(&b); ctx->probe_vmm[0] = 0; }
+            else cudaFree(ctx->d_probe);
+            ctx->d_probe = nullptr; ctx->probe_bytes = 0;
+            if (ctx->probe_vmm_align_mb > 0) {
+                VmmBlock b;
+                if (!vmm_alloc(ctx->device, table_bytes, (size_t)ctx->probe_vmm_align_mb << 20, &b)) return fail(ctx, MOVI_GPU_ERR_NOMEM, "VMM allocation of the probe table failed");
+                ctx->probe_vmm[0] = b.ptr; ctx->probe_vmm[1] = b.size; ctx->probe_vmm[2] = b.handle;
+                ctx->d_probe = reinterpret_cast<uint2*>(b.ptr);
+            } else
             CU(cudaMalloc(&ctx->d_probe, table_bytes));
             ctx->probe_bytes = table_bytes;
             probe_fill_kernel<<<ctx->num_sms * 8, 256>>>(ctx->d_probe, table_bytes / 8);

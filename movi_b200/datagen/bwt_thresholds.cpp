@@ -172,21 +172,35 @@ int generate(const std::vector<uint8_t>& T, const std::string& out, bool rle, bo
       for (int x = 0; x < 256; x++) if (occ[x]) syms.push_back(x); }
     std::vector<char> bwt_buf; bwt_buf.reserve(1 << 20);
     uint64_t runs = 0, run_len = 0; int prev_c = -1;
-    for (Idx p = 0; p < n; p++) {
-        Idx sa = SA[p];
-        int c = T[sa == 0 ? n - 1 : sa - 1];
-        uint64_t lcp = static_cast<uint64_t>(plcp[sa]);
-        for (int x : syms) if (lcp < minv[x]) { minv[x] = lcp; minp[x] = static_cast<uint64_t>(p); }
-        if (c != prev_c) {
-            if (prev_c >= 0 && rle) { char h = static_cast<char>(prev_c); heads_f.write(&h, 1); write5(len_f, run_len); }
-            write5(thr_f, seen[c] ? minp[c] : 0);
-            seen[c] = true; runs++; run_len = 0; prev_c = c;
+    // gather BWT[p] and LCP[p] in SA order block by block (the two random gathers are the expensive part: parallel),
+    // then scan the block sequentially
+    const Idx BLK = 1 << 24;
+    std::vector<uint8_t> bw(static_cast<size_t>(std::min<Idx>(BLK, n)));
+    std::vector<Idx> lc(bw.size());
+    for (Idx base = 0; base < n; base += BLK) {
+        const Idx cnt = std::min<Idx>(BLK, n - base);
+        #pragma omp parallel for schedule(static)
+        for (Idx k = 0; k < cnt; k++) {
+            const Idx sa = SA[base + k];
+            bw[k] = T[sa == 0 ? n - 1 : sa - 1];
+            lc[k] = plcp[sa];
         }
-        run_len++;
-        minv[c] = INF; minp[c] = static_cast<uint64_t>(p) + 1;
-        if (!rle) {
-            bwt_buf.push_back(static_cast<char>(c));
-            if (bwt_buf.size() == (1 << 20)) { bwt_f.write(bwt_buf.data(), bwt_buf.size()); bwt_buf.clear(); }
+        for (Idx k = 0; k < cnt; k++) {
+            const Idx p = base + k;
+            const int c = bw[k];
+            const uint64_t lcp = static_cast<uint64_t>(lc[k]);
+            for (int x : syms) if (lcp < minv[x]) { minv[x] = lcp; minp[x] = static_cast<uint64_t>(p); }
+            if (c != prev_c) {
+                if (prev_c >= 0 && rle) { char h = static_cast<char>(prev_c); heads_f.write(&h, 1); write5(len_f, run_len); }
+                write5(thr_f, seen[c] ? minp[c] : 0);
+                seen[c] = true; runs++; run_len = 0; prev_c = c;
+            }
+            run_len++;
+            minv[c] = INF; minp[c] = static_cast<uint64_t>(p) + 1;
+            if (!rle) {
+                bwt_buf.push_back(static_cast<char>(c));
+                if (bwt_buf.size() == (1 << 20)) { bwt_f.write(bwt_buf.data(), bwt_buf.size()); bwt_buf.clear(); }
+            }
         }
     }
     if (rle) { char h = static_cast<char>(prev_c); heads_f.write(&h, 1); write5(len_f, run_len); }
