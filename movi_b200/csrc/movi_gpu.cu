@@ -65,6 +65,7 @@ struct movi_gpu_ctx {
     int64_t pml_variant = 4;          // 0/1: branchy kernel (2-byte / 16-byte stores); 2/3: convergent kernel (+/- L2 hints); 4: convergent + sector staging in smem
     int64_t l2_persist_mb = 0;        // > 0: mark the row table persisting in L2 (access policy window) for query launches
     int64_t l2_fetch_granularity = 0; // 0: leave the device default; 32 / 64 / 128: cudaLimitMaxL2FetchGranularity
+    int64_t pml_min_blocks = 0;       // 0: by table size; 6 / 8: force the occupancy flavour of movi_pml_kernel3
     int64_t bs_variant = 1;           // count / ZML kernel: 0 = branch-per-state (bs_kernel.cuh), 1 = convergent + sector staging
     int64_t force_wide = 0;           // tests: run the 64-bit-index instantiations on a small table
     int64_t row_ld_mode = 0;          // cache recipe of the row fetch (pml_kernel2.cuh: ld_row)
@@ -212,8 +213,18 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
         else if (ctx->pml_variant == 1) { if (wide) LAUNCH((movi_pml_kernel<unsigned long long, 1>)); else LAUNCH((movi_pml_kernel<uint32_t, 1>)); }
         else if (ctx->pml_variant == 2) { if (wide) LAUNCH((movi_pml_kernel2<unsigned long long, true>)); else LAUNCH((movi_pml_kernel2<uint32_t, true>)); }
         else if (ctx->pml_variant == 3) { if (wide) LAUNCH((movi_pml_kernel2<unsigned long long, false>)); else LAUNCH((movi_pml_kernel2<uint32_t, false>)); }
-        else if (ctx->ix.sep) { if (wide) LAUNCH((movi_pml_kernel3<unsigned long long, true>)); else LAUNCH((movi_pml_kernel3<uint32_t, true>)); }
-        else { if (wide) LAUNCH((movi_pml_kernel3<unsigned long long, false>)); else LAUNCH((movi_pml_kernel3<uint32_t, false>)); }
+        else {
+            // occupancy flavour: 6 blocks/SM (40 registers) measured fastest on both L2-sized (c2) and HBM-resident (8-64 GB)
+            // tables -- the latter are bound by the translation / DRAM request rate, not by exposed latency; 8 stays selectable
+            const bool dense = ctx->pml_min_blocks >= 8;
+            if (ctx->ix.sep) {
+                if (wide) { if (dense) LAUNCH((movi_pml_kernel3<unsigned long long, true, 8>)); else LAUNCH((movi_pml_kernel3<unsigned long long, true, 6>)); }
+                else      { if (dense) LAUNCH((movi_pml_kernel3<uint32_t, true, 8>)); else LAUNCH((movi_pml_kernel3<uint32_t, true, 6>)); }
+            } else {
+                if (wide) { if (dense) LAUNCH((movi_pml_kernel3<unsigned long long, false, 8>)); else LAUNCH((movi_pml_kernel3<unsigned long long, false, 6>)); }
+                else      { if (dense) LAUNCH((movi_pml_kernel3<uint32_t, false, 8>)); else LAUNCH((movi_pml_kernel3<uint32_t, false, 6>)); }
+            }
+        }
     } else if (kind == Q_ZML) {
         if (ctx->bs_variant == 0) { if (wide) LAUNCH((movi_bs_kernel<unsigned long long, KIND_ZML>)); else LAUNCH((movi_bs_kernel<uint32_t, KIND_ZML>)); }
         else { if (wide) LAUNCH((movi_bs_kernel2<unsigned long long, KIND_ZML>)); else LAUNCH((movi_bs_kernel2<uint32_t, KIND_ZML>)); }
@@ -409,6 +420,7 @@ int movi_gpu_set_option(movi_gpu_ctx* ctx, const char* key, int64_t value) {
     const std::string k(key);
     if (k == "pml_variant") { if (value < 0 || value > 4) return fail(ctx, MOVI_GPU_ERR_ARG, "pml_variant: 0..4"); ctx->pml_variant = value; }
     else if (k == "probe_vmm_align_mb") { if (value < 0 || value > 4096) return fail(ctx, MOVI_GPU_ERR_ARG, "probe_vmm_align_mb: 0..4096"); ctx->probe_vmm_align_mb = value; }
+    else if (k == "pml_min_blocks") { if (value != 0 && value != 6 && value != 8) return fail(ctx, MOVI_GPU_ERR_ARG, "pml_min_blocks: 0, 6 or 8"); ctx->pml_min_blocks = value; }
     else if (k == "bs_variant") { if (value < 0 || value > 1) return fail(ctx, MOVI_GPU_ERR_ARG, "bs_variant: 0 or 1"); ctx->bs_variant = value; }
     else if (k == "force_wide") { ctx->force_wide = value ? 1 : 0; }
     else if (k == "row_ld_mode") { if (value < 0 || value > 7) return fail(ctx, MOVI_GPU_ERR_ARG, "row_ld_mode: 0..7"); ctx->row_ld_mode = value; }
@@ -446,6 +458,7 @@ int64_t movi_gpu_get_option(const movi_gpu_ctx* ctx, const char* key) {
     if (k == "row_ld_mode") return ctx->row_ld_mode;
     if (k == "force_wide") return ctx->force_wide;
     if (k == "bs_variant") return ctx->bs_variant;
+    if (k == "pml_min_blocks") return ctx->pml_min_blocks;
     if (k == "l2_persist_mb") return ctx->l2_persist_mb;
     if (k == "l2_persist_max_mb") return ctx->max_persist_bytes >> 20;
     if (k == "l2_fetch_granularity") {

@@ -27,8 +27,11 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 constexpr int PML3_THREADS = 256;
 
 // SEP: the index has separators ("%ACGT"; threshold slots shift by one, '%' rows use a side table) -- compiled out otherwise
-template <typename IdxT, bool SEP>
-__global__ void __launch_bounds__(PML3_THREADS)
+// MINB: resident blocks per SM the register allocation must allow.  6 (40 registers) is the default; 8 (32 registers,
+// 2048 walks per SM, one spilled word) was measured slower both on the L2-sized c2 table (issue bound) and on 8-64 GB
+// tables (bound by the memory system's random-request rate, not by exposed latency): profiles/r01_big_tables.jsonl.
+template <typename IdxT, bool SEP, int MINB>
+__global__ void __launch_bounds__(PML3_THREADS, MINB)
 movi_pml_kernel3(const DevIndex ix, const QueryArgs q) {
     __shared__ uint8_t s_code[256];
     __shared__ uint32_t s_end_thr[4];

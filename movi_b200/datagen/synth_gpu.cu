@@ -29,7 +29,7 @@ __host__ __device__ inline u64 mix(u64 x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
     return x;
 }
-struct Gen { u64 r, end_idx, seed; };
+struct Gen { u64 r, end_idx, seed; uint32_t profile; };   // profile 0: short runs (mean ~8), 1: pangenome-like runs (mean ~40)
 
 __host__ __device__ inline uint32_t run_c(const Gen& g, u64 i) { return i == g.end_idx ? 0u : (uint32_t)(2 * (i & 1) + (mix(i ^ g.seed) & 1)); }
 __host__ __device__ inline uint32_t run_n(const Gen& g, u64 i) {
@@ -37,6 +37,12 @@ __host__ __device__ inline uint32_t run_n(const Gen& g, u64 i) {
     const u64 h = mix(i * 0x9E3779B97F4A7C15ULL + g.seed);
     // mixture: mostly short runs, a tail of long ones (mean ~ 8)
     const uint32_t k = (uint32_t)(h & 0xFF);
+    if (g.profile == 1) {                              // n/r ~ 40, like the c2 pangenome index (n/r = 41)
+        uint32_t m = 1 + (uint32_t)((h >> 8) % 64);
+        if (k < 32) m = 64 + (uint32_t)((h >> 20) % 192);
+        if (k < 3) m = 256 + (uint32_t)((h >> 32) % 1024);
+        return m;
+    }
     uint32_t n = 1 + (uint32_t)((h >> 8) % 6);
     if (k < 40) n = 8 + (uint32_t)((h >> 20) % 24);
     if (k < 4) n = 64 + (uint32_t)((h >> 32) % 448);
@@ -167,9 +173,9 @@ extern "C" {
 
 // Build a synthetic table of r rows on the current device of `ctx` and make it the context's index.
 // Returns 0 on success; *n_out = BWT length.
-int movi_synth_index(movi_gpu_ctx* ctx, uint64_t r, uint64_t seed, uint64_t* n_out, MoviGpuIndexDesc* desc_out) {
+int movi_synth_index(movi_gpu_ctx* ctx, uint64_t r, uint64_t seed, uint32_t profile, uint64_t* n_out, MoviGpuIndexDesc* desc_out) {
     if (!ctx || r < 1024) return 1;
-    Gen g{r, mix(seed) % (r / 2) + r / 4, seed};
+    Gen g{r, mix(seed) % (r / 2) + r / 4, seed, profile};
     const u64 n_blocks = (r + 1 + SB - 1) / SB;
     uint2* rows = nullptr; u64* p = nullptr; Sum5* tot = nullptr; Sum5* grand = nullptr;
     CK(cudaMalloc(&rows, (r + 4) * sizeof(uint2)));
@@ -217,7 +223,7 @@ int movi_synth_index(movi_gpu_ctx* ctx, uint64_t r, uint64_t seed, uint64_t* n_o
 // Fill d_bases (n_reads * len bytes, device) with reads that match the table of a context built by movi_synth_index.
 int movi_synth_reads(const void* d_rows, uint64_t r, uint64_t seed, void* d_bases, uint64_t n_reads, uint32_t len,
                      uint32_t sub_per_1024, uint32_t rand_every) {
-    Gen g{r, mix(seed) % (r / 2) + r / 4, seed};
+    Gen g{r, mix(seed) % (r / 2) + r / 4, seed, 0};   // the walk only reads the finished rows
     make_reads<<<148 * 8, 128>>>(g, static_cast<const uint2*>(d_rows), static_cast<uint8_t*>(d_bases), n_reads, len, sub_per_1024, rand_every);
     CK(cudaDeviceSynchronize());
     CK(cudaGetLastError());

@@ -18,7 +18,7 @@ def lib():
         _build.build_synth()
         N.gpu_lib()
         L = C.CDLL(_build.SYNTH_LIB)
-        L.movi_synth_index.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(N.MoviGpuIndexDesc)]
+        L.movi_synth_index.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(N.MoviGpuIndexDesc)]
         L.movi_synth_index.restype = C.c_int
         L.movi_synth_reads.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
         L.movi_synth_reads.restype = C.c_int
@@ -31,7 +31,7 @@ def lib():
 class SyntheticStructure(MoveStructure):
     """A MoveStructure whose row table was synthesised on the GPU (r rows, seeded)."""
 
-    def __init__(self, r, seed=44, device=0):
+    def __init__(self, r, seed=44, device=0, profile=0):
         self._L = N.gpu_lib()
         self._ctx = C.c_void_p()
         rc = self._L.movi_gpu_create(device, C.byref(self._ctx))
@@ -40,7 +40,7 @@ class SyntheticStructure(MoveStructure):
         self.device, self.seed = device, seed
         n = C.c_uint64()
         self.desc = N.MoviGpuIndexDesc()
-        rc = lib().movi_synth_index(self._ctx, r, seed, C.byref(n), C.byref(self.desc))
+        rc = lib().movi_synth_index(self._ctx, r, seed, profile, C.byref(n), C.byref(self.desc))
         if rc != 0:
             raise MoviGpuError(rc, self._L.movi_gpu_last_error(self._ctx).decode() or "synthetic index generation failed")
         self.r, self.n, self.mode, self.host_index = r, n.value, 6, None

@@ -7,11 +7,12 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def test_synthetic_table_matches_oracle(tmp_path):
+@pytest.mark.parametrize("profile", [0, 1])
+def test_synthetic_table_matches_oracle(tmp_path, profile):
     import torch
     from movi_b200.datagen.synth_gpu import SyntheticStructure
     from oracle.port import OracleIndex
-    ms = SyntheticStructure(1 << 20, seed=44)
+    ms = SyntheticStructure(1 << 20, seed=44, profile=profile)
     n_reads, L = 3000, 400
     dev = torch.device("cuda:0")
     d_bases = torch.zeros(n_reads * L + 64, dtype=torch.uint8, device=dev)
