@@ -47,7 +47,8 @@ movi_bs_kernel2(const DevIndex ix, const QueryArgs q) {
     uint16_t* const out_slot = s_out + (KIND == KIND_ZML ? threadIdx.x * 16 : 0);
     const uint32_t n_reads = q.n_reads;
 
-    uint32_t q_next = 0, q_end = 0;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t q_next = 0, q_end = 0, chunk = min(QUEUE_CHUNK, max(1u, n_reads / (2u * n_warps)));
     bool exhausted = false;
     uint32_t pst = B_IDLE;
     uint32_t ri = 0;
@@ -64,12 +65,16 @@ movi_bs_kernel2(const DevIndex ix, const QueryArgs q) {
         const unsigned bm = __ballot_sync(FULL, want);
         if (bm) {
             if (q_next == q_end) {
+                // guided self-scheduling: take 32 reads per refill while plenty remain, fewer as the batch drains, so that
+                // no warp sits on a private backlog while the lanes of other warps have already gone idle
                 unsigned long long b = 0;
-                if (lane == 0) b = atomicAdd(q.counter, (unsigned long long)QUEUE_CHUNK);
+                if (lane == 0) b = atomicAdd(q.counter, (unsigned long long)chunk);
                 b = __shfl_sync(FULL, b, 0);
                 q_next = b < n_reads ? (uint32_t)b : n_reads;
-                q_end = b + QUEUE_CHUNK < n_reads ? (uint32_t)(b + QUEUE_CHUNK) : n_reads;
+                q_end = b + chunk < n_reads ? (uint32_t)(b + chunk) : n_reads;
                 if (q_next == q_end) exhausted = true;
+                const uint32_t left = n_reads - q_end;
+                chunk = min(QUEUE_CHUNK, max(1u, left / (2u * n_warps)));
             }
             const uint32_t avail = q_end - q_next;
             const uint32_t rank = __popc(bm & lt_mask);

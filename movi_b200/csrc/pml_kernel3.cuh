@@ -54,7 +54,8 @@ movi_pml_kernel3(const DevIndex ix, const QueryArgs q) {
     constexpr uint32_t sep = SEP ? 1u : 0u;
     const uint32_t n_reads = q.n_reads;
 
-    uint32_t q_next = 0, q_end = 0;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t q_next = 0, q_end = 0, chunk = min(QUEUE_CHUNK, max(1u, n_reads / (2u * n_warps)));
     bool exhausted = false;
     uint32_t st = ST_IDLE;
     IdxT idx = 0;
@@ -66,12 +67,16 @@ movi_pml_kernel3(const DevIndex ix, const QueryArgs q) {
         const unsigned m = __ballot_sync(FULL, want);
         if (m) {
             if (q_next == q_end) {
+                // guided self-scheduling: take 32 reads per refill while plenty remain, fewer as the batch drains, so that
+                // no warp sits on a private backlog while the lanes of other warps have already gone idle
                 unsigned long long b = 0;
-                if (lane == 0) b = atomicAdd(q.counter, (unsigned long long)QUEUE_CHUNK);
+                if (lane == 0) b = atomicAdd(q.counter, (unsigned long long)chunk);
                 b = __shfl_sync(FULL, b, 0);
                 q_next = b < n_reads ? (uint32_t)b : n_reads;
-                q_end = b + QUEUE_CHUNK < n_reads ? (uint32_t)(b + QUEUE_CHUNK) : n_reads;
+                q_end = b + chunk < n_reads ? (uint32_t)(b + chunk) : n_reads;
                 if (q_next == q_end) exhausted = true;
+                const uint32_t left = n_reads - q_end;
+                chunk = min(QUEUE_CHUNK, max(1u, left / (2u * n_warps)));
             }
             const uint32_t avail = q_end - q_next;
             const uint32_t rank = __popc(m & lt_mask);
@@ -84,14 +89,12 @@ movi_pml_kernel3(const DevIndex ix, const QueryArgs q) {
         // ---- loads: row fetch for every walking lane; a lane that ran out of staged read bytes pulls the next sector
         const bool is_new = (st == ST_NEW);
         const bool proc = (st >= ST_FF);
-        uint2 v = make_uint2(0u, 0u);
-        if (proc) {
-            v = ld_keep(rows + idx, pol_keep);
-            if (need_chunk) {
-                const uint8_t* src = bases + (rp & ~31u);
-                cp_async16(in_slot, src);
-                cp_async16(in_slot + 16, src + 16);
-            }
+        // (lanes that are not walking fetch row 0: harmless and keeps the fetch out of a divergent branch)
+        const uint2 v = ld_keep(rows + (proc ? idx : (IdxT)0), pol_keep);
+        if (proc && need_chunk) {
+            const uint8_t* src = bases + (rp & ~31u);
+            cp_async16(in_slot, src);
+            cp_async16(in_slot + 16, src + 16);
         }
         if (is_new) {       // rare per lane: start a read (query_pml :237-240)
             const uint2 a = ldg64(offs8 + idx), b = ldg64(offs8 + idx + 1);

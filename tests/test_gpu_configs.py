@@ -123,8 +123,10 @@ def test_full_size_c2_properties():
     from movi_b200 import MoveStructure
     from movi_b200.datagen import synth
     d = synth.cache_dir("c2")
+    for t in TYPES:
+        synth._unpack(d, t)             # the cache ships xz-compressed
     if not os.path.exists(os.path.join(d, "regular-thresholds", "index.movi")):
-        pytest.skip("full-size c2 cache not present")
+        pytest.skip("full-size c2 cache not present (bench.py builds it on demand: ~4 min)")
     cfg = synth.CONFIGS["c2"]
     haps = synth.pangenome(cfg["genome_len"], cfg["n_hap"])
     bases, offsets = synth.make_reads(haps, 200000, 150, seed=43)
