@@ -181,64 +181,88 @@ void movi_host_index_close(movi_host_index* ix) {
 }
 
 // BatchLoader::loadBatch + grabNextRead (reference src/batch_loader.cpp:26-143) over the whole input.
+// The file is mapped (stdin: slurped) and split with memchr: the reference's getline / stringstream loader parses a few
+// hundred MB/s, which is slower than the GPU consumes reads by two orders of magnitude.
+namespace {
+struct LineCursor {
+    const char* p; const char* end;
+    bool next(const char*& b, const char*& e) {          // one line without its '\n'; false at end of input
+        if (p >= end) return false;
+        const char* nl = static_cast<const char*>(memchr(p, '\n', (size_t)(end - p)));
+        b = p; e = nl ? nl : end; p = nl ? nl + 1 : end;
+        return true;
+    }
+    bool peek_is(char c) const { return p < end && *p == c; }
+};
+inline const char* rtrim_end(const char* b, const char* e) {
+    while (e > b && std::isspace(static_cast<unsigned char>(e[-1]))) e--;
+    return e;
+}
+}  // namespace
+
 int movi_host_reads_load(const char* path, int reverse, movi_host_reads** out) {
     if (!path || !out) return fail("null argument");
     *out = nullptr;
-    std::ifstream file;
-    std::istream* in = &std::cin;
-    if (std::string(path) != "-") {                     // "-" = stdin, reference src/movi.cpp:106-118
-        file.open(path);
-        if (!file) return fail("The input file " + std::string(path) + " does not exist.");
-        in = &file;
+    const char* data = nullptr; size_t size = 0;
+    std::string slurp; void* map = nullptr; int fd = -1;
+    if (std::string(path) == "-") {                      // "-" = stdin, reference src/movi.cpp:106-118
+        char buf[1 << 16]; ssize_t n;
+        while ((n = ::read(STDIN_FILENO, buf, sizeof buf)) > 0) slurp.append(buf, (size_t)n);
+        data = slurp.data(); size = slurp.size();
+    } else {
+        fd = open(path, O_RDONLY);
+        struct stat sb;
+        if (fd < 0 || fstat(fd, &sb) != 0) { if (fd >= 0) close(fd); return fail("The input file " + std::string(path) + " does not exist."); }
+        size = (size_t)sb.st_size;
+        if (size) {
+            map = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (map == MAP_FAILED) { close(fd); return fail("mmap failed for " + std::string(path)); }
+            madvise(map, size, MADV_SEQUENTIAL);
+            data = static_cast<const char*>(map);
+        }
     }
+    auto cleanup = [&]() { if (map) munmap(map, size); if (fd >= 0) close(fd); };
     movi_host_reads* rd = new movi_host_reads();
-    const int first = in->peek();
-    if (first == EOF) { *out = rd; return 0; }
+    if (size == 0) { cleanup(); *out = rd; return 0; }
     bool fastq;
-    if (first == '>') fastq = false;
-    else if (first == '@') fastq = true;
-    else { delete rd; return fail("unrecognized input query file type - expects FASTA or FASTQ."); }
+    if (data[0] == '>') fastq = false;
+    else if (data[0] == '@') fastq = true;
+    else { delete rd; cleanup(); return fail("unrecognized input query file type - expects FASTA or FASTQ."); }
+    rd->bases.reserve(fastq ? size / 2 + 64 : size);
+    rd->offsets.reserve(size / 160 + 16); rd->id_offsets.reserve(size / 160 + 16);
 
-    std::string line, seq;
-    auto rtrim = [](std::string& s) { while (!s.empty() && std::isspace(static_cast<unsigned char>(s.back()))) s.pop_back(); };
-    auto add = [&](const std::string& header, std::string& s) {
-        // id: header[1 .. first whitespace] INCLUDING that whitespace character (batch_loader.cpp:117-119)
-        size_t idl = header.find_first_of(" \t\r", 1);
-        idl = (idl == std::string::npos) ? header.size() : idl;
-        rd->ids.append(header.substr(1, idl));
+    LineCursor lc{data, data + size};
+    const char *b, *e;
+    auto fail_free = [&](const std::string& m) { delete rd; cleanup(); return fail(m); };
+    while (lc.next(b, e)) {
+        if (b == e) break;                               // grabNextRead: an empty line ends the batch
+        if (fastq ? *b != '@' : *b != '>')
+            return fail_free(std::string("Incorrect ") + (fastq ? "FASTQ entry, it should start with '@'" : "FASTA entry, it should start with '>'"));
+        if (e - b <= 2) return fail_free("header line is missing an id. invalid query cannot be processed.");
+        // id: header[1 .. first blank / tab / CR] INCLUDING that character (batch_loader.cpp:117-119)
+        const char* w = b + 1;
+        while (w < e && *w != ' ' && *w != '\t' && *w != '\r') w++;
+        const size_t idl = (w < e) ? (size_t)(w - b) : (size_t)(e - b);    // == find_first_of position, or header size
+        rd->ids.append(b + 1, std::min<size_t>(idl, (size_t)(e - b) - 1));
         rd->id_offsets.push_back(rd->ids.size());
-        if (reverse) std::reverse(s.begin(), s.end());   // read_processor.cpp:49-51, movi.cpp:351-352
-        rd->bases.append(s);
-        rd->offsets.push_back(rd->bases.size());
-    };
-    bool have_line = static_cast<bool>(std::getline(*in, line));
-    while (have_line) {
-        if (line.empty()) break;                         // grabNextRead: an empty line ends the batch
-        if (fastq ? line[0] != '@' : line[0] != '>') {
-            delete rd;
-            return fail(std::string("Incorrect ") + (fastq ? "FASTQ entry, it should start with '@'" : "FASTA entry, it should start with '>'"));
-        }
-        if (line.size() <= 2) { delete rd; return fail("header line is missing an id. invalid query cannot be processed."); }
-        const std::string header = line;
-        seq.clear();
+        const size_t seq_begin = rd->bases.size();
         if (fastq) {
-            if (!std::getline(*in, seq)) break;
-            rtrim(seq);
-            std::string plus, qual;
-            if (!std::getline(*in, plus)) break;
-            if (!std::getline(*in, qual)) break;
-            add(header, seq);
-            have_line = static_cast<bool>(std::getline(*in, line));
-        } else {
-            have_line = false;
-            while (std::getline(*in, line)) {
-                if (!line.empty() && line[0] == '>') { have_line = true; break; }
-                rtrim(line);
-                seq.append(line);
+            const char *sb_, *se_, *x0, *x1;
+            if (!lc.next(sb_, se_)) { rd->ids.resize(rd->id_offsets[rd->id_offsets.size() - 2]); rd->id_offsets.pop_back(); break; }
+            rd->bases.append(sb_, (size_t)(rtrim_end(sb_, se_) - sb_));
+            if (!lc.next(x0, x1) || !lc.next(x0, x1)) {  // '+' line and qualities: a truncated record is dropped
+                rd->bases.resize(seq_begin); rd->ids.resize(rd->id_offsets[rd->id_offsets.size() - 2]); rd->id_offsets.pop_back(); break;
             }
-            add(header, seq);
+        } else {
+            while (lc.p < lc.end && !lc.peek_is('>')) {
+                lc.next(b, e);
+                rd->bases.append(b, (size_t)(rtrim_end(b, e) - b));
+            }
         }
+        if (reverse) std::reverse(rd->bases.begin() + (std::ptrdiff_t)seq_begin, rd->bases.end());   // read_processor.cpp:49-51, movi.cpp:351-352
+        rd->offsets.push_back(rd->bases.size());
     }
+    cleanup();
     *out = rd;
     return 0;
 }
@@ -252,20 +276,6 @@ const char* movi_host_reads_id(const movi_host_reads* rd, uint64_t i, uint32_t* 
     return rd->ids.data() + rd->id_offsets[i];
 }
 void movi_host_reads_free(movi_host_reads* rd) { delete rd; }
-
-// Classifier::initialize_report_file :24-32 + EmpNullDatabase::deserialize (emperical_null_database.cpp:106-126)
-int movi_host_nulldb_threshold(const char* index_dir, const char* query_type, uint64_t* max_value_thr) {
-    if (!index_dir || !query_type || !max_value_thr) return fail("null argument");
-    const std::string name = std::string(index_dir) + "/movi." + query_type + ".nulldb";
-    std::ifstream f(name, std::ios::binary);
-    if (!f) return fail("cannot open null database " + name);
-    uint64_t num = 0, percentile = 0; double mean = 0;
-    f.read(reinterpret_cast<char*>(&num), 8); f.read(reinterpret_cast<char*>(&mean), 8); f.read(reinterpret_cast<char*>(&percentile), 8);
-    if (!f) return fail("truncated null database " + name);
-    // max_value_thr is a uint16_t member in the reference (include/classifier.hpp:30)
-    *max_value_thr = (uint16_t)(std::max<uint64_t>(percentile, 3) + 1);   // MIN_MATCHING_LENGTH = 3, include/utils.hpp:152
-    return 0;
-}
 
 namespace {
 struct FdWriter {
@@ -281,26 +291,41 @@ struct FdWriter {
 };
 }  // namespace
 
+// Classifier::initialize_report_file :24-32 + EmpNullDatabase::deserialize (emperical_null_database.cpp:106-126)
+int movi_host_nulldb_threshold(const char* index_dir, const char* query_type, uint64_t* max_value_thr) {
+    if (!index_dir || !query_type || !max_value_thr) return fail("null argument");
+    const std::string name = std::string(index_dir) + "/movi." + query_type + ".nulldb";
+    std::ifstream f(name, std::ios::binary);
+    if (!f) return fail("cannot open null database " + name);
+    uint64_t num = 0, percentile = 0; double mean = 0;
+    f.read(reinterpret_cast<char*>(&num), 8); f.read(reinterpret_cast<char*>(&mean), 8); f.read(reinterpret_cast<char*>(&percentile), 8);
+    if (!f) return fail("truncated null database " + name);
+    // max_value_thr is a uint16_t member in the reference (include/classifier.hpp:30)
+    *max_value_thr = (uint16_t)(std::max<uint64_t>(percentile, 3) + 1);   // MIN_MATCHING_LENGTH = 3, include/utils.hpp:152
+    return 0;
+}
+
+
 // output_base_stats (binary branch) + BPFHeader, reference src/utils.cpp:202-246, include/utils.hpp:64-86
 int movi_host_write_bpf(const char* file, const movi_host_reads* rd, const uint16_t* ml) {
     if (!file || !rd || (!ml && !rd->bases.empty())) return fail("null argument");
-    FILE* f = std::fopen(file, "wb");
-    if (!f) return fail(std::string("cannot open ") + file);
+    const int fd = open(file, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return fail(std::string("cannot open ") + file);
+    FdWriter w(fd);
     uint8_t header[12] = {0};
     std::memcpy(header, &BPF_MAGIC, 4);
     header[4] = 1; header[5] = 0; header[6] = 0;         // BPF_VERSION 1.0.0, include/version.hpp:13-15
     header[7] = 16;                                      // entry size in bits
-    std::fwrite(header, 1, 12, f);
+    bool ok = w.put(reinterpret_cast<const char*>(header), 12);
     const uint64_t n = rd->offsets.size() - 1;
-    for (uint64_t i = 0; i < n; i++) {
+    for (uint64_t i = 0; i < n && ok; i++) {
         const uint16_t idl = (uint16_t)(rd->id_offsets[i + 1] - rd->id_offsets[i]);
-        std::fwrite(&idl, 2, 1, f);
-        std::fwrite(rd->ids.data() + rd->id_offsets[i], 1, idl, f);
         const uint64_t len = rd->offsets[i + 1] - rd->offsets[i];
-        std::fwrite(&len, 8, 1, f);
-        std::fwrite(ml + rd->offsets[i], 2, len, f);
+        ok = w.put(reinterpret_cast<const char*>(&idl), 2) && w.put(rd->ids.data() + rd->id_offsets[i], idl) &&
+             w.put(reinterpret_cast<const char*>(&len), 8) && w.put(reinterpret_cast<const char*>(ml + rd->offsets[i]), len * 2);
     }
-    const bool ok = std::fclose(f) == 0;
+    ok = ok && w.flush();
+    ok = (close(fd) == 0) && ok;
     return ok ? 0 : fail(std::string("write failed: ") + file);
 }
 
