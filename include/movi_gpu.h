@@ -85,9 +85,11 @@ typedef struct movi_gpu_ctx movi_gpu_ctx;
 #define MOVI_GPU_FLAG_NONE 0u
 
 /* Device-resident row layouts (chosen at upload). */
-#define MOVI_GPU_LAYOUT_AUTO     0   /* EXPANDED8 when it fits, else the compact layout of the mode */
+#define MOVI_GPU_LAYOUT_AUTO     0   /* EXPANDED8 when it fits in free HBM, else COMPACT where the mode has one */
 #define MOVI_GPU_LAYOUT_EXPANDED8 1  /* every mode re-laid out as 8-byte rows with the full id resolved:
                                         one 32-byte sector holds 4 rows, one sector fetch per LF step */
+#define MOVI_GPU_LAYOUT_COMPACT  2   /* blocked-thresholds only: the 6-byte rows stay as they are on disk (25 % less HBM),
+                                        the destination id is completed per step from id_blocks (shared memory / L2) */
 
 int  movi_gpu_abi_version(void);
 int  movi_gpu_device_count(void);
@@ -106,6 +108,8 @@ int  movi_gpu_upload_index(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* desc, int 
 int  movi_gpu_adopt_device_rows(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* desc, void* d_rows);
 /* device pointer of the resident 8-byte row table (read-only; NULL without an index) */
 const void* movi_gpu_index_device_rows(const movi_gpu_ctx* ctx);
+/* MOVI_GPU_LAYOUT_EXPANDED8 or MOVI_GPU_LAYOUT_COMPACT of the resident index (-1 without one) */
+int  movi_gpu_index_device_layout(const movi_gpu_ctx* ctx);
 /* bytes of HBM held by the uploaded index */
 uint64_t movi_gpu_index_device_bytes(const movi_gpu_ctx* ctx);
 

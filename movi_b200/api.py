@@ -6,7 +6,7 @@ import numpy as np
 
 from . import _native as N
 
-LAYOUT_AUTO, LAYOUT_EXPANDED8 = 0, 1
+LAYOUT_AUTO, LAYOUT_EXPANDED8, LAYOUT_COMPACT = 0, 1, 2
 
 
 class MoviGpuError(RuntimeError):
@@ -139,6 +139,10 @@ class MoveStructure:
     @property
     def launch_count(self):
         return self._L.movi_gpu_launch_count(self._ctx)
+
+    @property
+    def device_layout(self):
+        return self._L.movi_gpu_index_device_layout(self._ctx)
 
     @property
     def index_device_bytes(self):

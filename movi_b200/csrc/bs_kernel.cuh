@@ -25,7 +25,7 @@ constexpr int KIND_ZML = 0, KIND_COUNT = 1;
 // sum of n(k) for k in [0, x): sampled prefix + at most 15 row reads
 __device__ __forceinline__ unsigned long long rows_before(const DevIndex& ix, unsigned long long x) {
     unsigned long long s = ix.prefix[x >> PREFIX_SHIFT];
-    for (unsigned long long k = (x >> PREFIX_SHIFT) << PREFIX_SHIFT; k < x; k++) s += row_n(ix.rows[k].y);
+    for (unsigned long long k = (x >> PREFIX_SHIFT) << PREFIX_SHIFT; k < x; k++) s += row_len_at(ix, k);
     return s;
 }
 

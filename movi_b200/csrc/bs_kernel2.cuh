@@ -20,10 +20,15 @@ namespace movi {
 
 constexpr uint32_t B_IDLE = 0, B_NEW = 1, B_SKIP = 2, B_RUN = 3, B_FAIL = 4, B_FIN = 5, B_COUNT = 6;
 
-template <typename IdxT, int KIND>
+template <typename IdxT, int KIND, int LAYOUT>
 __global__ void __launch_bounds__(PML3_THREADS)
 movi_bs_kernel2(const DevIndex ix, const QueryArgs q) {
     __shared__ uint8_t s_code[256];
+    __shared__ uint32_t s_idb[LAYOUT == LAYOUT_B6 ? IDB_SMEM : 1];
+    const uint32_t idb_n = ix.id_blocks_size * ix.sigma;
+    const bool idb_in_smem = LAYOUT == LAYOUT_B6 && idb_n <= IDB_SMEM;
+    if (LAYOUT == LAYOUT_B6 && idb_in_smem) for (uint32_t i = threadIdx.x; i < idb_n; i += blockDim.x) s_idb[i] = ix.id_blocks[i];
+    const uint32_t* const idb = idb_in_smem ? s_idb : ix.id_blocks;
     __shared__ unsigned long long s_first_runs[8], s_last_runs[8];
     __shared__ uint32_t s_first_offsets[8], s_last_offsets[8];
     __shared__ __align__(32) uint8_t s_in[PML3_THREADS * 32];
@@ -88,7 +93,14 @@ movi_bs_kernel2(const DevIndex ix, const QueryArgs q) {
         const bool run = (pst == B_RUN);
         const bool chunk_user = run || (pst == B_SKIP);
         uint2 vS = make_uint2(0u, 0u), vE = make_uint2(0u, 0u);
-        if (run) { vS = ld_keep(rows + rs, pol_keep); vE = ld_keep(rows + re, pol_keep); }
+        if (run) {
+            if (LAYOUT == LAYOUT_R8) { vS = ld_keep(rows + rs, pol_keep); vE = ld_keep(rows + re, pol_keep); }
+            else {
+                // first_runs indexed by code + 1 is exactly what get_id needs (first_runs[c + 1])
+                vS = fetch_row_b6<IdxT>(ix.rows6, rs, end_idx, idb, ix.id_blocks_size, ix.block_shift, s_first_runs);
+                vE = fetch_row_b6<IdxT>(ix.rows6, re, end_idx, idb, ix.id_blocks_size, ix.block_shift, s_first_runs);
+            }
+        }
         if (chunk_user && need_chunk) {
             const uint8_t* src = bases + (cur & ~31u);
             cp_async16(in_slot, src);
@@ -225,7 +237,7 @@ movi_bs_kernel2(const DevIndex ix, const QueryArgs q) {
             unsigned long long cnt;
             if (prs == pre) cnt = (unsigned long long)poe - pos_ + 1;
             else {
-                cnt = (unsigned long long)(row_n(rows[prs].y) - pos_) + (poe + 1);
+                cnt = (unsigned long long)(row_len_at(ix, (unsigned long long)prs) - pos_) + (poe + 1);
                 if (pre > prs + 1) cnt += rows_before(ix, (unsigned long long)pre) - rows_before(ix, (unsigned long long)prs + 1);
             }
             q.out_count[ri] = cnt;

@@ -96,7 +96,7 @@ __global__ void convert_sampled_kernel(const uint8_t* __restrict__ raw, uint2* _
 // ---- sampled prefix sums of run lengths (for MoveInterval::count in O(1): include/move_intervals.hpp:47-58)
 // pass 1: group sums (one u32 per 2^PREFIX_SHIFT rows) and per-block totals
 constexpr int SCAN_BLOCK = 1024;
-__global__ void prefix_group_sums_kernel(const uint2* __restrict__ rows, unsigned long long r,
+__global__ void prefix_group_sums_kernel(const DevIndex ix, unsigned long long r,
                                          unsigned long long n_groups, unsigned long long* __restrict__ group_sum,
                                          unsigned long long* __restrict__ block_sum) {
     __shared__ unsigned long long s[SCAN_BLOCK / 32];
@@ -104,7 +104,7 @@ __global__ void prefix_group_sums_kernel(const uint2* __restrict__ rows, unsigne
     unsigned long long sum = 0;
     if (g < n_groups) {
         const unsigned long long b = g << PREFIX_SHIFT;
-        for (int k = 0; k < (1 << PREFIX_SHIFT); k++) if (b + k < r) sum += row_n(rows[b + k].y);
+        for (int k = 0; k < (1 << PREFIX_SHIFT); k++) if (b + k < r) sum += row_len_at(ix, b + k);
         group_sum[g] = sum;
     }
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);

@@ -16,8 +16,16 @@
 
 namespace movi {
 
+constexpr int LAYOUT_R8 = 0;      // 8-byte rows, full destination id in the row
+constexpr int LAYOUT_B6 = 1;      // the reference's blocked-thresholds rows as they are on disk: 6 bytes per row + id_blocks
+
 struct DevIndex {
-    const uint2* rows;            // R8 rows
+    const uint2* rows;            // LAYOUT_R8: R8 rows
+    const uint32_t* rows6;        // LAYOUT_B6: packed 6-byte rows viewed as 32-bit words (table padded by 8 bytes)
+    const uint32_t* id_blocks;    // LAYOUT_B6: sigma x id_blocks_size checkpoints of the destination id (src/move_structure.cpp:95-102)
+    uint32_t id_blocks_size;
+    uint32_t block_shift;         // block_size == 1 << block_shift
+    uint32_t layout;
     unsigned long long r;
     unsigned long long end_idx;   // row of '$'
     uint32_t n_last;              // n(r-1)
@@ -56,6 +64,32 @@ __host__ __device__ __forceinline__ uint2 make_r8(unsigned long long id, uint32_
 }
 
 __device__ __forceinline__ uint2 ldg64(const uint2* p) { return __ldg(p); }
+
+// Run length of row k whatever the device layout (count query: sums over the rows an interval spans)
+__device__ __forceinline__ uint32_t row_len_at(const DevIndex& ix, unsigned long long k) {
+    if (ix.layout == LAYOUT_B6) return (uint32_t)reinterpret_cast<const uint16_t*>(ix.rows6)[3 * k + 1] & 0x3FFu;
+    return row_n(ix.rows[k].y);
+}
+
+// LAYOUT_B6: the packed blocked-thresholds row (include/move_row.hpp:128-130,139-142; bit fields
+// include/move_row_configs.hpp:76-104) fetched with two aligned 32-bit loads and re-expressed as an R8 word pair, with
+// MoveStructure::get_id for BLOCKED_MODES (src/move_structure.cpp:95-102) applied: id22 + id_blocks[c][idx / block_size]
+// + first_runs[c + 1] (the '$' row keeps its raw id).  idb points at the id_blocks copy to use (shared memory when it fits).
+template <typename IdxT>
+__device__ __forceinline__ uint2 fetch_row_b6(const uint32_t* __restrict__ w, IdxT idx, IdxT end_idx, const uint32_t* idb,
+                                              uint32_t nb, uint32_t shift, const unsigned long long* first_runs) {
+    const unsigned long long a = 6ull * (unsigned long long)idx;
+    const uint32_t* p = w + (a >> 2);
+    const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1);
+    const uint32_t sh = (uint32_t)(a & 2u) * 8u;
+    const uint32_t lo = __funnelshift_r(w0, w1, sh);          // f_id | f_n << 16
+    const uint32_t f_off = (w1 >> sh) & 0xFFFFu;
+    const uint32_t f_id = lo & 0xFFFFu, f_n = lo >> 16;
+    const uint32_t n = f_n & 0x3FFu, off = f_off & 0x3FFu, c = (f_off >> 10) & 7u, thr = f_off >> 13;
+    unsigned long long id = (unsigned long long)f_id | ((unsigned long long)(f_n >> 10) << 16);
+    if (idx != end_idx) id += (unsigned long long)idb[c * nb + (uint32_t)((unsigned long long)idx >> shift)] + first_runs[c + 1];
+    return make_r8(id, n, off, c, thr);
+}
 
 // alphamap_3 (src/utils.cpp:5-8): slot of read character b among the three thresholds of a row with character a
 __device__ __forceinline__ uint32_t thr_slot(uint32_t a, uint32_t b) { return b - (b > a ? 1u : 0u); }

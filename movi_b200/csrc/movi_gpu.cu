@@ -51,6 +51,8 @@ struct movi_gpu_ctx {
     bool has_index = false;
     DevIndex ix{};
     uint2* d_rows = nullptr;
+    uint32_t* d_rows6 = nullptr;      // LAYOUT_B6: packed blocked-thresholds rows
+    uint32_t* d_id_blocks = nullptr;
     unsigned long long* d_sep_keys = nullptr; uint16_t* d_sep_vals = nullptr;
     unsigned long long* d_prefix = nullptr;
     uint64_t index_bytes = 0;
@@ -65,7 +67,6 @@ struct movi_gpu_ctx {
     int64_t pml_variant = 4;          // 0/1: branchy kernel (2-byte / 16-byte stores); 2/3: convergent kernel (+/- L2 hints); 4: convergent + sector staging in smem
     int64_t l2_persist_mb = 0;        // > 0: mark the row table persisting in L2 (access policy window) for query launches
     int64_t l2_fetch_granularity = 0; // 0: leave the device default; 32 / 64 / 128: cudaLimitMaxL2FetchGranularity
-    int64_t pml_min_blocks = 0;       // 0: by table size; 6 / 8: force the occupancy flavour of movi_pml_kernel3
     int64_t bs_variant = 1;           // count / ZML kernel: 0 = branch-per-state (bs_kernel.cuh), 1 = convergent + sector staging
     int64_t force_wide = 0;           // tests: run the 64-bit-index instantiations on a small table
     int64_t row_ld_mode = 0;          // cache recipe of the row fetch (pml_kernel2.cuh: ld_row)
@@ -152,6 +153,8 @@ int blocks_for(movi_gpu_ctx* ctx, K kernel, int threads) {
 
 void free_index(movi_gpu_ctx* ctx) {
     cudaFree(ctx->d_rows); ctx->d_rows = nullptr;
+    cudaFree(ctx->d_rows6); ctx->d_rows6 = nullptr;
+    cudaFree(ctx->d_id_blocks); ctx->d_id_blocks = nullptr;
     cudaFree(ctx->d_sep_keys); ctx->d_sep_keys = nullptr;
     cudaFree(ctx->d_sep_vals); ctx->d_sep_vals = nullptr;
     cudaFree(ctx->d_prefix); ctx->d_prefix = nullptr;
@@ -166,7 +169,7 @@ int ensure_prefix(movi_gpu_ctx* ctx, cudaStream_t st) {
     unsigned long long* d_block = nullptr;
     CU(cudaMalloc(&ctx->d_prefix, n_groups * sizeof(unsigned long long)));
     CU(cudaMalloc(&d_block, n_blocks * sizeof(unsigned long long)));
-    prefix_group_sums_kernel<<<(unsigned)n_blocks, SCAN_BLOCK, 0, st>>>(ctx->d_rows, r, n_groups, ctx->d_prefix, d_block);
+    prefix_group_sums_kernel<<<(unsigned)n_blocks, SCAN_BLOCK, 0, st>>>(ctx->ix, r, n_groups, ctx->d_prefix, d_block);
     prefix_scan_blocks_kernel<<<1, SCAN_BLOCK, 0, st>>>(d_block, n_blocks);
     prefix_finish_kernel<<<(unsigned)n_blocks, SCAN_BLOCK, 0, st>>>(ctx->d_prefix, n_groups, d_block);
     ctx->launches += 3;
@@ -209,28 +212,28 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
         CU(cudaLaunchKernelEx(&cfg_, k_, ctx->ix, qa));                           \
     } while (0)
     if (kind == Q_PML) {
-        if (ctx->pml_variant == 0) { if (wide) LAUNCH((movi_pml_kernel<unsigned long long, 0>)); else LAUNCH((movi_pml_kernel<uint32_t, 0>)); }
-        else if (ctx->pml_variant == 1) { if (wide) LAUNCH((movi_pml_kernel<unsigned long long, 1>)); else LAUNCH((movi_pml_kernel<uint32_t, 1>)); }
-        else if (ctx->pml_variant == 2) { if (wide) LAUNCH((movi_pml_kernel2<unsigned long long, true>)); else LAUNCH((movi_pml_kernel2<uint32_t, true>)); }
-        else if (ctx->pml_variant == 3) { if (wide) LAUNCH((movi_pml_kernel2<unsigned long long, false>)); else LAUNCH((movi_pml_kernel2<uint32_t, false>)); }
+        const int64_t variant = ctx->ix.layout == LAYOUT_B6 ? 4 : ctx->pml_variant;   // the compact layout exists for the default kernel only
+        if (variant == 0) { if (wide) LAUNCH((movi_pml_kernel<unsigned long long, 0>)); else LAUNCH((movi_pml_kernel<uint32_t, 0>)); }
+        else if (variant == 1) { if (wide) LAUNCH((movi_pml_kernel<unsigned long long, 1>)); else LAUNCH((movi_pml_kernel<uint32_t, 1>)); }
+        else if (variant == 2) { if (wide) LAUNCH((movi_pml_kernel2<unsigned long long, true>)); else LAUNCH((movi_pml_kernel2<uint32_t, true>)); }
+        else if (variant == 3) { if (wide) LAUNCH((movi_pml_kernel2<unsigned long long, false>)); else LAUNCH((movi_pml_kernel2<uint32_t, false>)); }
         else {
-            // occupancy flavour: 6 blocks/SM (40 registers) measured fastest on both L2-sized (c2) and HBM-resident (8-64 GB)
-            // tables -- the latter are bound by the translation / DRAM request rate, not by exposed latency; 8 stays selectable
-            const bool dense = ctx->pml_min_blocks >= 8;
-            if (ctx->ix.sep) {
-                if (wide) { if (dense) LAUNCH((movi_pml_kernel3<unsigned long long, true, 8>)); else LAUNCH((movi_pml_kernel3<unsigned long long, true, 6>)); }
-                else      { if (dense) LAUNCH((movi_pml_kernel3<uint32_t, true, 8>)); else LAUNCH((movi_pml_kernel3<uint32_t, true, 6>)); }
-            } else {
-                if (wide) { if (dense) LAUNCH((movi_pml_kernel3<unsigned long long, false, 8>)); else LAUNCH((movi_pml_kernel3<unsigned long long, false, 6>)); }
-                else      { if (dense) LAUNCH((movi_pml_kernel3<uint32_t, false, 8>)); else LAUNCH((movi_pml_kernel3<uint32_t, false, 6>)); }
-            }
+            // 6 blocks/SM (40 registers) measured fastest on both L2-sized (c2) and HBM-resident (8-64 GB) tables -- the
+            // latter are bound by the memory system's random-request rate, not by exposed latency (profiles/r01_big_tables.jsonl)
+            const bool b6 = ctx->ix.layout == LAYOUT_B6;
+#define PML3(IDX, SEPV) do { if (b6) LAUNCH((movi_pml_kernel3<IDX, SEPV, 6, LAYOUT_B6>)); else LAUNCH((movi_pml_kernel3<IDX, SEPV, 6, LAYOUT_R8>)); } while (0)
+            if (ctx->ix.sep) { if (wide) PML3(unsigned long long, true); else PML3(uint32_t, true); }
+            else             { if (wide) PML3(unsigned long long, false); else PML3(uint32_t, false); }
+#undef PML3
         }
-    } else if (kind == Q_ZML) {
-        if (ctx->bs_variant == 0) { if (wide) LAUNCH((movi_bs_kernel<unsigned long long, KIND_ZML>)); else LAUNCH((movi_bs_kernel<uint32_t, KIND_ZML>)); }
-        else { if (wide) LAUNCH((movi_bs_kernel2<unsigned long long, KIND_ZML>)); else LAUNCH((movi_bs_kernel2<uint32_t, KIND_ZML>)); }
     } else {
-        if (ctx->bs_variant == 0) { if (wide) LAUNCH((movi_bs_kernel<unsigned long long, KIND_COUNT>)); else LAUNCH((movi_bs_kernel<uint32_t, KIND_COUNT>)); }
-        else { if (wide) LAUNCH((movi_bs_kernel2<unsigned long long, KIND_COUNT>)); else LAUNCH((movi_bs_kernel2<uint32_t, KIND_COUNT>)); }
+        const bool b6 = ctx->ix.layout == LAYOUT_B6;
+        const bool v0 = ctx->bs_variant == 0 && !b6;
+#define BS(IDX, KINDV) do { if (v0) LAUNCH((movi_bs_kernel<IDX, KINDV>)); \
+                            else if (b6) LAUNCH((movi_bs_kernel2<IDX, KINDV, LAYOUT_B6>)); else LAUNCH((movi_bs_kernel2<IDX, KINDV, LAYOUT_R8>)); } while (0)
+        if (kind == Q_ZML) { if (wide) BS(unsigned long long, KIND_ZML); else BS(uint32_t, KIND_ZML); }
+        else               { if (wide) BS(unsigned long long, KIND_COUNT); else BS(uint32_t, KIND_COUNT); }
+#undef BS
     }
 #undef LAUNCH
     ctx->launches += 1;
@@ -413,6 +416,7 @@ int movi_gpu_destroy(movi_gpu_ctx* ctx) {
 
 uint64_t movi_gpu_index_device_bytes(const movi_gpu_ctx* ctx) { return ctx ? ctx->index_bytes : 0; }
 const void* movi_gpu_index_device_rows(const movi_gpu_ctx* ctx) { return ctx && ctx->has_index ? ctx->d_rows : nullptr; }
+int movi_gpu_index_device_layout(const movi_gpu_ctx* ctx) { return ctx && ctx->has_index ? (ctx->ix.layout == LAYOUT_B6 ? MOVI_GPU_LAYOUT_COMPACT : MOVI_GPU_LAYOUT_EXPANDED8) : -1; }
 uint64_t movi_gpu_launch_count(const movi_gpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int movi_gpu_set_option(movi_gpu_ctx* ctx, const char* key, int64_t value) {
@@ -420,7 +424,6 @@ int movi_gpu_set_option(movi_gpu_ctx* ctx, const char* key, int64_t value) {
     const std::string k(key);
     if (k == "pml_variant") { if (value < 0 || value > 4) return fail(ctx, MOVI_GPU_ERR_ARG, "pml_variant: 0..4"); ctx->pml_variant = value; }
     else if (k == "probe_vmm_align_mb") { if (value < 0 || value > 4096) return fail(ctx, MOVI_GPU_ERR_ARG, "probe_vmm_align_mb: 0..4096"); ctx->probe_vmm_align_mb = value; }
-    else if (k == "pml_min_blocks") { if (value != 0 && value != 6 && value != 8) return fail(ctx, MOVI_GPU_ERR_ARG, "pml_min_blocks: 0, 6 or 8"); ctx->pml_min_blocks = value; }
     else if (k == "bs_variant") { if (value < 0 || value > 1) return fail(ctx, MOVI_GPU_ERR_ARG, "bs_variant: 0 or 1"); ctx->bs_variant = value; }
     else if (k == "force_wide") { ctx->force_wide = value ? 1 : 0; }
     else if (k == "row_ld_mode") { if (value < 0 || value > 7) return fail(ctx, MOVI_GPU_ERR_ARG, "row_ld_mode: 0..7"); ctx->row_ld_mode = value; }
@@ -458,7 +461,6 @@ int64_t movi_gpu_get_option(const movi_gpu_ctx* ctx, const char* key) {
     if (k == "row_ld_mode") return ctx->row_ld_mode;
     if (k == "force_wide") return ctx->force_wide;
     if (k == "bs_variant") return ctx->bs_variant;
-    if (k == "pml_min_blocks") return ctx->pml_min_blocks;
     if (k == "l2_persist_mb") return ctx->l2_persist_mb;
     if (k == "l2_persist_max_mb") return ctx->max_persist_bytes >> 20;
     if (k == "l2_fetch_granularity") {
@@ -484,7 +486,7 @@ int movi_gpu_adopt_device_rows(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, voi
 
 static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout, uint2* adopt_rows) {
     if (!ctx || !d) return MOVI_GPU_ERR_ARG;
-    if (layout != MOVI_GPU_LAYOUT_AUTO && layout != MOVI_GPU_LAYOUT_EXPANDED8)
+    if (layout != MOVI_GPU_LAYOUT_AUTO && layout != MOVI_GPU_LAYOUT_EXPANDED8 && layout != MOVI_GPU_LAYOUT_COMPACT)
         return fail(ctx, MOVI_GPU_ERR_ARG, "unknown device layout");
     if (d->mode != MOVI_MODE_REGULAR_THRESHOLDS && d->mode != MOVI_MODE_BLOCKED_THRESHOLDS && d->mode != MOVI_MODE_SAMPLED_THRESHOLDS)
         return fail(ctx, MOVI_GPU_ERR_INDEX, "unsupported index mode " + std::to_string(d->mode) +
@@ -506,13 +508,40 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
     free_index(ctx);
     cudaStream_t st = ctx->slot[0].stream;
     const unsigned long long r = d->r;
+    // Device layout: EXPANDED8 unless the caller asks for COMPACT, or AUTO finds that the expanded table (plus the raw
+    // copy the conversion needs) does not fit in free HBM.  COMPACT exists for blocked-thresholds (its 6-byte rows are
+    // kept as they are on disk); regular-thresholds is 8 bytes on disk anyway; sampled-thresholds is always expanded.
+    bool compact = false;
+    if (!adopt_rows && d->mode == MOVI_MODE_BLOCKED_THRESHOLDS && (d->block_size & (d->block_size - 1)) == 0) {
+        if (layout == MOVI_GPU_LAYOUT_COMPACT) compact = true;
+        else if (layout == MOVI_GPU_LAYOUT_AUTO) {
+            size_t free_b = 0, total_b = 0;
+            CU(cudaMemGetInfo(&free_b, &total_b));
+            compact = (double)r * (8 + 6) + (256ull << 20) > (double)free_b;
+        }
+    }
+    if (layout == MOVI_GPU_LAYOUT_COMPACT && !compact && d->mode == MOVI_MODE_BLOCKED_THRESHOLDS)
+        return fail(ctx, MOVI_GPU_ERR_INDEX, "compact layout needs a power-of-two id block size");
+    uint32_t n_last_host = 0;
+    if (compact) {
+        CU(cudaMalloc(&ctx->d_rows6, r * 6 + 16));
+        CU(cudaMemsetAsync(reinterpret_cast<uint8_t*>(ctx->d_rows6) + r * 6, 0, 16, st));
+        CU(cudaMemcpyAsync(ctx->d_rows6, d->rows, r * 6, cudaMemcpyHostToDevice, st));
+        const size_t nb_bytes = (size_t)d->sigma * d->id_blocks_size * sizeof(uint32_t);
+        CU(cudaMalloc(&ctx->d_id_blocks, nb_bytes));
+        CU(cudaMemcpyAsync(ctx->d_id_blocks, d->id_blocks, nb_bytes, cudaMemcpyHostToDevice, st));
+        ctx->index_bytes = r * 6 + 16 + nb_bytes;
+        uint16_t f_n; std::memcpy(&f_n, static_cast<const uint8_t*>(d->rows) + (r - 1) * 6 + 2, 2);
+        n_last_host = f_n & 0x3FFu;
+    } else {
     if (adopt_rows) ctx->d_rows = adopt_rows;        // already resident (r + 4 rows, 8-byte format); ownership moves to the context
     else CU(cudaMalloc(&ctx->d_rows, (r + 4) * sizeof(uint2)));
     CU(cudaMemsetAsync(ctx->d_rows + r, 0, 4 * sizeof(uint2), st));
     ctx->index_bytes = (r + 4) * sizeof(uint2);
+    }
 
-    if (adopt_rows) {
-        // nothing to copy
+    if (adopt_rows || compact) {
+        // nothing to convert
     } else if (d->mode == MOVI_MODE_REGULAR_THRESHOLDS) {
         // the on-disk row IS the device row: one copy
         CU(cudaMemcpyAsync(ctx->d_rows, d->rows, r * sizeof(uint2), cudaMemcpyHostToDevice, st));
@@ -556,6 +585,14 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
     DevIndex& ix = ctx->ix;
     std::memset(&ix, 0, sizeof(ix));
     ix.rows = ctx->d_rows;
+    ix.rows6 = ctx->d_rows6;
+    ix.id_blocks = ctx->d_id_blocks;
+    ix.layout = compact ? LAYOUT_B6 : LAYOUT_R8;
+    if (compact) {
+        ix.id_blocks_size = (uint32_t)d->id_blocks_size;
+        ix.block_shift = 0;
+        while ((1ull << ix.block_shift) < d->block_size) ix.block_shift++;
+    }
     ix.r = r;
     ix.end_idx = d->end_bwt_idx;
     ix.sep = sep ? 1u : 0u;
@@ -572,8 +609,8 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
     }
     CU(cudaStreamSynchronize(st));   // the table copy / conversion ran on a non-blocking stream
     {   // n(r-1) for the start state of query_pml
-        uint2 last;
-        CU(cudaMemcpy(&last, ctx->d_rows + (r - 1), sizeof(last), cudaMemcpyDeviceToHost));
+        uint2 last = make_uint2(0u, n_last_host);
+        if (!compact) CU(cudaMemcpy(&last, ctx->d_rows + (r - 1), sizeof(last), cudaMemcpyDeviceToHost));
         ix.n_last = last.y & 0x7FFu;
         if (ix.n_last == 0) { free_index(ctx); return fail(ctx, MOVI_GPU_ERR_INDEX, "last row has length 0"); }
     }
@@ -697,7 +734,7 @@ int movi_gpu_gather_probe(movi_gpu_ctx* ctx, uint64_t table_bytes, uint32_t load
     CU(cudaSetDevice(ctx->device));
     const uint2* table; uint64_t n_rows;
     if (table_bytes == 0) {
-        if (!ctx->has_index) return fail(ctx, MOVI_GPU_ERR_ARG, "no index uploaded and table_bytes == 0");
+        if (!ctx->has_index || !ctx->d_rows) return fail(ctx, MOVI_GPU_ERR_ARG, "no 8-byte index table uploaded and table_bytes == 0");
         table = ctx->d_rows; n_rows = ctx->ix.r & ~3ull;
     } else {
         table_bytes &= ~255ull;

@@ -30,11 +30,23 @@ constexpr int PML3_THREADS = 256;
 // MINB: resident blocks per SM the register allocation must allow.  6 (40 registers) is the default; 8 (32 registers,
 // 2048 walks per SM, one spilled word) was measured slower both on the L2-sized c2 table (issue bound) and on 8-64 GB
 // tables (bound by the memory system's random-request rate, not by exposed latency): profiles/r01_big_tables.jsonl.
-template <typename IdxT, bool SEP, int MINB>
+// LAYOUT: LAYOUT_R8 (one 8-byte fetch per step) or LAYOUT_B6 (6-byte blocked rows + id_blocks, 25 % less HBM).
+constexpr int IDB_SMEM = 1024;       // id_blocks entries kept in shared memory (covers r <= 2.7e8 rows at block_size 2^20)
+
+template <typename IdxT, bool SEP, int MINB, int LAYOUT>
 __global__ void __launch_bounds__(PML3_THREADS, MINB)
 movi_pml_kernel3(const DevIndex ix, const QueryArgs q) {
     __shared__ uint8_t s_code[256];
     __shared__ uint32_t s_end_thr[4];
+    __shared__ uint32_t s_idb[LAYOUT == LAYOUT_B6 ? IDB_SMEM : 1];
+    __shared__ unsigned long long s_first[8];
+    const uint32_t idb_n = ix.id_blocks_size * ix.sigma;
+    const bool idb_in_smem = LAYOUT == LAYOUT_B6 && idb_n <= IDB_SMEM;
+    if (LAYOUT == LAYOUT_B6) {
+        if (idb_in_smem) for (uint32_t i = threadIdx.x; i < idb_n; i += blockDim.x) s_idb[i] = ix.id_blocks[i];
+        if (threadIdx.x < 8) s_first[threadIdx.x] = ix.first_runs[threadIdx.x];
+    }
+    const uint32_t* const idb = idb_in_smem ? s_idb : ix.id_blocks;
     __shared__ __align__(32) uint8_t s_in[PML3_THREADS * 32];      // per lane: the 32-byte sector of its read that holds bases[rp]
     __shared__ __align__(32) uint16_t s_out[PML3_THREADS * 16];    // per lane: the 32-byte sector of its output being filled
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_code[i] = ix.code_of[i];
@@ -90,7 +102,9 @@ movi_pml_kernel3(const DevIndex ix, const QueryArgs q) {
         const bool is_new = (st == ST_NEW);
         const bool proc = (st >= ST_FF);
         // (lanes that are not walking fetch row 0: harmless and keeps the fetch out of a divergent branch)
-        const uint2 v = ld_keep(rows + (proc ? idx : (IdxT)0), pol_keep);
+        const IdxT fidx = proc ? idx : (IdxT)0;
+        const uint2 v = LAYOUT == LAYOUT_R8 ? ld_keep(rows + fidx, pol_keep)
+                                            : fetch_row_b6<IdxT>(ix.rows6, fidx, end_idx, idb, ix.id_blocks_size, ix.block_shift, s_first);
         if (proc && need_chunk) {
             const uint8_t* src = bases + (rp & ~31u);
             cp_async16(in_slot, src);

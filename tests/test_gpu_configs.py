@@ -42,10 +42,17 @@ def test_c2_c3_shape_short_reads_all_layouts(small, small_structs):
         ref_pml = want if ref_pml is None else ref_pml
         assert np.array_equal(want, ref_pml)            # layouts agree (reference tests/test_pml.cpp:57-115)
         if t != "sampled-thresholds":
-            assert np.array_equal(small_structs[t].query_zml(bases, offsets), orc.query_zml(bases, offsets, threads=0))
-            c, p = small_structs[t].query_backward_search(bases, offsets)
-            c2, p2 = orc.query_count(bases, offsets, threads=0)
-            assert np.array_equal(c, c2) and np.array_equal(p, p2)
+            structs = [small_structs[t]]
+            if t == "blocked-thresholds":       # configs[2] names the blocked layout: also with its 6-byte rows kept in HBM
+                from movi_b200 import MoveStructure
+                from movi_b200.api import LAYOUT_COMPACT
+                structs.append(MoveStructure(os.path.join(d, t), layout=LAYOUT_COMPACT))
+                assert np.array_equal(structs[-1].query_pml(bases, offsets), want)
+            for ms_ in structs:
+                assert np.array_equal(ms_.query_zml(bases, offsets), orc.query_zml(bases, offsets, threads=0))
+                c, p = ms_.query_backward_search(bases, offsets)
+                c2, p2 = orc.query_count(bases, offsets, threads=0)
+                assert np.array_equal(c, c2) and np.array_equal(p, p2)
 
 
 def _long_reads(haps, n, seed):

@@ -176,3 +176,37 @@ def test_device_entry_points_with_torch(structures, index_dirs, ref_seq):
     c2, p2 = orc.query_count(bases, offsets, threads=0)
     assert np.array_equal(d_cnt.cpu().numpy().view(np.uint64), c2) and np.array_equal(d_pos.cpu().numpy(), p2)
     assert np.array_equal(d_out.cpu().numpy().view(np.uint16)[: len(bases)], orc.query_zml(bases, offsets, threads=0))
+
+
+@pytest.mark.parametrize("sep", [False, True])
+def test_blocked_compact_device_layout(index_dirs, read_sets, ref_seq, sep):
+    """MOVI_GPU_LAYOUT_COMPACT: blocked-thresholds rows stay 6 bytes in HBM, the id is completed per step from id_blocks."""
+    from movi_b200 import MoveStructure
+    from movi_b200.api import LAYOUT_COMPACT, LAYOUT_EXPANDED8
+    from oracle.port import OracleIndex, pack_reads
+    d = index_dirs[("blocked-thresholds", sep)]
+    ms = MoveStructure(d, layout=LAYOUT_COMPACT)
+    try:
+        assert ms.device_layout == LAYOUT_COMPACT
+        assert ms.index_device_bytes < 6.1 * ms.r + 4096          # 6 bytes per row (+ id_blocks), not 8
+        for read_set in READ_SETS:
+            rd = read_sets[read_set]
+            assert ml_text(rd.ids(), rd.offsets, ms.query_pml(rd.bases, rd.offsets)) == expected_text(read_set, "pml", sep)
+            assert ml_text(rd.ids(), rd.offsets, ms.query_zml(rd.bases, rd.offsets)) == expected_text(read_set, "zml", sep)
+            c, p = ms.query_backward_search(rd.bases, rd.offsets)
+            assert count_text(rd.ids(), rd.offsets, c, p) == expected_text(read_set, "count", sep)
+        bases, offsets = pack_reads(_random_reads(17, 20000, 600, ref_seq))
+        orc = OracleIndex(d)
+        for wide in (0, 1):
+            ms.set_option("force_wide", wide)
+            assert np.array_equal(ms.query_pml(bases, offsets), orc.query_pml(bases, offsets, threads=0))
+            assert np.array_equal(ms.query_zml(bases, offsets), orc.query_zml(bases, offsets, threads=0))
+            c1, p1 = ms.query_backward_search(bases, offsets)
+            c2, p2 = orc.query_count(bases, offsets, threads=0)
+            assert np.array_equal(c1, c2) and np.array_equal(p1, p2)
+    finally:
+        ms.close()
+    # the same index expanded: 8 bytes per row
+    ms8 = MoveStructure(d, layout=LAYOUT_EXPANDED8)
+    assert ms8.device_layout == LAYOUT_EXPANDED8 and ms8.index_device_bytes >= 8 * ms8.r
+    ms8.close()

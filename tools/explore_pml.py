@@ -23,16 +23,17 @@ def main():
     d, haps = synth.prepare(name, ("regular-thresholds",))
     bases, offsets = synth.make_reads(haps, cfg["n_reads"], cfg["read_len"], seed=43)
     n_reads, n_bases = cfg["n_reads"], len(bases)
-    ms = MoveStructure(os.path.join(d, "regular-thresholds"))
+    itype = os.environ.get("MOVI_EXPLORE_TYPE", "regular-thresholds")
+    if itype != "regular-thresholds":
+        d, _ = synth.prepare(name, (itype,), want_reads=False)
+    ms = MoveStructure(os.path.join(d, itype), layout=int(os.environ.get("MOVI_EXPLORE_LAYOUT", "0")))
+    print("index", itype, "device layout", ms.device_layout, "bytes", ms.index_device_bytes, flush=True)
     dev = torch.device("cuda:0")
     d_bases = torch.from_numpy(np.concatenate([bases, np.zeros(64, np.uint8)])).to(dev)
     d_off = torch.from_numpy(offsets.astype(np.int64)).to(dev)
     d_out = torch.zeros(n_bases + 64, dtype=torch.int16, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
     first = None
-    for dep in (1, 0):
-        sec, loads = ms.gather_probe(0, 8, bool(dep), 512, 8, 256)
-        print(json.dumps({"kind": "probe_on_index_table", "dependent": dep, "loads_per_s": loads / sec}), flush=True)
     print("l2 persist max MB", ms.get_option("l2_persist_max_mb"), "fetch granularity", ms.get_option("l2_fetch_granularity"), flush=True)
     for spec in specs:
         f = [int(x) for x in spec.split(":")]
