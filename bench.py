@@ -28,9 +28,17 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "c2"
-INDEX_TYPE = "regular-thresholds"
-ALGO_BYTES_PER_BASE = 32          # one 32-byte HBM sector (holding the 8-byte move row) per base; DESIGN.md section 4
+WORKLOAD = "c2"                   # synthetic data set (movi_b200/datagen/synth.py); every workload below queries it
+# --workload: c2 is the bench line of BASELINE.json (configs[1]); the c3-* lines are configs[2] (same pangenome, blocked-thresholds
+# index, ZML / count).  Algorithmic bytes per base: one 32-byte row sector per LF step (PML), two interval ends for ZML / count.
+WORKLOADS = {
+    "c2": dict(index="regular-thresholds", query="pml", metric="PML query bases/sec", algo=32, kernel="movi_pml_kernel3<uint32_t,false,6,R8>"),
+    "c3-zml": dict(index="blocked-thresholds", query="zml", metric="ZML query bases/sec", algo=64, kernel="movi_bs_kernel2<uint32_t,ZML,R8>"),
+    "c3-count": dict(index="blocked-thresholds", query="count", metric="count query bases/sec (all bases of the reads)", algo=64,
+                     kernel="movi_bs_kernel2<uint32_t,COUNT,R8>"),
+}
+W = WORKLOADS["c2"]               # replaced in main() from --workload
+ARGS_WORKLOAD = "c2"
 
 
 def log(*a):
@@ -103,10 +111,10 @@ def prepare_workload(rank, need_haps=True):
     from movi_b200.datagen import synth
     cfg = synth.CONFIGS[WORKLOAD]
     t0 = time.time()
-    d, haps = synth.prepare(WORKLOAD, (INDEX_TYPE,), want_reads=need_haps, log=sys.stderr)
+    d, haps = synth.prepare(WORKLOAD, (W["index"],), want_reads=need_haps, log=sys.stderr)
     bases, offsets = synth.make_reads(haps, cfg["n_reads"], cfg["read_len"], seed=43 + rank)
     log("[bench] rank %d: workload ready in %.1f s (%d reads, %d bases)" % (rank, time.time() - t0, cfg["n_reads"], len(bases)))
-    return os.path.join(d, INDEX_TYPE), bases, offsets, cfg
+    return os.path.join(d, W["index"]), bases, offsets, cfg
 
 
 def write_fasta(path, bases, offsets, n_reads):
@@ -128,12 +136,12 @@ def cpu_reference_run(index_dir, bases, offsets, n_reads, threads, tmpdir):
     """Time the reference's own CPU query (oracle/_ref, prefetch path = its fastest mode, all host threads) or,
     if that binary is not there, the C oracle with OpenMP.  Returns (bases_per_s, kind, cores, seconds)."""
     n_bases = int(offsets[n_reads])
-    ref_bin = os.path.join(ROOT, "oracle", "_ref", "movi-" + INDEX_TYPE)
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "movi-" + W["index"])
     if os.path.exists(ref_bin):
         fa = os.path.join(tmpdir, "reads_%d.fa" % n_reads)
         if not os.path.exists(fa):
             write_fasta(fa, bases, offsets, n_reads)
-        cmd = [ref_bin, "query", "--index", index_dir, "--read", fa, "--pml", "--no-output", "-t", str(threads), "-s", "16"]
+        cmd = [ref_bin, "query", "--index", index_dir, "--read", fa, "--" + W["query"], "--no-output", "-t", str(threads), "-s", "16"]
         # stderr goes to a FILE: the reference prints progress inside a critical section and a pipe would
         # serialise its threads (SURVEY section 5)
         errf = os.path.join(tmpdir, "ref_stderr.txt")
@@ -156,7 +164,7 @@ def cpu_reference_run(index_dir, bases, offsets, n_reads, threads, tmpdir):
     from oracle.port import OracleIndex
     orc = OracleIndex(index_dir)
     t0 = time.time()
-    orc.query_pml(bases[:n_bases], offsets[: n_reads + 1], threads=threads)
+    getattr(orc, "query_" + W["query"])(bases[:n_bases], offsets[: n_reads + 1], threads=threads)
     sec = time.time() - t0
     return n_bases / sec, "port", threads, sec
 
@@ -176,7 +184,7 @@ def run_reference(args, rank, world):
     value = float(np.sum([int(offsets[n_reads])] * len(secs)) / np.sum(secs))
     sample = "%d x %d bp reads of the c2 workload per step (the full per-GPU batch), index load excluded" % (n_reads, cfg["read_len"])
     line = {
-        "impl": "reference", "metric": "PML query bases/sec", "value": value, "unit": "bases/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": W["metric"], "value": value, "unit": "bases/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs) * 1e3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
         "config": workload_config(cfg, None),
@@ -189,9 +197,9 @@ def run_reference(args, rank, world):
 
 
 def workload_config(cfg, index_bytes):
-    c = {"workload": "c2: 64-haplotype x 5 Mbp synthetic bacterial pangenome (0.1% divergence, +reverse complements), "
-                     "regular-thresholds index, 1M x 150 bp reads PML per GPU",
-         "index": INDEX_TYPE, "reads_per_gpu": cfg["n_reads"], "read_len": cfg["read_len"],
+    c = {"workload": "%s: 64-haplotype x 5 Mbp synthetic bacterial pangenome (0.1%% divergence, +reverse complements), "
+                     "%s index, 1M x 150 bp reads %s per GPU" % (ARGS_WORKLOAD, W["index"], W["query"].upper() if W["query"] != "count" else "count"),
+         "index": W["index"], "reads_per_gpu": cfg["n_reads"], "read_len": cfg["read_len"],
          "l2": "per-step streamed inputs+outputs (450 MB) exceed the 126 MB L2; the row table stays resident in HBM/L2 as in production",
          "launch": "steps alternate over 2 CUDA streams (batch i+1 ramps up while batch i drains); one kernel launch per step",
          "parallelism": "reads sharded per GPU, index replicated, no collective on the query path"}
@@ -207,7 +215,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    global W, ARGS_WORKLOAD
+    W, ARGS_WORKLOAD = WORKLOADS[args.workload], args.workload
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -249,12 +260,31 @@ def main():
     d_bases = h_bases.to(dev)
     d_off = h_off.to(dev)
     d_out = torch.zeros(n_bases + 16, dtype=torch.int16, device=dev)
+    is_count = W["query"] == "count"
+    h_cnt, h_pos = torch.zeros(n_reads, dtype=torch.int64).pin_memory(), torch.zeros(n_reads, dtype=torch.int32).pin_memory()
+    d_cnts = [torch.zeros(n_reads, dtype=torch.int64, device=dev) for _ in range(2)]
+    d_poss = [torch.zeros(n_reads, dtype=torch.int32, device=dev) for _ in range(2)]
+    d_outs = [d_out, torch.zeros_like(d_out)]
+
+    def launch(i, cuda_stream):
+        if W["query"] == "pml":
+            ms.query_pml_device(d_bases.data_ptr(), d_off.data_ptr(), n_reads, d_outs[i % 2].data_ptr(), cuda_stream)
+        elif W["query"] == "zml":
+            ms.query_zml_device(d_bases.data_ptr(), d_off.data_ptr(), n_reads, d_outs[i % 2].data_ptr(), cuda_stream)
+        else:
+            ms.query_count_device(d_bases.data_ptr(), d_off.data_ptr(), n_reads, d_cnts[i % 2].data_ptr(), d_poss[i % 2].data_ptr(), cuda_stream)
 
     def step_device():
-        ms.query_pml_device(d_bases.data_ptr(), d_off.data_ptr(), n_reads, d_out.data_ptr(), stream)
+        launch(0, stream)
 
     def step_e2e():
-        ms.query_pml_ptr(h_bases.data_ptr(), h_off.data_ptr(), n_reads, h_out.data_ptr())
+        L, c = ms._L, ms._ctx
+        if W["query"] == "pml":
+            ms._check(L.movi_gpu_query_pml(c, h_bases.data_ptr(), h_off.data_ptr(), n_reads, 0, h_out.data_ptr()))
+        elif W["query"] == "zml":
+            ms._check(L.movi_gpu_query_zml(c, h_bases.data_ptr(), h_off.data_ptr(), n_reads, 0, h_out.data_ptr()))
+        else:
+            ms._check(L.movi_gpu_query_count(c, h_bases.data_ptr(), h_off.data_ptr(), n_reads, 0, h_cnt.data_ptr(), h_pos.data_ptr()))
 
     for _ in range(args.warmup):
         step_device()
@@ -269,12 +299,11 @@ def main():
     # steps alternate between two streams so that the drain of one batch (lanes finishing their last reads) overlaps
     # the ramp-up of the next one, as in a production stream of batches; every step is a complete pass over the batch
     side = [torch.cuda.Stream(device=dev) for _ in range(2)]
-    d_outs = [d_out, torch.zeros_like(d_out)]
     e0.record()
     for s_ in side:
         s_.wait_stream(torch.cuda.current_stream())
     for i in range(args.steps):
-        ms.query_pml_device(d_bases.data_ptr(), d_off.data_ptr(), n_reads, d_outs[i % 2].data_ptr(), side[i % 2].cuda_stream)
+        launch(i, side[i % 2].cuda_stream)
     for s_ in side:
         torch.cuda.current_stream().wait_stream(s_)
     e1.record()
@@ -304,7 +333,10 @@ def main():
     clocks = sampler.stop() if sampler is not None else None
 
     # consistency inside the bench: the device-resident result equals the result of the host-buffer entry point
-    same = bool(torch.equal(d_out[: n_bases].cpu(), h_out[: n_bases]))
+    if is_count:
+        same = bool(torch.equal(d_cnts[0].cpu(), h_cnt) and torch.equal(d_poss[0].cpu(), h_pos))
+    else:
+        same = bool(torch.equal(d_out[: n_bases].cpu(), h_out[: n_bases]))
 
     if world > 1:
         t = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=dev)
@@ -320,24 +352,24 @@ def main():
         e2e_value = total_bases / (e2e_ms * 1e-3)
         peak, peak_src = measured_peaks()
         per_launch_s = elapsed_ms * 1e-3 / args.steps
-        achieved = ALGO_BYTES_PER_BASE * n_bases / per_launch_s / 1e9
+        achieved = W["algo"] * n_bases / per_launch_s / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "pml_c2_traffic.json")
-        if os.path.exists(tp):
+        if args.workload == "c2" and os.path.exists(tp):
             try:
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
         line = {
-            "metric": "PML query bases/sec", "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps,
+            "metric": W["metric"], "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u16", "data": "synthetic",
             "config": workload_config(cfg, ms.index_device_bytes),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "movi_pml_kernel3<uint32_t,false>", "algorithmic_bytes_per_base": ALGO_BYTES_PER_BASE},
+                         "kernel": W["kernel"], "algorithmic_bytes_per_base": W["algo"]},
             "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": int(n_bases + 8 * (n_reads + 1)),
-                    "d2h_bytes_per_step": int(2 * n_bases), "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": int(12 * n_reads if is_count else 2 * n_bases), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "parity_checked": same,
@@ -349,8 +381,14 @@ def main():
             # the CPU leg doubles as the checker: the first 2000 reads of the GPU result against the C oracle
             from oracle.port import OracleIndex
             ns = min(2000, n_reads)
-            want = OracleIndex(index_dir).query_pml(bases[: int(offsets[ns])], offsets[: ns + 1], threads=0)
-            line["parity_checked"] = bool(same and np.array_equal(want, h_out[: int(offsets[ns])].numpy().view(np.uint16)))
+            orc = OracleIndex(index_dir)
+            if is_count:
+                wc, wp = orc.query_count(bases[: int(offsets[ns])], offsets[: ns + 1], threads=0)
+                ok = np.array_equal(wc, h_cnt[:ns].numpy().view(np.uint64)) and np.array_equal(wp, h_pos[:ns].numpy())
+            else:
+                want = getattr(orc, "query_" + W["query"])(bases[: int(offsets[ns])], offsets[: ns + 1], threads=0)
+                ok = np.array_equal(want, h_out[: int(offsets[ns])].numpy().view(np.uint16))
+            line["parity_checked"] = bool(same and ok)
             line["cpu_baseline"] = {"value": v, "unit": "bases/s", "cores": cores, "kind": kind,
                                     "sample": "the full per-GPU batch (%d x %d bp), %.2f s of wall time on %d threads, index load excluded"
                                               % (n_reads, cfg["read_len"], sec, cores)}

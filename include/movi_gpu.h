@@ -88,8 +88,10 @@ typedef struct movi_gpu_ctx movi_gpu_ctx;
 #define MOVI_GPU_LAYOUT_AUTO     0   /* EXPANDED8 when it fits in free HBM, else COMPACT where the mode has one */
 #define MOVI_GPU_LAYOUT_EXPANDED8 1  /* every mode re-laid out as 8-byte rows with the full id resolved:
                                         one 32-byte sector holds 4 rows, one sector fetch per LF step */
-#define MOVI_GPU_LAYOUT_COMPACT  2   /* blocked-thresholds only: the 6-byte rows stay as they are on disk (25 % less HBM),
-                                        the destination id is completed per step from id_blocks (shared memory / L2) */
+#define MOVI_GPU_LAYOUT_COMPACT  2   /* the packed rows stay as they are on disk.  blocked-thresholds: 6 bytes per row, the
+                                        destination id is completed per step from id_blocks (shared memory / L2).
+                                        sampled-thresholds: 3 bytes per row + id checkpoints (4 bytes per row in all), the
+                                        destination id costs a checkpoint scan + walk-back per LF step, as in the reference */
 
 int  movi_gpu_abi_version(void);
 int  movi_gpu_device_count(void);

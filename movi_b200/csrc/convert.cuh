@@ -30,66 +30,21 @@ __global__ void convert_blocked_kernel(const uint16_t* __restrict__ raw, uint2* 
     }
 }
 
-// ---- MODE 7: 3-byte rows {u8 n; u8 offset; u8 c} (include/move_row.hpp:122-126; bit fields
-//      include/move_row_configs.hpp:120-136), MoveTally = {u32 right; u8 left} (include/move_row.hpp:13-39)
-struct Raw3 {
-    const uint8_t* p;
-    unsigned long long end_idx;
-    __device__ __forceinline__ uint32_t n(unsigned long long i) const { return (uint32_t)p[3 * i] | (((uint32_t)p[3 * i + 2] >> 1) & 1u) << 8; }
-    __device__ __forceinline__ uint32_t off(unsigned long long i) const { return (uint32_t)p[3 * i + 1] | ((uint32_t)p[3 * i + 2] & 1u) << 8; }
-    __device__ __forceinline__ uint32_t c(unsigned long long i) const { return ((uint32_t)p[3 * i + 2] >> 2) & 7u; }
-    __device__ __forceinline__ uint32_t thr(unsigned long long i) const { return ((uint32_t)p[3 * i + 2] >> 5) & 7u; }
-    // get_char (src/move_structure.cpp:288-293): '$' (here 8) for the end row
-    __device__ __forceinline__ uint32_t ch(unsigned long long i) const { return i == end_idx ? 8u : c(i); }
-};
-
-__device__ __forceinline__ unsigned long long tally_get(const uint8_t* tally, unsigned long long tally_len, uint32_t c, unsigned long long k) {
-    const uint8_t* q = tally + (c * tally_len + k) * 5;
-    return (unsigned long long)q[0] | ((unsigned long long)q[1] << 8) | ((unsigned long long)q[2] << 16) |
-           ((unsigned long long)q[3] << 24) | ((unsigned long long)q[4] << 32);
-}
-
-__global__ void convert_sampled_kernel(const uint8_t* __restrict__ raw, uint2* __restrict__ out,
+// ---- MODE 7 -> R8: one thread per row runs sampled_get_id (dev_index.cuh) on the packed table
+__global__ void convert_sampled_kernel(const uint32_t* __restrict__ raw_words, uint2* __restrict__ out,
                                        unsigned long long r, unsigned long long end_idx,
                                        const uint8_t* __restrict__ tally, unsigned long long tally_len, uint32_t cp,
                                        unsigned int* __restrict__ status) {
-    const Raw3 R{raw, end_idx};
+    const Rows3 R{raw_words, end_idx};
     unsigned long long idx = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (; idx < r; idx += stride) {
-        unsigned long long id;
-        const uint32_t ci = R.c(idx);
-        if (idx == end_idx) {
-            id = 0;                                                           // :106-108
-        } else if (idx == r - 1) {
-            id = tally_get(tally, tally_len, ci, tally_len - 1);              // :114-117
-        } else if (idx % cp == 0) {
-            id = tally_get(tally, tally_len, ci, idx / cp);                   // :121-124
-        } else {
-            const unsigned long long tally_b = idx / cp + 1;
-            unsigned long long next_cp = tally_b * cp;
-            if (next_cp >= r) next_cp = r - 1;                                // :135-139
-            id = tally_get(tally, tally_len, ci, tally_b);
-            unsigned long long rows_until = 0, last_id = r;
-            const uint32_t my_ch = R.ch(idx);
-            for (unsigned long long i = idx; i < next_cp; i++)                // :165-171
-                if (R.ch(i) == my_ch) { rows_until += R.n(i); last_id = i; }
-            const bool same_as_cp = (my_ch == R.ch(next_cp));
-            if (!(last_id == idx && !same_as_cp)) {                           // :175-177
-                uint32_t off = R.off(next_cp);
-                if (!same_as_cp) { rows_until -= R.n(last_id); off = R.off(last_id); }   // :190-193
-                if (id >= r || off >= R.n(id)) { atomicOr(status, 2u); }      // :196-199 (reference throws)
-                else if (off < rows_until) {                                  // :200-215
-                    rows_until -= (off + 1);
-                    id -= 1;
-                    while (rows_until != 0) {
-                        const uint32_t nn = R.n(id);
-                        if (rows_until >= nn) { rows_until -= nn; id -= 1; } else rows_until = 0;
-                    }
-                }
-            }
-        }
-        out[idx] = make_r8(id, R.n(idx), R.off(idx), ci, R.thr(idx));
+        const uint32_t x = R.raw(idx);
+        const uint32_t ci = Rows3::c_of(x);
+        bool bad = false;
+        const unsigned long long id = sampled_get_id(R, tally, tally_len, cp, r, end_idx, idx, ci, &bad);
+        if (bad) atomicOr(status, 2u);
+        out[idx] = make_r8(id, Rows3::n_of(x), Rows3::off_of(x), ci, Rows3::thr_of(x));
     }
 }
 

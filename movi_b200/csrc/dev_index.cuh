@@ -18,6 +18,7 @@ namespace movi {
 
 constexpr int LAYOUT_R8 = 0;      // 8-byte rows, full destination id in the row
 constexpr int LAYOUT_B6 = 1;      // the reference's blocked-thresholds rows as they are on disk: 6 bytes per row + id_blocks
+constexpr int LAYOUT_T3 = 2;      // the reference's sampled-thresholds rows as they are on disk: 3 bytes per row + id checkpoints
 
 struct DevIndex {
     const uint2* rows;            // LAYOUT_R8: R8 rows
@@ -26,6 +27,10 @@ struct DevIndex {
     uint32_t id_blocks_size;
     uint32_t block_shift;         // block_size == 1 << block_shift
     uint32_t layout;
+    const uint32_t* rows3;        // LAYOUT_T3: packed 3-byte rows viewed as 32-bit words (table padded by 8 bytes)
+    const uint8_t* tally;         // LAYOUT_T3: sigma x tally_len MoveTally entries (5 bytes each)
+    unsigned long long tally_len;
+    uint32_t tally_cp;            // id checkpoint interval (tally_checkpoints)
     unsigned long long r;
     unsigned long long end_idx;   // row of '$'
     uint32_t n_last;              // n(r-1)
@@ -104,6 +109,65 @@ __device__ __forceinline__ uint32_t sep_threshold(const DevIndex& ix, unsigned l
     }
     if (lo < ix.sep_cnt && ix.sep_keys[lo] == idx) return ix.sep_vals[lo * 4 + ai];
     return ix.sep_vals[ix.sep_cnt * 4 + ai];   // entry sep_cnt mirrors slot 0 (set at upload)
+}
+
+// ---- sampled-thresholds (MODE 7): 3-byte rows {u8 n; u8 offset; u8 c} (include/move_row.hpp:122-126; bit fields
+//      include/move_row_configs.hpp:120-136), MoveTally = {u32 right; u8 left} (include/move_row.hpp:13-39)
+struct Rows3 {              // the packed table read through aligned 32-bit words (two loads per row)
+    const uint32_t* w;
+    unsigned long long end_idx;
+    __device__ __forceinline__ uint32_t raw(unsigned long long i) const {
+        const unsigned long long a = 3ull * i;
+        const uint32_t* p = w + (a >> 2);
+        return __funnelshift_r(__ldg(p), __ldg(p + 1), (uint32_t)(a & 3u) * 8u) & 0xFFFFFFu;
+    }
+    static __device__ __forceinline__ uint32_t n_of(uint32_t x) { return (x & 0xFFu) | (((x >> 17) & 1u) << 8); }
+    static __device__ __forceinline__ uint32_t off_of(uint32_t x) { return ((x >> 8) & 0xFFu) | (((x >> 16) & 1u) << 8); }
+    static __device__ __forceinline__ uint32_t c_of(uint32_t x) { return (x >> 18) & 7u; }
+    static __device__ __forceinline__ uint32_t thr_of(uint32_t x) { return (x >> 21) & 7u; }
+    __device__ __forceinline__ uint32_t n(unsigned long long i) const { return n_of(raw(i)); }
+    __device__ __forceinline__ uint32_t off(unsigned long long i) const { return off_of(raw(i)); }
+    // get_char (src/move_structure.cpp:288-293): '$' (here 8) for the end row
+    __device__ __forceinline__ uint32_t ch(unsigned long long i) const { return i == end_idx ? 8u : c_of(raw(i)); }
+};
+
+__device__ __forceinline__ unsigned long long tally_get(const uint8_t* tally, unsigned long long tally_len, uint32_t c, unsigned long long k) {
+    const uint8_t* q = tally + (c * tally_len + k) * 5;
+    return (unsigned long long)q[0] | ((unsigned long long)q[1] << 8) | ((unsigned long long)q[2] << 16) |
+           ((unsigned long long)q[3] << 24) | ((unsigned long long)q[4] << 32);
+}
+
+// MoveStructure::get_id for TALLY_MODES (src/move_structure.cpp:103-219; the forward direction is always taken, :147-148):
+// scan from idx to the next id checkpoint summing the lengths of the rows with idx's character, then walk back from the
+// checkpoint's id.  R is any accessor with n(i), off(i), ch(i).  *bad is set where the reference throws (:196-199).
+template <typename R>
+__device__ __forceinline__ unsigned long long sampled_get_id(const R& rows, const uint8_t* tally, unsigned long long tally_len, uint32_t cp,
+                                                             unsigned long long r, unsigned long long end_idx, unsigned long long idx,
+                                                             uint32_t ci, bool* bad) {
+    if (idx == end_idx) return 0;                                                        // :106-108
+    if (idx == r - 1) return tally_get(tally, tally_len, ci, tally_len - 1);             // :114-117
+    if (idx % cp == 0) return tally_get(tally, tally_len, ci, idx / cp);                 // :121-124
+    const unsigned long long tally_b = idx / cp + 1;
+    unsigned long long next_cp = tally_b * cp;
+    if (next_cp >= r) next_cp = r - 1;                                                   // :135-139
+    unsigned long long id = tally_get(tally, tally_len, ci, tally_b);
+    unsigned long long rows_until = 0, last_id = r;
+    const uint32_t my_ch = rows.ch(idx);
+    for (unsigned long long i = idx; i < next_cp; i++)                                   // :165-171
+        if (rows.ch(i) == my_ch) { rows_until += rows.n(i); last_id = i; }
+    const bool same_as_cp = (my_ch == rows.ch(next_cp));
+    if (last_id == idx && !same_as_cp) return id;                                        // :175-177
+    uint32_t off = rows.off(next_cp);
+    if (!same_as_cp) { rows_until -= rows.n(last_id); off = rows.off(last_id); }         // :190-193
+    if (id >= r || off >= rows.n(id)) { *bad = true; return id < r ? id : 0; }           // :196-199 (reference throws)
+    if (off >= rows_until) return id;                                                    // :200-201
+    rows_until -= (off + 1);
+    id -= 1;
+    while (rows_until != 0) {                                                            // :207-215
+        const uint32_t nn = rows.n(id);
+        if (rows_until >= nn) { rows_until -= nn; id -= 1; } else rows_until = 0;
+    }
+    return id;
 }
 
 }  // namespace movi

@@ -53,6 +53,8 @@ struct movi_gpu_ctx {
     uint2* d_rows = nullptr;
     uint32_t* d_rows6 = nullptr;      // LAYOUT_B6: packed blocked-thresholds rows
     uint32_t* d_id_blocks = nullptr;
+    uint32_t* d_rows3 = nullptr;      // LAYOUT_T3: packed sampled-thresholds rows
+    uint8_t* d_tally = nullptr;
     unsigned long long* d_sep_keys = nullptr; uint16_t* d_sep_vals = nullptr;
     unsigned long long* d_prefix = nullptr;
     uint64_t index_bytes = 0;
@@ -155,6 +157,8 @@ void free_index(movi_gpu_ctx* ctx) {
     cudaFree(ctx->d_rows); ctx->d_rows = nullptr;
     cudaFree(ctx->d_rows6); ctx->d_rows6 = nullptr;
     cudaFree(ctx->d_id_blocks); ctx->d_id_blocks = nullptr;
+    cudaFree(ctx->d_rows3); ctx->d_rows3 = nullptr;
+    cudaFree(ctx->d_tally); ctx->d_tally = nullptr;
     cudaFree(ctx->d_sep_keys); ctx->d_sep_keys = nullptr;
     cudaFree(ctx->d_sep_vals); ctx->d_sep_vals = nullptr;
     cudaFree(ctx->d_prefix); ctx->d_prefix = nullptr;
@@ -212,7 +216,7 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
         CU(cudaLaunchKernelEx(&cfg_, k_, ctx->ix, qa));                           \
     } while (0)
     if (kind == Q_PML) {
-        const int64_t variant = ctx->ix.layout == LAYOUT_B6 ? 4 : ctx->pml_variant;   // the compact layout exists for the default kernel only
+        const int64_t variant = ctx->ix.layout != LAYOUT_R8 ? 4 : ctx->pml_variant;   // the compact layouts exist for the default kernel only
         if (variant == 0) { if (wide) LAUNCH((movi_pml_kernel<unsigned long long, 0>)); else LAUNCH((movi_pml_kernel<uint32_t, 0>)); }
         else if (variant == 1) { if (wide) LAUNCH((movi_pml_kernel<unsigned long long, 1>)); else LAUNCH((movi_pml_kernel<uint32_t, 1>)); }
         else if (variant == 2) { if (wide) LAUNCH((movi_pml_kernel2<unsigned long long, true>)); else LAUNCH((movi_pml_kernel2<uint32_t, true>)); }
@@ -220,8 +224,9 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
         else {
             // 6 blocks/SM (40 registers) measured fastest on both L2-sized (c2) and HBM-resident (8-64 GB) tables -- the
             // latter are bound by the memory system's random-request rate, not by exposed latency (profiles/r01_big_tables.jsonl)
-            const bool b6 = ctx->ix.layout == LAYOUT_B6;
-#define PML3(IDX, SEPV) do { if (b6) LAUNCH((movi_pml_kernel3<IDX, SEPV, 6, LAYOUT_B6>)); else LAUNCH((movi_pml_kernel3<IDX, SEPV, 6, LAYOUT_R8>)); } while (0)
+            const bool b6 = ctx->ix.layout == LAYOUT_B6, t3 = ctx->ix.layout == LAYOUT_T3;
+#define PML3(IDX, SEPV) do { if (t3) LAUNCH((movi_pml_kernel3<IDX, SEPV, 5, LAYOUT_T3>)); \
+                             else if (b6) LAUNCH((movi_pml_kernel3<IDX, SEPV, 6, LAYOUT_B6>)); else LAUNCH((movi_pml_kernel3<IDX, SEPV, 6, LAYOUT_R8>)); } while (0)
             if (ctx->ix.sep) { if (wide) PML3(unsigned long long, true); else PML3(uint32_t, true); }
             else             { if (wide) PML3(unsigned long long, false); else PML3(uint32_t, false); }
 #undef PML3
@@ -416,7 +421,7 @@ int movi_gpu_destroy(movi_gpu_ctx* ctx) {
 
 uint64_t movi_gpu_index_device_bytes(const movi_gpu_ctx* ctx) { return ctx ? ctx->index_bytes : 0; }
 const void* movi_gpu_index_device_rows(const movi_gpu_ctx* ctx) { return ctx && ctx->has_index ? ctx->d_rows : nullptr; }
-int movi_gpu_index_device_layout(const movi_gpu_ctx* ctx) { return ctx && ctx->has_index ? (ctx->ix.layout == LAYOUT_B6 ? MOVI_GPU_LAYOUT_COMPACT : MOVI_GPU_LAYOUT_EXPANDED8) : -1; }
+int movi_gpu_index_device_layout(const movi_gpu_ctx* ctx) { return ctx && ctx->has_index ? (ctx->ix.layout != LAYOUT_R8 ? MOVI_GPU_LAYOUT_COMPACT : MOVI_GPU_LAYOUT_EXPANDED8) : -1; }
 uint64_t movi_gpu_launch_count(const movi_gpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int movi_gpu_set_option(movi_gpu_ctx* ctx, const char* key, int64_t value) {
@@ -512,18 +517,32 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
     // copy the conversion needs) does not fit in free HBM.  COMPACT exists for blocked-thresholds (its 6-byte rows are
     // kept as they are on disk); regular-thresholds is 8 bytes on disk anyway; sampled-thresholds is always expanded.
     bool compact = false;
-    if (!adopt_rows && d->mode == MOVI_MODE_BLOCKED_THRESHOLDS && (d->block_size & (d->block_size - 1)) == 0) {
+    const bool can_compact = !adopt_rows && ((d->mode == MOVI_MODE_BLOCKED_THRESHOLDS && (d->block_size & (d->block_size - 1)) == 0) ||
+                                             d->mode == MOVI_MODE_SAMPLED_THRESHOLDS);
+    if (can_compact) {
         if (layout == MOVI_GPU_LAYOUT_COMPACT) compact = true;
         else if (layout == MOVI_GPU_LAYOUT_AUTO) {
             size_t free_b = 0, total_b = 0;
             CU(cudaMemGetInfo(&free_b, &total_b));
-            compact = (double)r * (8 + 6) + (256ull << 20) > (double)free_b;
+            const double raw_b = d->mode == MOVI_MODE_BLOCKED_THRESHOLDS ? 6.0 : 4.0;
+            compact = (double)r * (8 + raw_b) + (256ull << 20) > (double)free_b;
         }
     }
     if (layout == MOVI_GPU_LAYOUT_COMPACT && !compact && d->mode == MOVI_MODE_BLOCKED_THRESHOLDS)
         return fail(ctx, MOVI_GPU_ERR_INDEX, "compact layout needs a power-of-two id block size");
     uint32_t n_last_host = 0;
-    if (compact) {
+    const bool compact_t3 = compact && d->mode == MOVI_MODE_SAMPLED_THRESHOLDS;
+    if (compact_t3) {
+        const size_t tally_bytes = (size_t)d->sigma * d->tally_len * 5;
+        CU(cudaMalloc(&ctx->d_rows3, r * 3 + 16));
+        CU(cudaMemsetAsync(reinterpret_cast<uint8_t*>(ctx->d_rows3) + r * 3, 0, 16, st));
+        CU(cudaMemcpyAsync(ctx->d_rows3, d->rows, r * 3, cudaMemcpyHostToDevice, st));
+        CU(cudaMalloc(&ctx->d_tally, tally_bytes + 8));
+        CU(cudaMemcpyAsync(ctx->d_tally, d->tally_ids, tally_bytes, cudaMemcpyHostToDevice, st));
+        ctx->index_bytes = r * 3 + 16 + tally_bytes + 8;
+        const uint8_t* lastp = static_cast<const uint8_t*>(d->rows) + (r - 1) * 3;
+        n_last_host = (uint32_t)lastp[0] | (((uint32_t)lastp[2] >> 1) & 1u) << 8;
+    } else if (compact) {
         CU(cudaMalloc(&ctx->d_rows6, r * 6 + 16));
         CU(cudaMemsetAsync(reinterpret_cast<uint8_t*>(ctx->d_rows6) + r * 6, 0, 16, st));
         CU(cudaMemcpyAsync(ctx->d_rows6, d->rows, r * 6, cudaMemcpyHostToDevice, st));
@@ -562,12 +581,13 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
     } else {
         uint8_t* d_raw = nullptr; uint8_t* d_tally = nullptr;
         const size_t tally_bytes = (size_t)d->sigma * d->tally_len * 5;
-        CU(cudaMalloc(&d_raw, r * 3 + 8));
+        CU(cudaMalloc(&d_raw, r * 3 + 16));
+        CU(cudaMemsetAsync(d_raw + r * 3, 0, 16, st));
         CU(cudaMalloc(&d_tally, tally_bytes + 8));
         CU(cudaMemcpyAsync(d_raw, d->rows, r * 3, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_tally, d->tally_ids, tally_bytes, cudaMemcpyHostToDevice, st));
         CU(cudaMemsetAsync(ctx->d_status, 0, sizeof(unsigned int), st));
-        convert_sampled_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(d_raw, ctx->d_rows, r, d->end_bwt_idx, d_tally, d->tally_len,
+        convert_sampled_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_raw), ctx->d_rows, r, d->end_bwt_idx, d_tally, d->tally_len,
                                                                d->tally_checkpoints, ctx->d_status);
         ctx->launches += 1;
         unsigned int status = 0;
@@ -587,8 +607,9 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
     ix.rows = ctx->d_rows;
     ix.rows6 = ctx->d_rows6;
     ix.id_blocks = ctx->d_id_blocks;
-    ix.layout = compact ? LAYOUT_B6 : LAYOUT_R8;
-    if (compact) {
+    ix.layout = compact_t3 ? LAYOUT_T3 : compact ? LAYOUT_B6 : LAYOUT_R8;
+    ix.rows3 = ctx->d_rows3; ix.tally = ctx->d_tally; ix.tally_len = d->tally_len; ix.tally_cp = d->tally_checkpoints;
+    if (compact && !compact_t3) {
         ix.id_blocks_size = (uint32_t)d->id_blocks_size;
         ix.block_shift = 0;
         while ((1ull << ix.block_shift) < d->block_size) ix.block_shift++;
@@ -695,8 +716,11 @@ int movi_gpu_check_device_status(movi_gpu_ctx* ctx) {
     CU(cudaMemcpy(&status, ctx->d_status, sizeof(status), cudaMemcpyDeviceToHost));
     if (status) {
         CU(cudaMemset(ctx->d_status, 0, sizeof(unsigned int)));
-        return fail(ctx, MOVI_GPU_ERR_QUERY, "[reposition thresholds] no row with the read's character in the threshold direction: "
-                    "This should not happen! (the reference throws here, src/move_structure_query.cpp:348,582-598)");
+        return fail(ctx, MOVI_GPU_ERR_QUERY, (status & 2u)
+                    ? "[get id - tally mode] The offset in the destination run should be always smaller than the length of that run. "
+                      "(the reference throws here, src/move_structure.cpp:196-199)"
+                    : "[reposition thresholds] no row with the read's character in the threshold direction: "
+                      "This should not happen! (the reference throws here, src/move_structure_query.cpp:348,582-598)");
     }
     return MOVI_GPU_OK;
 }

@@ -30,7 +30,8 @@ constexpr int PML3_THREADS = 256;
 // MINB: resident blocks per SM the register allocation must allow.  6 (40 registers) is the default; 8 (32 registers,
 // 2048 walks per SM, one spilled word) was measured slower both on the L2-sized c2 table (issue bound) and on 8-64 GB
 // tables (bound by the memory system's random-request rate, not by exposed latency): profiles/r01_big_tables.jsonl.
-// LAYOUT: LAYOUT_R8 (one 8-byte fetch per step) or LAYOUT_B6 (6-byte blocked rows + id_blocks, 25 % less HBM).
+// LAYOUT: LAYOUT_R8 (one 8-byte fetch per step), LAYOUT_B6 (6-byte blocked rows + id_blocks, 25 % less HBM) or
+// LAYOUT_T3 (3-byte sampled rows + id checkpoints, half the HBM; the destination id costs a scan + walk per LF step).
 constexpr int IDB_SMEM = 1024;       // id_blocks entries kept in shared memory (covers r <= 2.7e8 rows at block_size 2^20)
 
 template <typename IdxT, bool SEP, int MINB, int LAYOUT>
@@ -103,8 +104,13 @@ movi_pml_kernel3(const DevIndex ix, const QueryArgs q) {
         const bool proc = (st >= ST_FF);
         // (lanes that are not walking fetch row 0: harmless and keeps the fetch out of a divergent branch)
         const IdxT fidx = proc ? idx : (IdxT)0;
-        const uint2 v = LAYOUT == LAYOUT_R8 ? ld_keep(rows + fidx, pol_keep)
-                                            : fetch_row_b6<IdxT>(ix.rows6, fidx, end_idx, idb, ix.id_blocks_size, ix.block_shift, s_first);
+        uint2 v;
+        if (LAYOUT == LAYOUT_R8) v = ld_keep(rows + fidx, pol_keep);
+        else if (LAYOUT == LAYOUT_B6) v = fetch_row_b6<IdxT>(ix.rows6, fidx, end_idx, idb, ix.id_blocks_size, ix.block_shift, s_first);
+        else {              // LAYOUT_T3: the 3-byte row without its destination id (resolved below, only when an LF step needs it)
+            const uint32_t x = Rows3{ix.rows3, (unsigned long long)end_idx}.raw((unsigned long long)fidx);
+            v = make_r8(0, Rows3::n_of(x), Rows3::off_of(x), Rows3::c_of(x), Rows3::thr_of(x));
+        }
         if (proc && need_chunk) {
             const uint8_t* src = bases + (rp & ~31u);
             cp_async16(in_slot, src);
@@ -184,9 +190,16 @@ movi_pml_kernel3(const DevIndex ix, const QueryArgs q) {
         need_chunk = need_chunk || (lf && (rp & 31u) == 0u);
         rp -= lf ? 1u : 0u;
         off += lf ? row_off(y) : 0u;                                        // LF_move, move_structure.cpp:66
-        idx = lf ? row_id<IdxT>(v) : (ffmove || mv_down) ? idx + 1 : (mv_up ? idx - 1 : idx);
+        IdxT lf_id = row_id<IdxT>(v);
+        bool bad_id = false;
+        if (LAYOUT == LAYOUT_T3) {
+            // sampled-thresholds: get_id = checkpoint scan + walk-back (src/move_structure.cpp:103-219), per LF step
+            if (lf) lf_id = (IdxT)sampled_get_id(Rows3{ix.rows3, (unsigned long long)end_idx}, ix.tally, ix.tally_len, ix.tally_cp, ix.r,
+                                                 (unsigned long long)end_idx, (unsigned long long)idx, c, &bad_id);
+        }
+        idx = lf ? lf_id : (ffmove || mv_down) ? idx + 1 : (mv_up ? idx - 1 : idx);
         st = fin ? ST_IDLE : lf ? ST_FF : base_mis ? (down ? ST_DOWN : ST_UP) : st;
-        if (bad) { atomicOr(q.status, 1u); st = ST_IDLE; }
+        if (bad || bad_id) { atomicOr(q.status, bad_id ? 2u : 1u); st = ST_IDLE; }
     }
 }
 

@@ -210,3 +210,29 @@ def test_blocked_compact_device_layout(index_dirs, read_sets, ref_seq, sep):
     ms8 = MoveStructure(d, layout=LAYOUT_EXPANDED8)
     assert ms8.device_layout == LAYOUT_EXPANDED8 and ms8.index_device_bytes >= 8 * ms8.r
     ms8.close()
+
+
+@pytest.mark.parametrize("sep", [False, True])
+def test_sampled_compact_device_layout(index_dirs, read_sets, ref_seq, sep):
+    """MOVI_GPU_LAYOUT_COMPACT for sampled-thresholds: 3-byte rows + id checkpoints stay in HBM (4 bytes per row in all);
+    MoveStructure::get_id's checkpoint scan + walk-back runs per LF step on the device."""
+    from movi_b200 import MoveStructure, MoviGpuError
+    from movi_b200.api import LAYOUT_COMPACT
+    from oracle.port import OracleIndex, pack_reads
+    d = index_dirs[("sampled-thresholds", sep)]
+    ms = MoveStructure(d, layout=LAYOUT_COMPACT)
+    try:
+        assert ms.device_layout == LAYOUT_COMPACT
+        assert ms.index_device_bytes < 4.3 * ms.r + 4096
+        for read_set in READ_SETS:
+            rd = read_sets[read_set]
+            assert ml_text(rd.ids(), rd.offsets, ms.query_pml(rd.bases, rd.offsets)) == expected_text(read_set, "pml", sep)
+        bases, offsets = pack_reads(_random_reads(19, 20000, 600, ref_seq))
+        want = OracleIndex(d).query_pml(bases, offsets, threads=0)
+        for wide in (0, 1):
+            ms.set_option("force_wide", wide)
+            assert np.array_equal(ms.query_pml(bases, offsets), want)
+        with pytest.raises(MoviGpuError, match="not suppported by the sampled modes"):
+            ms.query_zml(bases, offsets)
+    finally:
+        ms.close()
