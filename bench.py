@@ -323,6 +323,25 @@ def main():
     e2e_ms = (time.perf_counter() - t0) * 1e3
     barrier()
 
+    # ---- extra (c2 only): PML + binary classification through the fused host entry point -- only 16 bytes per read come back
+    e2e_cls_ms = None
+    if W["query"] == "pml":
+        h_above, h_below = torch.zeros(n_reads, dtype=torch.int32).pin_memory(), torch.zeros(n_reads, dtype=torch.int32).pin_memory()
+        h_sum = torch.zeros(n_reads, dtype=torch.int64).pin_memory()
+
+        def step_cls():
+            ms._check(ms._L.movi_gpu_query_classify(ms._ctx, 0, h_bases.data_ptr(), h_off.data_ptr(), n_reads, 0, 150, 7,
+                                                    h_above.data_ptr(), h_below.data_ptr(), h_sum.data_ptr(), None))
+        for _ in range(2):
+            step_cls()
+        barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_cls()
+        torch.cuda.synchronize()
+        e2e_cls_ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+
     # keep the GPU under the same load a little longer so that the clock sampler sees it (not part of any number)
     if sampler is not None:
         t_end = time.time() + 1.2
@@ -339,9 +358,10 @@ def main():
         same = bool(torch.equal(d_out[: n_bases].cpu(), h_out[: n_bases]))
 
     if world > 1:
-        t = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([elapsed_ms, e2e_ms, e2e_cls_ms or 0.0], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms, e2e_ms = float(t[0]), float(t[1])
+        e2e_cls_ms = float(t[2]) if e2e_cls_ms is not None else None
         ok = torch.tensor([1 if same else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         same = bool(ok.item())
@@ -352,7 +372,11 @@ def main():
         e2e_value = total_bases / (e2e_ms * 1e-3)
         peak, peak_src = measured_peaks()
         per_launch_s = elapsed_ms * 1e-3 / args.steps
-        achieved = W["algo"] * n_bases / per_launch_s / 1e9
+        work_bases = n_bases
+        if is_count:       # the backward search of a read stops at its first failed extension: count the steps it really took
+            L = np.diff(offsets.astype(np.int64))
+            work_bases = int(np.minimum(L, L - h_pos.numpy().astype(np.int64) + 1).sum())
+        achieved = W["algo"] * work_bases / per_launch_s / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "pml_c2_traffic.json")
         if args.workload == "c2" and os.path.exists(tp):
@@ -367,10 +391,14 @@ def main():
             "config": workload_config(cfg, ms.index_device_bytes),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": W["kernel"], "algorithmic_bytes_per_base": W["algo"]},
+                         "kernel": W["kernel"], "algorithmic_bytes_per_base": W["algo"], "bases_walked_per_launch": int(work_bases)},
             "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": int(n_bases + 8 * (n_reads + 1)),
                     "d2h_bytes_per_step": int(12 * n_reads if is_count else 2 * n_bases), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
+            "e2e_classify": None if e2e_cls_ms is None else {
+                "value": total_bases / (e2e_cls_ms * 1e-3), "unit": "bases/s", "ms_per_step": e2e_cls_ms / args.steps,
+                "h2d_bytes_per_step": int(n_bases + 8 * (n_reads + 1)), "d2h_bytes_per_step": int(16 * n_reads),
+                "what": "PML + Classifier::classify fused on the device (movi_gpu_query_classify): --classify / --filter workflows"},
             "clocks": clocks,
             "parity_checked": same,
         }

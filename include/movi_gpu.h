@@ -119,6 +119,14 @@ uint64_t movi_gpu_index_device_bytes(const movi_gpu_ctx* ctx);
  * HOST buffers.  out_ml has read_offsets[n_reads] entries.  Copies in, runs, copies out (pipelined). */
 int  movi_gpu_query_pml(movi_gpu_ctx* ctx, const char* bases, const uint64_t* read_offsets, uint64_t n_reads,
                         uint32_t flags, uint16_t* out_ml);
+/* replaces: query_pml / query_zml FOLLOWED BY Classifier::classify (handle_pml_zml, src/movi.cpp:23-60; src/classifier.cpp:99-143)
+ * for the --classify / --filter workflows: the matching lengths are binned where they sit in HBM and only the three report
+ * columns per read come back (bins_above, bins_below, sum of bin maxima; found = above / (above + below) > 0.5), i.e. 16 bytes
+ * per read instead of 2 bytes per base over PCIe.  zml != 0 classifies ZMLs.  out_ml may be NULL (e.g. --filter, which writes
+ * no .bpf); if given it also receives the matching lengths exactly as movi_gpu_query_pml / _zml would return them. */
+int  movi_gpu_query_classify(movi_gpu_ctx* ctx, int zml, const char* bases, const uint64_t* read_offsets, uint64_t n_reads,
+                             uint32_t flags, uint32_t bin_width, uint32_t max_value_thr,
+                             uint32_t* out_bins_above, uint32_t* out_bins_below, uint64_t* out_sum_max, uint16_t* out_ml);
 /* replaces: MoveStructure::query_zml (src/move_structure_query.cpp:690-786) */
 int  movi_gpu_query_zml(movi_gpu_ctx* ctx, const char* bases, const uint64_t* read_offsets, uint64_t n_reads,
                         uint32_t flags, uint16_t* out_ml);

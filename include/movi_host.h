@@ -54,6 +54,10 @@ int  movi_host_write_counts(int fd, const movi_host_reads* rd, const uint64_t* c
 int  movi_host_classify(int fd, int mode, const movi_host_reads* rd, const uint16_t* ml, uint64_t bin_width,
                         uint64_t max_value_thr, uint8_t* found_out);
 
+/* Same report / filter output from the per-read columns computed on the device (movi_gpu_query_classify). */
+int  movi_host_classify_bins(int fd, int mode, const movi_host_reads* rd, uint64_t max_value_thr, const uint32_t* bins_above,
+                             const uint32_t* bins_below, const uint64_t* sum_max, uint8_t* found_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,8 @@ GPU_SYMBOLS = {
     "movi_gpu_index_device_layout": (C.c_int, [C.c_void_p]),
     "movi_gpu_index_device_bytes": (C.c_uint64, [C.c_void_p]),
     "movi_gpu_query_pml": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]),
+    "movi_gpu_query_classify": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "movi_gpu_query_zml": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]),
     "movi_gpu_query_count": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
     "movi_gpu_query_pml_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
@@ -74,6 +76,7 @@ HOST_SYMBOLS = {
     "movi_host_write_bpf": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p]),
     "movi_host_write_ml_text": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
     "movi_host_write_counts": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "movi_host_classify_bins": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "movi_host_classify": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
 }
 

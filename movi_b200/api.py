@@ -162,6 +162,17 @@ class MoveStructure:
         self._check(self._L.movi_gpu_query_pml(self._ctx, _ptr(bases), _ptr(offsets), max(n, 0), 0, _ptr(out)))
         return out
 
+    def query_classify(self, bases, offsets, bin_width, max_value_thr, zml=False, want_ml=False):
+        """PML (or ZML) + binary classification on the device -> (bins_above, bins_below, sum_max[, ml])."""
+        bases, offsets, n = self._prep(bases, offsets)
+        n = max(n, 0)
+        above, below = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        total = np.zeros(n, np.uint64)
+        ml = np.empty(int(offsets[-1]) if len(offsets) else 0, dtype=np.uint16) if want_ml else None
+        self._check(self._L.movi_gpu_query_classify(self._ctx, int(zml), _ptr(bases), _ptr(offsets), n, 0, bin_width, max_value_thr,
+                                                    _ptr(above), _ptr(below), _ptr(total), _ptr(ml) if want_ml else None))
+        return (above, below, total, ml) if want_ml else (above, below, total)
+
     def query_zml(self, bases, offsets, out=None):
         bases, offsets, n = self._prep(bases, offsets)
         if out is None:

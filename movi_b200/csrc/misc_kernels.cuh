@@ -7,7 +7,7 @@ namespace movi {
 
 // Classifier::classify (src/classifier.cpp:99-143): bins of bin_width over the matching lengths (a short
 // tail is merged into the previous bin), bin maximum >= max_value_thr counts as "above".  One warp per read.
-__global__ void classify_kernel(const uint16_t* __restrict__ ml, const unsigned long long* __restrict__ offsets,
+__global__ void classify_kernel(const uint16_t* __restrict__ ml, const unsigned long long* __restrict__ offsets, unsigned long long origin,
                                 unsigned long long n_reads, uint32_t bin_width, uint32_t thr,
                                 uint32_t* __restrict__ above_out, uint32_t* __restrict__ below_out,
                                 unsigned long long* __restrict__ sum_out) {
@@ -15,7 +15,7 @@ __global__ void classify_kernel(const uint16_t* __restrict__ ml, const unsigned 
     unsigned long long w = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) >> 5;
     const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
     for (; w < n_reads; w += n_warps) {
-        const unsigned long long s = offsets[w], e = offsets[w + 1];
+        const unsigned long long s = offsets[w] - origin, e = offsets[w + 1] - origin;
         const unsigned long long len = e - s;
         uint32_t above = 0, below = 0;
         unsigned long long sum = 0;

@@ -36,6 +36,7 @@ struct Staging {                              // one pipeline slot
     unsigned long long* d_offsets = nullptr; size_t offsets_cap = 0;   // in elements
     uint16_t* d_ml = nullptr; size_t ml_cap = 0;                        // in elements
     unsigned long long* d_count = nullptr; int32_t* d_pos = nullptr; size_t count_cap = 0;
+    uint32_t* d_above = nullptr; uint32_t* d_below = nullptr; unsigned long long* d_sum = nullptr; size_t cls_cap = 0;
     unsigned long long* d_counter = nullptr;
     bool busy = false;
 };
@@ -291,8 +292,10 @@ int grow(movi_gpu_ctx* ctx, T*& p, size_t& cap, size_t need) {
 
 // Host-buffer entry point: split the batch into slices of ~batch_bases, run them through a 3-deep
 // pipeline (H2D on slot stream, kernel, D2H), results land directly in the caller's buffers.
+struct ClassifyOut { uint32_t bin_width = 0, thr = 0; uint32_t* above = nullptr; uint32_t* below = nullptr; uint64_t* sum = nullptr; };
+
 int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* offsets, uint64_t n_reads,
-               uint16_t* out_ml, uint64_t* out_count, int32_t* out_pos) {
+               uint16_t* out_ml, uint64_t* out_count, int32_t* out_pos, const ClassifyOut* cls = nullptr) {
     int rc = check_query_ready(ctx, kind, 0);
     if (rc) return rc;
     if (n_reads == 0) return MOVI_GPU_OK;
@@ -330,6 +333,12 @@ int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* 
         } else {
             if ((rc = grow(ctx, S.d_ml, S.ml_cap, nb + shift + 64))) return rc;
         }
+        if (cls) {
+            size_t c1 = S.cls_cap, c2 = S.cls_cap;
+            if ((rc = grow(ctx, S.d_above, S.cls_cap, nr))) return rc;
+            if ((rc = grow(ctx, S.d_below, c1, nr))) return rc;
+            if ((rc = grow(ctx, S.d_sum, c2, nr))) return rc;
+        }
         CU(cudaMemcpyAsync(S.d_bases + shift, bases + o0, nb, cudaMemcpyHostToDevice, S.stream));
         CU(cudaMemcpyAsync(S.d_offsets, offsets + i0, (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, S.stream));
         rc = device_query(ctx, kind, reinterpret_cast<const char*>(S.d_bases), reinterpret_cast<const uint64_t*>(S.d_offsets),
@@ -339,7 +348,18 @@ int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* 
             CU(cudaMemcpyAsync(out_count + i0, S.d_count, nr * sizeof(uint64_t), cudaMemcpyDeviceToHost, S.stream));
             CU(cudaMemcpyAsync(out_pos + i0, S.d_pos, nr * sizeof(int32_t), cudaMemcpyDeviceToHost, S.stream));
         } else {
-            CU(cudaMemcpyAsync(out_ml + o0, S.d_ml + shift, nb * sizeof(uint16_t), cudaMemcpyDeviceToHost, S.stream));
+            if (cls) {
+                // classify the slice where it sits: only 16 bytes per read travel back instead of 2 bytes per base
+                const unsigned blocks = (unsigned)std::min<uint64_t>((nr * 32 + 255) / 256, (uint64_t)ctx->num_sms * 16);
+                classify_kernel<<<blocks, 256, 0, S.stream>>>(S.d_ml, S.d_offsets, o0 - shift, nr, cls->bin_width, cls->thr,
+                                                             S.d_above, S.d_below, S.d_sum);
+                ctx->launches += 1;
+                CU(cudaGetLastError());
+                CU(cudaMemcpyAsync(cls->above + i0, S.d_above, nr * sizeof(uint32_t), cudaMemcpyDeviceToHost, S.stream));
+                CU(cudaMemcpyAsync(cls->below + i0, S.d_below, nr * sizeof(uint32_t), cudaMemcpyDeviceToHost, S.stream));
+                CU(cudaMemcpyAsync(cls->sum + i0, S.d_sum, nr * sizeof(uint64_t), cudaMemcpyDeviceToHost, S.stream));
+            }
+            if (out_ml) CU(cudaMemcpyAsync(out_ml + o0, S.d_ml + shift, nb * sizeof(uint16_t), cudaMemcpyDeviceToHost, S.stream));
         }
         CU(cudaEventRecord(S.done, S.stream));
         S.busy = true;
@@ -409,6 +429,7 @@ int movi_gpu_destroy(movi_gpu_ctx* ctx) {
     for (int k = 0; k < NBUF; k++) {
         Staging& S = ctx->slot[k];
         cudaFree(S.d_bases); cudaFree(S.d_offsets); cudaFree(S.d_ml); cudaFree(S.d_count); cudaFree(S.d_pos); cudaFree(S.d_counter);
+        cudaFree(S.d_above); cudaFree(S.d_below); cudaFree(S.d_sum);
         if (S.done) cudaEventDestroy(S.done);
         if (S.stream) cudaStreamDestroy(S.stream);
     }
@@ -668,6 +689,19 @@ int movi_gpu_query_pml(movi_gpu_ctx* ctx, const char* bases, const uint64_t* rea
     if (n_reads && !out_ml) return fail(ctx, MOVI_GPU_ERR_ARG, "null output buffer");
     return host_query(ctx, Q_PML, bases, read_offsets, n_reads, out_ml, nullptr, nullptr);
 }
+int movi_gpu_query_classify(movi_gpu_ctx* ctx, int zml, const char* bases, const uint64_t* read_offsets, uint64_t n_reads, uint32_t,
+                            uint32_t bin_width, uint32_t max_value_thr, uint32_t* out_bins_above, uint32_t* out_bins_below,
+                            uint64_t* out_sum_max, uint16_t* out_ml) {
+    if (!ctx) return MOVI_GPU_ERR_ARG;
+    if (bin_width == 0) return fail(ctx, MOVI_GPU_ERR_ARG, "bin_width must be positive");
+    if (n_reads && (!out_bins_above || !out_bins_below || !out_sum_max)) return fail(ctx, MOVI_GPU_ERR_ARG, "null output buffer");
+    const Kind kind = zml ? Q_ZML : Q_PML;
+    int rc = check_query_ready(ctx, kind, 0);
+    if (rc) return rc;
+    ClassifyOut c; c.bin_width = bin_width; c.thr = max_value_thr; c.above = out_bins_above; c.below = out_bins_below; c.sum = out_sum_max;
+    return host_query(ctx, kind, bases, read_offsets, n_reads, out_ml, nullptr, nullptr, &c);
+}
+
 int movi_gpu_query_zml(movi_gpu_ctx* ctx, const char* bases, const uint64_t* read_offsets, uint64_t n_reads,
                        uint32_t, uint16_t* out_ml) {
     if (!ctx) return MOVI_GPU_ERR_ARG;
@@ -734,7 +768,7 @@ int movi_gpu_classify_device(movi_gpu_ctx* ctx, const uint16_t* d_ml, const uint
     const int threads = 256;
     const uint64_t warps = n_reads;
     const unsigned blocks = (unsigned)std::min<uint64_t>((warps * 32 + threads - 1) / threads, (uint64_t)ctx->num_sms * 16);
-    classify_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(d_ml, reinterpret_cast<const unsigned long long*>(d_read_offsets), n_reads,
+    classify_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(d_ml, reinterpret_cast<const unsigned long long*>(d_read_offsets), 0ull, n_reads,
                                                                   bin_width, max_value_thr, d_above, d_below,
                                                                   reinterpret_cast<unsigned long long*>(d_sum_max));
     ctx->launches += 1;

@@ -160,8 +160,14 @@ int main(int argc, char** argv) {
         }
     }
 
+    // With --classify / --filter the binning runs on the device (movi_gpu_query_classify); the matching lengths only come
+    // back when something needs them (the .bpf file next to a --classify report; never for --filter or --no-output).
+    const bool fused_classify = o.classify && o.query != "count";
+    const bool need_ml = o.query != "count" && (!fused_classify || o.write_output_allowed());
     std::vector<uint16_t> ml; std::vector<uint64_t> counts; std::vector<int32_t> pos;
-    if (o.query == "count") { counts.resize(n_reads); pos.resize(n_reads); } else ml.resize(n_bases);
+    std::vector<uint32_t> bins_above, bins_below; std::vector<uint64_t> sum_max;
+    if (o.query == "count") { counts.resize(n_reads); pos.resize(n_reads); } else if (need_ml) ml.resize(n_bases);
+    if (fused_classify) { bins_above.resize(n_reads); bins_below.resize(n_reads); sum_max.resize(n_reads); }
 
     // contiguous shards balanced by bases (same decomposition as the reference's OpenMP batches, movi.cpp:274-301)
     std::vector<uint64_t> cut(gpus + 1, n_reads);
@@ -182,7 +188,10 @@ int main(int argc, char** argv) {
         if (!rc && cut[g + 1] > cut[g]) {
             const uint64_t i0 = cut[g], nr = cut[g + 1] - cut[g];
             // offsets stay absolute: the entry points index bases / outputs by them
-            if (o.query == "pml") rc = movi_gpu_query_pml(ctx, bases, offsets + i0, nr, 0, ml.data());
+            if (fused_classify)
+                rc = movi_gpu_query_classify(ctx, o.query == "zml", bases, offsets + i0, nr, 0, (uint32_t)o.bin_width, (uint32_t)max_value_thr,
+                                             bins_above.data() + i0, bins_below.data() + i0, sum_max.data() + i0, need_ml ? ml.data() : nullptr);
+            else if (o.query == "pml") rc = movi_gpu_query_pml(ctx, bases, offsets + i0, nr, 0, ml.data());
             else if (o.query == "zml") rc = movi_gpu_query_zml(ctx, bases, offsets + i0, nr, 0, ml.data());
             else rc = movi_gpu_query_count(ctx, bases, offsets + i0, nr, 0, counts.data() + i0, pos.data() + i0);
         }
@@ -227,10 +236,10 @@ int main(int argc, char** argv) {
                 // with --no-output the reference still prints the header but no rows (write_output_allowed)
                 movi_host_reads* none = nullptr;
                 if (o.no_output) { movi_host_reads_load("/dev/null", 0, &none); rc = movi_host_classify(fd, 0, none, nullptr, o.bin_width, max_value_thr, nullptr); movi_host_reads_free(none); }
-                else rc = movi_host_classify(fd, 0, rd, ml.data(), o.bin_width, max_value_thr, nullptr);
+                else rc = movi_host_classify_bins(fd, 0, rd, max_value_thr, bins_above.data(), bins_below.data(), sum_max.data(), nullptr);
                 if (f) fclose(f);
             } else if (!o.no_output) {
-                rc = movi_host_classify(STDOUT_FILENO, o.invert ? 2 : 1, rd, ml.data(), o.bin_width, max_value_thr, nullptr);
+                rc = movi_host_classify_bins(STDOUT_FILENO, o.invert ? 2 : 1, rd, max_value_thr, bins_above.data(), bins_below.data(), sum_max.data(), nullptr);
             }
         }
         if (!rc && o.write_output_allowed()) {

@@ -368,10 +368,11 @@ int movi_host_write_counts(int fd, const movi_host_reads* rd, const uint64_t* co
 }
 
 // Classifier::initialize_report_file (header) + classify (rows), reference src/classifier.cpp:49-60, 99-143;
-// filter output = output_read, src/utils.cpp:291-294 via src/movi.cpp:41-47
-int movi_host_classify(int fd, int mode, const movi_host_reads* rd, const uint16_t* ml, uint64_t bin_width,
-                       uint64_t max_value_thr, uint8_t* found_out) {
-    if (!rd || (!ml && !rd->bases.empty()) || bin_width == 0) return fail("bad argument");
+// filter output = output_read, src/utils.cpp:291-294 via src/movi.cpp:41-47.
+// The three report columns come either from the matching lengths (ml != NULL: binned here, classifier.cpp:108-126) or from
+// the device (movi_gpu_query_classify: above / below / sum arrays).
+static int classify_impl(int fd, int mode, const movi_host_reads* rd, const uint16_t* ml, uint64_t bin_width, uint64_t max_value_thr,
+                         const uint32_t* d_above, const uint32_t* d_below, const uint64_t* d_sum, uint8_t* found_out) {
     FdWriter w(fd);
     std::ostringstream out;
     const uint16_t thr = (uint16_t)max_value_thr;
@@ -384,16 +385,21 @@ int movi_host_classify(int fd, int mode, const movi_host_reads* rd, const uint16
     }
     const uint64_t n = rd->offsets.size() - 1;
     for (uint64_t i = 0; i < n; i++) {
-        const uint16_t* v = ml + rd->offsets[i];
         const size_t len = rd->offsets[i + 1] - rd->offsets[i];
-        size_t above = 0, below = 0, sum = 0, nbins = 0, start = 0, end = 0;
-        while (start < len) {
-            end = (start + bin_width < len) ? start + bin_width : len;
-            if (len - end < bin_width) end = len;
-            const uint16_t mx = *std::max_element(v + start, v + end);
-            if (mx >= thr) above++; else below++;
-            sum += mx; nbins++;
-            start += (end - start);
+        size_t above = 0, below = 0, sum = 0, nbins = 0;
+        if (ml) {
+            const uint16_t* v = ml + rd->offsets[i];
+            size_t start = 0, end = 0;
+            while (start < len) {
+                end = (start + bin_width < len) ? start + bin_width : len;
+                if (len - end < bin_width) end = len;
+                const uint16_t mx = *std::max_element(v + start, v + end);
+                if (mx >= thr) above++; else below++;
+                sum += mx; nbins++;
+                start += (end - start);
+            }
+        } else {
+            above = d_above[i]; below = d_below[i]; sum = d_sum[i]; nbins = above + below;
         }
         const bool found = (above / (above + below + 0.0) > 0.50);
         if (found_out) found_out[i] = found ? 1 : 0;
@@ -412,6 +418,19 @@ int movi_host_classify(int fd, int mode, const movi_host_reads* rd, const uint16
     }
     w.put(out.str());
     return w.flush() ? 0 : fail("write failed");
+}
+
+int movi_host_classify(int fd, int mode, const movi_host_reads* rd, const uint16_t* ml, uint64_t bin_width,
+                       uint64_t max_value_thr, uint8_t* found_out) {
+    if (!rd || (!ml && !rd->bases.empty()) || bin_width == 0) return fail("bad argument");
+    static const uint16_t none = 0;
+    return classify_impl(fd, mode, rd, ml ? ml : &none, bin_width, max_value_thr, nullptr, nullptr, nullptr, found_out);
+}
+
+int movi_host_classify_bins(int fd, int mode, const movi_host_reads* rd, uint64_t max_value_thr, const uint32_t* bins_above,
+                            const uint32_t* bins_below, const uint64_t* sum_max, uint8_t* found_out) {
+    if (!rd || ((!bins_above || !bins_below || !sum_max) && rd->offsets.size() > 1)) return fail("bad argument");
+    return classify_impl(fd, mode, rd, nullptr, 1, max_value_thr, bins_above, bins_below, sum_max, found_out);
 }
 
 }  // extern "C"

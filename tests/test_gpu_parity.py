@@ -236,3 +236,33 @@ def test_sampled_compact_device_layout(index_dirs, read_sets, ref_seq, sep):
             ms.query_zml(bases, offsets)
     finally:
         ms.close()
+
+
+def test_fused_query_classify_matches_oracle(structures, index_dirs, read_sets, ref_seq):
+    """movi_gpu_query_classify: PML / ZML binned on the device; the three report columns per read must equal
+    Classifier::classify on the oracle's matching lengths (and the lengths themselves, when asked for, are unchanged)."""
+    from oracle.port import OracleIndex, classify, pack_reads
+    ms = structures[("regular-thresholds", False)]
+    orc = OracleIndex(index_dirs[("regular-thresholds", False)])
+    sets = [(read_sets[s].bases, read_sets[s].offsets) for s in ("long6.fasta", "synth300.fasta", "edge.fasta")]
+    sets.append(pack_reads(_random_reads(23, 5000, 900, ref_seq)))
+    old = ms.get_option("batch_bases")
+    for bases, offsets in sets:
+        for zml in (False, True):
+            want = orc.query_zml(bases, offsets, threads=0) if zml else orc.query_pml(bases, offsets, threads=0)
+            for batch in (old, 65536):           # one slice and many small slices
+                ms.set_option("batch_bases", batch)
+                try:
+                    a, b, s, ml = ms.query_classify(bases, offsets, 150, 7, zml=zml, want_ml=True)
+                    a2, b2, s2 = ms.query_classify(bases, offsets, 150, 7, zml=zml)
+                finally:
+                    ms.set_option("batch_bases", old)
+                assert np.array_equal(ml, want)
+                assert np.array_equal(a, a2) and np.array_equal(b, b2) and np.array_equal(s, s2)
+                for i in range(0, len(offsets) - 1, max(1, (len(offsets) - 1) // 400)):
+                    v = want[int(offsets[i]):int(offsets[i + 1])]
+                    if len(v) == 0:
+                        assert (a[i], b[i], s[i]) == (0, 0, 0)
+                        continue
+                    _, ea, eb, es, _ = classify(v, 150, 7)
+                    assert (a[i], b[i], s[i]) == (ea, eb, es), i
