@@ -59,11 +59,11 @@ def build_host(force=False):
     os.makedirs(LIBDIR, exist_ok=True)
     if force or _newer(HOST_LIB, srcs):
         subprocess.check_call([HOST_CXX, "-std=c++17", "-O2", "-Wall", "-fPIC", "-shared",
-                               os.path.join(HERE, "host", "movi_host.cpp"), "-o", HOST_LIB])
+                               os.path.join(HERE, "host", "movi_host.cpp"), "-lz", "-o", HOST_LIB])
     cli_src = os.path.join(HERE, "host", "movi_cli.cpp")
     if os.path.exists(cli_src) and (force or _newer(CLI, srcs + [GPU_LIB])):
         subprocess.check_call([HOST_CXX, "-std=c++17", "-O2", "-Wall", cli_src, os.path.join(HERE, "host", "movi_host.cpp"),
-                               "-L" + LIBDIR, "-lmovi_gpu", "-Wl,-rpath,$ORIGIN", "-pthread", "-o", CLI])
+                               "-L" + LIBDIR, "-lmovi_gpu", "-lz", "-Wl,-rpath,$ORIGIN", "-pthread", "-o", CLI])
     return HOST_LIB
 
 

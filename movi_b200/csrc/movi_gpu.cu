@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -307,6 +308,11 @@ int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* 
     uint64_t i0 = 0;
     int s = 0;
     const uint64_t max_bases = (uint64_t)std::max<int64_t>(ctx->batch_bases, 1 << 16);
+    // MOVI_GPU_TRACE=1: per-slice device timeline (ms since the first copy was enqueued) on stderr -- a debugging aid for
+    // the copy / kernel overlap of this pipeline, off the product path
+    static const bool trace = getenv("MOVI_GPU_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
     while (i0 < n_reads) {
         // slice [i0, i1): at least one read, at most max_bases bases (a single longer read gets its own slice)
         uint64_t i1 = i0 + 1;
@@ -339,11 +345,14 @@ int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* 
             if ((rc = grow(ctx, S.d_below, c1, nr))) return rc;
             if ((rc = grow(ctx, S.d_sum, c2, nr))) return rc;
         }
+        mark(S.stream);
         CU(cudaMemcpyAsync(S.d_bases + shift, bases + o0, nb, cudaMemcpyHostToDevice, S.stream));
         CU(cudaMemcpyAsync(S.d_offsets, offsets + i0, (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, S.stream));
+        mark(S.stream);
         rc = device_query(ctx, kind, reinterpret_cast<const char*>(S.d_bases), reinterpret_cast<const uint64_t*>(S.d_offsets),
                           o0 - shift, nr, S.d_ml, reinterpret_cast<uint64_t*>(S.d_count), S.d_pos, S.d_counter, S.stream);
         if (rc) return rc;
+        mark(S.stream);
         if (kind == Q_COUNT) {
             CU(cudaMemcpyAsync(out_count + i0, S.d_count, nr * sizeof(uint64_t), cudaMemcpyDeviceToHost, S.stream));
             CU(cudaMemcpyAsync(out_pos + i0, S.d_pos, nr * sizeof(int32_t), cudaMemcpyDeviceToHost, S.stream));
@@ -361,6 +370,7 @@ int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* 
             }
             if (out_ml) CU(cudaMemcpyAsync(out_ml + o0, S.d_ml + shift, nb * sizeof(uint16_t), cudaMemcpyDeviceToHost, S.stream));
         }
+        mark(S.stream);
         CU(cudaEventRecord(S.done, S.stream));
         S.busy = true;
         s = (s + 1) % NBUF;
@@ -368,6 +378,14 @@ int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* 
     }
     for (int k = 0; k < NBUF; k++)
         if (ctx->slot[k].busy) { CU(cudaEventSynchronize(ctx->slot[k].done)); ctx->slot[k].busy = false; }
+    if (trace) {
+        for (size_t k = 0; k + 3 < tev.size(); k += 4) {
+            float t[4];
+            for (int j = 0; j < 4; j++) cudaEventElapsedTime(&t[j], tev[0], tev[k + j]);
+            fprintf(stderr, "[movi_gpu trace] slice %2zu  h2d %.3f..%.3f  kernel ..%.3f  d2h ..%.3f ms\n", k / 4, t[0], t[1], t[2], t[3]);
+        }
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    }
     return movi_gpu_check_device_status(ctx);
 }
 

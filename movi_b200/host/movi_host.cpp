@@ -4,6 +4,7 @@
 
 #include <fcntl.h>
 #include <sys/mman.h>
+#include <zlib.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -200,6 +201,37 @@ inline const char* rtrim_end(const char* b, const char* e) {
 }
 }  // namespace
 
+// The reference opens its read files through zlib (open_kseq, src/utils.cpp:69-80: gzopen), so FASTA / FASTQ may be
+// gzip-compressed.  Inflate a gzip stream (all of its members) held in memory.
+static bool gunzip_all(const char* in, size_t n, std::string& out) {
+    z_stream zs;
+    std::memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, 15 + 32) != Z_OK) return false;
+    out.clear();
+    out.reserve(n * 4);
+    std::vector<char> buf(4u << 20);
+    zs.next_in = reinterpret_cast<Bytef*>(const_cast<char*>(in));
+    size_t left = n;
+    int rc = Z_OK;
+    for (;;) {
+        if (zs.avail_in == 0) {
+            if (left == 0) break;
+            const size_t take = std::min<size_t>(left, 1u << 30);
+            zs.avail_in = (uInt)take; left -= take;
+        }
+        zs.next_out = reinterpret_cast<Bytef*>(buf.data()); zs.avail_out = (uInt)buf.size();
+        rc = inflate(&zs, Z_NO_FLUSH);
+        if (rc != Z_OK && rc != Z_STREAM_END && rc != Z_BUF_ERROR) { inflateEnd(&zs); return false; }
+        out.append(buf.data(), buf.size() - zs.avail_out);
+        if (rc == Z_STREAM_END) {                            // next member of a concatenated gzip file, if any
+            if (zs.avail_in == 0 && left == 0) break;
+            if (inflateReset(&zs) != Z_OK) { inflateEnd(&zs); return false; }
+        } else if (rc == Z_BUF_ERROR && zs.avail_in == 0 && left == 0) break;   // truncated stream: keep what inflated (gzread does)
+    }
+    inflateEnd(&zs);
+    return true;
+}
+
 int movi_host_reads_load(const char* path, int reverse, movi_host_reads** out) {
     if (!path || !out) return fail("null argument");
     *out = nullptr;
@@ -221,7 +253,13 @@ int movi_host_reads_load(const char* path, int reverse, movi_host_reads** out) {
             data = static_cast<const char*>(map);
         }
     }
-    auto cleanup = [&]() { if (map) munmap(map, size); if (fd >= 0) close(fd); };
+    const size_t map_size = size;
+    auto cleanup = [&]() { if (map) munmap(map, map_size); if (fd >= 0) close(fd); };
+    std::string inflated;
+    if (size >= 2 && (unsigned char)data[0] == 0x1f && (unsigned char)data[1] == 0x8b) {
+        if (!gunzip_all(data, size, inflated)) { cleanup(); return fail("corrupt gzip stream in " + std::string(path)); }
+        data = inflated.data(); size = inflated.size();
+    }
     movi_host_reads* rd = new movi_host_reads();
     if (size == 0) { cleanup(); *out = rd; return 0; }
     bool fastq;

@@ -89,6 +89,27 @@ def test_reads_loader_ids_and_sequences():
     assert rev.read(3) == fq.read(3)[::-1]
 
 
+def test_reads_loader_inflates_gzip(tmp_path):
+    """The reference reads its query files through zlib (open_kseq, src/utils.cpp:69-80): .gz inputs, multi-member too."""
+    import gzip
+    for name in ("sample.fastq", "synth300.fasta"):
+        raw = open(reads_path(name), "rb").read()
+        plain = Reads(reads_path(name))
+        one = tmp_path / (name + ".gz")
+        one.write_bytes(gzip.compress(raw))
+        half = raw.rfind(b"\n@" if name.endswith("q") else b"\n>", 0, len(raw) // 2) + 1
+        two = tmp_path / (name + ".2.gz")
+        two.write_bytes(gzip.compress(raw[:half]) + gzip.compress(raw[half:]))
+        for f in (one, two):
+            z = Reads(str(f))
+            assert z.count == plain.count and z.ids() == plain.ids()
+            assert np.array_equal(z.bases, plain.bases) and np.array_equal(z.offsets, plain.offsets)
+    bad = tmp_path / "bad.fa.gz"
+    bad.write_bytes(b"\x1f\x8b" + b"garbage" * 10)
+    with pytest.raises(RuntimeError):
+        Reads(str(bad))
+
+
 def _write_via(fn, *args):
     import tempfile
     with tempfile.TemporaryFile() as f:
