@@ -342,6 +342,25 @@ def main():
         e2e_cls_ms = (time.perf_counter() - t0) * 1e3
         barrier()
 
+    # ---- extra (150 bp reads): byte-wide results (movi_gpu_query_ml8) -- half the copy-back of the headline e2e
+    e2e_ml8_ms, ml8_same = None, True
+    if not is_count:
+        h_out8 = torch.empty(n_bases + 16, dtype=torch.uint8).pin_memory()
+
+        def step_ml8():
+            ms._check(ms._L.movi_gpu_query_ml8(ms._ctx, 1 if W["query"] == "zml" else 0, h_bases.data_ptr(), h_off.data_ptr(), n_reads, 0,
+                                               h_out8.data_ptr()))
+        for _ in range(2):
+            step_ml8()
+        barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_ml8()
+        torch.cuda.synchronize()
+        e2e_ml8_ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        ml8_same = bool(torch.equal(h_out8[: n_bases].to(torch.int16), h_out[: n_bases]))
+
     # keep the GPU under the same load a little longer so that the clock sampler sees it (not part of any number)
     if sampler is not None:
         t_end = time.time() + 1.2
@@ -355,13 +374,14 @@ def main():
     if is_count:
         same = bool(torch.equal(d_cnts[0].cpu(), h_cnt) and torch.equal(d_poss[0].cpu(), h_pos))
     else:
-        same = bool(torch.equal(d_out[: n_bases].cpu(), h_out[: n_bases]))
+        same = bool(torch.equal(d_out[: n_bases].cpu(), h_out[: n_bases])) and ml8_same
 
     if world > 1:
-        t = torch.tensor([elapsed_ms, e2e_ms, e2e_cls_ms or 0.0], dtype=torch.float64, device=dev)
+        t = torch.tensor([elapsed_ms, e2e_ms, e2e_cls_ms or 0.0, e2e_ml8_ms or 0.0], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms, e2e_ms = float(t[0]), float(t[1])
         e2e_cls_ms = float(t[2]) if e2e_cls_ms is not None else None
+        e2e_ml8_ms = float(t[3]) if e2e_ml8_ms is not None else None
         ok = torch.tensor([1 if same else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         same = bool(ok.item())
@@ -399,6 +419,10 @@ def main():
                 "value": total_bases / (e2e_cls_ms * 1e-3), "unit": "bases/s", "ms_per_step": e2e_cls_ms / args.steps,
                 "h2d_bytes_per_step": int(n_bases + 8 * (n_reads + 1)), "d2h_bytes_per_step": int(16 * n_reads),
                 "what": "PML + Classifier::classify fused on the device (movi_gpu_query_classify): --classify / --filter workflows"},
+            "e2e_ml8": None if e2e_ml8_ms is None else {
+                "value": total_bases / (e2e_ml8_ms * 1e-3), "unit": "bases/s", "ms_per_step": e2e_ml8_ms / args.steps,
+                "h2d_bytes_per_step": int(n_bases + 8 * (n_reads + 1)), "d2h_bytes_per_step": int(n_bases),
+                "what": "same query through movi_gpu_query_ml8: reads <= 255 bases, lengths returned as uint8 (identical values)"},
             "clocks": clocks,
             "parity_checked": same,
         }

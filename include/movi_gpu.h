@@ -119,6 +119,13 @@ uint64_t movi_gpu_index_device_bytes(const movi_gpu_ctx* ctx);
  * HOST buffers.  out_ml has read_offsets[n_reads] entries.  Copies in, runs, copies out (pipelined). */
 int  movi_gpu_query_pml(movi_gpu_ctx* ctx, const char* bases, const uint64_t* read_offsets, uint64_t n_reads,
                         uint32_t flags, uint16_t* out_ml);
+/* replaces: query_pml / query_zml for batches of SHORT reads (every read <= 255 bases, e.g. 150 bp Illumina).  A matching
+ * length never exceeds the number of bases consumed (match_len starts at 0 and grows by one per base,
+ * src/move_structure_query.cpp:237-275, :696-766), so it fits one byte: results come back as uint8 -- 1 byte per base over
+ * PCIe instead of 2, the copy that bounds the host-buffer path -- and widen in the caller's MoveQuery::add_ml loop
+ * (INTEGRATION.md).  Same values, same order as movi_gpu_query_pml / _zml.  MOVI_GPU_ERR_ARG if a read is longer. */
+int  movi_gpu_query_ml8(movi_gpu_ctx* ctx, int zml, const char* bases, const uint64_t* read_offsets, uint64_t n_reads,
+                        uint32_t flags, uint8_t* out_ml8);
 /* replaces: query_pml / query_zml FOLLOWED BY Classifier::classify (handle_pml_zml, src/movi.cpp:23-60; src/classifier.cpp:99-143)
  * for the --classify / --filter workflows: the matching lengths are binned where they sit in HBM and only the three report
  * columns per read come back (bins_above, bins_below, sum of bin maxima; found = above / (above + below) > 0.5), i.e. 16 bytes
@@ -160,7 +167,9 @@ int  movi_gpu_classify_device(movi_gpu_ctx* ctx, const uint16_t* d_ml, const uin
 /* Introspection for benchmarks: kernels launched by this context so far, name and time of the last one. */
 uint64_t movi_gpu_launch_count(const movi_gpu_ctx* ctx);
 /* Tuning knobs (benchmarks / profiling / tests): "pml_variant", "blocks_per_sm", "threads_per_block", "batch_bases",
- * "force_wide" (64-bit row indices on small tables), "row_ld_mode", "l2_persist_mb", "l2_fetch_granularity". */
+ * "force_wide" (64-bit row indices on small tables), "row_ld_mode", "l2_persist_mb", "l2_fetch_granularity";
+ * host-buffer pipeline: "batch_bases" (bases per slice), "pipeline_slots" (2..8 slices in flight), "kernel_streams"
+ * (1..4 slices walking concurrently), "size_grid_to_batch" (1: a small batch gets a grid of one read per lane). */
 int  movi_gpu_set_option(movi_gpu_ctx* ctx, const char* key, int64_t value);
 int64_t movi_gpu_get_option(const movi_gpu_ctx* ctx, const char* key);
 

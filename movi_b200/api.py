@@ -173,6 +173,14 @@ class MoveStructure:
                                                     _ptr(above), _ptr(below), _ptr(total), _ptr(ml) if want_ml else None))
         return (above, below, total, ml) if want_ml else (above, below, total)
 
+    def query_ml8(self, bases, offsets, zml=False, out=None):
+        """PML (or ZML) of a batch of reads of at most 255 bases, returned as uint8 (half the copy-back of query_pml)."""
+        bases, offsets, n = self._prep(bases, offsets)
+        if out is None:
+            out = np.empty(int(offsets[-1]) if len(offsets) else 0, dtype=np.uint8)
+        self._check(self._L.movi_gpu_query_ml8(self._ctx, int(zml), _ptr(bases), _ptr(offsets), max(n, 0), 0, _ptr(out)))
+        return out
+
     def query_zml(self, bases, offsets, out=None):
         bases, offsets, n = self._prep(bases, offsets)
         if out is None:

@@ -34,6 +34,22 @@ __global__ void classify_kernel(const uint16_t* __restrict__ ml, const unsigned 
     }
 }
 
+// u16 -> u8 re-pack of a slice of matching lengths (movi_gpu_query_ml8: every read of the batch is <= 255 bases, so no
+// value can exceed 255; clamped anyway).  16 values per thread: two 16-byte loads, one 16-byte store.
+__global__ void narrow_ml_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, unsigned long long n_groups) {
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (; i < n_groups; i += stride) {
+        const uint4 a = in[2 * i], b = in[2 * i + 1];
+        uint4 o;
+        o.x = __byte_perm(__vminu2(a.x, 0x00FF00FFu), __vminu2(a.y, 0x00FF00FFu), 0x6420);
+        o.y = __byte_perm(__vminu2(a.z, 0x00FF00FFu), __vminu2(a.w, 0x00FF00FFu), 0x6420);
+        o.z = __byte_perm(__vminu2(b.x, 0x00FF00FFu), __vminu2(b.y, 0x00FF00FFu), 0x6420);
+        o.w = __byte_perm(__vminu2(b.z, 0x00FF00FFu), __vminu2(b.w, 0x00FF00FFu), 0x6420);
+        out[i] = o;
+    }
+}
+
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
     return x;

@@ -27,15 +27,16 @@ using namespace movi;
 
 namespace {
 
-constexpr int NBUF = 4;                       // pipeline depth of the host-buffer entry points
+constexpr int NBUF = 8;                       // slices in flight in the host-buffer entry points
+constexpr int NKS = 4;                        // kernel streams the slices rotate over
 std::string g_create_error;
 
 struct Staging {                              // one pipeline slot
-    cudaStream_t stream = nullptr;
-    cudaEvent_t done = nullptr;
+    cudaEvent_t in_done = nullptr, k_done = nullptr, out_done = nullptr;
     uint8_t* d_bases = nullptr; size_t bases_cap = 0;
     unsigned long long* d_offsets = nullptr; size_t offsets_cap = 0;   // in elements
     uint16_t* d_ml = nullptr; size_t ml_cap = 0;                        // in elements
+    uint8_t* d_ml8 = nullptr; size_t ml8_cap = 0;                       // movi_gpu_query_ml8: the slice's lengths as bytes
     unsigned long long* d_count = nullptr; int32_t* d_pos = nullptr; size_t count_cap = 0;
     uint32_t* d_above = nullptr; uint32_t* d_below = nullptr; unsigned long long* d_sum = nullptr; size_t cls_cap = 0;
     unsigned long long* d_counter = nullptr;
@@ -66,6 +67,10 @@ struct movi_gpu_ctx {
     unsigned long long* d_counters = nullptr;        // ring of work-queue heads for the *_device calls
     uint32_t counter_slot = 0;
     Staging slot[NBUF];
+    // host-buffer pipeline: every H2D copy goes through st_in and every D2H copy through st_out, in slice order, so that a
+    // copy-back waiting for its kernel never sits in front of the next slice's upload in a copy queue (per-slot streams did
+    // exactly that: gpurun_out/trace_e2e.log of round 1); kernels rotate over st_k so that consecutive slices overlap
+    cudaStream_t st_in = nullptr, st_out = nullptr, st_k[NKS] = {nullptr, nullptr, nullptr, nullptr};
     uint64_t launches = 0;
     // options
     int64_t pml_variant = 4;          // 0/1: branchy kernel (2-byte / 16-byte stores); 2/3: convergent kernel (+/- L2 hints); 4: convergent + sector staging in smem
@@ -76,8 +81,11 @@ struct movi_gpu_ctx {
     int64_t row_ld_mode = 0;          // cache recipe of the row fetch (pml_kernel2.cuh: ld_row)
     int64_t blocks_per_sm = 0;        // 0: occupancy query
     int64_t threads_per_block = 256;
-    int64_t batch_bases = 16ll << 20; // bases per pipeline slot in the host-buffer entry points (D2H of the results is the
+    int64_t batch_bases = 12ll << 20; // bases per pipeline slice in the host-buffer entry points (D2H of the results is the
                                       // bottleneck of the host path: small slices keep the pipeline ramp short)
+    int64_t kernel_streams = 4;       // 1..NKS: slices whose kernels may run concurrently (sweep: profiles/r01_pipeline_sweep.jsonl)
+    int64_t pipeline_slots = NBUF;    // 2..NBUF
+    int64_t size_grid_to_batch = 1;   // 0: always launch the full persistent grid
     // gather probe scratch
     uint2* d_probe = nullptr; uint64_t probe_bytes = 0;
     int64_t probe_vmm_align_mb = 0;   // > 0: allocate the probe table through the VMM API at this alignment
@@ -192,6 +200,10 @@ enum Kind { Q_PML = 0, Q_ZML = 1, Q_COUNT = 2 };
 // enqueue one query kernel on `st` (device pointers)
 int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t st) {
     const int threads = (int)ctx->threads_per_block;
+    // a small batch (a pipeline slice) gets a grid sized to one read per lane instead of the whole machine: full warps
+    // issue a quarter of the instructions of warps holding a handful of reads each, and leave SM room for the kernels of
+    // the neighbouring slices
+    const uint64_t grid_cap = ctx->size_grid_to_batch ? std::max<uint64_t>(1, ((uint64_t)qa.n_reads + threads - 1) / threads) : ~0ull;
     const bool wide = ctx->ix.r > 0xFFFFFFF0ull || ctx->force_wide;   // 64-bit row indices (tables beyond 2^32 rows = 34 GB)
     // optional: keep the row table persisting in L2 (launch attribute; the carve-out is set in set_option)
     cudaLaunchAttribute attr[1];
@@ -211,7 +223,7 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
     do {                                                                          \
         auto k_ = KERNEL;                                                         \
         cudaLaunchConfig_t cfg_ = {};                                             \
-        cfg_.gridDim = dim3((unsigned)blocks_for(ctx, k_, threads));              \
+        cfg_.gridDim = dim3((unsigned)std::min<uint64_t>((uint64_t)blocks_for(ctx, k_, threads), grid_cap)); \
         cfg_.blockDim = dim3((unsigned)threads);                                  \
         cfg_.stream = st;                                                         \
         cfg_.attrs = attr; cfg_.numAttrs = n_attr;                                \
@@ -296,28 +308,32 @@ int grow(movi_gpu_ctx* ctx, T*& p, size_t& cap, size_t need) {
 struct ClassifyOut { uint32_t bin_width = 0, thr = 0; uint32_t* above = nullptr; uint32_t* below = nullptr; uint64_t* sum = nullptr; };
 
 int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* offsets, uint64_t n_reads,
-               uint16_t* out_ml, uint64_t* out_count, int32_t* out_pos, const ClassifyOut* cls = nullptr) {
+               uint16_t* out_ml, uint64_t* out_count, int32_t* out_pos, const ClassifyOut* cls = nullptr, uint8_t* out_ml8 = nullptr) {
     int rc = check_query_ready(ctx, kind, 0);
     if (rc) return rc;
     if (n_reads == 0) return MOVI_GPU_OK;
     if (!bases || !offsets) return fail(ctx, MOVI_GPU_ERR_ARG, "null input buffer");
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemset(ctx->d_status, 0, sizeof(unsigned int)));
-    if (kind == Q_COUNT) { rc = ensure_prefix(ctx, ctx->slot[0].stream); if (rc) return rc; }
+    if (kind == Q_COUNT) { rc = ensure_prefix(ctx, ctx->st_k[0]); if (rc) return rc; }
 
-    uint64_t i0 = 0;
-    int s = 0;
+    const int n_slots = (int)std::min<int64_t>(std::max<int64_t>(ctx->pipeline_slots, 2), NBUF);
+    const int n_ks = (int)std::min<int64_t>(std::max<int64_t>(ctx->kernel_streams, 1), NKS);
     const uint64_t max_bases = (uint64_t)std::max<int64_t>(ctx->batch_bases, 1 << 16);
     // MOVI_GPU_TRACE=1: per-slice device timeline (ms since the first copy was enqueued) on stderr -- a debugging aid for
     // the copy / kernel overlap of this pipeline, off the product path
     static const bool trace = getenv("MOVI_GPU_TRACE") != nullptr;
     std::vector<cudaEvent_t> tev;
     auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
+
+    uint64_t i0 = 0, slice = 0;
     while (i0 < n_reads) {
-        // slice [i0, i1): at least one read, at most max_bases bases (a single longer read gets its own slice)
+        // slice [i0, i1): at least one read, at most max_bases bases (a single longer read gets its own slice); the first
+        // slices are smaller so that the first results start travelling back early
+        const uint64_t want = slice < 2 ? std::max<uint64_t>(max_bases >> (2 - slice), 1 << 16) : max_bases;
         uint64_t i1 = i0 + 1;
         {
-            const uint64_t limit = offsets[i0] + max_bases;
+            const uint64_t limit = offsets[i0] + want;
             // offsets is non-decreasing: binary search the last read that still fits
             uint64_t lo = i0 + 1, hi = std::min<uint64_t>(n_reads, i0 + 0x7FFFFFF0ull);
             while (lo < hi) { uint64_t mid = (lo + hi + 1) / 2; if (offsets[mid] <= limit) lo = mid; else hi = mid - 1; }
@@ -326,8 +342,9 @@ int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* 
         const uint64_t o0 = offsets[i0], o1 = offsets[i1];
         const uint64_t nb = o1 - o0, nr = i1 - i0;
         if (nb >= 0xFFFFFFF0ull) return fail(ctx, MOVI_GPU_ERR_ARG, "a single read longer than 2^32 bases is not supported");
-        Staging& S = ctx->slot[s];
-        if (S.busy) { CU(cudaEventSynchronize(S.done)); S.busy = false; }
+        Staging& S = ctx->slot[slice % n_slots];
+        cudaStream_t kst = ctx->st_k[slice % n_ks];
+        if (S.busy) { CU(cudaEventSynchronize(S.out_done)); S.busy = false; }   // the slot's previous results have left
         // keep the device copy congruent to the host offsets modulo 32: the kernels stage whole aligned 32-byte sectors
         const uint64_t shift = o0 & 31u;
         if ((rc = grow(ctx, S.d_bases, S.bases_cap, nb + shift + 64))) return rc;
@@ -339,45 +356,63 @@ int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* 
         } else {
             if ((rc = grow(ctx, S.d_ml, S.ml_cap, nb + shift + 64))) return rc;
         }
+        if (out_ml8 && (rc = grow(ctx, S.d_ml8, S.ml8_cap, nb + shift + 64))) return rc;
         if (cls) {
             size_t c1 = S.cls_cap, c2 = S.cls_cap;
             if ((rc = grow(ctx, S.d_above, S.cls_cap, nr))) return rc;
             if ((rc = grow(ctx, S.d_below, c1, nr))) return rc;
             if ((rc = grow(ctx, S.d_sum, c2, nr))) return rc;
         }
-        mark(S.stream);
-        CU(cudaMemcpyAsync(S.d_bases + shift, bases + o0, nb, cudaMemcpyHostToDevice, S.stream));
-        CU(cudaMemcpyAsync(S.d_offsets, offsets + i0, (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, S.stream));
-        mark(S.stream);
+        // in
+        mark(ctx->st_in);
+        CU(cudaMemcpyAsync(S.d_bases + shift, bases + o0, nb, cudaMemcpyHostToDevice, ctx->st_in));
+        CU(cudaMemcpyAsync(S.d_offsets, offsets + i0, (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->st_in));
+        CU(cudaEventRecord(S.in_done, ctx->st_in));
+        mark(ctx->st_in);
+        // walk
+        CU(cudaStreamWaitEvent(kst, S.in_done, 0));
         rc = device_query(ctx, kind, reinterpret_cast<const char*>(S.d_bases), reinterpret_cast<const uint64_t*>(S.d_offsets),
-                          o0 - shift, nr, S.d_ml, reinterpret_cast<uint64_t*>(S.d_count), S.d_pos, S.d_counter, S.stream);
+                          o0 - shift, nr, S.d_ml, reinterpret_cast<uint64_t*>(S.d_count), S.d_pos, S.d_counter, kst);
         if (rc) return rc;
-        mark(S.stream);
+        if (cls) {
+            // classify the slice where it sits: only 16 bytes per read travel back instead of 2 bytes per base
+            const unsigned blocks = (unsigned)std::min<uint64_t>((nr * 32 + 255) / 256, (uint64_t)ctx->num_sms * 16);
+            classify_kernel<<<blocks, 256, 0, kst>>>(S.d_ml, S.d_offsets, o0 - shift, nr, cls->bin_width, cls->thr,
+                                                    S.d_above, S.d_below, S.d_sum);
+            ctx->launches += 1;
+            CU(cudaGetLastError());
+        }
+        if (out_ml8) {
+            const unsigned long long groups = (nb + shift + 15) / 16;
+            const unsigned blocks = (unsigned)std::min<uint64_t>((groups + 255) / 256, (uint64_t)ctx->num_sms * 8);
+            narrow_ml_kernel<<<blocks, 256, 0, kst>>>(reinterpret_cast<const uint4*>(S.d_ml), reinterpret_cast<uint4*>(S.d_ml8), groups);
+            ctx->launches += 1;
+            CU(cudaGetLastError());
+        }
+        CU(cudaEventRecord(S.k_done, kst));
+        mark(kst);
+        // out
+        CU(cudaStreamWaitEvent(ctx->st_out, S.k_done, 0));
         if (kind == Q_COUNT) {
-            CU(cudaMemcpyAsync(out_count + i0, S.d_count, nr * sizeof(uint64_t), cudaMemcpyDeviceToHost, S.stream));
-            CU(cudaMemcpyAsync(out_pos + i0, S.d_pos, nr * sizeof(int32_t), cudaMemcpyDeviceToHost, S.stream));
+            CU(cudaMemcpyAsync(out_count + i0, S.d_count, nr * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->st_out));
+            CU(cudaMemcpyAsync(out_pos + i0, S.d_pos, nr * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->st_out));
         } else {
             if (cls) {
-                // classify the slice where it sits: only 16 bytes per read travel back instead of 2 bytes per base
-                const unsigned blocks = (unsigned)std::min<uint64_t>((nr * 32 + 255) / 256, (uint64_t)ctx->num_sms * 16);
-                classify_kernel<<<blocks, 256, 0, S.stream>>>(S.d_ml, S.d_offsets, o0 - shift, nr, cls->bin_width, cls->thr,
-                                                             S.d_above, S.d_below, S.d_sum);
-                ctx->launches += 1;
-                CU(cudaGetLastError());
-                CU(cudaMemcpyAsync(cls->above + i0, S.d_above, nr * sizeof(uint32_t), cudaMemcpyDeviceToHost, S.stream));
-                CU(cudaMemcpyAsync(cls->below + i0, S.d_below, nr * sizeof(uint32_t), cudaMemcpyDeviceToHost, S.stream));
-                CU(cudaMemcpyAsync(cls->sum + i0, S.d_sum, nr * sizeof(uint64_t), cudaMemcpyDeviceToHost, S.stream));
+                CU(cudaMemcpyAsync(cls->above + i0, S.d_above, nr * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->st_out));
+                CU(cudaMemcpyAsync(cls->below + i0, S.d_below, nr * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->st_out));
+                CU(cudaMemcpyAsync(cls->sum + i0, S.d_sum, nr * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->st_out));
             }
-            if (out_ml) CU(cudaMemcpyAsync(out_ml + o0, S.d_ml + shift, nb * sizeof(uint16_t), cudaMemcpyDeviceToHost, S.stream));
+            if (out_ml) CU(cudaMemcpyAsync(out_ml + o0, S.d_ml + shift, nb * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->st_out));
+            if (out_ml8) CU(cudaMemcpyAsync(out_ml8 + o0, S.d_ml8 + shift, nb, cudaMemcpyDeviceToHost, ctx->st_out));
         }
-        mark(S.stream);
-        CU(cudaEventRecord(S.done, S.stream));
+        CU(cudaEventRecord(S.out_done, ctx->st_out));
+        mark(ctx->st_out);
         S.busy = true;
-        s = (s + 1) % NBUF;
+        slice += 1;
         i0 = i1;
     }
-    for (int k = 0; k < NBUF; k++)
-        if (ctx->slot[k].busy) { CU(cudaEventSynchronize(ctx->slot[k].done)); ctx->slot[k].busy = false; }
+    CU(cudaStreamSynchronize(ctx->st_out));            // st_out runs in slice order: its end is the end of the batch
+    for (int k = 0; k < NBUF; k++) ctx->slot[k].busy = false;
     if (trace) {
         for (size_t k = 0; k + 3 < tev.size(); k += 4) {
             float t[4];
@@ -425,9 +460,13 @@ int movi_gpu_create(int device, movi_gpu_ctx** out) {
     cudaError_t e2 = cudaMalloc(&c->d_status, sizeof(unsigned int));
     if (e2 == cudaSuccess) e2 = cudaMemset(c->d_status, 0, sizeof(unsigned int));
     if (e2 == cudaSuccess) e2 = cudaMalloc(&c->d_counters, 64 * sizeof(unsigned long long));
+    if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking);
+    if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking);
+    for (int k = 0; k < NKS && e2 == cudaSuccess; k++) e2 = cudaStreamCreateWithFlags(&c->st_k[k], cudaStreamNonBlocking);
     for (int k = 0; k < NBUF && e2 == cudaSuccess; k++) {
-        e2 = cudaStreamCreateWithFlags(&c->slot[k].stream, cudaStreamNonBlocking);
-        if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&c->slot[k].done, cudaEventDisableTiming);
+        e2 = cudaEventCreateWithFlags(&c->slot[k].in_done, cudaEventDisableTiming);
+        if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&c->slot[k].k_done, cudaEventDisableTiming);
+        if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&c->slot[k].out_done, cudaEventDisableTiming);
         if (e2 == cudaSuccess) e2 = cudaMalloc(&c->slot[k].d_counter, sizeof(unsigned long long));
     }
     if (e2 != cudaSuccess) {
@@ -446,11 +485,15 @@ int movi_gpu_destroy(movi_gpu_ctx* ctx) {
     free_index(ctx);
     for (int k = 0; k < NBUF; k++) {
         Staging& S = ctx->slot[k];
-        cudaFree(S.d_bases); cudaFree(S.d_offsets); cudaFree(S.d_ml); cudaFree(S.d_count); cudaFree(S.d_pos); cudaFree(S.d_counter);
+        cudaFree(S.d_bases); cudaFree(S.d_offsets); cudaFree(S.d_ml); cudaFree(S.d_ml8); cudaFree(S.d_count); cudaFree(S.d_pos); cudaFree(S.d_counter);
         cudaFree(S.d_above); cudaFree(S.d_below); cudaFree(S.d_sum);
-        if (S.done) cudaEventDestroy(S.done);
-        if (S.stream) cudaStreamDestroy(S.stream);
+        if (S.in_done) cudaEventDestroy(S.in_done);
+        if (S.k_done) cudaEventDestroy(S.k_done);
+        if (S.out_done) cudaEventDestroy(S.out_done);
     }
+    if (ctx->st_in) cudaStreamDestroy(ctx->st_in);
+    if (ctx->st_out) cudaStreamDestroy(ctx->st_out);
+    for (int k = 0; k < NKS; k++) if (ctx->st_k[k]) cudaStreamDestroy(ctx->st_k[k]);
     cudaFree(ctx->d_status); cudaFree(ctx->d_counters);
     if (ctx->probe_vmm[0]) { VmmBlock b; b.ptr = ctx->probe_vmm[0]; b.size = ctx->probe_vmm[1]; b.handle = ctx->probe_vmm[2]; vmm_free(&b); }
     else cudaFree(ctx->d_probe);
@@ -491,6 +534,9 @@ int movi_gpu_set_option(movi_gpu_ctx* ctx, const char* key, int64_t value) {
         ctx->threads_per_block = value;
     }
     else if (k == "batch_bases") { if (value < (1 << 16)) return fail(ctx, MOVI_GPU_ERR_ARG, "batch_bases: >= 65536"); ctx->batch_bases = value; }
+    else if (k == "kernel_streams") { if (value < 1 || value > NKS) return fail(ctx, MOVI_GPU_ERR_ARG, "kernel_streams: 1..4"); ctx->kernel_streams = value; }
+    else if (k == "pipeline_slots") { if (value < 2 || value > NBUF) return fail(ctx, MOVI_GPU_ERR_ARG, "pipeline_slots: 2..8"); ctx->pipeline_slots = value; }
+    else if (k == "size_grid_to_batch") { ctx->size_grid_to_batch = value != 0; }
     else return fail(ctx, MOVI_GPU_ERR_ARG, "unknown option " + k);
     return MOVI_GPU_OK;
 }
@@ -501,6 +547,9 @@ int64_t movi_gpu_get_option(const movi_gpu_ctx* ctx, const char* key) {
     if (k == "blocks_per_sm") return ctx->blocks_per_sm;
     if (k == "threads_per_block") return ctx->threads_per_block;
     if (k == "batch_bases") return ctx->batch_bases;
+    if (k == "kernel_streams") return ctx->kernel_streams;
+    if (k == "pipeline_slots") return ctx->pipeline_slots;
+    if (k == "size_grid_to_batch") return ctx->size_grid_to_batch;
     if (k == "num_sms") return ctx->num_sms;
     if (k == "row_ld_mode") return ctx->row_ld_mode;
     if (k == "force_wide") return ctx->force_wide;
@@ -550,7 +599,7 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
 
     CU(cudaSetDevice(ctx->device));
     free_index(ctx);
-    cudaStream_t st = ctx->slot[0].stream;
+    cudaStream_t st = ctx->st_k[0];
     const unsigned long long r = d->r;
     // Device layout: EXPANDED8 unless the caller asks for COMPACT, or AUTO finds that the expanded table (plus the raw
     // copy the conversion needs) does not fit in free HBM.  COMPACT exists for blocked-thresholds (its 6-byte rows are
@@ -718,6 +767,18 @@ int movi_gpu_query_classify(movi_gpu_ctx* ctx, int zml, const char* bases, const
     if (rc) return rc;
     ClassifyOut c; c.bin_width = bin_width; c.thr = max_value_thr; c.above = out_bins_above; c.below = out_bins_below; c.sum = out_sum_max;
     return host_query(ctx, kind, bases, read_offsets, n_reads, out_ml, nullptr, nullptr, &c);
+}
+
+int movi_gpu_query_ml8(movi_gpu_ctx* ctx, int zml, const char* bases, const uint64_t* read_offsets, uint64_t n_reads, uint32_t,
+                       uint8_t* out_ml8) {
+    const Kind kind = zml ? Q_ZML : Q_PML;
+    int rc = check_query_ready(ctx, kind, n_reads);
+    if (rc) return rc;
+    if (n_reads && (!read_offsets || !out_ml8)) return fail(ctx, MOVI_GPU_ERR_ARG, "null buffer");
+    uint64_t longest = 0;
+    for (uint64_t i = 0; i < n_reads; i++) longest = std::max(longest, read_offsets[i + 1] - read_offsets[i]);
+    if (longest > 255) return fail(ctx, MOVI_GPU_ERR_ARG, "movi_gpu_query_ml8: a read is longer than 255 bases (its lengths may not fit one byte); use the 16-bit entry points");
+    return host_query(ctx, kind, bases, read_offsets, n_reads, nullptr, nullptr, nullptr, nullptr, out_ml8);
 }
 
 int movi_gpu_query_zml(movi_gpu_ctx* ctx, const char* bases, const uint64_t* read_offsets, uint64_t n_reads,

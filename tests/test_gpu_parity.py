@@ -266,3 +266,29 @@ def test_fused_query_classify_matches_oracle(structures, index_dirs, read_sets, 
                         continue
                     _, ea, eb, es, _ = classify(v, 150, 7)
                     assert (a[i], b[i], s[i]) == (ea, eb, es), i
+
+
+@pytest.mark.parametrize("typ", ["regular-thresholds", "blocked-thresholds", "sampled-thresholds"])
+def test_byte_wide_results_for_short_reads(structures, index_dirs, read_sets, ref_seq, typ):
+    """movi_gpu_query_ml8: reads of <= 255 bases come back as uint8, equal to the oracle's uint16 values; a longer read is
+    refused (its lengths may not fit one byte)."""
+    from movi_b200 import MoviGpuError
+    from oracle.port import OracleIndex, pack_reads
+    ms = structures[(typ, False)]
+    orc = OracleIndex(index_dirs[(typ, False)])
+    sets = [(read_sets["sample.fastq"].bases, read_sets["sample.fastq"].offsets), pack_reads(_random_reads(31, 6000, 255, ref_seq))]
+    old = ms.get_option("batch_bases")
+    for bases, offsets in sets:
+        for zml in ((False,) if typ == "sampled-thresholds" else (False, True)):
+            want = orc.query_zml(bases, offsets, threads=0) if zml else orc.query_pml(bases, offsets, threads=0)
+            assert want.max() <= 255
+            for batch in (old, 65536):
+                ms.set_option("batch_bases", batch)
+                try:
+                    got = ms.query_ml8(bases, offsets, zml=zml)
+                finally:
+                    ms.set_option("batch_bases", old)
+                assert got.dtype == np.uint8 and np.array_equal(got, want.astype(np.uint8))
+    bases, offsets = pack_reads([b"ACGT" * 64])          # 256 bases
+    with pytest.raises(MoviGpuError, match="longer than 255"):
+        ms.query_ml8(bases, offsets)
