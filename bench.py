@@ -32,7 +32,7 @@ WORKLOAD = "c2"                   # synthetic data set (movi_b200/datagen/synth.
 # --workload: c2 is the bench line of BASELINE.json (configs[1]); the c3-* lines are configs[2] (same pangenome, blocked-thresholds
 # index, ZML / count).  Algorithmic bytes per base: one 32-byte row sector per LF step (PML), two interval ends for ZML / count.
 WORKLOADS = {
-    "c2": dict(index="regular-thresholds", query="pml", metric="PML query bases/sec", algo=32, kernel="movi_pml_kernel3<uint32_t,false,6,R8>"),
+    "c2": dict(index="regular-thresholds", query="pml", metric="PML query bases/sec", algo=32, kernel="movi_pml_kernel4<uint32_t,false,6,R8>"),
     "c3-zml": dict(index="blocked-thresholds", query="zml", metric="ZML query bases/sec", algo=64, kernel="movi_bs_kernel2<uint32_t,ZML,R8>"),
     "c3-count": dict(index="blocked-thresholds", query="count", metric="count query bases/sec (all bases of the reads)", algo=64,
                      kernel="movi_bs_kernel2<uint32_t,COUNT,R8>"),

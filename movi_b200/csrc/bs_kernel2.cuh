@@ -65,9 +65,12 @@ movi_bs_kernel2(const DevIndex ix, const QueryArgs q) {
     uint32_t cur = 0, start = 0, op = 0, m = 0, code = 0, pend = 0;
     bool need_chunk = false;
 
+    constexpr uint32_t REFILL_EVERY = 4;      // idle lanes are looked after every 4th iteration only (see pml_kernel4.cuh)
+    uint32_t tick = 0;
     for (;;) {
-        const bool want = (pst == B_IDLE) && !exhausted;
-        const unsigned bm = __ballot_sync(FULL, want);
+        const bool service = (tick++ & (REFILL_EVERY - 1u)) == 0u;
+        const bool want = service && (pst == B_IDLE) && !exhausted;
+        const unsigned bm = service ? __ballot_sync(FULL, want) : 0u;
         if (bm) {
             if (q_next == q_end) {
                 // guided self-scheduling: take 32 reads per refill while plenty remain, fewer as the batch drains, so that
@@ -83,11 +86,23 @@ movi_bs_kernel2(const DevIndex ix, const QueryArgs q) {
             }
             const uint32_t avail = q_end - q_next;
             const uint32_t rank = __popc(bm & lt_mask);
-            if (want && rank < avail) { ri = q_next + rank; pst = B_NEW; }
+            if (want && rank < avail) {          // start a read where it is handed out (rare branch)
+                ri = q_next + rank;
+                const uint2 a = ldg64(offs8 + ri), b = ldg64(offs8 + ri + 1);
+                const unsigned long long s = (((unsigned long long)a.y << 32) | a.x) - q.origin;
+                const unsigned long long e = (((unsigned long long)b.y << 32) | b.x) - q.origin;
+                start = (uint32_t)s; op = (uint32_t)s; m = 0; pend = 0; inscan = false;
+                if (e == s) {                       // empty read: outside the reference's domain (it indexes R[-1])
+                    if (KIND == KIND_COUNT) { q.out_count[ri] = 0; q.out_pos[ri] = 0; }
+                    pst = B_IDLE;
+                } else {
+                    cur = (uint32_t)e - 1; need_chunk = true; pst = B_SKIP;
+                }
+            }
             const uint32_t cnt = __popc(bm);
             q_next += cnt < avail ? cnt : avail;
         }
-        if (exhausted && __all_sync(FULL, pst == B_IDLE)) break;
+        if (service && exhausted && __all_sync(FULL, pst == B_IDLE)) break;
 
         // ---- loads
         const bool run = (pst == B_RUN);
@@ -101,26 +116,16 @@ movi_bs_kernel2(const DevIndex ix, const QueryArgs q) {
                 vE = fetch_row_b6<IdxT>(ix.rows6, re, end_idx, idb, ix.id_blocks_size, ix.block_shift, s_first_runs);
             }
         }
-        if (chunk_user && need_chunk) {
-            const uint8_t* src = bases + (cur & ~31u);
-            cp_async16(in_slot, src);
-            cp_async16(in_slot + 16, src + 16);
-        }
         const bool staged = chunk_user && need_chunk;
-        if (pst == B_NEW) {
-            const uint2 a = ldg64(offs8 + ri), b = ldg64(offs8 + ri + 1);
-            const unsigned long long s = (((unsigned long long)a.y << 32) | a.x) - q.origin;
-            const unsigned long long e = (((unsigned long long)b.y << 32) | b.x) - q.origin;
-            start = (uint32_t)s; op = (uint32_t)s; m = 0; pend = 0; inscan = false;
-            if (e == s) {                       // empty read: outside the reference's domain (it indexes R[-1])
-                if (KIND == KIND_COUNT) { q.out_count[ri] = 0; q.out_pos[ri] = 0; }
-                pst = B_IDLE;
-            } else {
-                cur = (uint32_t)e - 1; need_chunk = true; pst = B_SKIP;
+        if (__any_sync(FULL, staged)) {          // about half of the iterations have no lane that needs a new sector
+            if (staged) {
+                const uint8_t* src = bases + (cur & ~31u);
+                cp_async16(in_slot, src);
+                cp_async16(in_slot + 16, src + 16);
             }
+            cp_async_wait_all();
+            if (staged) need_chunk = false;
         }
-        cp_async_wait_all();
-        if (staged) need_chunk = false;
 
         bool do_emit = false, last = false;
         uint32_t val = 0;

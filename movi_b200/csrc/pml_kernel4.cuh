@@ -1,0 +1,206 @@
+// pml_kernel4.cuh -- PML kernel, variant 5: variant 4 (pml_kernel3.cuh) with a leaner hot loop.
+//
+// Same state machine, same streaming through shared memory; what changed (all aimed at the instruction count of the
+// warp iteration, which bounds variant 4 on L2-sized tables -- profiles/r01_summary.md):
+//   * a read is started where it is handed out (inside the rarely taken refill branch) instead of spending one warp
+//     iteration in a ST_NEW state: one iteration per read less, and the common path loses the ST_NEW bookkeeping;
+//   * staging of the next 32-byte sector of read bytes (cp.async + wait) sits behind a warp vote: about half of the
+//     iterations have no lane that needs it;
+//   * per-lane shared-memory slots are addressed through 32-bit shared-window addresses (ld.shared / st.shared), not
+//     generic pointers.
+#pragma once
+#include "dev_index.cuh"
+#include "pml_kernel.cuh"
+#include "pml_kernel2.cuh"
+#include "pml_kernel3.cuh"
+
+namespace movi {
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "h"((unsigned short)v) : "memory"); }
+__device__ __forceinline__ uint4 lds_128(uint32_t a) {
+    uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ void cp_async16_s(uint32_t s, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem) : "memory");
+}
+
+template <typename IdxT, bool SEP, int MINB, int LAYOUT>
+__global__ void __launch_bounds__(PML3_THREADS, MINB)
+movi_pml_kernel4(const DevIndex ix, const QueryArgs q) {
+    __shared__ uint8_t s_code[256];
+    __shared__ uint32_t s_end_thr[4];
+    __shared__ uint32_t s_idb[LAYOUT == LAYOUT_B6 ? IDB_SMEM : 1];
+    __shared__ unsigned long long s_first[8];
+    const uint32_t idb_n = ix.id_blocks_size * ix.sigma;
+    const bool idb_in_smem = LAYOUT == LAYOUT_B6 && idb_n <= IDB_SMEM;
+    if (LAYOUT == LAYOUT_B6) {
+        if (idb_in_smem) for (uint32_t i = threadIdx.x; i < idb_n; i += blockDim.x) s_idb[i] = ix.id_blocks[i];
+        if (threadIdx.x < 8) s_first[threadIdx.x] = ix.first_runs[threadIdx.x];
+    }
+    const uint32_t* const idb = idb_in_smem ? s_idb : ix.id_blocks;
+    __shared__ __align__(32) uint8_t s_in[PML3_THREADS * 32];      // per lane: the 32-byte sector of its read that holds bases[rp]
+    __shared__ __align__(32) uint16_t s_out[PML3_THREADS * 16];    // per lane: the 32-byte sector of its output being filled
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_code[i] = ix.code_of[i];
+    if (threadIdx.x < 4) s_end_thr[threadIdx.x] = ix.end_thr[threadIdx.x];
+    __syncthreads();
+
+    const unsigned long long pol_keep = policy_evict_last();
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const IdxT r1 = (IdxT)(ix.r - 1);
+    const IdxT end_idx = (IdxT)ix.end_idx;
+    const uint2* __restrict__ rows = ix.rows;
+    const uint8_t* __restrict__ bases = q.bases;
+    const uint2* __restrict__ offs8 = reinterpret_cast<const uint2*>(q.offsets);
+    uint16_t* const out_slot = s_out + threadIdx.x * 16;              // (generic pointer: only the rare ragged flush uses it)
+    const uint32_t sa_in = smem_addr(s_in) + threadIdx.x * 32u;       // shared-window addresses of this lane's slots
+    const uint32_t sa_out = smem_addr(s_out) + threadIdx.x * 32u;
+    const uint32_t sa_code = smem_addr(s_code);
+    constexpr uint32_t sep = SEP ? 1u : 0u;
+    constexpr uint32_t REFILL_EVERY = 4;
+    const uint32_t n_reads = q.n_reads;
+
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t q_next = 0, q_end = 0, chunk = min(QUEUE_CHUNK, max(1u, n_reads / (2u * n_warps)));
+    bool exhausted = false;
+    uint32_t st = ST_IDLE;
+    IdxT idx = 0;
+    uint32_t off = 0, ml = 0, rp = 0, op = 0, rem = 0, pend = 0;
+    bool need_chunk = false;
+
+    uint32_t tick = 0;
+    for (;;) {
+        // idle lanes are looked after every REFILL_EVERY-th iteration only: a finished lane waits <= 3 of the ~240
+        // iterations of a 150-base read, and the other iterations skip the vote / queue bookkeeping
+        const bool service = (tick++ & (REFILL_EVERY - 1u)) == 0u;
+        const bool want = service && (st == ST_IDLE) && !exhausted;
+        const unsigned m = service ? __ballot_sync(FULL, want) : 0u;
+        if (m) {
+            if (q_next == q_end) {
+                // guided self-scheduling: take 32 reads per refill while plenty remain, fewer as the batch drains, so that
+                // no warp sits on a private backlog while the lanes of other warps have already gone idle
+                unsigned long long b = 0;
+                if (lane == 0) b = atomicAdd(q.counter, (unsigned long long)chunk);
+                b = __shfl_sync(FULL, b, 0);
+                q_next = b < n_reads ? (uint32_t)b : n_reads;
+                q_end = b + chunk < n_reads ? (uint32_t)(b + chunk) : n_reads;
+                if (q_next == q_end) exhausted = true;
+                const uint32_t left = n_reads - q_end;
+                chunk = min(QUEUE_CHUNK, max(1u, left / (2u * n_warps)));
+            }
+            const uint32_t avail = q_end - q_next;
+            const uint32_t rank = __popc(m & lt_mask);
+            if (want && rank < avail) {                                   // start a read (query_pml :237-240)
+                const uint32_t ri = q_next + rank;
+                const uint2 a = ldg64(offs8 + ri), b = ldg64(offs8 + ri + 1);
+                const unsigned long long s = (((unsigned long long)a.y << 32) | a.x) - q.origin;
+                const unsigned long long e = (((unsigned long long)b.y << 32) | b.x) - q.origin;
+                rem = (uint32_t)(e - s);
+                rp = (uint32_t)e - 1; op = (uint32_t)s;
+                idx = r1; off = ix.n_last - 1; ml = 0; pend = 0;
+                st = rem ? ST_FF : ST_IDLE;                                // (an empty read leaves the lane idle: it asks again)
+                need_chunk = true;
+            }
+            const uint32_t cnt = __popc(m);
+            q_next += cnt < avail ? cnt : avail;
+        }
+        if (service && exhausted && __all_sync(FULL, st == ST_IDLE)) break;
+
+        // ---- loads: row fetch for every walking lane; a lane that ran out of staged read bytes pulls the next sector
+        const bool proc = (st != ST_IDLE);
+        // (lanes that are not walking fetch row 0: harmless and keeps the fetch out of a divergent branch)
+        const IdxT fidx = proc ? idx : (IdxT)0;
+        uint2 v;
+        if (LAYOUT == LAYOUT_R8) v = ld_keep(rows + fidx, pol_keep);
+        else if (LAYOUT == LAYOUT_B6) v = fetch_row_b6<IdxT>(ix.rows6, fidx, end_idx, idb, ix.id_blocks_size, ix.block_shift, s_first);
+        else {              // LAYOUT_T3: the 3-byte row without its destination id (resolved below, only when an LF step needs it)
+            const uint32_t x = Rows3{ix.rows3, (unsigned long long)end_idx}.raw((unsigned long long)fidx);
+            v = make_r8(0, Rows3::n_of(x), Rows3::off_of(x), Rows3::c_of(x), Rows3::thr_of(x));
+        }
+        if (__any_sync(FULL, proc && need_chunk)) {
+            if (proc && need_chunk) {
+                const uint8_t* src = bases + (rp & ~31u);
+                cp_async16_s(sa_in, src);
+                cp_async16_s(sa_in + 16u, src + 16);
+            }
+            cp_async_wait_all();
+            need_chunk = need_chunk && !proc;
+        }
+
+        // ---- one predicate-driven step of the state machine for every lane
+        const uint32_t y = v.y;
+        const uint32_t n = row_n(y);
+        const uint32_t c = row_c(y);
+        const uint32_t code = lds_u8(sa_code + lds_u8(sa_in + (rp & 31u)));
+        const bool is_ff = (st == ST_FF);
+        const bool is_scan = (st >= ST_UP);
+        const bool scan_up = (st == ST_UP);
+        const bool hit = (c == code);
+        const bool ffmove = is_ff && (idx < r1) && (off >= n);            // fast_forward, move_structure.cpp:524-545
+        const bool at_base = is_ff && !ffmove;
+        const bool base_mis = at_base && !hit && (code != CODE_ILLEGAL);   // Case 2, query.cpp:297-350
+        const bool scan_hit = is_scan && hit;
+        const bool scan_move = is_scan && !hit;
+        const bool emit = (at_base && !base_mis) || scan_hit;
+
+        const uint32_t ai = code - sep;
+        uint32_t thr = ((row_thr_bits(y) >> (thr_slot(c - sep, ai) & 3u)) & 1u) ? n : 0u;
+        if (base_mis & ((idx == end_idx) | (SEP & (c == 0)))) {            // '$' row / '%' rows: rare, skipped warp-wide
+            thr = (idx == end_idx) ? s_end_thr[ai & 3u] : sep_threshold(ix, (unsigned long long)idx, ai);
+        }
+        const bool down = off >= thr;
+        const bool mv_down = (scan_move && !scan_up) || (base_mis && down);
+        const bool mv_up = (scan_move && scan_up) || (base_mis && !down);
+        const bool bad = (mv_up && idx == 0) || (mv_down && idx == r1);
+
+        ml = (at_base && hit) ? ml + 1 : (emit ? 0u : ml);
+        off = ffmove ? off - n : (scan_hit ? (scan_up ? n - 1 : 0u) : off);
+
+        const bool fin = emit && (rem == 1u);
+        const bool lf = emit && !fin;
+        if (emit) {
+            sts_u16(sa_out + 2u * (op & 15u), ml < 65535u ? ml : 65535u);  // add_ml clamp
+            pend += 1;
+            if ((op & 15u) == 15u || fin) {
+                uint16_t* g = q.out_ml + (op & ~15u);
+                if (pend == 16u) {
+                    const uint4 lo = lds_128(sa_out);
+                    const uint4 hi = lds_128(sa_out + 16u);
+                    *reinterpret_cast<uint4*>(g) = lo;
+                    *reinterpret_cast<uint4*>(g + 8) = hi;
+                } else {
+                    // ragged head / tail of a read: only our own slots [lo, hi] of the sector, widest aligned pieces first
+                    uint32_t lo = (op & 15u) + 1u - pend;
+                    const uint32_t hi1 = (op & 15u) + 1u;                  // one past the last slot
+                    if ((lo & 1u) && lo < hi1) { g[lo] = out_slot[lo]; lo += 1; }
+                    if ((lo & 2u) && lo + 2 <= hi1) { *reinterpret_cast<uint32_t*>(g + lo) = *reinterpret_cast<const uint32_t*>(out_slot + lo); lo += 2; }
+                    if ((lo & 4u) && lo + 4 <= hi1) { *reinterpret_cast<uint2*>(g + lo) = *reinterpret_cast<const uint2*>(out_slot + lo); lo += 4; }
+                    if (lo + 8 <= hi1) { *reinterpret_cast<uint4*>(g + lo) = *reinterpret_cast<const uint4*>(out_slot + lo); lo += 8; }
+                    if (lo + 4 <= hi1) { *reinterpret_cast<uint2*>(g + lo) = *reinterpret_cast<const uint2*>(out_slot + lo); lo += 4; }
+                    if (lo + 2 <= hi1) { *reinterpret_cast<uint32_t*>(g + lo) = *reinterpret_cast<const uint32_t*>(out_slot + lo); lo += 2; }
+                    if (lo < hi1) g[lo] = out_slot[lo];
+                }
+                pend = 0;
+            }
+        }
+        op += emit ? 1u : 0u;
+        rem -= emit ? 1u : 0u;
+        need_chunk = need_chunk || (lf && (rp & 31u) == 0u);
+        rp -= lf ? 1u : 0u;
+        off += lf ? row_off(y) : 0u;                                        // LF_move, move_structure.cpp:66
+        IdxT lf_id = row_id<IdxT>(v);
+        bool bad_id = false;
+        if (LAYOUT == LAYOUT_T3) {
+            // sampled-thresholds: get_id = checkpoint scan + walk-back (src/move_structure.cpp:103-219), per LF step
+            if (lf) lf_id = (IdxT)sampled_get_id(Rows3{ix.rows3, (unsigned long long)end_idx}, ix.tally, ix.tally_len, ix.tally_cp, ix.r,
+                                                 (unsigned long long)end_idx, (unsigned long long)idx, c, &bad_id);
+        }
+        idx = lf ? lf_id : (ffmove || mv_down) ? idx + 1 : (mv_up ? idx - 1 : idx);
+        st = fin ? ST_IDLE : lf ? ST_FF : base_mis ? (down ? ST_DOWN : ST_UP) : st;
+        if (bad || bad_id) { atomicOr(q.status, bad_id ? 2u : 1u); st = ST_IDLE; }
+    }
+}
+
+}  // namespace movi
