@@ -398,8 +398,8 @@ def main():
             work_bases = int(np.minimum(L, L - h_pos.numpy().astype(np.int64) + 1).sum())
         achieved = W["algo"] * work_bases / per_launch_s / 1e9
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "pml_c2_traffic.json")
-        if args.workload == "c2" and os.path.exists(tp):
+        tp = os.path.join(ROOT, "profiles", {"c2": "pml_c2_traffic.json", "c3-zml": "zml_c3_traffic.json", "c3-count": "count_c3_traffic.json"}[args.workload])
+        if os.path.exists(tp):
             try:
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             except Exception:

@@ -15,6 +15,7 @@
 #pragma once
 #include "bs_kernel.cuh"
 #include "pml_kernel3.cuh"
+#include "pml_kernel4.cuh"
 
 namespace movi {
 
@@ -41,6 +42,7 @@ movi_bs_kernel2(const DevIndex ix, const QueryArgs q) {
     __syncthreads();
 
     const unsigned long long pol_keep = policy_evict_last();
+    const unsigned long long pol_stream = policy_evict_first();
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     const IdxT r1 = (IdxT)(ix.r - 1);
@@ -49,6 +51,7 @@ movi_bs_kernel2(const DevIndex ix, const QueryArgs q) {
     const uint8_t* __restrict__ bases = q.bases;
     const uint2* __restrict__ offs8 = reinterpret_cast<const uint2*>(q.offsets);
     uint8_t* const in_slot = s_in + threadIdx.x * 32;
+    const uint32_t sa_in = smem_addr(s_in) + threadIdx.x * 32u;
     uint16_t* const out_slot = s_out + (KIND == KIND_ZML ? threadIdx.x * 16 : 0);
     const uint32_t n_reads = q.n_reads;
 
@@ -120,8 +123,8 @@ movi_bs_kernel2(const DevIndex ix, const QueryArgs q) {
         if (__any_sync(FULL, staged)) {          // about half of the iterations have no lane that needs a new sector
             if (staged) {
                 const uint8_t* src = bases + (cur & ~31u);
-                cp_async16(in_slot, src);
-                cp_async16(in_slot + 16, src + 16);
+                cp_async16_stream(sa_in, src, pol_stream);            // streamed data: evict_first in L2 (pml_kernel4.cuh)
+                cp_async16_stream(sa_in + 16u, src + 16, pol_stream);
             }
             cp_async_wait_all();
             if (staged) need_chunk = false;
@@ -220,8 +223,8 @@ movi_bs_kernel2(const DevIndex ix, const QueryArgs q) {
                     if (pend == 16u) {
                         const uint4 lo4 = *reinterpret_cast<const uint4*>(out_slot);
                         const uint4 hi4 = *reinterpret_cast<const uint4*>(out_slot + 8);
-                        *reinterpret_cast<uint4*>(g) = lo4;
-                        *reinterpret_cast<uint4*>(g + 8) = hi4;
+                        st_stream128(g, lo4, pol_stream);
+                        st_stream128(g + 8, hi4, pol_stream);
                     } else {
                         uint32_t lo = (op & 15u) + 1u - pend;
                         const uint32_t hi1 = (op & 15u) + 1u;

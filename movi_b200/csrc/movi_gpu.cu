@@ -75,6 +75,7 @@ struct movi_gpu_ctx {
     uint64_t launches = 0;
     // options
     int64_t pml_variant = 5;          // 0/1: branchy kernel (2-byte / 16-byte stores); 2/3: convergent kernel (+/- L2 hints); 4: convergent + sector staging in smem; 5: 4 with a leaner loop + evict_first on the streamed data (pml_kernel4.cuh); 6: 5 without those hints
+    int64_t pml_sector = 0;           // sector-cached row fetch: -1 by table size (> 512 MB), 0 off, 1 on  (off until measured)
     int64_t l2_persist_mb = 0;        // > 0: mark the row table persisting in L2 (access policy window) for query launches
     int64_t l2_fetch_granularity = 0; // 0: leave the device default; 32 / 64 / 128: cudaLimitMaxL2FetchGranularity
     int64_t bs_variant = 1;           // count / ZML kernel: 0 = branch-per-state (bs_kernel.cuh), 1 = convergent + sector staging
@@ -240,7 +241,11 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
             // 6 blocks/SM (40 registers) measured fastest on both L2-sized (c2) and HBM-resident (8-64 GB) tables -- the
             // latter are bound by the memory system's random-request rate, not by exposed latency (profiles/r01_big_tables.jsonl)
             const bool b6 = ctx->ix.layout == LAYOUT_B6, t3 = ctx->ix.layout == LAYOUT_T3;
+            // tables far beyond the L2 are bound by the request rate of the memory system, not by issue: there the kernel keeps
+            // the last fetched 32-byte sector in registers (variant 7; "pml_sector" -1 = by table size, 0 / 1 = off / on)
+            const bool sector = variant == 7 || (variant == 5 && (ctx->pml_sector == 1 || (ctx->pml_sector < 0 && ctx->ix.r * sizeof(uint2) > (512ull << 20))));
 #define PML3(IDX, SEPV) do { if (variant == 6 && !t3 && !b6) LAUNCH((movi_pml_kernel4<IDX, SEPV, 6, LAYOUT_R8, false>)); \
+                             else if (sector && !t3 && !b6) LAUNCH((movi_pml_kernel4<IDX, SEPV, 5, LAYOUT_R8, true, true>)); \
                              else if (variant >= 5) { \
                                  if (t3) LAUNCH((movi_pml_kernel4<IDX, SEPV, 5, LAYOUT_T3>)); \
                                  else if (b6) LAUNCH((movi_pml_kernel4<IDX, SEPV, 6, LAYOUT_B6>)); else LAUNCH((movi_pml_kernel4<IDX, SEPV, 6, LAYOUT_R8>)); \
@@ -515,7 +520,7 @@ uint64_t movi_gpu_launch_count(const movi_gpu_ctx* ctx) { return ctx ? ctx->laun
 int movi_gpu_set_option(movi_gpu_ctx* ctx, const char* key, int64_t value) {
     if (!ctx || !key) return MOVI_GPU_ERR_ARG;
     const std::string k(key);
-    if (k == "pml_variant") { if (value < 0 || value > 6) return fail(ctx, MOVI_GPU_ERR_ARG, "pml_variant: 0..6"); ctx->pml_variant = value; }
+    if (k == "pml_variant") { if (value < 0 || value > 7) return fail(ctx, MOVI_GPU_ERR_ARG, "pml_variant: 0..7"); ctx->pml_variant = value; }
     else if (k == "probe_vmm_align_mb") { if (value < 0 || value > 4096) return fail(ctx, MOVI_GPU_ERR_ARG, "probe_vmm_align_mb: 0..4096"); ctx->probe_vmm_align_mb = value; }
     else if (k == "bs_variant") { if (value < 0 || value > 1) return fail(ctx, MOVI_GPU_ERR_ARG, "bs_variant: 0 or 1"); ctx->bs_variant = value; }
     else if (k == "force_wide") { ctx->force_wide = value ? 1 : 0; }
@@ -540,6 +545,7 @@ int movi_gpu_set_option(movi_gpu_ctx* ctx, const char* key, int64_t value) {
         ctx->threads_per_block = value;
     }
     else if (k == "batch_bases") { if (value < (1 << 16)) return fail(ctx, MOVI_GPU_ERR_ARG, "batch_bases: >= 65536"); ctx->batch_bases = value; }
+    else if (k == "pml_sector") { if (value < -1 || value > 1) return fail(ctx, MOVI_GPU_ERR_ARG, "pml_sector: -1 (by table size), 0, 1"); ctx->pml_sector = value; }
     else if (k == "kernel_streams") { if (value < 1 || value > NKS) return fail(ctx, MOVI_GPU_ERR_ARG, "kernel_streams: 1..4"); ctx->kernel_streams = value; }
     else if (k == "pipeline_slots") { if (value < 2 || value > NBUF) return fail(ctx, MOVI_GPU_ERR_ARG, "pipeline_slots: 2..8"); ctx->pipeline_slots = value; }
     else if (k == "size_grid_to_batch") { ctx->size_grid_to_batch = value != 0; }
@@ -554,6 +560,7 @@ int64_t movi_gpu_get_option(const movi_gpu_ctx* ctx, const char* key) {
     if (k == "threads_per_block") return ctx->threads_per_block;
     if (k == "batch_bases") return ctx->batch_bases;
     if (k == "kernel_streams") return ctx->kernel_streams;
+    if (k == "pml_sector") return ctx->pml_sector;
     if (k == "pipeline_slots") return ctx->pipeline_slots;
     if (k == "size_grid_to_batch") return ctx->size_grid_to_batch;
     if (k == "num_sms") return ctx->num_sms;

@@ -38,7 +38,18 @@ __device__ __forceinline__ void st_stream128(void* p, uint4 v, unsigned long lon
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
 }
 
-template <typename IdxT, bool SEP, int MINB, int LAYOUT, bool HINTS = true>
+// SECTOR: keep the aligned 32-byte sector (4 rows) of the last row fetch in registers and serve fast-forward / scan steps
+// that stay inside it from there.  Costs ~10 instructions per iteration, saves ~20 % of the row requests: a loss on
+// L2-sized tables (issue bound), a gain on tables far beyond the L2, which are bound by the request rate of the memory
+// system (profiles/r01_big_tables.jsonl) -- selected by table size in movi_gpu.cu.
+__device__ __forceinline__ uint4 ld_keep128(const uint4* p, unsigned long long pol) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+
+template <typename IdxT, bool SEP, int MINB, int LAYOUT, bool HINTS = true, bool SECTOR = false>
 __global__ void __launch_bounds__(PML3_THREADS, MINB)
 movi_pml_kernel4(const DevIndex ix, const QueryArgs q) {
     __shared__ uint8_t s_code[256];
@@ -84,6 +95,8 @@ movi_pml_kernel4(const DevIndex ix, const QueryArgs q) {
     bool need_chunk = false;
 
     uint32_t tick = 0;
+    uint4 sec_lo = make_uint4(0, 0, 0, 0), sec_hi = make_uint4(0, 0, 0, 0);   // SECTOR: rows 4*sec_base .. 4*sec_base + 3
+    IdxT sec_base = ~(IdxT)0;
     for (;;) {
         // idle lanes are looked after every REFILL_EVERY-th iteration only: a finished lane waits <= 3 of the ~240
         // iterations of a 150-base read, and the other iterations skip the vote / queue bookkeeping
@@ -126,7 +139,17 @@ movi_pml_kernel4(const DevIndex ix, const QueryArgs q) {
         // (lanes that are not walking fetch row 0: harmless and keeps the fetch out of a divergent branch)
         const IdxT fidx = proc ? idx : (IdxT)0;
         uint2 v;
-        if (LAYOUT == LAYOUT_R8) v = ld_keep(rows + fidx, pol_keep);
+        if (LAYOUT == LAYOUT_R8 && SECTOR) {
+            const IdxT fb = fidx >> 2;
+            if (proc && fb != sec_base) {
+                const uint4* sp = reinterpret_cast<const uint4*>(rows) + 2 * (size_t)fb;
+                sec_lo = ld_keep128(sp, pol_keep); sec_hi = ld_keep128(sp + 1, pol_keep);
+                sec_base = fb;
+            }
+            const uint4 h = (fidx & 2) ? sec_hi : sec_lo;
+            v = (fidx & 1) ? make_uint2(h.z, h.w) : make_uint2(h.x, h.y);
+        }
+        else if (LAYOUT == LAYOUT_R8) v = ld_keep(rows + fidx, pol_keep);
         else if (LAYOUT == LAYOUT_B6) v = fetch_row_b6<IdxT>(ix.rows6, fidx, end_idx, idb, ix.id_blocks_size, ix.block_shift, s_first);
         else {              // LAYOUT_T3: the 3-byte row without its destination id (resolved below, only when an LF step needs it)
             const uint32_t x = Rows3{ix.rows3, (unsigned long long)end_idx}.raw((unsigned long long)fidx);
