@@ -75,7 +75,7 @@ struct movi_gpu_ctx {
     uint64_t launches = 0;
     // options
     int64_t pml_variant = 5;          // 0/1: branchy kernel (2-byte / 16-byte stores); 2/3: convergent kernel (+/- L2 hints); 4: convergent + sector staging in smem; 5: 4 with a leaner loop + evict_first on the streamed data (pml_kernel4.cuh); 6: 5 without those hints
-    int64_t pml_sector = 0;           // sector-cached row fetch: -1 by table size (> 512 MB), 0 off, 1 on  (off until measured)
+    int64_t pml_sector = -1;          // sector-cached row fetch: -1 by table size (> 512 MB) and batch size, 0 off, 1 on
     int64_t l2_persist_mb = 0;        // > 0: mark the row table persisting in L2 (access policy window) for query launches
     int64_t l2_fetch_granularity = 0; // 0: leave the device default; 32 / 64 / 128: cudaLimitMaxL2FetchGranularity
     int64_t bs_variant = 1;           // count / ZML kernel: 0 = branch-per-state (bs_kernel.cuh), 1 = convergent + sector staging
@@ -243,7 +243,10 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
             const bool b6 = ctx->ix.layout == LAYOUT_B6, t3 = ctx->ix.layout == LAYOUT_T3;
             // tables far beyond the L2 are bound by the request rate of the memory system, not by issue: there the kernel keeps
             // the last fetched 32-byte sector in registers (variant 7; "pml_sector" -1 = by table size, 0 / 1 = off / on)
-            const bool sector = variant == 7 || (variant == 5 && (ctx->pml_sector == 1 || (ctx->pml_sector < 0 && ctx->ix.r * sizeof(uint2) > (512ull << 20))));
+            // (measured, profiles/r01_big_tables.jsonl: 8 and 32 GB tables 1.2 -> 2.2-2.5e10 bases/s; the 124 MB c2 table -27 %;
+            //  a batch of few long reads, which leaves most lanes empty and is latency bound, -10 %: those keep the plain fetch)
+            const bool sector = variant == 7 || (variant == 5 && (ctx->pml_sector == 1 || (ctx->pml_sector < 0 &&
+                                ctx->ix.r * sizeof(uint2) > (512ull << 20) && qa.n_reads >= (1u << 17))));
 #define PML3(IDX, SEPV) do { if (variant == 6 && !t3 && !b6) LAUNCH((movi_pml_kernel4<IDX, SEPV, 6, LAYOUT_R8, false>)); \
                              else if (sector && !t3 && !b6) LAUNCH((movi_pml_kernel4<IDX, SEPV, 5, LAYOUT_R8, true, true>)); \
                              else if (variant >= 5) { \

@@ -74,6 +74,11 @@ def test_c4_shape_long_reads_classify_and_wide_indices(small, small_structs):
         ms.set_option("force_wide", wide)
         try:
             assert np.array_equal(ms.query_pml(bases, offsets), want)
+            ms.set_option("pml_sector", 1)           # sector-cached row fetch (what tables beyond the L2 use)
+            try:
+                assert np.array_equal(ms.query_pml(bases, offsets), want)
+            finally:
+                ms.set_option("pml_sector", -1)
             assert np.array_equal(ms.query_zml(bases, offsets), orc.query_zml(bases, offsets, threads=0))
             c, p = ms.query_backward_search(bases, offsets)
             c2, p2 = orc.query_count(bases, offsets, threads=0)

@@ -27,8 +27,8 @@ def main():
             d_off = (torch.arange(n_reads + 1, dtype=torch.int64, device=dev) * L)
             d_out = torch.zeros(n_bases + 64, dtype=torch.int16, device=dev)
             stream = torch.cuda.current_stream().cuda_stream
-            for minb in (6, 8):
-                ms.set_option("pml_min_blocks", minb)
+            for sector in (0, 1):
+                ms.set_option("pml_sector", sector)
                 for _ in range(2):
                     ms.query_pml_device(d_bases.data_ptr(), d_off.data_ptr(), n_reads, d_out.data_ptr(), stream)
                 torch.cuda.synchronize()
@@ -41,7 +41,7 @@ def main():
                 t = e0.elapsed_time(e1) / reps
                 mean_pml = float(d_out[:n_bases].float().mean().item())
                 rec = {"kind": "pml_synth", "table_gb": gb, "run_profile": profile, "rows": r, "n_over_r": round(ms.n / r, 1), "wide_idx": r > 0xFFFFFFF0,
-                       "blocks_per_sm": minb, "n_reads": n_reads, "read_len": L, "sub_per_1024": sub, "random_every": rnd,
+                       "pml_sector": sector, "n_reads": n_reads, "read_len": L, "sub_per_1024": sub, "random_every": rnd,
                        "ms": round(t, 3), "Gbases_per_s": round(n_bases / t / 1e6, 2), "mean_pml": round(mean_pml, 1)}
                 print(json.dumps(rec), flush=True)
                 open(os.path.join(OUT, "explore_big.jsonl"), "a").write(json.dumps(rec) + "\n")
