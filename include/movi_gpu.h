@@ -106,7 +106,8 @@ const char* movi_gpu_last_error(const movi_gpu_ctx* ctx);   /* ctx may be NULL: 
 int  movi_gpu_upload_index(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* desc, int layout);
 /* Same, for a row table that is ALREADY resident in this GPU's HBM in the 8-byte regular-thresholds format
  * (r + 4 rows allocated with cudaMalloc; e.g. produced by another component or a generator): desc->rows is ignored,
- * the side tables are taken from desc, ownership of d_rows moves to the context. */
+ * the side tables are taken from desc, ownership of d_rows moves to the context when the call succeeds (on failure it stays
+ * with the caller). */
 int  movi_gpu_adopt_device_rows(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* desc, void* d_rows);
 /* device pointer of the resident 8-byte row table (read-only; NULL without an index) */
 const void* movi_gpu_index_device_rows(const movi_gpu_ctx* ctx);

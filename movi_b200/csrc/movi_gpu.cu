@@ -617,6 +617,13 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
     free_index(ctx);
     cudaStream_t st = ctx->st_k[0];
     const unsigned long long r = d->r;
+    // whatever path leaves this function before the index is complete: nothing stays allocated (adopted rows go back to
+    // the caller), and the conversion scratch below frees itself
+    struct Rollback {
+        movi_gpu_ctx* c; uint2* adopted; bool done = false;
+        ~Rollback() { if (!done) { if (adopted && c->d_rows == adopted) c->d_rows = nullptr; free_index(c); } }
+    } rollback{ctx, adopt_rows};
+    struct Scratch { void* p = nullptr; ~Scratch() { if (p) cudaFree(p); } };
     // Device layout: EXPANDED8 unless the caller asks for COMPACT, or AUTO finds that the expanded table (plus the raw
     // copy the conversion needs) does not fit in free HBM.  COMPACT exists for blocked-thresholds (its 6-byte rows are
     // kept as they are on disk); regular-thresholds is 8 bytes on disk anyway; sampled-thresholds is always expanded.
@@ -669,10 +676,12 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
         // the on-disk row IS the device row: one copy
         CU(cudaMemcpyAsync(ctx->d_rows, d->rows, r * sizeof(uint2), cudaMemcpyHostToDevice, st));
     } else if (d->mode == MOVI_MODE_BLOCKED_THRESHOLDS) {
-        uint16_t* d_raw = nullptr; uint32_t* d_blocks = nullptr; unsigned long long* d_first = nullptr;
-        CU(cudaMalloc(&d_raw, r * 6 + 8));
-        CU(cudaMalloc(&d_blocks, (size_t)d->sigma * d->id_blocks_size * sizeof(uint32_t)));
-        CU(cudaMalloc(&d_first, 8 * sizeof(unsigned long long)));
+        Scratch s_raw, s_blocks, s_first;
+        CU(cudaMalloc(&s_raw.p, r * 6 + 8));
+        CU(cudaMalloc(&s_blocks.p, (size_t)d->sigma * d->id_blocks_size * sizeof(uint32_t)));
+        CU(cudaMalloc(&s_first.p, 8 * sizeof(unsigned long long)));
+        uint16_t* d_raw = static_cast<uint16_t*>(s_raw.p); uint32_t* d_blocks = static_cast<uint32_t*>(s_blocks.p);
+        unsigned long long* d_first = static_cast<unsigned long long*>(s_first.p);
         CU(cudaMemcpyAsync(d_raw, d->rows, r * 6, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_blocks, d->id_blocks, (size_t)d->sigma * d->id_blocks_size * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_first, d->first_runs, 8 * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
@@ -681,13 +690,14 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
         ctx->launches += 1;
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());
-        cudaFree(d_raw); cudaFree(d_blocks); cudaFree(d_first);
     } else {
-        uint8_t* d_raw = nullptr; uint8_t* d_tally = nullptr;
+        Scratch s_raw, s_tally;
         const size_t tally_bytes = (size_t)d->sigma * d->tally_len * 5;
-        CU(cudaMalloc(&d_raw, r * 3 + 16));
+        CU(cudaMalloc(&s_raw.p, r * 3 + 16));
+        uint8_t* d_raw = static_cast<uint8_t*>(s_raw.p);
         CU(cudaMemsetAsync(d_raw + r * 3, 0, 16, st));
-        CU(cudaMalloc(&d_tally, tally_bytes + 8));
+        CU(cudaMalloc(&s_tally.p, tally_bytes + 8));
+        uint8_t* d_tally = static_cast<uint8_t*>(s_tally.p);
         CU(cudaMemcpyAsync(d_raw, d->rows, r * 3, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_tally, d->tally_ids, tally_bytes, cudaMemcpyHostToDevice, st));
         CU(cudaMemsetAsync(ctx->d_status, 0, sizeof(unsigned int), st));
@@ -698,10 +708,8 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
         CU(cudaMemcpyAsync(&status, ctx->d_status, sizeof(status), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());
-        cudaFree(d_raw); cudaFree(d_tally);
         if (status) {
             CU(cudaMemset(ctx->d_status, 0, sizeof(unsigned int)));
-            free_index(ctx);
             return fail(ctx, MOVI_GPU_ERR_INDEX, "[get id - tally mode] The offset in the destination run should be always smaller than the length of that run.");
         }
     }
@@ -737,7 +745,7 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
         uint2 last = make_uint2(0u, n_last_host);
         if (!compact) CU(cudaMemcpy(&last, ctx->d_rows + (r - 1), sizeof(last), cudaMemcpyDeviceToHost));
         ix.n_last = last.y & 0x7FFu;
-        if (ix.n_last == 0) { free_index(ctx); return fail(ctx, MOVI_GPU_ERR_INDEX, "last row has length 0"); }
+        if (ix.n_last == 0) return fail(ctx, MOVI_GPU_ERR_INDEX, "last row has length 0");
     }
     if (sep) {
         // separators_thresholds_map: row -> slot; keep it as a sorted key array + thresholds in key order,
@@ -749,7 +757,7 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
         std::vector<uint16_t> vals((kv.size() + 1) * 4, 0);
         for (size_t i = 0; i < kv.size(); i++) {
             keys[i] = kv[i].first;
-            if (kv[i].second >= d->sep_count) { free_index(ctx); return fail(ctx, MOVI_GPU_ERR_INDEX, "separators map points outside the thresholds table"); }
+            if (kv[i].second >= d->sep_count) return fail(ctx, MOVI_GPU_ERR_INDEX, "separators map points outside the thresholds table");
             for (int k = 0; k < 4; k++) vals[i * 4 + k] = d->separators_thresholds[kv[i].second * 4 + k];
         }
         if (d->sep_count) for (int k = 0; k < 4; k++) vals[kv.size() * 4 + k] = d->separators_thresholds[k];
@@ -763,6 +771,7 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
     CU(cudaStreamSynchronize(st));
     ctx->mode = d->mode;
     ctx->has_index = true;
+    rollback.done = true;
     return MOVI_GPU_OK;
 }
 

@@ -217,7 +217,9 @@ int movi_synth_index(movi_gpu_ctx* ctx, uint64_t r, uint64_t seed, uint32_t prof
     }
     cudaFree(p); cudaFree(tot); cudaFree(grand);
     if (desc_out) { *desc_out = d; desc_out->rows = nullptr; }
-    return movi_gpu_adopt_device_rows(ctx, &d, rows);
+    const int rc = movi_gpu_adopt_device_rows(ctx, &d, rows);
+    if (rc) cudaFree(rows);                          // ownership only moves on success
+    return rc;
 }
 
 // Fill d_bases (n_reads * len bytes, device) with reads that match the table of a context built by movi_synth_index.
