@@ -192,7 +192,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     return 0
 
 
@@ -208,7 +208,21 @@ def workload_config(cfg, index_bytes):
     return c
 
 
+def emit_line(line):
+    """The one JSON line of this run, on the process's ORIGINAL stdout (see main)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    # stdout carries exactly one line, the JSON record: libraries that write to fd 1 on their own (NCCL prints its version there
+    # on the first communicator) are sent to stderr for the duration of the run
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -444,7 +458,7 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "bases/s", "cores": cores, "kind": kind,
                                     "sample": "the full per-GPU batch (%d x %d bp), %.2f s of wall time on %d threads, index load excluded"
                                               % (n_reads, cfg["read_len"], sec, cores)}
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     ms.close()
     if world > 1:
         dist.destroy_process_group()
