@@ -23,6 +23,7 @@
 #include "pml_kernel2.cuh"
 #include "pml_kernel3.cuh"
 #include "pml_kernel4.cuh"
+#include "pml_kernel5.cuh"
 
 using namespace movi;
 
@@ -74,8 +75,9 @@ struct movi_gpu_ctx {
     cudaStream_t st_in = nullptr, st_out = nullptr, st_k[NKS] = {nullptr, nullptr, nullptr, nullptr};
     uint64_t launches = 0;
     // options
-    int64_t pml_variant = 5;          // 0/1: branchy kernel (2-byte / 16-byte stores); 2/3: convergent kernel (+/- L2 hints); 4: convergent + sector staging in smem; 5: 4 with a leaner loop + evict_first on the streamed data (pml_kernel4.cuh); 6: 5 without those hints
+    int64_t pml_variant = 5;          // 0/1: branchy kernel (2-byte / 16-byte stores); 2/3: convergent kernel (+/- L2 hints); 4: convergent + sector staging in smem; 5: 4 with a leaner loop + evict_first on the streamed data (pml_kernel4.cuh); 6: 5 without those hints; 7: 5 with the sector-cached row fetch; 8: batched service rings (pml_kernel5.cuh)
     int64_t pml_sector = -1;          // sector-cached row fetch: -1 by table size (> 512 MB) and batch size, 0 off, 1 on
+    int64_t smem_carveout = -1;       // >= 0: preferred shared-memory carve-out of the query kernels, percent of the maximum (exploration)
     int64_t l2_persist_mb = 0;        // > 0: mark the row table persisting in L2 (access policy window) for query launches
     int64_t l2_fetch_granularity = 0; // 0: leave the device default; 32 / 64 / 128: cudaLimitMaxL2FetchGranularity
     int64_t bs_variant = 1;           // count / ZML kernel: 0 = branch-per-state (bs_kernel.cuh), 1 = convergent + sector staging
@@ -224,6 +226,7 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
 #define LAUNCH(KERNEL)                                                            \
     do {                                                                          \
         auto k_ = KERNEL;                                                         \
+        if (ctx->smem_carveout >= 0) cudaFuncSetAttribute(k_, cudaFuncAttributePreferredSharedMemoryCarveout, (int)ctx->smem_carveout); \
         cudaLaunchConfig_t cfg_ = {};                                             \
         cfg_.gridDim = dim3((unsigned)std::min<uint64_t>((uint64_t)blocks_for(ctx, k_, threads), grid_cap)); \
         cfg_.blockDim = dim3((unsigned)threads);                                  \
@@ -245,9 +248,16 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
             // the last fetched 32-byte sector in registers (variant 7; "pml_sector" -1 = by table size, 0 / 1 = off / on)
             // (measured, profiles/r01_big_tables.jsonl: 8 and 32 GB tables 1.2 -> 2.2-2.5e10 bases/s; the 124 MB c2 table -27 %;
             //  a batch of few long reads, which leaves most lanes empty and is latency bound, -10 %: those keep the plain fetch)
+            const bool sector8 = variant == 8 && (ctx->pml_sector == 1 || (ctx->pml_sector < 0 &&
+                                 ctx->ix.r * sizeof(uint2) > (512ull << 20) && qa.n_reads >= (1u << 17)));
             const bool sector = variant == 7 || (variant == 5 && (ctx->pml_sector == 1 || (ctx->pml_sector < 0 &&
                                 ctx->ix.r * sizeof(uint2) > (512ull << 20) && qa.n_reads >= (1u << 17))));
-#define PML3(IDX, SEPV) do { if (variant == 6 && !t3 && !b6) LAUNCH((movi_pml_kernel4<IDX, SEPV, 6, LAYOUT_R8, false>)); \
+#define PML3(IDX, SEPV) do { if (variant == 8) { \
+                                 if (t3) LAUNCH((movi_pml_kernel5<IDX, SEPV, 5, LAYOUT_T3>)); \
+                                 else if (b6) LAUNCH((movi_pml_kernel5<IDX, SEPV, 6, LAYOUT_B6>)); \
+                                 else if (sector8) LAUNCH((movi_pml_kernel5<IDX, SEPV, 5, LAYOUT_R8, true>)); \
+                                 else LAUNCH((movi_pml_kernel5<IDX, SEPV, 6, LAYOUT_R8>)); } \
+                             else if (variant == 6 && !t3 && !b6) LAUNCH((movi_pml_kernel4<IDX, SEPV, 6, LAYOUT_R8, false>)); \
                              else if (sector && !t3 && !b6) LAUNCH((movi_pml_kernel4<IDX, SEPV, 5, LAYOUT_R8, true, true>)); \
                              else if (variant >= 5) { \
                                  if (t3) LAUNCH((movi_pml_kernel4<IDX, SEPV, 5, LAYOUT_T3>)); \
@@ -523,7 +533,7 @@ uint64_t movi_gpu_launch_count(const movi_gpu_ctx* ctx) { return ctx ? ctx->laun
 int movi_gpu_set_option(movi_gpu_ctx* ctx, const char* key, int64_t value) {
     if (!ctx || !key) return MOVI_GPU_ERR_ARG;
     const std::string k(key);
-    if (k == "pml_variant") { if (value < 0 || value > 7) return fail(ctx, MOVI_GPU_ERR_ARG, "pml_variant: 0..7"); ctx->pml_variant = value; }
+    if (k == "pml_variant") { if (value < 0 || value > 8) return fail(ctx, MOVI_GPU_ERR_ARG, "pml_variant: 0..8"); ctx->pml_variant = value; }
     else if (k == "probe_vmm_align_mb") { if (value < 0 || value > 4096) return fail(ctx, MOVI_GPU_ERR_ARG, "probe_vmm_align_mb: 0..4096"); ctx->probe_vmm_align_mb = value; }
     else if (k == "bs_variant") { if (value < 0 || value > 1) return fail(ctx, MOVI_GPU_ERR_ARG, "bs_variant: 0 or 1"); ctx->bs_variant = value; }
     else if (k == "force_wide") { ctx->force_wide = value ? 1 : 0; }
@@ -549,6 +559,7 @@ int movi_gpu_set_option(movi_gpu_ctx* ctx, const char* key, int64_t value) {
     }
     else if (k == "batch_bases") { if (value < (1 << 16)) return fail(ctx, MOVI_GPU_ERR_ARG, "batch_bases: >= 65536"); ctx->batch_bases = value; }
     else if (k == "pml_sector") { if (value < -1 || value > 1) return fail(ctx, MOVI_GPU_ERR_ARG, "pml_sector: -1 (by table size), 0, 1"); ctx->pml_sector = value; }
+    else if (k == "smem_carveout") { if (value < -1 || value > 100) return fail(ctx, MOVI_GPU_ERR_ARG, "smem_carveout: -1, 0..100"); ctx->smem_carveout = value; }
     else if (k == "kernel_streams") { if (value < 1 || value > NKS) return fail(ctx, MOVI_GPU_ERR_ARG, "kernel_streams: 1..4"); ctx->kernel_streams = value; }
     else if (k == "pipeline_slots") { if (value < 2 || value > NBUF) return fail(ctx, MOVI_GPU_ERR_ARG, "pipeline_slots: 2..8"); ctx->pipeline_slots = value; }
     else if (k == "size_grid_to_batch") { ctx->size_grid_to_batch = value != 0; }

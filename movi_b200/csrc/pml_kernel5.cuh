@@ -1,60 +1,28 @@
-// pml_kernel4.cuh -- PML kernel, variant 5: variant 4 (pml_kernel3.cuh) with a leaner hot loop.
+// pml_kernel5.cuh -- PML kernel, variant 8: variant 5 (pml_kernel4.cuh) with batched streaming service.
 //
-// Same state machine, same streaming through shared memory; what changed (all aimed at the instruction count of the
-// warp iteration, which bounds variant 4 on L2-sized tables -- profiles/r01_summary.md):
-//   * a read is started where it is handed out (inside the rarely taken refill branch) instead of spending one warp
-//     iteration in a ST_NEW state: one iteration per read less, and the common path loses the ST_NEW bookkeeping;
-//   * staging of the next 32-byte sector of read bytes (cp.async + wait) sits behind a warp vote: about half of the
-//     iterations have no lane that needs it;
-//   * per-lane shared-memory slots are addressed through 32-bit shared-window addresses (ld.shared / st.shared), not
-//     generic pointers;
-//   * idle lanes are looked after every 4th iteration only;
-//   * the streamed data (read bytes in, lengths out) carries an L2 evict_first policy (-1.6 % time: the row table keeps
-//     a little more of the L2).
+// Variant 5 spends ~35 of its ~150 instructions per warp iteration on service code that one or two lanes need (stage the
+// next 32 bytes of a read, write out 16 results, the ragged ends of a read) but the whole warp issues.  Here every lane
+// owns a ring of two input sectors and a ring of 32 results, and a service event -- forced by the one lane that cannot go
+// on -- is used by every lane of the warp: the lane that ran dry stages its sector and all the others prefetch theirs; the
+// lane whose ring is full writes out and so do all the others.  Events come round every 30-50 iterations instead of in
+// most of them.  The ragged ends are written with 4-byte pieces in a short loop instead of seven predicated pieces.
+// Same state machine, same results (tests/test_gpu_parity.py runs every variant against the oracle).
+//
+// MEASURED (profiles/r01_explore.jsonl, "8:..."): -8 % instructions and 28 instead of 25 lanes per instruction, but the two
+// rings cost 33 KB of shared memory per block; six blocks per SM then leave 23 KB of L1 and the row fetches starve
+// (5.6 ms per c2 batch instead of 1.97), and at the three blocks per SM that keep the L1 at 124 KB it reaches 2.30 ms.
+// Not the default; kept as the record of that experiment (pml_variant 8).
 #pragma once
-#include "dev_index.cuh"
-#include "pml_kernel.cuh"
-#include "pml_kernel2.cuh"
-#include "pml_kernel3.cuh"
+#include "pml_kernel4.cuh"
 
 namespace movi {
 
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "h"((unsigned short)v) : "memory"); }
-__device__ __forceinline__ uint4 lds_128(uint32_t a) {
-    uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
-}
-__device__ __forceinline__ void cp_async16_s(uint32_t s, const void* gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem) : "memory");
-}
-// streamed data (read bytes in, lengths out) marked evict_first in L2, so that the 450 MB that pass through per batch
-// displace as little of the row table as possible
-__device__ __forceinline__ void cp_async16_stream(uint32_t s, const void* gmem, unsigned long long pol) {
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(s), "l"(gmem), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void st_stream128(void* p, uint4 v, unsigned long long pol) {
-    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;"
-                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
-}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 
-// SECTOR: keep the aligned 32-byte sector (4 rows) of the last row fetch in registers and serve fast-forward / scan steps
-// that stay inside it from there.  Costs ~10 instructions per iteration, saves ~20 % of the row requests: a loss on
-// L2-sized tables (issue bound), a gain on tables far beyond the L2, which are bound by the request rate of the memory
-// system (profiles/r01_big_tables.jsonl) -- selected by table size in movi_gpu.cu.
-__device__ __forceinline__ uint4 ld_keep128(const uint4* p, unsigned long long pol) {
-    uint4 v;
-    asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
-    return v;
-}
-
-// (Tried and dropped: fetching the row with cp.async.cg into shared memory instead of a load through L1 -- 5x slower,
-//  profiles/r01_explore.jsonl "9:..."; and the row fetches need their L1: with the shared-memory carve-out at its maximum
-//  the same kernel runs 2.8x slower, which is also what limits the per-lane staging buffers to 32 + 32 bytes.)
-template <typename IdxT, bool SEP, int MINB, int LAYOUT, bool HINTS = true, bool SECTOR = false>
+template <typename IdxT, bool SEP, int MINB, int LAYOUT, bool SECTOR = false>
 __global__ void __launch_bounds__(PML3_THREADS, MINB)
-movi_pml_kernel4(const DevIndex ix, const QueryArgs q) {
+movi_pml_kernel5(const DevIndex ix, const QueryArgs q) {
     __shared__ uint8_t s_code[256];
     __shared__ uint32_t s_end_thr[4];
     __shared__ uint32_t s_idb[LAYOUT == LAYOUT_B6 ? IDB_SMEM : 1];
@@ -66,8 +34,8 @@ movi_pml_kernel4(const DevIndex ix, const QueryArgs q) {
         if (threadIdx.x < 8) s_first[threadIdx.x] = ix.first_runs[threadIdx.x];
     }
     const uint32_t* const idb = idb_in_smem ? s_idb : ix.id_blocks;
-    __shared__ __align__(32) uint8_t s_in[PML3_THREADS * 32];      // per lane: the 32-byte sector of its read that holds bases[rp]
-    __shared__ __align__(32) uint16_t s_out[PML3_THREADS * 16];    // per lane: the 32-byte sector of its output being filled
+    __shared__ __align__(32) uint8_t s_in[PML3_THREADS * 64];      // per lane: ring of two 32-byte sectors of its read (slot = sector & 1)
+    __shared__ __align__(32) uint16_t s_out[PML3_THREADS * 32];    // per lane: ring of 32 results (slot = output index & 31)
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_code[i] = ix.code_of[i];
     if (threadIdx.x < 4) s_end_thr[threadIdx.x] = ix.end_thr[threadIdx.x];
     __syncthreads();
@@ -81,9 +49,8 @@ movi_pml_kernel4(const DevIndex ix, const QueryArgs q) {
     const uint2* __restrict__ rows = ix.rows;
     const uint8_t* __restrict__ bases = q.bases;
     const uint2* __restrict__ offs8 = reinterpret_cast<const uint2*>(q.offsets);
-    uint16_t* const out_slot = s_out + threadIdx.x * 16;              // (generic pointer: only the rare ragged flush uses it)
-    const uint32_t sa_in = smem_addr(s_in) + threadIdx.x * 32u;       // shared-window addresses of this lane's slots
-    const uint32_t sa_out = smem_addr(s_out) + threadIdx.x * 32u;
+    const uint32_t sa_in = smem_addr(s_in) + threadIdx.x * 64u;       // shared-window addresses of this lane's rings
+    const uint32_t sa_out = smem_addr(s_out) + threadIdx.x * 64u;
     const uint32_t sa_code = smem_addr(s_code);
     constexpr uint32_t sep = SEP ? 1u : 0u;
     constexpr uint32_t REFILL_EVERY = 4;
@@ -94,8 +61,29 @@ movi_pml_kernel4(const DevIndex ix, const QueryArgs q) {
     bool exhausted = false;
     uint32_t st = ST_IDLE;
     IdxT idx = 0;
-    uint32_t off = 0, ml = 0, rp = 0, op = 0, rem = 0, pend = 0;
-    bool need_chunk = false;
+    uint32_t off = 0, ml = 0, rp = 0, op = 0, rem = 0;
+    uint32_t fl = 0;          // results [fl, op) are still in the ring
+    uint32_t in_lo = 0;       // sectors in_lo .. rp >> 5 of the read bytes are staged (at most two)
+
+    // write results [fl, target) of this lane from the ring to global memory: whole aligned 16-value groups with two
+    // 16-byte stores, the ragged ends of a read (they share their sector with the neighbouring read) piecewise
+    auto flush_to = [&](uint32_t target) {
+        while (fl < target) {
+            const uint32_t gend = min((fl | 15u) + 1u, target);
+            uint16_t* g = q.out_ml + fl;
+            const uint32_t sl = sa_out + 2u * (fl & 31u);
+            if (gend - fl == 16u) {
+                const uint4 lo = lds_128(sl), hi = lds_128(sl + 16u);
+                st_stream128(g, lo, pol_stream); st_stream128(g + 8, hi, pol_stream);
+            } else {
+                uint32_t k = 0; const uint32_t cnt = gend - fl;
+                if ((fl & 1u) && k < cnt) { g[0] = (uint16_t)lds_u16(sl); k = 1; }
+                for (; k + 2 <= cnt; k += 2) *reinterpret_cast<uint32_t*>(g + k) = lds_u32(sl + 2u * k);
+                if (k < cnt) g[k] = (uint16_t)lds_u16(sl + 2u * k);
+            }
+            fl = gend;
+        }
+    };
 
     uint32_t tick = 0;
     uint4 sec_lo = make_uint4(0, 0, 0, 0), sec_hi = make_uint4(0, 0, 0, 0);   // SECTOR: rows 4*sec_base .. 4*sec_base + 3
@@ -128,9 +116,9 @@ movi_pml_kernel4(const DevIndex ix, const QueryArgs q) {
                 const unsigned long long e = (((unsigned long long)b.y << 32) | b.x) - q.origin;
                 rem = (uint32_t)(e - s);
                 rp = (uint32_t)e - 1; op = (uint32_t)s;
-                idx = r1; off = ix.n_last - 1; ml = 0; pend = 0;
+                idx = r1; off = ix.n_last - 1; ml = 0;
+                fl = op; in_lo = (rp >> 5) + 1u;                           // nothing pending, nothing staged
                 st = rem ? ST_FF : ST_IDLE;                                // (an empty read leaves the lane idle: it asks again)
-                need_chunk = true;
             }
             const uint32_t cnt = __popc(m);
             q_next += cnt < avail ? cnt : avail;
@@ -158,21 +146,36 @@ movi_pml_kernel4(const DevIndex ix, const QueryArgs q) {
             const uint32_t x = Rows3{ix.rows3, (unsigned long long)end_idx}.raw((unsigned long long)fidx);
             v = make_r8(0, Rows3::n_of(x), Rows3::off_of(x), Rows3::c_of(x), Rows3::thr_of(x));
         }
-        if (__any_sync(FULL, proc && need_chunk)) {
-            if (proc && need_chunk) {
-                const uint8_t* src = bases + (rp & ~31u);
-                if (HINTS) { cp_async16_stream(sa_in, src, pol_stream); cp_async16_stream(sa_in + 16u, src + 16, pol_stream); }
-                else { cp_async16_s(sa_in, src); cp_async16_s(sa_in + 16u, src + 16); }
+        // ---- service events.  Both are forced by one lane and then served for every lane of the warp that can use them, so
+        // that they come round every few dozen iterations instead of in most of them:
+        //   input:  a lane stepped below its staged sectors -> every walking lane stages what it is missing of its current
+        //           sector and the one below it (never below the start of its read);
+        //   output: a lane's ring is full -> every walking lane writes out its complete 16-value groups.
+        if (__any_sync(FULL, proc && (rp >> 5) < in_lo)) {
+            if (proc) {
+                const uint32_t cur = rp >> 5, first_sec = (rp - rem + 1u) >> 5;
+                if (cur < in_lo) {
+                    const uint8_t* src = bases + ((size_t)cur << 5); const uint32_t dst = sa_in + ((cur & 1u) << 5);
+                    cp_async16_stream(dst, src, pol_stream); cp_async16_stream(dst + 16u, src + 16, pol_stream);
+                    in_lo = cur;
+                }
+                if (in_lo == cur && cur > first_sec) {
+                    const uint8_t* src = bases + ((size_t)(cur - 1u) << 5); const uint32_t dst = sa_in + (((cur - 1u) & 1u) << 5);
+                    cp_async16_stream(dst, src, pol_stream); cp_async16_stream(dst + 16u, src + 16, pol_stream);
+                    in_lo = cur - 1u;
+                }
             }
             cp_async_wait_all();
-            need_chunk = need_chunk && !proc;
+        }
+        if (__any_sync(FULL, proc && (op - fl) >= 32u)) {
+            if (proc) flush_to(op & ~15u);
         }
 
         // ---- one predicate-driven step of the state machine for every lane
         const uint32_t y = v.y;
         const uint32_t n = row_n(y);
         const uint32_t c = row_c(y);
-        const uint32_t code = lds_u8(sa_code + lds_u8(sa_in + (rp & 31u)));
+        const uint32_t code = lds_u8(sa_code + lds_u8(sa_in + (rp & 63u)));
         const bool is_ff = (st == ST_FF);
         const bool is_scan = (st >= ST_UP);
         const bool scan_up = (st == ST_UP);
@@ -199,34 +202,9 @@ movi_pml_kernel4(const DevIndex ix, const QueryArgs q) {
 
         const bool fin = emit && (rem == 1u);
         const bool lf = emit && !fin;
-        if (emit) {
-            sts_u16(sa_out + 2u * (op & 15u), ml < 65535u ? ml : 65535u);  // add_ml clamp
-            pend += 1;
-            if ((op & 15u) == 15u || fin) {
-                uint16_t* g = q.out_ml + (op & ~15u);
-                if (pend == 16u) {
-                    const uint4 lo = lds_128(sa_out);
-                    const uint4 hi = lds_128(sa_out + 16u);
-                    if (HINTS) { st_stream128(g, lo, pol_stream); st_stream128(g + 8, hi, pol_stream); }
-                    else { *reinterpret_cast<uint4*>(g) = lo; *reinterpret_cast<uint4*>(g + 8) = hi; }
-                } else {
-                    // ragged head / tail of a read: only our own slots [lo, hi] of the sector, widest aligned pieces first
-                    uint32_t lo = (op & 15u) + 1u - pend;
-                    const uint32_t hi1 = (op & 15u) + 1u;                  // one past the last slot
-                    if ((lo & 1u) && lo < hi1) { g[lo] = out_slot[lo]; lo += 1; }
-                    if ((lo & 2u) && lo + 2 <= hi1) { *reinterpret_cast<uint32_t*>(g + lo) = *reinterpret_cast<const uint32_t*>(out_slot + lo); lo += 2; }
-                    if ((lo & 4u) && lo + 4 <= hi1) { *reinterpret_cast<uint2*>(g + lo) = *reinterpret_cast<const uint2*>(out_slot + lo); lo += 4; }
-                    if (lo + 8 <= hi1) { *reinterpret_cast<uint4*>(g + lo) = *reinterpret_cast<const uint4*>(out_slot + lo); lo += 8; }
-                    if (lo + 4 <= hi1) { *reinterpret_cast<uint2*>(g + lo) = *reinterpret_cast<const uint2*>(out_slot + lo); lo += 4; }
-                    if (lo + 2 <= hi1) { *reinterpret_cast<uint32_t*>(g + lo) = *reinterpret_cast<const uint32_t*>(out_slot + lo); lo += 2; }
-                    if (lo < hi1) g[lo] = out_slot[lo];
-                }
-                pend = 0;
-            }
-        }
+        if (emit) sts_u16(sa_out + 2u * (op & 31u), ml < 65535u ? ml : 65535u);   // add_ml clamp
         op += emit ? 1u : 0u;
         rem -= emit ? 1u : 0u;
-        need_chunk = need_chunk || (lf && (rp & 31u) == 0u);
         rp -= lf ? 1u : 0u;
         off += lf ? row_off(y) : 0u;                                        // LF_move, move_structure.cpp:66
         IdxT lf_id = row_id<IdxT>(v);
@@ -238,6 +216,9 @@ movi_pml_kernel4(const DevIndex ix, const QueryArgs q) {
         }
         idx = lf ? lf_id : (ffmove || mv_down) ? idx + 1 : (mv_up ? idx - 1 : idx);
         st = fin ? ST_IDLE : lf ? ST_FF : base_mis ? (down ? ST_DOWN : ST_UP) : st;
+        if (__any_sync(FULL, fin)) {                 // end of a read: everything it still holds, ragged tail included
+            if (fin) flush_to(op);
+        }
         if (bad || bad_id) { atomicOr(q.status, bad_id ? 2u : 1u); st = ST_IDLE; }
     }
 }

@@ -24,7 +24,22 @@ def read_sets():
     return {s: Reads(reads_path(s)) for s in READ_SETS}
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7])
+_DEFAULTS = {}
+
+
+@pytest.fixture(autouse=True)
+def _default_kernels_after_each_test(structures):
+    """Tests that walk through the kernel variants leave the shared contexts on the library's defaults."""
+    if not _DEFAULTS:
+        ms = next(iter(structures.values()))
+        _DEFAULTS.update(pml_variant=ms.get_option("pml_variant"), bs_variant=ms.get_option("bs_variant"))
+    yield
+    for ms in structures.values():
+        for k, v in _DEFAULTS.items():
+            ms.set_option(k, v)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8])
 @pytest.mark.parametrize("sep", [False, True])
 @pytest.mark.parametrize("typ", TYPES)
 @pytest.mark.parametrize("read_set", READ_SETS)
@@ -102,7 +117,7 @@ def test_random_reads_vs_oracle(structures, index_dirs, ref_seq, typ, sep):
     bases, offsets = pack_reads(reads)
     orc = OracleIndex(index_dirs[(typ, sep)])
     ms = structures[(typ, sep)]
-    for variant in (0, 1, 2, 3, 4, 5, 6, 7):
+    for variant in (0, 1, 2, 3, 4, 5, 6, 7, 8):
         ms.set_option("pml_variant", variant)
         assert np.array_equal(ms.query_pml(bases, offsets), orc.query_pml(bases, offsets, threads=0))
     if typ != "sampled-thresholds":
