@@ -21,8 +21,11 @@ namespace movi {
 
 constexpr uint32_t B_IDLE = 0, B_NEW = 1, B_SKIP = 2, B_RUN = 3, B_FAIL = 4, B_FIN = 5, B_COUNT = 6;
 
-template <typename IdxT, int KIND, int LAYOUT>
-__global__ void __launch_bounds__(PML3_THREADS)
+// SECTOR (tables far beyond the L2, which are bound by the request rate of the memory system -- see pml_kernel4.cuh): each
+// interval end keeps the aligned 32-byte sector (4 rows) of its last fetch in registers; scan and fast-forward steps that
+// stay inside it, and the very common case of both ends sitting in the same rows, cost no new request.
+template <typename IdxT, int KIND, int LAYOUT, bool SECTOR = false>
+__global__ void __launch_bounds__(PML3_THREADS, SECTOR ? 3 : 1)
 movi_bs_kernel2(const DevIndex ix, const QueryArgs q) {
     __shared__ uint8_t s_code[256];
     __shared__ uint32_t s_idb[LAYOUT == LAYOUT_B6 ? IDB_SMEM : 1];
@@ -68,6 +71,8 @@ movi_bs_kernel2(const DevIndex ix, const QueryArgs q) {
     uint32_t cur = 0, start = 0, op = 0, m = 0, code = 0, pend = 0;
     bool need_chunk = false;
 
+    uint4 loS = make_uint4(0, 0, 0, 0), hiS = loS, loE = loS, hiE = loS;      // SECTOR: rows 4*base .. 4*base + 3 of each end
+    IdxT baseS = ~(IdxT)0, baseE = ~(IdxT)0;
     constexpr uint32_t REFILL_EVERY = 4;      // idle lanes are looked after every 4th iteration only (see pml_kernel4.cuh)
     uint32_t tick = 0;
     for (;;) {
@@ -111,7 +116,24 @@ movi_bs_kernel2(const DevIndex ix, const QueryArgs q) {
         const bool run = (pst == B_RUN);
         const bool chunk_user = run || (pst == B_SKIP);
         uint2 vS = make_uint2(0u, 0u), vE = make_uint2(0u, 0u);
-        if (run) {
+        if (SECTOR && LAYOUT == LAYOUT_R8) {
+            if (run) {
+                const IdxT fbS = rs >> 2, fbE = re >> 2;
+                if (fbS != baseS) {
+                    const uint4* sp = reinterpret_cast<const uint4*>(rows) + 2 * (size_t)fbS;
+                    loS = ld_keep128(sp, pol_keep); hiS = ld_keep128(sp + 1, pol_keep); baseS = fbS;
+                }
+                if (fbE != baseE) {
+                    if (fbE == baseS) { loE = loS; hiE = hiS; }
+                    else { const uint4* sp = reinterpret_cast<const uint4*>(rows) + 2 * (size_t)fbE;
+                           loE = ld_keep128(sp, pol_keep); hiE = ld_keep128(sp + 1, pol_keep); }
+                    baseE = fbE;
+                }
+                const uint4 hS = (rs & 2) ? hiS : loS, hE = (re & 2) ? hiE : loE;
+                vS = (rs & 1) ? make_uint2(hS.z, hS.w) : make_uint2(hS.x, hS.y);
+                vE = (re & 1) ? make_uint2(hE.z, hE.w) : make_uint2(hE.x, hE.y);
+            }
+        } else if (run) {
             if (LAYOUT == LAYOUT_R8) { vS = ld_keep(rows + rs, pol_keep); vE = ld_keep(rows + re, pol_keep); }
             else {
                 // first_runs indexed by code + 1 is exactly what get_id needs (first_runs[c + 1])

@@ -272,8 +272,12 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
     } else {
         const bool b6 = ctx->ix.layout == LAYOUT_B6;
         const bool v0 = ctx->bs_variant == 0 && !b6;
+        const bool bs_sector = !b6 && !v0 && (ctx->pml_sector == 1 || (ctx->pml_sector < 0 &&
+                               ctx->ix.r * sizeof(uint2) > (512ull << 20) && qa.n_reads >= (1u << 17)));
 #define BS(IDX, KINDV) do { if (v0) LAUNCH((movi_bs_kernel<IDX, KINDV>)); \
-                            else if (b6) LAUNCH((movi_bs_kernel2<IDX, KINDV, LAYOUT_B6>)); else LAUNCH((movi_bs_kernel2<IDX, KINDV, LAYOUT_R8>)); } while (0)
+                            else if (b6) LAUNCH((movi_bs_kernel2<IDX, KINDV, LAYOUT_B6>)); \
+                            else if (bs_sector) LAUNCH((movi_bs_kernel2<IDX, KINDV, LAYOUT_R8, true>)); \
+                            else LAUNCH((movi_bs_kernel2<IDX, KINDV, LAYOUT_R8>)); } while (0)
         if (kind == Q_ZML) { if (wide) BS(unsigned long long, KIND_ZML); else BS(uint32_t, KIND_ZML); }
         else               { if (wide) BS(unsigned long long, KIND_COUNT); else BS(uint32_t, KIND_COUNT); }
 #undef BS

@@ -124,11 +124,15 @@ def test_random_reads_vs_oracle(structures, index_dirs, ref_seq, typ, sep):
         # (reads of length 0 are outside the reference's domain for zml/count -- it indexes R[-1]; both sides emit nothing / 0)
         want_z = orc.query_zml(bases, offsets, threads=0)
         c2, p2 = orc.query_count(bases, offsets, threads=0)
-        for bs_variant in (0, 1):
+        for bs_variant, sector in ((0, -1), (1, -1), (1, 1)):      # (1, 1): the sector-cached form big tables use
             ms.set_option("bs_variant", bs_variant)
-            assert np.array_equal(ms.query_zml(bases, offsets), want_z)
-            c1, p1 = ms.query_backward_search(bases, offsets)
-            assert np.array_equal(c1, c2) and np.array_equal(p1, p2)
+            ms.set_option("pml_sector", sector)
+            try:
+                assert np.array_equal(ms.query_zml(bases, offsets), want_z)
+                c1, p1 = ms.query_backward_search(bases, offsets)
+                assert np.array_equal(c1, c2) and np.array_equal(p1, p2)
+            finally:
+                ms.set_option("pml_sector", -1)
 
 
 def test_small_pipeline_slices(structures, index_dirs, ref_seq):

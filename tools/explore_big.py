@@ -45,6 +45,21 @@ def main():
                        "ms": round(t, 3), "Gbases_per_s": round(n_bases / t / 1e6, 2), "mean_pml": round(mean_pml, 1)}
                 print(json.dumps(rec), flush=True)
                 open(os.path.join(OUT, "explore_big.jsonl"), "a").write(json.dumps(rec) + "\n")
+            if os.environ.get("MOVI_EXPLORE_BS"):        # count / ZML on the same table and reads
+                d_cnt = torch.zeros(n_reads, dtype=torch.int64, device=dev); d_pos = torch.zeros(n_reads, dtype=torch.int32, device=dev)
+                for kind in ("zml", "count"):
+                    def go():
+                        if kind == "zml": ms.query_zml_device(d_bases.data_ptr(), d_off.data_ptr(), n_reads, d_out.data_ptr(), stream)
+                        else: ms.query_count_device(d_bases.data_ptr(), d_off.data_ptr(), n_reads, d_cnt.data_ptr(), d_pos.data_ptr(), stream)
+                    go(); go(); torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); go(); go(); go(); e1.record(); torch.cuda.synchronize(); ms.check_device_status()
+                    t = e0.elapsed_time(e1) / 3
+                    rec = {"kind": kind + "_synth", "table_gb": gb, "n_reads": n_reads, "read_len": L, "sub_per_1024": sub, "random_every": rnd,
+                           "ms": round(t, 3), "Gbases_per_s": round(n_bases / t / 1e6, 2)}
+                    if kind == "count": rec["mean_matched"] = float((L - d_pos.float()).mean().item())
+                    print(json.dumps(rec), flush=True)
+                    open(os.path.join(OUT, "explore_big.jsonl"), "a").write(json.dumps(rec) + "\n")
             del d_bases, d_out, d_off
         sec, loads = ms.gather_probe(0, 8, True, 256, 8, 256)
         rec = {"kind": "probe_on_synth_table", "table_gb": gb, "loads_per_s": loads / sec}
