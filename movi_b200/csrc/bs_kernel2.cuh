@@ -44,7 +44,7 @@ movi_bs_kernel2(const DevIndex ix, const QueryArgs q) {
     }
     __syncthreads();
 
-    const unsigned long long pol_keep = policy_evict_last();
+    const unsigned long long pol_keep = q.keep_frac < 1.0f ? policy_keep_fraction(q.keep_frac) : policy_evict_last();
     const unsigned long long pol_stream = policy_evict_first();
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;

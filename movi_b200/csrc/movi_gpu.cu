@@ -77,6 +77,7 @@ struct movi_gpu_ctx {
     // options
     int64_t pml_variant = 5;          // 0/1: branchy kernel (2-byte / 16-byte stores); 2/3: convergent kernel (+/- L2 hints); 4: convergent + sector staging in smem; 5: 4 with a leaner loop + evict_first on the streamed data (pml_kernel4.cuh); 6: 5 without those hints; 7: 5 with the sector-cached row fetch; 8: batched service rings (pml_kernel5.cuh)
     int64_t pml_sector = -1;          // sector-cached row fetch: -1 by table size (> 512 MB) and batch size, 0 off, 1 on
+    int64_t row_keep_pct = 100;       // percent of the row table fetched with L2 evict_last (the rest evict_first); exploration
     int64_t smem_carveout = -1;       // >= 0: preferred shared-memory carve-out of the query kernels, percent of the maximum (exploration)
     int64_t l2_persist_mb = 0;        // > 0: mark the row table persisting in L2 (access policy window) for query launches
     int64_t l2_fetch_granularity = 0; // 0: leave the device default; 32 / 64 / 128: cudaLimitMaxL2FetchGranularity
@@ -317,6 +318,7 @@ int device_query(movi_gpu_ctx* ctx, Kind kind, const char* d_bases, const uint64
     qa.counter = d_counter;
     qa.status = ctx->d_status;
     qa.ld_mode = (uint32_t)ctx->row_ld_mode;
+    qa.keep_frac = ctx->row_keep_pct >= 100 ? 1.0f : (float)ctx->row_keep_pct / 100.0f;
     return launch_query(ctx, kind, qa, st);
 }
 
@@ -563,6 +565,7 @@ int movi_gpu_set_option(movi_gpu_ctx* ctx, const char* key, int64_t value) {
     }
     else if (k == "batch_bases") { if (value < (1 << 16)) return fail(ctx, MOVI_GPU_ERR_ARG, "batch_bases: >= 65536"); ctx->batch_bases = value; }
     else if (k == "pml_sector") { if (value < -1 || value > 1) return fail(ctx, MOVI_GPU_ERR_ARG, "pml_sector: -1 (by table size), 0, 1"); ctx->pml_sector = value; }
+    else if (k == "row_keep_pct") { if (value < 0 || value > 100) return fail(ctx, MOVI_GPU_ERR_ARG, "row_keep_pct: 0..100"); ctx->row_keep_pct = value; }
     else if (k == "smem_carveout") { if (value < -1 || value > 100) return fail(ctx, MOVI_GPU_ERR_ARG, "smem_carveout: -1, 0..100"); ctx->smem_carveout = value; }
     else if (k == "kernel_streams") { if (value < 1 || value > NKS) return fail(ctx, MOVI_GPU_ERR_ARG, "kernel_streams: 1..4"); ctx->kernel_streams = value; }
     else if (k == "pipeline_slots") { if (value < 2 || value > NBUF) return fail(ctx, MOVI_GPU_ERR_ARG, "pipeline_slots: 2..8"); ctx->pipeline_slots = value; }

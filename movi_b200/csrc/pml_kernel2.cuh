@@ -20,6 +20,13 @@ namespace movi {
 __device__ __forceinline__ unsigned long long policy_evict_last() {
     unsigned long long p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
 }
+// evict_last for a fixed `frac` of the addresses (the hardware picks them by address), evict_first for the others: when the
+// row table is larger than what the L2 can hold, protecting the part that fits beats letting all of it thrash
+__device__ __forceinline__ unsigned long long policy_keep_fraction(float frac) {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(p) : "f"(frac));
+    return p;
+}
 __device__ __forceinline__ unsigned long long policy_evict_first() {
     unsigned long long p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
 }

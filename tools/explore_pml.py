@@ -42,6 +42,7 @@ def main():
         ld_mode = f[5] if len(f) > 5 else 0
         n_streams = f[6] if len(f) > 6 else 1
         ms.set_option("smem_carveout", f[7] if len(f) > 7 else -1)
+        ms.set_option("row_keep_pct", f[8] if len(f) > 8 else 100)
         ms.set_option("row_ld_mode", ld_mode)
         ms.set_option("pml_variant", variant)
         ms.set_option("blocks_per_sm", bps)
