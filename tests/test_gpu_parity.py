@@ -311,3 +311,26 @@ def test_byte_wide_results_for_short_reads(structures, index_dirs, read_sets, re
     bases, offsets = pack_reads([b"ACGT" * 64])          # 256 bases
     with pytest.raises(MoviGpuError, match="longer than 255"):
         ms.query_ml8(bases, offsets)
+
+
+@pytest.mark.parametrize("typ", TYPES)
+def test_matching_lengths_saturate_at_65535(structures, index_dirs, ref_seq, typ):
+    """A 75 kbp read that is a substring of the indexed text: the running match length passes 2^16; the stored value saturates
+    at 65535 (MoveQuery::add_ml, include/move_query.hpp:26-38) while the count goes on (tests/test_basics.cpp:304-315)."""
+    from oracle.port import OracleIndex, pack_reads
+    read = ref_seq[2000:77000]
+    bases, offsets = pack_reads([read, read[:300], read[-70000:]])
+    ms = structures[(typ, False)]
+    orc = OracleIndex(index_dirs[(typ, False)])
+    want = orc.query_pml(bases, offsets, threads=0)
+    assert want.max() == 65535 and (want == 65535).sum() > 5000
+    for variant in (4, 5, 7, 8):
+        ms.set_option("pml_variant", variant)
+        assert np.array_equal(ms.query_pml(bases, offsets), want)
+    if typ != "sampled-thresholds":
+        want_z = orc.query_zml(bases, offsets, threads=0)
+        assert want_z.max() == 65535
+        assert np.array_equal(ms.query_zml(bases, offsets), want_z)
+        c, p = ms.query_backward_search(bases, offsets)
+        c2, p2 = orc.query_count(bases, offsets, threads=0)
+        assert np.array_equal(c, c2) and np.array_equal(p, p2) and p[0] == 0 and c[0] >= 1
