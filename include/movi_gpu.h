@@ -107,10 +107,15 @@ int  movi_gpu_upload_index(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* desc, int 
 /* Same, for a row table that is ALREADY resident in this GPU's HBM in the 8-byte regular-thresholds format
  * (r + 4 rows allocated with cudaMalloc; e.g. produced by another component or a generator): desc->rows is ignored,
  * the side tables are taken from desc, ownership of d_rows moves to the context when the call succeeds (on failure it stays
- * with the caller). */
+ * with the caller).  The rows are rewritten IN PLACE into the device row format (same fields, other bit positions). */
 int  movi_gpu_adopt_device_rows(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* desc, void* d_rows);
-/* device pointer of the resident 8-byte row table (read-only; NULL without an index) */
+/* device pointer of the resident 8-byte row table in the DEVICE row format (movi_b200/csrc/dev_index.cuh; read-only;
+ * NULL without an index or with a compact layout) */
 const void* movi_gpu_index_device_rows(const movi_gpu_ctx* ctx);
+/* rows [first, first + count) of the resident 8-byte table, converted back to the reference's regular-thresholds MoveRow
+ * (include/move_row.hpp:131-142) in host memory -- the inverse of what upload / adopt do.  Tests and generators use it to
+ * hand a device-built table to the CPU side. */
+int  movi_gpu_index_export_rows(movi_gpu_ctx* ctx, uint64_t first, uint64_t count, void* host_rows);
 /* MOVI_GPU_LAYOUT_EXPANDED8 or MOVI_GPU_LAYOUT_COMPACT of the resident index (-1 without one) */
 int  movi_gpu_index_device_layout(const movi_gpu_ctx* ctx);
 /* bytes of HBM held by the uploaded index */

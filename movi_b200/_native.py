@@ -38,6 +38,7 @@ GPU_SYMBOLS = {
     "movi_gpu_adopt_device_rows": (C.c_int, [C.c_void_p, C.POINTER(MoviGpuIndexDesc), C.c_void_p]),
     "movi_gpu_index_device_rows": (C.c_void_p, [C.c_void_p]),
     "movi_gpu_index_device_layout": (C.c_int, [C.c_void_p]),
+    "movi_gpu_index_export_rows": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "movi_gpu_index_device_bytes": (C.c_uint64, [C.c_void_p]),
     "movi_gpu_query_pml": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]),
     "movi_gpu_query_ml8": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]),

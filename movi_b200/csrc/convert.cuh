@@ -1,4 +1,4 @@
-// convert.cuh -- upload-time re-layout kernels: packed on-disk rows -> R8 device rows.
+// convert.cuh -- upload-time re-layout kernels: on-disk rows -> R8 device rows.
 //
 // Each kernel decodes one on-disk layout exactly as the reference's per-MODE getters do and resolves
 // MoveStructure::get_id (src/move_structure.cpp:91-286) ONCE per row:
@@ -12,8 +12,21 @@ namespace movi {
 
 // ---- MODE 8: 6-byte rows {u16 id; u16 n; u16 offset} (include/move_row.hpp:128-130,139-142;
 //      bit fields include/move_row_configs.hpp:76-104)
+// ---- MODE 6: the 8-byte rows are already in HBM (copied or adopted); permute their bit fields into R8 in place
+__global__ void relayout_regular_kernel(uint2* __restrict__ rows, unsigned long long r, uint32_t sep) {
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (; i < r; i += stride) rows[i] = r8_from_file(rows[i], sep);
+}
+// the inverse, into a separate buffer (generators / tests that hand a device table to the CPU oracle)
+__global__ void relayout_to_file_kernel(const uint2* __restrict__ rows, uint2* __restrict__ out, unsigned long long r, uint32_t sep) {
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (; i < r; i += stride) out[i] = r8_to_file(rows[i], sep);
+}
+
 __global__ void convert_blocked_kernel(const uint16_t* __restrict__ raw, uint2* __restrict__ out,
-                                       unsigned long long r, unsigned long long end_idx,
+                                       unsigned long long r, unsigned long long end_idx, uint32_t sep,
                                        const uint32_t* __restrict__ id_blocks, unsigned long long id_blocks_size,
                                        unsigned long long block_size, const unsigned long long* __restrict__ first_runs) {
     unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
@@ -26,13 +39,13 @@ __global__ void convert_blocked_kernel(const uint16_t* __restrict__ raw, uint2* 
         const uint32_t thr = (f_off >> 13) & 7u;                       // thresholds #0..#2 = offset bits 13..15
         unsigned long long id = (unsigned long long)f_id | ((unsigned long long)((f_n >> 10) & 0x3Fu) << 16);
         if (i != end_idx) id += (unsigned long long)id_blocks[c * id_blocks_size + i / block_size] + first_runs[c + 1];
-        out[i] = make_r8(id, n, off, c, thr);
+        out[i] = make_r8(id, n, off, c, thr, sep);
     }
 }
 
 // ---- MODE 7 -> R8: one thread per row runs sampled_get_id (dev_index.cuh) on the packed table
 __global__ void convert_sampled_kernel(const uint32_t* __restrict__ raw_words, uint2* __restrict__ out,
-                                       unsigned long long r, unsigned long long end_idx,
+                                       unsigned long long r, unsigned long long end_idx, uint32_t sep,
                                        const uint8_t* __restrict__ tally, unsigned long long tally_len, uint32_t cp,
                                        unsigned int* __restrict__ status) {
     const Rows3 R{raw_words, end_idx};
@@ -44,7 +57,7 @@ __global__ void convert_sampled_kernel(const uint32_t* __restrict__ raw_words, u
         bool bad = false;
         const unsigned long long id = sampled_get_id(R, tally, tally_len, cp, r, end_idx, idx, ci, &bad);
         if (bad) atomicOr(status, 2u);
-        out[idx] = make_r8(id, Rows3::n_of(x), Rows3::off_of(x), ci, Rows3::thr_of(x));
+        out[idx] = make_r8(id, Rows3::n_of(x), Rows3::off_of(x), ci, Rows3::thr_of(x), sep);
     }
 }
 

@@ -1,15 +1,19 @@
 // dev_index.cuh -- device-resident form of a Movi index and the row decode.
 //
-// Device row format "R8" (one 64-bit word per move row, 4 rows per 32-byte HBM sector).  It is bit
-// for bit the reference's regular-thresholds MoveRow (include/move_row.hpp:131-142 with
-// include/move_row_configs.hpp:34-51), so a MODE 6 table is uploaded with a plain copy:
-//     x (low 32)  : id bits 0..31
-//     y bits 0..10: n (run length, <= 2047)        y bit 11 : threshold #1     y bit 12 : threshold #2
-//     y bits13..15: c (alphabet index)             y bits 16..26: offset       y bit 27 : threshold #0
-//     y bits28..31: id bits 32..35
-// blocked-thresholds (6-byte rows + id_blocks) and sampled-thresholds (3-byte rows + id checkpoints)
-// tables are re-laid out into R8 on the device at upload time (convert.cuh), resolving the full
-// destination id once per row instead of once per LF step.
+// Device row format "R8": one 64-bit word per move row, 4 rows per 32-byte HBM sector.  Same fields as the reference's
+// regular-thresholds MoveRow (include/move_row.hpp:131-142, include/move_row_configs.hpp:34-51), placed so that the query
+// kernels -- bound by the ALU pipe, DESIGN.md section 7 -- decode them with the fewest instructions:
+//     x (low 32)   : id bits 0..31
+//     y bits  0..10: n (run length, <= 2047)            y bits 11..21: offset
+//     y bits 22..24: id bits 32..34                      y bits 29..31: c (alphabet index; one shift, no mask)
+//     y bits 25..28: threshold mask, bit 25 + a = "the threshold against read character a is n (else 0)" for the four
+//                    alphabet indices a (with separators: a = code - 1).  The reference stores three bits and finds the one
+//                    to use through alphamap_3[c][a] (src/utils.cpp:5-8, move_structure_query.cpp:545-556); that lookup is
+//                    resolved once per row at upload.  (Rows assembled on the fly from the packed layouts carry the
+//                    reference's three bits in 25..27 instead: make_r8_raw3 / row_thr_raw3.)
+// Every index type is re-laid out into R8 on the device at upload time (convert.cuh): regular-thresholds by permuting the
+// bits of its 8-byte rows in place, blocked-thresholds (6-byte rows + id_blocks) and sampled-thresholds (3-byte rows + id
+// checkpoints) by also resolving the full destination id once per row instead of once per LF step.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -50,22 +54,62 @@ struct DevIndex {
 constexpr int PREFIX_SHIFT = 4;   // one u64 prefix per 16 rows (0.5 B/row)
 constexpr uint32_t CODE_ILLEGAL = 0xFFu;
 
-__device__ __forceinline__ uint32_t row_n(uint32_t y) { return y & 0x7FFu; }
-__device__ __forceinline__ uint32_t row_c(uint32_t y) { return (y >> 13) & 7u; }
-__device__ __forceinline__ uint32_t row_off(uint32_t y) { return (y >> 16) & 0x7FFu; }
-// thresholds #0..#2 gathered into bits 0..2
-__device__ __forceinline__ uint32_t row_thr_bits(uint32_t y) { return ((y >> 27) & 1u) | ((y >> 10) & 6u); }
+constexpr int R8_MAX_ROW_BITS = 35;     // 32 + 3 id bits: 3.4e10 rows = 275 GB of rows, more than a B200 holds
+
+__host__ __device__ __forceinline__ uint32_t row_n(uint32_t y) { return y & 0x7FFu; }
+__host__ __device__ __forceinline__ uint32_t row_c(uint32_t y) { return y >> 29; }
+__host__ __device__ __forceinline__ uint32_t row_off(uint32_t y) { return (y >> 11) & 0x7FFu; }
 template <typename IdxT>
-__device__ __forceinline__ IdxT row_id(uint2 v) {
-    if constexpr (sizeof(IdxT) == 8) return (IdxT)v.x | ((IdxT)(v.y >> 28) << 32);
+__host__ __device__ __forceinline__ IdxT row_id(uint2 v) {
+    if constexpr (sizeof(IdxT) == 8) return (IdxT)v.x | ((IdxT)((v.y >> 22) & 7u) << 32);
     else return (IdxT)v.x;
 }
-__host__ __device__ __forceinline__ uint2 make_r8(unsigned long long id, uint32_t n, uint32_t off, uint32_t c, uint32_t thr_bits) {
+// alphamap_3 (src/utils.cpp:5-8): slot of read character b among the three thresholds of a row with character a
+__host__ __device__ __forceinline__ uint32_t thr_slot(uint32_t a, uint32_t b) { return b - (b > a ? 1u : 0u); }
+// threshold of a resident row against read character index ai (get_thresholds, move_structure.cpp:306-308): n or 0
+__device__ __forceinline__ uint32_t row_thr(uint32_t y, uint32_t ai, uint32_t n) { return ((y >> (ai & 3u)) & (1u << 25)) ? n : 0u; }
+// the same for a row assembled on the fly from a packed layout (three reference bits in 25..27); a = c - sep
+__device__ __forceinline__ uint32_t row_thr_raw3(uint32_t y, uint32_t a, uint32_t ai, uint32_t n) {
+    return ((y >> (25u + (thr_slot(a, ai) & 3u))) & 1u) ? n : 0u;
+}
+__host__ __device__ __forceinline__ uint32_t r8_word(unsigned long long id, uint32_t n, uint32_t off, uint32_t c, uint32_t bits25) {
+    return (n & 0x7FFu) | ((off & 0x7FFu) << 11) | ((uint32_t)((id >> 32) & 7ull) << 22) | ((bits25 & 15u) << 25) | ((c & 7u) << 29);
+}
+// thr_bits = the reference's thresholds #0..#2 in bits 0..2; sep = 1 for the "%ACGT" alphabet
+__host__ __device__ __forceinline__ uint2 make_r8(unsigned long long id, uint32_t n, uint32_t off, uint32_t c, uint32_t thr_bits, uint32_t sep) {
+    const uint32_t a = c - sep;                     // ('%' rows: a wraps; their thresholds live in the side table)
+    uint32_t mask = 0;
+    for (uint32_t ai = 0; ai < 4; ai++)
+        if (ai != a) mask |= ((thr_bits >> (thr_slot(a, ai) & 3u)) & 1u) << ai;
     uint2 v;
     v.x = (uint32_t)(id & 0xFFFFFFFFull);
-    v.y = (n & 0x7FFu) | (((thr_bits >> 1) & 1u) << 11) | (((thr_bits >> 2) & 1u) << 12) | ((c & 7u) << 13) |
-          ((off & 0x7FFu) << 16) | ((thr_bits & 1u) << 27) | ((uint32_t)((id >> 32) & 0xFull) << 28);
+    v.y = r8_word(id, n, off, c, mask);
     return v;
+}
+__host__ __device__ __forceinline__ uint2 make_r8_raw3(unsigned long long id, uint32_t n, uint32_t off, uint32_t c, uint32_t thr_bits) {
+    uint2 v;
+    v.x = (uint32_t)(id & 0xFFFFFFFFull);
+    v.y = r8_word(id, n, off, c, thr_bits & 7u);
+    return v;
+}
+// The reference's regular-thresholds row (MODE 6 bit fields: n 0..10, thr#1 11, thr#2 12, c 13..15, offset 16..26, thr#0 27,
+// id high 28..31) <-> R8
+__host__ __device__ __forceinline__ uint2 r8_from_file(uint2 f, uint32_t sep) {
+    const uint32_t y = f.y;
+    const uint32_t thr = ((y >> 27) & 1u) | ((y >> 10) & 6u);
+    return make_r8((unsigned long long)f.x | ((unsigned long long)(y >> 28) << 32), y & 0x7FFu, (y >> 16) & 0x7FFu, (y >> 13) & 7u, thr, sep);
+}
+__host__ __device__ __forceinline__ uint2 r8_to_file(uint2 v, uint32_t sep) {
+    const uint32_t y = v.y, c = row_c(y), a = c - sep, mask = (y >> 25) & 15u;
+    uint32_t thr = 0;
+    for (uint32_t ai = 0; ai < 4; ai++)
+        if (ai != a) thr |= ((mask >> ai) & 1u) << (thr_slot(a, ai) & 3u);
+    thr &= 7u;
+    uint2 f;
+    f.x = v.x;
+    f.y = row_n(y) | (((thr >> 1) & 1u) << 11) | (((thr >> 2) & 1u) << 12) | (c << 13) | (row_off(y) << 16) | ((thr & 1u) << 27) |
+          (((y >> 22) & 7u) << 28);
+    return f;
 }
 
 __device__ __forceinline__ uint2 ldg64(const uint2* p) { return __ldg(p); }
@@ -93,11 +137,8 @@ __device__ __forceinline__ uint2 fetch_row_b6(const uint32_t* __restrict__ w, Id
     const uint32_t n = f_n & 0x3FFu, off = f_off & 0x3FFu, c = (f_off >> 10) & 7u, thr = f_off >> 13;
     unsigned long long id = (unsigned long long)f_id | ((unsigned long long)(f_n >> 10) << 16);
     if (idx != end_idx) id += (unsigned long long)idb[c * nb + (uint32_t)((unsigned long long)idx >> shift)] + first_runs[c + 1];
-    return make_r8(id, n, off, c, thr);
+    return make_r8_raw3(id, n, off, c, thr);
 }
-
-// alphamap_3 (src/utils.cpp:5-8): slot of read character b among the three thresholds of a row with character a
-__device__ __forceinline__ uint32_t thr_slot(uint32_t a, uint32_t b) { return b - (b > a ? 1u : 0u); }
 
 // threshold value of a '%' row (separators_thresholds[separators_thresholds_map[idx]].values[ai],
 // src/move_structure_query.cpp:540-541); rows missing from the map read slot 0 like unordered_map::operator[]

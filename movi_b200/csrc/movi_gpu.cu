@@ -619,7 +619,7 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
         return fail(ctx, MOVI_GPU_ERR_INDEX, "unsupported index mode " + std::to_string(d->mode) +
                     " (regular-thresholds 6, blocked-thresholds 8, sampled-thresholds 7)");
     if ((!d->rows && !adopt_rows) || !d->alphamap || d->r == 0) return fail(ctx, MOVI_GPU_ERR_INDEX, "empty index description");
-    if (d->r >= (1ull << 36)) return fail(ctx, MOVI_GPU_ERR_INDEX, "more than 2^36 rows");
+    if (d->r >= (1ull << R8_MAX_ROW_BITS)) return fail(ctx, MOVI_GPU_ERR_INDEX, "more than 2^35 rows");
     if (d->end_bwt_idx >= d->r) return fail(ctx, MOVI_GPU_ERR_INDEX, "end_bwt_idx out of range");
     const bool sep = (d->sigma == 5 && d->alphabet[0] == '%');       // use_separator(), src/move_structure.cpp:547-552
     if (!sep && (d->sigma < 1 || d->sigma > 4))
@@ -688,11 +688,14 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
     ctx->index_bytes = (r + 4) * sizeof(uint2);
     }
 
-    if (adopt_rows || compact) {
+    if (compact) {
         // nothing to convert
-    } else if (d->mode == MOVI_MODE_REGULAR_THRESHOLDS) {
-        // the on-disk row IS the device row: one copy
-        CU(cudaMemcpyAsync(ctx->d_rows, d->rows, r * sizeof(uint2), cudaMemcpyHostToDevice, st));
+    } else if (adopt_rows || d->mode == MOVI_MODE_REGULAR_THRESHOLDS) {
+        // the 8-byte rows of the reference: copy (unless already resident), then permute the bit fields into R8 in place
+        if (!adopt_rows) CU(cudaMemcpyAsync(ctx->d_rows, d->rows, r * sizeof(uint2), cudaMemcpyHostToDevice, st));
+        relayout_regular_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(ctx->d_rows, r, sep ? 1u : 0u);
+        ctx->launches += 1;
+        CU(cudaGetLastError());
     } else if (d->mode == MOVI_MODE_BLOCKED_THRESHOLDS) {
         Scratch s_raw, s_blocks, s_first;
         CU(cudaMalloc(&s_raw.p, r * 6 + 8));
@@ -703,7 +706,7 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
         CU(cudaMemcpyAsync(d_raw, d->rows, r * 6, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_blocks, d->id_blocks, (size_t)d->sigma * d->id_blocks_size * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_first, d->first_runs, 8 * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
-        convert_blocked_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(d_raw, ctx->d_rows, r, d->end_bwt_idx, d_blocks, d->id_blocks_size,
+        convert_blocked_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(d_raw, ctx->d_rows, r, d->end_bwt_idx, sep ? 1u : 0u, d_blocks, d->id_blocks_size,
                                                                d->block_size, d_first);
         ctx->launches += 1;
         CU(cudaStreamSynchronize(st));
@@ -719,7 +722,7 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
         CU(cudaMemcpyAsync(d_raw, d->rows, r * 3, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_tally, d->tally_ids, tally_bytes, cudaMemcpyHostToDevice, st));
         CU(cudaMemsetAsync(ctx->d_status, 0, sizeof(unsigned int), st));
-        convert_sampled_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_raw), ctx->d_rows, r, d->end_bwt_idx, d_tally, d->tally_len,
+        convert_sampled_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_raw), ctx->d_rows, r, d->end_bwt_idx, sep ? 1u : 0u, d_tally, d->tally_len,
                                                                d->tally_checkpoints, ctx->d_status);
         ctx->launches += 1;
         unsigned int status = 0;
@@ -791,6 +794,26 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
     ctx->has_index = true;
     rollback.done = true;
     return MOVI_GPU_OK;
+}
+
+int movi_gpu_index_export_rows(movi_gpu_ctx* ctx, uint64_t first, uint64_t count, void* host_rows) {
+    if (!ctx || (count && !host_rows)) return MOVI_GPU_ERR_ARG;
+    if (!ctx->has_index || !ctx->d_rows) return fail(ctx, MOVI_GPU_ERR_INDEX, "no 8-byte row table resident");
+    if (first > ctx->ix.r || count > ctx->ix.r - first) return fail(ctx, MOVI_GPU_ERR_ARG, "row range out of bounds");
+    CU(cudaSetDevice(ctx->device));
+    const uint64_t chunk = 1ull << 24;              // 128 MB of scratch at a time
+    uint2* d_tmp = nullptr;
+    CU(cudaMalloc(&d_tmp, std::min(chunk, std::max<uint64_t>(count, 1)) * sizeof(uint2)));
+    int rc = MOVI_GPU_OK;
+    for (uint64_t done = 0; done < count && rc == MOVI_GPU_OK; done += chunk) {
+        const uint64_t m = std::min(chunk, count - done);
+        relayout_to_file_kernel<<<ctx->num_sms * 8, 256, 0, ctx->st_k[0]>>>(ctx->d_rows + first + done, d_tmp, m, ctx->ix.sep);
+        if (cudaMemcpyAsync(static_cast<uint2*>(host_rows) + done, d_tmp, m * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->st_k[0]) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->st_k[0]) != cudaSuccess)
+            rc = fail(ctx, MOVI_GPU_ERR_CUDA, std::string("export rows: ") + cudaGetErrorString(cudaGetLastError()));
+    }
+    cudaFree(d_tmp);
+    return rc;
 }
 
 int movi_gpu_query_pml(movi_gpu_ctx* ctx, const char* bases, const uint64_t* read_offsets, uint64_t n_reads,

@@ -147,7 +147,7 @@ movi_pml_kernel(const DevIndex ix, const QueryArgs q) {
                         const uint32_t ai = code - sep;
                         if (idx == end_idx) thr = s_end_thr[ai & 3u];
                         else if (sep && c == 0) thr = sep_threshold(ix, (unsigned long long)idx, ai);
-                        else thr = ((row_thr_bits(y) >> thr_slot(c - sep, ai)) & 1u) ? n : 0u;   // get_thresholds
+                        else thr = row_thr(y, ai, n);                                        // get_thresholds
                         if (off >= thr) { if (idx == r1) bad = true; else { idx += 1; st = ST_DOWN; } }
                         else            { if (idx == 0)  bad = true; else { idx -= 1; st = ST_UP; } }
                     }

@@ -153,7 +153,7 @@ movi_pml_kernel2(const DevIndex ix, const QueryArgs q) {
 
         // threshold decision (reposition_thresholds :513-601); the '$' row and '%' rows are rare special cases
         const uint32_t ai = code - sep;
-        uint32_t thr = ((row_thr_bits(y) >> (thr_slot(c - sep, ai) & 3u)) & 1u) ? n : 0u;
+        uint32_t thr = row_thr(y, ai, n);
         if (base_mis & ((idx == end_idx) | ((sep != 0) & (c == 0)))) {     // one predicate: skipped by the whole warp
             thr = (idx == end_idx) ? s_end_thr[ai & 3u] : sep_threshold(ix, (unsigned long long)idx, ai);
         }

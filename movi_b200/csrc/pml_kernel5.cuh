@@ -144,7 +144,7 @@ movi_pml_kernel5(const DevIndex ix, const QueryArgs q) {
         else if (LAYOUT == LAYOUT_B6) v = fetch_row_b6<IdxT>(ix.rows6, fidx, end_idx, idb, ix.id_blocks_size, ix.block_shift, s_first);
         else {              // LAYOUT_T3: the 3-byte row without its destination id (resolved below, only when an LF step needs it)
             const uint32_t x = Rows3{ix.rows3, (unsigned long long)end_idx}.raw((unsigned long long)fidx);
-            v = make_r8(0, Rows3::n_of(x), Rows3::off_of(x), Rows3::c_of(x), Rows3::thr_of(x));
+            v = make_r8_raw3(0, Rows3::n_of(x), Rows3::off_of(x), Rows3::c_of(x), Rows3::thr_of(x));
         }
         // ---- service events.  Both are forced by one lane and then served for every lane of the warp that can use them, so
         // that they come round every few dozen iterations instead of in most of them:
@@ -188,7 +188,7 @@ movi_pml_kernel5(const DevIndex ix, const QueryArgs q) {
         const bool emit = (at_base && !base_mis) || scan_hit;
 
         const uint32_t ai = code - sep;
-        uint32_t thr = ((row_thr_bits(y) >> (thr_slot(c - sep, ai) & 3u)) & 1u) ? n : 0u;
+        uint32_t thr = (LAYOUT == LAYOUT_R8) ? row_thr(y, ai, n) : row_thr_raw3(y, c - sep, ai, n);
         if (base_mis & ((idx == end_idx) | (SEP & (c == 0)))) {            // '$' row / '%' rows: rare, skipped warp-wide
             thr = (idx == end_idx) ? s_end_thr[ai & 3u] : sep_threshold(ix, (unsigned long long)idx, ai);
         }

@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/movi_gpu.h"
+#include "../csrc/dev_index.cuh"          // the device row format the adopted table is rewritten into (make_reads walks it)
 
 namespace {
 
@@ -152,15 +153,15 @@ __global__ void make_reads(Gen g, const uint2* __restrict__ rows, uint8_t* __res
         for (uint32_t k = 0; k < len; k++) {
             h = mix(h + k);
             uint2 v = rows[idx];
-            uint32_t c = (v.y >> 13) & 7u;
-            if (idx == g.end_idx) { idx = (idx + 1 < g.r) ? idx + 1 : 0; off = 0; v = rows[idx]; c = (v.y >> 13) & 7u; }   // never emit '$'
+            uint32_t c = movi::row_c(v.y);
+            if (idx == g.end_idx) { idx = (idx + 1 < g.r) ? idx + 1 : 0; off = 0; v = rows[idx]; c = movi::row_c(v.y); }   // never emit '$'
             uint32_t e = c;
             if (rnd || (h & 1023u) < sub_per_1024) e = (uint32_t)((h >> 12) & 3u);
             out[len - 1 - k] = (uint8_t)ACGT[e & 3u];
             // LF_move (reference src/move_structure.cpp:59-87)
-            off += (v.y >> 16) & 0x7FFu;
-            idx = (u64)v.x | ((u64)(v.y >> 28) << 32);
-            for (;;) { const uint32_t n = rows[idx].y & 0x7FFu; if (idx < g.r - 1 && off >= n) { off -= n; idx++; } else break; }
+            off += movi::row_off(v.y);
+            idx = movi::row_id<u64>(v);
+            for (;;) { const uint32_t n = movi::row_n(rows[idx].y); if (idx < g.r - 1 && off >= n) { off -= n; idx++; } else break; }
         }
     }
 }
@@ -232,10 +233,5 @@ int movi_synth_reads(const void* d_rows, uint64_t r, uint64_t seed, void* d_base
     return 0;
 }
 
-// Copy the first `count` rows of a device table to the host (tests: hand a small synthetic table to the CPU oracle).
-int movi_synth_download_rows(const void* d_rows, uint64_t count, void* host) {
-    CK(cudaMemcpy(host, d_rows, count * sizeof(uint2), cudaMemcpyDeviceToHost));
-    return 0;
-}
 
 }  // extern "C"

@@ -22,8 +22,6 @@ def lib():
         L.movi_synth_index.restype = C.c_int
         L.movi_synth_reads.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
         L.movi_synth_reads.restype = C.c_int
-        L.movi_synth_download_rows.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
-        L.movi_synth_download_rows.restype = C.c_int
         _lib = L
     return _lib
 
@@ -58,8 +56,7 @@ class SyntheticStructure(MoveStructure):
     def write_index_file(self, directory):
         """index.movi (regular-thresholds) of this table, for the CPU oracle / the reference (small tables only)."""
         rows = np.empty(self.r * 2, dtype=np.uint32)
-        if lib().movi_synth_download_rows(self.device_rows, self.r, rows.ctypes.data) != 0:
-            raise RuntimeError("download failed")
+        self._check(self._L.movi_gpu_index_export_rows(self._ctx, 0, self.r, rows.ctypes.data))   # back in the reference's row format
         d = self.desc
         os.makedirs(directory, exist_ok=True)
         alphamap = np.full(256, 256, dtype=np.uint64)
