@@ -19,6 +19,7 @@ extern "C" {
 
 typedef struct movi_host_index movi_host_index;
 typedef struct movi_host_reads movi_host_reads;
+typedef struct movi_host_reader movi_host_reader;
 
 const char* movi_host_last_error(void);
 
@@ -34,6 +35,12 @@ void movi_host_index_close(movi_host_index* ix);
  * Read ids follow the reference: header from its 2nd character through AND INCLUDING the first
  * blank / tab / CR (src/batch_loader.cpp:117-119).  reverse != 0 reverses every read (--reverse). */
 int  movi_host_reads_load(const char* path, int reverse, movi_host_reads** out);
+/* The same parser batch by batch (the reference's BatchLoader hands out batches too, src/batch_loader.cpp:26-75): every call
+ * returns the next whole records holding about max_bases bases (at least one record), *out = NULL at the end of the input.
+ * The file stays memory-mapped, so inputs larger than RAM stream through. */
+int  movi_host_reader_open(const char* path, int reverse, movi_host_reader** out);
+int  movi_host_reader_next(movi_host_reader* r, uint64_t max_bases, movi_host_reads** out);
+void movi_host_reader_close(movi_host_reader* r);
 uint64_t movi_host_reads_count(const movi_host_reads* rd);
 const char* movi_host_reads_bases(const movi_host_reads* rd);          /* concatenated */
 const uint64_t* movi_host_reads_offsets(const movi_host_reads* rd);    /* count + 1 */
@@ -47,10 +54,16 @@ int  movi_host_nulldb_threshold(const char* index_dir, const char* query_type, u
 /* Writers.  `ml` holds the matching lengths of read i at offsets[i]..offsets[i+1] in storage order
  * (element 0 = last base), exactly what movi_gpu_query_pml / _zml return. */
 int  movi_host_write_bpf(const char* file, const movi_host_reads* rd, const uint16_t* ml);          /* src/utils.cpp:202-246 + BPFHeader */
+/* the same file written batch by batch: begin returns the descriptor (-1 on error) after writing the header */
+int  movi_host_bpf_begin(const char* file);
+int  movi_host_bpf_append(int fd, const movi_host_reads* rd, const uint16_t* ml);
+int  movi_host_bpf_end(int fd);
 int  movi_host_write_ml_text(int fd, const movi_host_reads* rd, const uint16_t* ml);                /* --stdout form */
 int  movi_host_write_counts(int fd, const movi_host_reads* rd, const uint64_t* counts, const int32_t* pos_on_r);   /* src/utils.cpp:248-256 */
 /* Classification report / filter (src/classifier.cpp:99-143, src/movi.cpp:36-47).
- * mode: 0 = report (with header) to fd, 1 = filter: print FOUND reads, 2 = filter --invert. found_out may be NULL. */
+ * mode: 0 = report (with header) to fd, 1 = filter: print FOUND reads, 2 = filter --invert; | MOVI_HOST_CLASSIFY_CONTINUE for the
+ * second and later batches of one report (no header).  found_out may be NULL. */
+#define MOVI_HOST_CLASSIFY_CONTINUE 4
 int  movi_host_classify(int fd, int mode, const movi_host_reads* rd, const uint16_t* ml, uint64_t bin_width,
                         uint64_t max_value_thr, uint8_t* found_out);
 

@@ -69,6 +69,9 @@ HOST_SYMBOLS = {
     "movi_host_index_type_name": (C.c_char_p, [C.c_void_p]),
     "movi_host_index_close": (None, [C.c_void_p]),
     "movi_host_reads_load": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "movi_host_reader_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "movi_host_reader_next": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "movi_host_reader_close": (None, [C.c_void_p]),
     "movi_host_reads_count": (C.c_uint64, [C.c_void_p]),
     "movi_host_reads_bases": (C.c_void_p, [C.c_void_p]),
     "movi_host_reads_offsets": (C.c_void_p, [C.c_void_p]),
@@ -76,6 +79,9 @@ HOST_SYMBOLS = {
     "movi_host_reads_free": (None, [C.c_void_p]),
     "movi_host_nulldb_threshold": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_uint64)]),
     "movi_host_write_bpf": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p]),
+    "movi_host_bpf_begin": (C.c_int, [C.c_char_p]),
+    "movi_host_bpf_append": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
+    "movi_host_bpf_end": (C.c_int, [C.c_int]),
     "movi_host_write_ml_text": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
     "movi_host_write_counts": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "movi_host_classify_bins": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -2,8 +2,9 @@
 //
 // Mirrors the query action of the reference (flags: src/movi_parser.cpp:132-162; driver: query() in
 // src/movi.cpp:221-400; output routing: include/movi_options.hpp:70-71, src/utils.cpp:319-384,
-// src/classifier.cpp:24-63).  Reads are loaded on the host, sharded over --gpus GPUs (index replicated,
-// one host thread + one context per GPU), results are written in read order (= reference --no-prefetch -t1).
+// src/classifier.cpp:24-63).  The read file streams through in batches (--chunk-bases; the next batch is parsed while the
+// GPUs walk the current one); each batch is sharded over --gpus GPUs (index replicated, one host thread + one context per
+// GPU) and its results are appended to the outputs in read order (= reference --no-prefetch -t1).
 // `movi-b200 view --bpf F` prints a .bpf file like the reference's view action (src/movi.cpp:402-503).
 #include <unistd.h>
 
@@ -11,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <random>
 #include <string>
 #include <thread>
@@ -27,6 +29,7 @@ struct Options {
     bool classify = false, filter = false, invert = false, to_stdout = false, no_output = false, reverse = false, verbose = false;
     int ignore_illegal = 0, gpus = 1, device = 0, threads = 1, strands = 16;
     uint64_t bin_width = 150;     // include/movi_options.hpp default
+    uint64_t chunk_bases = 1ull << 29;   // bases per batch of the streaming loop (host memory: ~3 bytes per base in flight)
     bool write_output_allowed() const { return !no_output && !filter; }          // movi_options.hpp:70
     bool write_stdout_enabled() const { return to_stdout && !classify; }         // movi_options.hpp:71
 };
@@ -35,7 +38,7 @@ struct Options {
     fprintf(stderr, "\033[31m\n\n[ERROR] %s\n\033[0m\n", m.c_str());
     fprintf(stderr, "usage: movi-b200 query -i <index dir> -r <reads.fa|fq|-> [--pml|--zml|--count] [--classify|--filter [-v]]\n"
                     "                       [--stdout] [-o prefix] [--no-output] [--reverse] [--ignore-illegal-chars 1|2]\n"
-                    "                       [--bin-width N] [--gpus N] [--device D] [-t N] [-s N] [-n]\n"
+                    "                       [--bin-width N] [--gpus N] [--device D] [--chunk-bases N] [-t N] [-s N] [-n]\n"
                     "       movi-b200 view --bpf <file.bpf>\n");
     exit(1);
 }
@@ -70,6 +73,7 @@ Options parse(int argc, char** argv) {
         else if (take_value(argc, argv, i, nullptr, "--gpus", v)) o.gpus = atoi(v.c_str());
         else if (take_value(argc, argv, i, nullptr, "--device", v)) o.device = atoi(v.c_str());
         else if (take_value(argc, argv, i, nullptr, "--bpf", v)) o.bpf_file = v;
+        else if (take_value(argc, argv, i, nullptr, "--chunk-bases", v)) o.chunk_bases = std::max<uint64_t>(1, strtoull(v.c_str(), nullptr, 10));
         else if (a == "--pml") o.query = "pml";
         else if (a == "--zml") o.query = "zml";
         else if (a == "--count") o.query = "count";
@@ -112,6 +116,9 @@ int view_bpf(const std::string& file) {   // reference src/movi.cpp:402-503 (16-
 }
 
 struct ShardResult { int rc = 0; std::string err; };
+struct Fetched { int rc = 0; movi_host_reads* rd = nullptr; std::string err; };
+
+void die(const std::string& m) { fprintf(stderr, "\033[31m\n\n[ERROR] %s\n\033[0m", m.c_str()); exit(1); }
 
 }  // namespace
 
@@ -123,132 +130,164 @@ int main(int argc, char** argv) {
 
     auto t_load0 = std::chrono::steady_clock::now();
     movi_host_index* hix = nullptr;
-    if (movi_host_index_open(o.index_dir.c_str(), &hix)) { fprintf(stderr, "\033[31m\n\n[ERROR] %s\n\033[0m", movi_host_last_error()); return 1; }
+    if (movi_host_index_open(o.index_dir.c_str(), &hix)) die(movi_host_last_error());
     MoviGpuIndexDesc desc;
     movi_host_index_desc(hix, &desc);
     const std::string type = movi_host_index_type_name(hix);
-    if (desc.mode == MOVI_MODE_SAMPLED_THRESHOLDS && o.query != "pml") {   // src/movi.cpp:228-233
-        fprintf(stderr, "\033[31m\n\n[ERROR] This query type is not suppported by the sampled modes yet.\n\033[0m");
-        return 1;
-    }
-    movi_host_reads* rd = nullptr;
-    if (movi_host_reads_load(o.read_file.c_str(), o.reverse ? 1 : 0, &rd)) { fprintf(stderr, "\033[31m\n\n[ERROR] %s\n\033[0m", movi_host_last_error()); return 1; }
-    const uint64_t n_reads = movi_host_reads_count(rd);
-    const uint64_t* offsets = movi_host_reads_offsets(rd);
-    char* bases = const_cast<char*>(movi_host_reads_bases(rd));
-    const uint64_t n_bases = n_reads ? offsets[n_reads] : 0;
-
-    if (o.ignore_illegal > 0) {   // check_alphabet's in-place substitution, src/move_structure.cpp:389-395
-        std::mt19937 gen{std::random_device{}()};
-        std::uniform_int_distribution<int> dist(1, 100);
-        const bool sep = (desc.sigma == 5 && desc.alphabet[0] == '%');
-        for (uint64_t i = 0; i < n_bases; i++) {
-            const unsigned char c = (unsigned char)bases[i];
-            if (sep && c == '%') continue;
-            if (desc.alphamap[c] == 256) bases[i] = o.ignore_illegal == 1 ? 'A' : (char)desc.alphabet[dist(gen) % desc.sigma];
-        }
-    }
+    if (desc.mode == MOVI_MODE_SAMPLED_THRESHOLDS && o.query != "pml")     // src/movi.cpp:228-233
+        die("This query type is not suppported by the sampled modes yet.");
+    movi_host_reader* reader = nullptr;
+    if (movi_host_reader_open(o.read_file.c_str(), o.reverse ? 1 : 0, &reader)) die(movi_host_last_error());
 
     int n_dev = movi_gpu_device_count();
-    if (n_dev <= 0) { fprintf(stderr, "\033[31m\n\n[ERROR] no CUDA device: movi-b200 has no CPU path (use the reference binaries on CPU-only hosts)\n\033[0m"); return 1; }
+    if (n_dev <= 0) die("no CUDA device: movi-b200 has no CPU path (use the reference binaries on CPU-only hosts)");
     const int gpus = std::max(1, std::min(o.gpus, n_dev));
 
     uint64_t max_value_thr = 0;
-    if (o.classify) {
-        if (movi_host_nulldb_threshold(o.index_dir.c_str(), o.query.c_str(), &max_value_thr)) {
-            fprintf(stderr, "\033[31m\n\n[ERROR] %s\n\033[0m", movi_host_last_error()); return 1;
-        }
+    if (o.classify && movi_host_nulldb_threshold(o.index_dir.c_str(), o.query.c_str(), &max_value_thr)) die(movi_host_last_error());
+
+    // the input streams through in batches of --chunk-bases bases: batch k + 1 is parsed while the GPUs walk batch k
+    auto fetch = [&]() { Fetched f; f.rc = movi_host_reader_next(reader, o.chunk_bases, &f.rd); if (f.rc) f.err = movi_host_last_error(); return f; };
+    std::future<Fetched> ahead = std::async(std::launch::async, fetch);
+
+    // one context per GPU, index replicated (uploaded while the first batch is being parsed)
+    std::vector<movi_gpu_ctx*> ctx(gpus, nullptr);
+    std::vector<ShardResult> res(gpus);
+    {
+        std::vector<std::thread> th;
+        for (int g = 0; g < gpus; g++) th.emplace_back([&, g]() {
+            int rc = movi_gpu_create(o.device + g, &ctx[g]);
+            if (rc) { res[g] = {rc, movi_gpu_last_error(nullptr)}; return; }
+            rc = movi_gpu_upload_index(ctx[g], &desc, MOVI_GPU_LAYOUT_AUTO);
+            if (rc) res[g] = {rc, movi_gpu_last_error(ctx[g])};
+        });
+        for (auto& t : th) t.join();
+        for (int g = 0; g < gpus; g++) if (res[g].rc) die("GPU " + std::to_string(o.device + g) + ": " + res[g].err);
     }
+    auto t_q0 = std::chrono::steady_clock::now();
 
     // With --classify / --filter the binning runs on the device (movi_gpu_query_classify); the matching lengths only come
     // back when something needs them (the .bpf file next to a --classify report; never for --filter or --no-output).
     const bool fused_classify = o.classify && o.query != "count";
     const bool need_ml = o.query != "count" && (!fused_classify || o.write_output_allowed());
-    std::vector<uint16_t> ml; std::vector<uint64_t> counts; std::vector<int32_t> pos;
-    std::vector<uint32_t> bins_above, bins_below; std::vector<uint64_t> sum_max;
-    if (o.query == "count") { counts.resize(n_reads); pos.resize(n_reads); } else if (need_ml) ml.resize(n_bases);
-    if (fused_classify) { bins_above.resize(n_reads); bins_below.resize(n_reads); sum_max.resize(n_reads); }
 
-    // contiguous shards balanced by bases (same decomposition as the reference's OpenMP batches, movi.cpp:274-301)
-    std::vector<uint64_t> cut(gpus + 1, n_reads);
-    cut[0] = 0;
-    for (int g = 1; g < gpus; g++) {
-        const uint64_t target = n_bases / gpus * g;
-        uint64_t i = cut[g - 1];
-        while (i < n_reads && offsets[i] < target) i++;
-        cut[g] = i;
-    }
-    std::vector<ShardResult> res(gpus);
-    auto t_q0 = std::chrono::steady_clock::now();
-    auto worker = [&](int g) {
-        movi_gpu_ctx* ctx = nullptr;
-        int rc = movi_gpu_create(o.device + g, &ctx);
-        if (rc) { res[g] = {rc, movi_gpu_last_error(nullptr)}; return; }
-        rc = movi_gpu_upload_index(ctx, &desc, MOVI_GPU_LAYOUT_AUTO);
-        if (!rc && cut[g + 1] > cut[g]) {
-            const uint64_t i0 = cut[g], nr = cut[g + 1] - cut[g];
-            // offsets stay absolute: the entry points index bases / outputs by them
-            if (fused_classify)
-                rc = movi_gpu_query_classify(ctx, o.query == "zml", bases, offsets + i0, nr, 0, (uint32_t)o.bin_width, (uint32_t)max_value_thr,
-                                             bins_above.data() + i0, bins_below.data() + i0, sum_max.data() + i0, need_ml ? ml.data() : nullptr);
-            else if (o.query == "pml") rc = movi_gpu_query_pml(ctx, bases, offsets + i0, nr, 0, ml.data());
-            else if (o.query == "zml") rc = movi_gpu_query_zml(ctx, bases, offsets + i0, nr, 0, ml.data());
-            else rc = movi_gpu_query_count(ctx, bases, offsets + i0, nr, 0, counts.data() + i0, pos.data() + i0);
-        }
-        if (rc) res[g] = {rc, movi_gpu_last_error(ctx)};
-        movi_gpu_destroy(ctx);
-    };
-    std::vector<std::thread> th;
-    for (int g = 0; g < gpus; g++) th.emplace_back(worker, g);
-    for (auto& t : th) t.join();
-    for (int g = 0; g < gpus; g++)
-        if (res[g].rc) { fprintf(stderr, "\033[31m\n\n[ERROR] GPU %d: %s\n\033[0m", o.device + g, res[g].err.c_str()); return 1; }
-    auto t_q1 = std::chrono::steady_clock::now();
-    if (o.verbose)
-        fprintf(stderr, "[INFO] index + reads loaded in %.3f s; index upload + query on %d GPU(s): %.3f s for %llu reads / %llu bases\n",
-                std::chrono::duration<double>(t_q0 - t_load0).count(), gpus, std::chrono::duration<double>(t_q1 - t_q0).count(),
-                (unsigned long long)n_reads, (unsigned long long)n_bases);
-
-    // ---- outputs, in the order of handle_pml_zml / handle_count (src/movi.cpp:23-76)
+    // ---- output sinks, routed like handle_pml_zml / handle_count (src/movi.cpp:23-76)
     const std::string prefix = (o.out_file.empty() ? o.read_file + "." + type : o.out_file) + "." + o.query;   // utils.cpp:348-351
-    int rc = 0;
+    FILE* f_counts = nullptr; FILE* f_report = nullptr; int fd_bpf = -1;
     if (o.query == "count") {
-        if (o.write_output_allowed()) {
-            if (o.write_stdout_enabled()) rc = movi_host_write_counts(STDOUT_FILENO, rd, counts.data(), pos.data());
-            else {
-                FILE* f = fopen((prefix + ".matches").c_str(), "w");
-                if (!f) { fprintf(stderr, "cannot open %s.matches\n", prefix.c_str()); return 1; }
-                fflush(f);
-                rc = movi_host_write_counts(fileno(f), rd, counts.data(), pos.data());
-                fclose(f);
-            }
+        if (o.write_output_allowed() && !o.write_stdout_enabled()) {
+            f_counts = fopen((prefix + ".matches").c_str(), "w");
+            if (!f_counts) die("cannot open " + prefix + ".matches");
         }
     } else {
-        if (o.classify) {
-            if (!o.filter) {
-                // report: stdout with --stdout, else <reads>.<type>.<q>.report (classifier.cpp:39-60)
-                FILE* f = nullptr; int fd = STDOUT_FILENO;
-                if (!o.to_stdout) {
-                    f = fopen((o.read_file + "." + type + "." + o.query + ".report").c_str(), "w");
-                    if (!f) { fprintf(stderr, "cannot open the report file\n"); return 1; }
-                    fd = fileno(f);
-                }
-                // with --no-output the reference still prints the header but no rows (write_output_allowed)
-                movi_host_reads* none = nullptr;
-                if (o.no_output) { movi_host_reads_load("/dev/null", 0, &none); rc = movi_host_classify(fd, 0, none, nullptr, o.bin_width, max_value_thr, nullptr); movi_host_reads_free(none); }
-                else rc = movi_host_classify_bins(fd, 0, rd, max_value_thr, bins_above.data(), bins_below.data(), sum_max.data(), nullptr);
-                if (f) fclose(f);
-            } else if (!o.no_output) {
-                rc = movi_host_classify_bins(STDOUT_FILENO, o.invert ? 2 : 1, rd, max_value_thr, bins_above.data(), bins_below.data(), sum_max.data(), nullptr);
-            }
+        if (o.classify && !o.filter && !o.to_stdout) {          // <reads>.<type>.<q>.report (classifier.cpp:39-60)
+            f_report = fopen((o.read_file + "." + type + "." + o.query + ".report").c_str(), "w");
+            if (!f_report) die("cannot open the report file");
         }
-        if (!rc && o.write_output_allowed()) {
-            if (o.write_stdout_enabled()) rc = movi_host_write_ml_text(STDOUT_FILENO, rd, ml.data());
-            else rc = movi_host_write_bpf((prefix + ".bpf").c_str(), rd, ml.data());
+        if (o.write_output_allowed() && !o.write_stdout_enabled()) {
+            fd_bpf = movi_host_bpf_begin((prefix + ".bpf").c_str());
+            if (fd_bpf < 0) die(movi_host_last_error());
         }
     }
-    if (rc) { fprintf(stderr, "\033[31m\n\n[ERROR] %s\n\033[0m", movi_host_last_error()); return 1; }
-    movi_host_reads_free(rd);
+
+    std::vector<uint16_t> ml; std::vector<uint64_t> counts; std::vector<int32_t> pos;
+    std::vector<uint32_t> bins_above, bins_below; std::vector<uint64_t> sum_max;
+    std::mt19937 gen{std::random_device{}()};
+    std::uniform_int_distribution<int> dist(1, 100);
+    uint64_t total_reads = 0, total_bases = 0, batches = 0;
+    bool report_started = false;
+    int rc = 0;
+
+    for (;;) {
+        Fetched cur = ahead.get();
+        if (cur.rc) die(cur.err);
+        movi_host_reads* rd = cur.rd;
+        const bool last = (rd == nullptr);
+        if (!last) ahead = std::async(std::launch::async, fetch);
+        // an empty input still produces its (empty) outputs: run the writers once on an empty batch
+        movi_host_reads* empty = nullptr;
+        if (last) { if (batches) break; movi_host_reads_load("/dev/null", 0, &empty); rd = empty; }
+        const uint64_t n_reads = movi_host_reads_count(rd);
+        const uint64_t* offsets = movi_host_reads_offsets(rd);
+        char* bases = const_cast<char*>(movi_host_reads_bases(rd));
+        const uint64_t n_bases = n_reads ? offsets[n_reads] : 0;
+
+        if (o.ignore_illegal > 0) {   // check_alphabet's in-place substitution, src/move_structure.cpp:389-395
+            const bool sep = (desc.sigma == 5 && desc.alphabet[0] == '%');
+            for (uint64_t i = 0; i < n_bases; i++) {
+                const unsigned char c = (unsigned char)bases[i];
+                if (sep && c == '%') continue;
+                if (desc.alphamap[c] == 256) bases[i] = o.ignore_illegal == 1 ? 'A' : (char)desc.alphabet[dist(gen) % desc.sigma];
+            }
+        }
+        if (o.query == "count") { counts.resize(n_reads); pos.resize(n_reads); } else if (need_ml) ml.resize(n_bases);
+        if (fused_classify) { bins_above.resize(n_reads); bins_below.resize(n_reads); sum_max.resize(n_reads); }
+
+        // contiguous shards balanced by bases (same decomposition as the reference's OpenMP batches, movi.cpp:274-301)
+        std::vector<uint64_t> cut(gpus + 1, n_reads);
+        cut[0] = 0;
+        for (int g = 1; g < gpus; g++) {
+            const uint64_t target = n_bases / gpus * g;
+            uint64_t i = cut[g - 1];
+            while (i < n_reads && offsets[i] < target) i++;
+            cut[g] = i;
+        }
+        auto worker = [&](int g) {
+            if (cut[g + 1] <= cut[g]) return;
+            const uint64_t i0 = cut[g], nr = cut[g + 1] - cut[g];
+            int r;
+            // offsets stay absolute: the entry points index bases / outputs by them
+            if (fused_classify)
+                r = movi_gpu_query_classify(ctx[g], o.query == "zml", bases, offsets + i0, nr, 0, (uint32_t)o.bin_width, (uint32_t)max_value_thr,
+                                            bins_above.data() + i0, bins_below.data() + i0, sum_max.data() + i0, need_ml ? ml.data() : nullptr);
+            else if (o.query == "pml") r = movi_gpu_query_pml(ctx[g], bases, offsets + i0, nr, 0, ml.data());
+            else if (o.query == "zml") r = movi_gpu_query_zml(ctx[g], bases, offsets + i0, nr, 0, ml.data());
+            else r = movi_gpu_query_count(ctx[g], bases, offsets + i0, nr, 0, counts.data() + i0, pos.data() + i0);
+            if (r) res[g] = {r, movi_gpu_last_error(ctx[g])};
+        };
+        std::vector<std::thread> th;
+        for (int g = 0; g < gpus; g++) th.emplace_back(worker, g);
+        for (auto& t : th) t.join();
+        for (int g = 0; g < gpus; g++) if (res[g].rc) die("GPU " + std::to_string(o.device + g) + ": " + res[g].err);
+
+        // ---- this batch's share of the outputs
+        if (o.query == "count") {
+            if (o.write_output_allowed())
+                rc = movi_host_write_counts(f_counts ? (fflush(f_counts), fileno(f_counts)) : STDOUT_FILENO, rd, counts.data(), pos.data());
+        } else {
+            if (o.classify) {
+                const int cont = report_started ? MOVI_HOST_CLASSIFY_CONTINUE : 0;
+                if (!o.filter) {
+                    const int fd = f_report ? (fflush(f_report), fileno(f_report)) : STDOUT_FILENO;
+                    // with --no-output the reference still prints the header but no rows (write_output_allowed)
+                    if (o.no_output) { if (!report_started) { movi_host_reads* none = nullptr; movi_host_reads_load("/dev/null", 0, &none);
+                                                              rc = movi_host_classify(fd, 0, none, nullptr, o.bin_width, max_value_thr, nullptr); movi_host_reads_free(none); } }
+                    else rc = movi_host_classify_bins(fd, 0 | cont, rd, max_value_thr, bins_above.data(), bins_below.data(), sum_max.data(), nullptr);
+                } else if (!o.no_output) {
+                    rc = movi_host_classify_bins(STDOUT_FILENO, (o.invert ? 2 : 1) | cont, rd, max_value_thr, bins_above.data(), bins_below.data(), sum_max.data(), nullptr);
+                }
+                report_started = true;
+            }
+            if (!rc && o.write_output_allowed()) {
+                if (o.write_stdout_enabled()) rc = movi_host_write_ml_text(STDOUT_FILENO, rd, ml.data());
+                else rc = movi_host_bpf_append(fd_bpf, rd, ml.data());
+            }
+        }
+        if (rc) die(movi_host_last_error());
+        total_reads += n_reads; total_bases += n_bases; batches += 1;
+        movi_host_reads_free(rd);
+        if (last) break;
+    }
+    auto t_q1 = std::chrono::steady_clock::now();
+    if (o.verbose)
+        fprintf(stderr, "[INFO] index loaded + uploaded in %.3f s; %llu batch(es) parsed, queried on %d GPU(s) and written in %.3f s: %llu reads / %llu bases\n",
+                std::chrono::duration<double>(t_q0 - t_load0).count(), (unsigned long long)batches, gpus,
+                std::chrono::duration<double>(t_q1 - t_q0).count(), (unsigned long long)total_reads, (unsigned long long)total_bases);
+    if (f_counts) fclose(f_counts);
+    if (f_report) fclose(f_report);
+    if (fd_bpf >= 0 && movi_host_bpf_end(fd_bpf)) die(movi_host_last_error());
+    for (int g = 0; g < gpus; g++) movi_gpu_destroy(ctx[g]);
+    movi_host_reader_close(reader);
     movi_host_index_close(hix);
     return 0;
 }

@@ -14,6 +14,7 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <memory>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -232,51 +233,72 @@ static bool gunzip_all(const char* in, size_t n, std::string& out) {
     return true;
 }
 
-int movi_host_reads_load(const char* path, int reverse, movi_host_reads** out) {
+// A read file opened for batch-wise parsing: the file stays mapped (stdin: slurped; gzip: inflated in memory) and every
+// movi_host_reader_next() call parses the next run of whole records.
+struct movi_host_reader {
+    const char* data = nullptr; size_t size = 0;
+    std::string slurp, inflated; void* map = nullptr; size_t map_size = 0; int fd = -1;
+    bool fastq = false, eof = false; int reverse = 0;
+    LineCursor lc{nullptr, nullptr};
+    ~movi_host_reader() { if (map) munmap(map, map_size); if (fd >= 0) close(fd); }
+};
+
+int movi_host_reader_open(const char* path, int reverse, movi_host_reader** out) {
     if (!path || !out) return fail("null argument");
     *out = nullptr;
-    const char* data = nullptr; size_t size = 0;
-    std::string slurp; void* map = nullptr; int fd = -1;
+    std::unique_ptr<movi_host_reader> r(new movi_host_reader());
+    r->reverse = reverse;
     if (std::string(path) == "-") {                      // "-" = stdin, reference src/movi.cpp:106-118
         char buf[1 << 16]; ssize_t n;
-        while ((n = ::read(STDIN_FILENO, buf, sizeof buf)) > 0) slurp.append(buf, (size_t)n);
-        data = slurp.data(); size = slurp.size();
+        while ((n = ::read(STDIN_FILENO, buf, sizeof buf)) > 0) r->slurp.append(buf, (size_t)n);
+        r->data = r->slurp.data(); r->size = r->slurp.size();
     } else {
-        fd = open(path, O_RDONLY);
+        r->fd = open(path, O_RDONLY);
         struct stat sb;
-        if (fd < 0 || fstat(fd, &sb) != 0) { if (fd >= 0) close(fd); return fail("The input file " + std::string(path) + " does not exist."); }
-        size = (size_t)sb.st_size;
-        if (size) {
-            map = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
-            if (map == MAP_FAILED) { close(fd); return fail("mmap failed for " + std::string(path)); }
-            madvise(map, size, MADV_SEQUENTIAL);
-            data = static_cast<const char*>(map);
+        if (r->fd < 0 || fstat(r->fd, &sb) != 0) return fail("The input file " + std::string(path) + " does not exist.");
+        r->size = (size_t)sb.st_size;
+        if (r->size) {
+            void* m = mmap(nullptr, r->size, PROT_READ, MAP_PRIVATE, r->fd, 0);
+            if (m == MAP_FAILED) return fail("mmap failed for " + std::string(path));
+            r->map = m; r->map_size = r->size;
+            madvise(m, r->size, MADV_SEQUENTIAL);
+            r->data = static_cast<const char*>(m);
         }
     }
-    const size_t map_size = size;
-    auto cleanup = [&]() { if (map) munmap(map, map_size); if (fd >= 0) close(fd); };
-    std::string inflated;
-    if (size >= 2 && (unsigned char)data[0] == 0x1f && (unsigned char)data[1] == 0x8b) {
-        if (!gunzip_all(data, size, inflated)) { cleanup(); return fail("corrupt gzip stream in " + std::string(path)); }
-        data = inflated.data(); size = inflated.size();
+    if (r->size >= 2 && (unsigned char)r->data[0] == 0x1f && (unsigned char)r->data[1] == 0x8b) {
+        if (!gunzip_all(r->data, r->size, r->inflated)) return fail("corrupt gzip stream in " + std::string(path));
+        r->data = r->inflated.data(); r->size = r->inflated.size();
     }
-    movi_host_reads* rd = new movi_host_reads();
-    if (size == 0) { cleanup(); *out = rd; return 0; }
-    bool fastq;
-    if (data[0] == '>') fastq = false;
-    else if (data[0] == '@') fastq = true;
-    else { delete rd; cleanup(); return fail("unrecognized input query file type - expects FASTA or FASTQ."); }
-    rd->bases.reserve(fastq ? size / 2 + 64 : size);
-    rd->offsets.reserve(size / 160 + 16); rd->id_offsets.reserve(size / 160 + 16);
+    if (r->size == 0) r->eof = true;
+    else if (r->data[0] == '>') r->fastq = false;
+    else if (r->data[0] == '@') r->fastq = true;
+    else return fail("unrecognized input query file type - expects FASTA or FASTQ.");
+    r->lc = LineCursor{r->data, r->data + r->size};
+    *out = r.release();
+    return 0;
+}
 
-    LineCursor lc{data, data + size};
+void movi_host_reader_close(movi_host_reader* r) { delete r; }
+
+// Whole records until the batch holds max_bases bases (at least one record); *out = NULL once the input is exhausted.
+int movi_host_reader_next(movi_host_reader* r, uint64_t max_bases, movi_host_reads** out) {
+    if (!r || !out) return fail("null argument");
+    *out = nullptr;
+    if (r->eof) return 0;
+    const bool fastq = r->fastq;
+    LineCursor& lc = r->lc;
+    std::unique_ptr<movi_host_reads> rd(new movi_host_reads());
+    const size_t left = (size_t)(lc.end - lc.p);
+    const size_t expect = (size_t)std::min<uint64_t>(left, max_bases + (max_bases >> 3) + 4096);
+    rd->bases.reserve(fastq ? std::min(expect, left / 2 + 64) : expect);
+    rd->offsets.reserve(expect / 160 + 16); rd->id_offsets.reserve(expect / 160 + 16);
     const char *b, *e;
-    auto fail_free = [&](const std::string& m) { delete rd; cleanup(); return fail(m); };
-    while (lc.next(b, e)) {
-        if (b == e) break;                               // grabNextRead: an empty line ends the batch
+    while (rd->bases.size() < max_bases) {
+        if (!lc.next(b, e)) { r->eof = true; break; }
+        if (b == e) { r->eof = true; break; }            // grabNextRead: an empty line ends the input
         if (fastq ? *b != '@' : *b != '>')
-            return fail_free(std::string("Incorrect ") + (fastq ? "FASTQ entry, it should start with '@'" : "FASTA entry, it should start with '>'"));
-        if (e - b <= 2) return fail_free("header line is missing an id. invalid query cannot be processed.");
+            return fail(std::string("Incorrect ") + (fastq ? "FASTQ entry, it should start with '@'" : "FASTA entry, it should start with '>'"));
+        if (e - b <= 2) return fail("header line is missing an id. invalid query cannot be processed.");
         // id: header[1 .. first blank / tab / CR] INCLUDING that character (batch_loader.cpp:117-119)
         const char* w = b + 1;
         while (w < e && *w != ' ' && *w != '\t' && *w != '\r') w++;
@@ -284,24 +306,39 @@ int movi_host_reads_load(const char* path, int reverse, movi_host_reads** out) {
         rd->ids.append(b + 1, std::min<size_t>(idl, (size_t)(e - b) - 1));
         rd->id_offsets.push_back(rd->ids.size());
         const size_t seq_begin = rd->bases.size();
+        auto drop_record = [&]() {                       // a truncated last record is dropped
+            rd->bases.resize(seq_begin); rd->ids.resize(rd->id_offsets[rd->id_offsets.size() - 2]); rd->id_offsets.pop_back(); r->eof = true;
+        };
         if (fastq) {
             const char *sb_, *se_, *x0, *x1;
-            if (!lc.next(sb_, se_)) { rd->ids.resize(rd->id_offsets[rd->id_offsets.size() - 2]); rd->id_offsets.pop_back(); break; }
+            if (!lc.next(sb_, se_)) { drop_record(); break; }
             rd->bases.append(sb_, (size_t)(rtrim_end(sb_, se_) - sb_));
-            if (!lc.next(x0, x1) || !lc.next(x0, x1)) {  // '+' line and qualities: a truncated record is dropped
-                rd->bases.resize(seq_begin); rd->ids.resize(rd->id_offsets[rd->id_offsets.size() - 2]); rd->id_offsets.pop_back(); break;
-            }
+            if (!lc.next(x0, x1) || !lc.next(x0, x1)) { drop_record(); break; }   // '+' line and qualities
         } else {
             while (lc.p < lc.end && !lc.peek_is('>')) {
                 lc.next(b, e);
                 rd->bases.append(b, (size_t)(rtrim_end(b, e) - b));
             }
         }
-        if (reverse) std::reverse(rd->bases.begin() + (std::ptrdiff_t)seq_begin, rd->bases.end());   // read_processor.cpp:49-51, movi.cpp:351-352
+        if (r->reverse) std::reverse(rd->bases.begin() + (std::ptrdiff_t)seq_begin, rd->bases.end());   // read_processor.cpp:49-51, movi.cpp:351-352
         rd->offsets.push_back(rd->bases.size());
     }
-    cleanup();
-    *out = rd;
+    if (lc.p >= lc.end) r->eof = true;
+    if (rd->offsets.size() == 1) return 0;               // nothing parsed: end of input
+    *out = rd.release();
+    return 0;
+}
+
+int movi_host_reads_load(const char* path, int reverse, movi_host_reads** out) {
+    if (!path || !out) return fail("null argument");
+    *out = nullptr;
+    movi_host_reader* r = nullptr;
+    if (movi_host_reader_open(path, reverse, &r)) return 1;
+    movi_host_reads* rd = nullptr;
+    const int rc = movi_host_reader_next(r, ~0ull, &rd);
+    movi_host_reader_close(r);
+    if (rc) return rc;
+    *out = rd ? rd : new movi_host_reads();              // an empty file is an empty batch
     return 0;
 }
 
@@ -345,16 +382,22 @@ int movi_host_nulldb_threshold(const char* index_dir, const char* query_type, ui
 
 
 // output_base_stats (binary branch) + BPFHeader, reference src/utils.cpp:202-246, include/utils.hpp:64-86
-int movi_host_write_bpf(const char* file, const movi_host_reads* rd, const uint16_t* ml) {
-    if (!file || !rd || (!ml && !rd->bases.empty())) return fail("null argument");
+int movi_host_bpf_begin(const char* file) {
+    if (!file) { fail("null argument"); return -1; }
     const int fd = open(file, O_WRONLY | O_CREAT | O_TRUNC, 0644);
-    if (fd < 0) return fail(std::string("cannot open ") + file);
-    FdWriter w(fd);
+    if (fd < 0) { fail(std::string("cannot open ") + file); return -1; }
     uint8_t header[12] = {0};
     std::memcpy(header, &BPF_MAGIC, 4);
     header[4] = 1; header[5] = 0; header[6] = 0;         // BPF_VERSION 1.0.0, include/version.hpp:13-15
     header[7] = 16;                                      // entry size in bits
-    bool ok = w.put(reinterpret_cast<const char*>(header), 12);
+    if (::write(fd, header, 12) != 12) { close(fd); fail(std::string("write failed: ") + file); return -1; }
+    return fd;
+}
+
+int movi_host_bpf_append(int fd, const movi_host_reads* rd, const uint16_t* ml) {
+    if (fd < 0 || !rd || (!ml && !rd->bases.empty())) return fail("null argument");
+    FdWriter w(fd);
+    bool ok = true;
     const uint64_t n = rd->offsets.size() - 1;
     for (uint64_t i = 0; i < n && ok; i++) {
         const uint16_t idl = (uint16_t)(rd->id_offsets[i + 1] - rd->id_offsets[i]);
@@ -363,8 +406,17 @@ int movi_host_write_bpf(const char* file, const movi_host_reads* rd, const uint1
              w.put(reinterpret_cast<const char*>(&len), 8) && w.put(reinterpret_cast<const char*>(ml + rd->offsets[i]), len * 2);
     }
     ok = ok && w.flush();
-    ok = (close(fd) == 0) && ok;
-    return ok ? 0 : fail(std::string("write failed: ") + file);
+    return ok ? 0 : fail("write failed: .bpf");
+}
+
+int movi_host_bpf_end(int fd) { return (fd >= 0 && close(fd) == 0) ? 0 : fail("close failed: .bpf"); }
+
+int movi_host_write_bpf(const char* file, const movi_host_reads* rd, const uint16_t* ml) {
+    if (!file || !rd || (!ml && !rd->bases.empty())) return fail("null argument");
+    const int fd = movi_host_bpf_begin(file);
+    if (fd < 0) return 1;
+    const int rc = movi_host_bpf_append(fd, rd, ml);
+    return movi_host_bpf_end(fd) | rc;
 }
 
 // output_base_stats (--stdout branch), reference src/utils.cpp:204-209 with MoveQuery::add_ml's string
@@ -414,8 +466,10 @@ static int classify_impl(int fd, int mode, const movi_host_reads* rd, const uint
     FdWriter w(fd);
     std::ostringstream out;
     const uint16_t thr = (uint16_t)max_value_thr;
-    if (mode == 0) {
-        out.precision(4);
+    const bool continuation = (mode & MOVI_HOST_CLASSIFY_CONTINUE) != 0;      // a later batch of the same report: no header
+    mode &= ~MOVI_HOST_CLASSIFY_CONTINUE;
+    out.precision(4);
+    if (mode == 0 && !continuation) {
         out << std::setw(30) << std::left << "read id:" << std::setw(15) << std::left << "status:"
             << std::setw(19) << std::left << "avg max-value (thr=" << std::setw(2) << std::left << thr
             << std::setw(5) << std::left << "):" << std::setw(12) << std::left << "above thr:"

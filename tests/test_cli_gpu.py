@@ -97,3 +97,31 @@ def test_reverse_and_ignore_illegal(cli, index_dirs):
     sub = ["".join(c if c in "ACGT" else "A" for c in rd.read(i)) for i in range(rd.count)]
     b, o = pack_reads(sub)
     assert run(cli, "query", "-i", d, "-r", reads_path("edge.fasta"), "--pml", "--ignore-illegal-chars", "1", "--stdout") == ml_text(rd.ids(), o, orc.query_pml(b, o))
+
+
+def test_streaming_batches_give_the_same_files(cli, index_dirs, tmp_path):
+    """--chunk-bases: the read file goes through in many small batches (parse-ahead, appended outputs, two GPUs' worth of
+    sharding logic on one device); every output must be byte-identical to the single-batch run."""
+    d = index_dirs[("regular-thresholds", False)]
+    for read_set, q in (("synth300.fasta", "pml"), ("synth300.fasta", "zml"), ("synth300.fasta", "count"), ("sample.fastq", "pml")):
+        out = run(cli, "query", "-i", d, "-r", reads_path(read_set), "--" + q, "--stdout", "--chunk-bases", "3000")
+        assert out == expected_text(read_set, q)
+    reads = tmp_path / "long6.fasta"
+    shutil.copy(reads_path("long6.fasta"), reads)
+    out = run(cli, "query", "-i", d, "-r", str(reads), "--pml", "--classify", "--stdout", "--chunk-bases", "1")    # one read per batch
+    assert out == open(os.path.join(GOLD, "expected", "long6.fasta.pml.report")).read()
+    reads = tmp_path / "sample.fasta"
+    shutil.copy(reads_path("sample.fasta"), reads)
+    run(cli, "query", "-i", d, "-r", str(reads), "--pml", "--chunk-bases", "500")
+    got = open(str(reads) + ".regular-thresholds.pml.bpf", "rb").read()
+    want = lzma.open(os.path.join(GOLD, "expected", "sample.fasta.pml.bpf.xz")).read()
+    assert got[:10] == want[:10] and got[12:] == want[12:]
+    for inv, name in ((False, "filtered"), (True, "filtered_notfound")):
+        out = run(cli, "query", "-i", d, "-r", str(reads), "--pml", "--filter", "--chunk-bases", "700", *(["-v"] if inv else []))
+        assert out == lzma.open(os.path.join(GOLD, "expected", "sample.fasta.pml.%s.xz" % name)).read().decode()
+    # an empty read file still yields its (empty) outputs
+    empty = tmp_path / "none.fasta"
+    empty.write_bytes(b"")
+    assert run(cli, "query", "-i", d, "-r", str(empty), "--pml", "--stdout") == ""
+    run(cli, "query", "-i", d, "-r", str(empty), "--pml")
+    assert len(open(str(empty) + ".regular-thresholds.pml.bpf", "rb").read()) == 12

@@ -110,6 +110,36 @@ def test_reads_loader_inflates_gzip(tmp_path):
         Reads(str(bad))
 
 
+def test_batch_reader_equals_whole_file_loader():
+    """movi_host_reader_*: the same records as movi_host_reads_load, whatever the batch size (the CLI streams with it)."""
+    import ctypes as C
+    L = N.host_lib()
+    for name in ("synth300.fasta", "sample.fastq", "edge.fasta"):
+        whole = Reads(reads_path(name))
+        for max_bases in (1, 700, 10**9):
+            h = C.c_void_p()
+            assert L.movi_host_reader_open(os.fsencode(reads_path(name)), 0, C.byref(h)) == 0
+            ids, seqs, batches = [], [], 0
+            while True:
+                b = C.c_void_p()
+                assert L.movi_host_reader_next(h, max_bases, C.byref(b)) == 0
+                if not b.value:
+                    break
+                batches += 1
+                n = L.movi_host_reads_count(b)
+                off = np.ctypeslib.as_array(C.cast(L.movi_host_reads_offsets(b), N.u64p), shape=(n + 1,))
+                data = C.string_at(L.movi_host_reads_bases(b), int(off[-1]))
+                for i in range(n):
+                    ln = C.c_uint32()
+                    p = L.movi_host_reads_id(b, i, C.byref(ln))
+                    ids.append(C.string_at(p, ln.value).decode())
+                    seqs.append(data[int(off[i]):int(off[i + 1])].decode())
+                L.movi_host_reads_free(b)
+            L.movi_host_reader_close(h)
+            assert ids == whole.ids() and seqs == [whole.read(i) for i in range(whole.count)]
+            assert batches == 1 if max_bases == 10**9 else batches > 1
+
+
 def _write_via(fn, *args):
     import tempfile
     with tempfile.TemporaryFile() as f:
