@@ -29,7 +29,7 @@ struct Options {
     bool classify = false, filter = false, invert = false, to_stdout = false, no_output = false, reverse = false, verbose = false;
     int ignore_illegal = 0, gpus = 1, device = 0, threads = 1, strands = 16;
     uint64_t bin_width = 150;     // include/movi_options.hpp default
-    uint64_t chunk_bases = 1ull << 29;   // bases per batch of the streaming loop (host memory: ~3 bytes per base in flight)
+    uint64_t chunk_bases = 1ull << 26;   // bases per batch of the streaming loop (host memory: ~10 bytes per base of a batch)
     bool write_output_allowed() const { return !no_output && !filter; }          // movi_options.hpp:70
     bool write_stdout_enabled() const { return to_stdout && !classify; }         // movi_options.hpp:71
 };
@@ -118,6 +118,27 @@ int view_bpf(const std::string& file) {   // reference src/movi.cpp:402-503 (16-
 struct ShardResult { int rc = 0; std::string err; };
 struct Fetched { int rc = 0; movi_host_reads* rd = nullptr; std::string err; };
 
+// results of one batch in pinned host memory (grown on demand, reused by every second batch)
+template <typename T> struct PinnedBuf {
+    T* p = nullptr; size_t cap = 0;
+    bool need(size_t n) {
+        if (n <= cap && p) return true;
+        if (p) movi_gpu_host_free(p);
+        p = nullptr; cap = 0;
+        const size_t want = n + n / 8 + 4096;
+        void* q = nullptr;
+        if (movi_gpu_host_alloc(&q, want * sizeof(T))) return false;
+        p = static_cast<T*>(q); cap = want;
+        return true;
+    }
+    ~PinnedBuf() { if (p) movi_gpu_host_free(p); }
+};
+struct Results {
+    movi_host_reads* rd = nullptr;
+    PinnedBuf<uint16_t> ml; PinnedBuf<uint64_t> counts; PinnedBuf<int32_t> pos;
+    PinnedBuf<uint32_t> above, below; PinnedBuf<uint64_t> sum;
+};
+
 void die(const std::string& m) { fprintf(stderr, "\033[31m\n\n[ERROR] %s\n\033[0m", m.c_str()); exit(1); }
 
 }  // namespace
@@ -190,13 +211,48 @@ int main(int argc, char** argv) {
         }
     }
 
-    std::vector<uint16_t> ml; std::vector<uint64_t> counts; std::vector<int32_t> pos;
-    std::vector<uint32_t> bins_above, bins_below; std::vector<uint64_t> sum_max;
+    // Three stages run side by side: the parser thread reads batch k + 1, the GPUs walk batch k, the writer thread appends
+    // batch k - 1 to the outputs.  Results land in pinned host buffers (DMA speed, no page faults), two sets alternating.
+    Results slot[2];
     std::mt19937 gen{std::random_device{}()};
     std::uniform_int_distribution<int> dist(1, 100);
     uint64_t total_reads = 0, total_bases = 0, batches = 0;
     bool report_started = false;
-    int rc = 0;
+
+    auto write_batch = [&](Results& R) -> std::string {       // returns an error message, empty on success
+        movi_host_reads* rd = R.rd;
+        int rc = 0;
+        if (o.query == "count") {
+            if (o.write_output_allowed())
+                rc = movi_host_write_counts(f_counts ? (fflush(f_counts), fileno(f_counts)) : STDOUT_FILENO, rd, R.counts.p, R.pos.p);
+        } else {
+            if (o.classify) {
+                const int cont = report_started ? MOVI_HOST_CLASSIFY_CONTINUE : 0;
+                if (!o.filter) {
+                    const int fd = f_report ? (fflush(f_report), fileno(f_report)) : STDOUT_FILENO;
+                    // with --no-output the reference still prints the header but no rows (write_output_allowed)
+                    if (o.no_output) {
+                        if (!report_started) {
+                            movi_host_reads* none = nullptr; movi_host_reads_load("/dev/null", 0, &none);
+                            rc = movi_host_classify(fd, 0, none, nullptr, o.bin_width, max_value_thr, nullptr); movi_host_reads_free(none);
+                        }
+                    } else rc = movi_host_classify_bins(fd, 0 | cont, rd, max_value_thr, R.above.p, R.below.p, R.sum.p, nullptr);
+                } else if (!o.no_output) {
+                    rc = movi_host_classify_bins(STDOUT_FILENO, (o.invert ? 2 : 1) | cont, rd, max_value_thr, R.above.p, R.below.p, R.sum.p, nullptr);
+                }
+                report_started = true;
+            }
+            if (!rc && o.write_output_allowed()) {
+                if (o.write_stdout_enabled()) rc = movi_host_write_ml_text(STDOUT_FILENO, rd, R.ml.p);
+                else rc = movi_host_bpf_append(fd_bpf, rd, R.ml.p);
+            }
+        }
+        std::string err = rc ? movi_host_last_error() : "";
+        movi_host_reads_free(rd);
+        R.rd = nullptr;
+        return err;
+    };
+    std::future<std::string> writing;
 
     for (;;) {
         Fetched cur = ahead.get();
@@ -205,8 +261,9 @@ int main(int argc, char** argv) {
         const bool last = (rd == nullptr);
         if (!last) ahead = std::async(std::launch::async, fetch);
         // an empty input still produces its (empty) outputs: run the writers once on an empty batch
-        movi_host_reads* empty = nullptr;
-        if (last) { if (batches) break; movi_host_reads_load("/dev/null", 0, &empty); rd = empty; }
+        if (last) { if (batches) break; movi_host_reads_load("/dev/null", 0, &rd); }
+        Results& R = slot[batches & 1];                  // (its previous batch has been written: see the wait below)
+        R.rd = rd;
         const uint64_t n_reads = movi_host_reads_count(rd);
         const uint64_t* offsets = movi_host_reads_offsets(rd);
         char* bases = const_cast<char*>(movi_host_reads_bases(rd));
@@ -220,8 +277,11 @@ int main(int argc, char** argv) {
                 if (desc.alphamap[c] == 256) bases[i] = o.ignore_illegal == 1 ? 'A' : (char)desc.alphabet[dist(gen) % desc.sigma];
             }
         }
-        if (o.query == "count") { counts.resize(n_reads); pos.resize(n_reads); } else if (need_ml) ml.resize(n_bases);
-        if (fused_classify) { bins_above.resize(n_reads); bins_below.resize(n_reads); sum_max.resize(n_reads); }
+        bool ok = true;
+        if (o.query == "count") ok = R.counts.need(n_reads) && R.pos.need(n_reads);
+        else if (need_ml) ok = R.ml.need(n_bases);
+        if (ok && fused_classify) ok = R.above.need(n_reads) && R.below.need(n_reads) && R.sum.need(n_reads);
+        if (!ok) die("cannot allocate pinned host memory for the results of a batch (try a smaller --chunk-bases)");
 
         // contiguous shards balanced by bases (same decomposition as the reference's OpenMP batches, movi.cpp:274-301)
         std::vector<uint64_t> cut(gpus + 1, n_reads);
@@ -239,45 +299,27 @@ int main(int argc, char** argv) {
             // offsets stay absolute: the entry points index bases / outputs by them
             if (fused_classify)
                 r = movi_gpu_query_classify(ctx[g], o.query == "zml", bases, offsets + i0, nr, 0, (uint32_t)o.bin_width, (uint32_t)max_value_thr,
-                                            bins_above.data() + i0, bins_below.data() + i0, sum_max.data() + i0, need_ml ? ml.data() : nullptr);
-            else if (o.query == "pml") r = movi_gpu_query_pml(ctx[g], bases, offsets + i0, nr, 0, ml.data());
-            else if (o.query == "zml") r = movi_gpu_query_zml(ctx[g], bases, offsets + i0, nr, 0, ml.data());
-            else r = movi_gpu_query_count(ctx[g], bases, offsets + i0, nr, 0, counts.data() + i0, pos.data() + i0);
+                                            R.above.p + i0, R.below.p + i0, R.sum.p + i0, need_ml ? R.ml.p : nullptr);
+            else if (o.query == "pml") r = movi_gpu_query_pml(ctx[g], bases, offsets + i0, nr, 0, R.ml.p);
+            else if (o.query == "zml") r = movi_gpu_query_zml(ctx[g], bases, offsets + i0, nr, 0, R.ml.p);
+            else r = movi_gpu_query_count(ctx[g], bases, offsets + i0, nr, 0, R.counts.p + i0, R.pos.p + i0);
             if (r) res[g] = {r, movi_gpu_last_error(ctx[g])};
         };
-        std::vector<std::thread> th;
-        for (int g = 0; g < gpus; g++) th.emplace_back(worker, g);
-        for (auto& t : th) t.join();
+        if (gpus == 1) worker(0);
+        else {
+            std::vector<std::thread> th;
+            for (int g = 0; g < gpus; g++) th.emplace_back(worker, g);
+            for (auto& t : th) t.join();
+        }
         for (int g = 0; g < gpus; g++) if (res[g].rc) die("GPU " + std::to_string(o.device + g) + ": " + res[g].err);
 
-        // ---- this batch's share of the outputs
-        if (o.query == "count") {
-            if (o.write_output_allowed())
-                rc = movi_host_write_counts(f_counts ? (fflush(f_counts), fileno(f_counts)) : STDOUT_FILENO, rd, counts.data(), pos.data());
-        } else {
-            if (o.classify) {
-                const int cont = report_started ? MOVI_HOST_CLASSIFY_CONTINUE : 0;
-                if (!o.filter) {
-                    const int fd = f_report ? (fflush(f_report), fileno(f_report)) : STDOUT_FILENO;
-                    // with --no-output the reference still prints the header but no rows (write_output_allowed)
-                    if (o.no_output) { if (!report_started) { movi_host_reads* none = nullptr; movi_host_reads_load("/dev/null", 0, &none);
-                                                              rc = movi_host_classify(fd, 0, none, nullptr, o.bin_width, max_value_thr, nullptr); movi_host_reads_free(none); } }
-                    else rc = movi_host_classify_bins(fd, 0 | cont, rd, max_value_thr, bins_above.data(), bins_below.data(), sum_max.data(), nullptr);
-                } else if (!o.no_output) {
-                    rc = movi_host_classify_bins(STDOUT_FILENO, (o.invert ? 2 : 1) | cont, rd, max_value_thr, bins_above.data(), bins_below.data(), sum_max.data(), nullptr);
-                }
-                report_started = true;
-            }
-            if (!rc && o.write_output_allowed()) {
-                if (o.write_stdout_enabled()) rc = movi_host_write_ml_text(STDOUT_FILENO, rd, ml.data());
-                else rc = movi_host_bpf_append(fd_bpf, rd, ml.data());
-            }
-        }
-        if (rc) die(movi_host_last_error());
+        // hand the batch to the writer once the previous one is on disk (outputs are appended in read order)
+        if (writing.valid()) { const std::string err = writing.get(); if (!err.empty()) die(err); }
+        writing = std::async(std::launch::async, write_batch, std::ref(R));
         total_reads += n_reads; total_bases += n_bases; batches += 1;
-        movi_host_reads_free(rd);
         if (last) break;
     }
+    if (writing.valid()) { const std::string err = writing.get(); if (!err.empty()) die(err); }
     auto t_q1 = std::chrono::steady_clock::now();
     if (o.verbose)
         fprintf(stderr, "[INFO] index loaded + uploaded in %.3f s; %llu batch(es) parsed, queried on %d GPU(s) and written in %.3f s: %llu reads / %llu bases\n",
