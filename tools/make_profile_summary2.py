@@ -44,13 +44,15 @@ for title, src, dst, tfile, wl, algo, nb in runs:
                "algorithmic_bytes_per_base": algo, "source": "profiles/%s (ncu --set full, one full-batch launch)" % dst},
               open(os.path.join('profiles', tfile), 'w'), indent=1)
 md += ["",
-       "* PML variant 5 against variant 4 (table above): warp instructions 1.70 -> 1.58e9 (-7 %), DRAM traffic 8.79 -> 8.30 GB (evict_first on the streamed bytes), time in the bench 2.12 -> 1.97 ms.  Still the same regime: ~68 % issue active, 34 % L2 hits on the 124 MB table.",
+       "* PML variant 5 against variant 4 (table above): warp instructions 1.70 -> 1.5-1.6e9, DRAM traffic 8.79 -> 8.3 GB (evict_first on the streamed bytes), time in the bench 2.12 -> 1.94 ms.  Still the same regime: ~68 % issue active (the ALU pipe at ~70 % of its peak, the FMA pipe at 15 %), 34 % L2 hits on the 124 MB table.",
        "* ZML moves the same DRAM bytes per base as PML (the two interval ends sit in the same or neighbouring rows once a few bases have matched) but issues 1.7x the instructions (two walkers per lane): it is issue bound, not memory bound; 64 B/base is the SURVEY's accounting, 54 B/base is what DRAM sees.",
        "* count stops at the first failed extension (mean 104 of 150 bases): 1.41e9 instructions, 5.3 GB.",
        "* `r01_launches_bench.csv`: launch list of the same bench command -- the timed region holds `movi_pml_kernel4` launches only (full-batch launches on two alternating streams; the 82..328-block launches are the slices of the host-buffer legs `e2e`, `e2e_classify` (+ `classify_kernel`) and `e2e_ml8` (+ `narrow_ml_kernel`)).",
        "* `r01_pipeline_sweep.jsonl`, `r01_host_probe.jsonl`: host-buffer pipeline shapes and what the box's PCIe / host memory can do (H2D 55 GB/s, D2H 57 GB/s alone, 150 MB up + 300 MB down together 5.9 ms)."]
-open('profiles/r01_summary.md', 'a').write("\n".join(md) + "\n")
+old = open('profiles/r01_summary.md').read()
+marker = "\n## Final default kernels of the round"
+if marker in old:
+    old = old[:old.index(marker)] + "\n"          # regenerate this section
+open('profiles/r01_summary.md', 'w').write(old.rstrip("\n") + "\n" + "\n".join(md) + "\n")
 shutil.copy('gpurun_out/launches_f.csv', 'profiles/r01_launches_bench.csv')
-for s, d in (('bench_f.json', 'r01_bench.json'), ('bench_f_c3-zml.json', 'r01_bench_c3_zml.json'), ('bench_f_c3-count.json', 'r01_bench_c3_count.json')):
-    shutil.copy(os.path.join('gpurun_out', s), os.path.join('profiles', d))
 print("\n".join(md))
