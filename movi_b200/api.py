@@ -173,6 +173,14 @@ class MoveStructure:
                                                     _ptr(above), _ptr(below), _ptr(total), _ptr(ml) if want_ml else None))
         return (above, below, total, ml) if want_ml else (above, below, total)
 
+    def export_rows(self, first=0, count=None):
+        """Rows of the resident 8-byte table back in the reference's regular-thresholds MoveRow format -> uint32[count, 2]."""
+        if count is None:
+            count = self.r - first
+        out = np.empty((count, 2), dtype=np.uint32)
+        self._check(self._L.movi_gpu_index_export_rows(self._ctx, first, count, _ptr(out)))
+        return out
+
     def query_ml8(self, bases, offsets, zml=False, out=None):
         """PML (or ZML) of a batch of reads of at most 255 bases, returned as uint8 (half the copy-back of query_pml)."""
         bases, offsets, n = self._prep(bases, offsets)

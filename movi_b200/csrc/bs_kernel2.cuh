@@ -25,7 +25,7 @@ constexpr uint32_t B_IDLE = 0, B_NEW = 1, B_SKIP = 2, B_RUN = 3, B_FAIL = 4, B_F
 // interval end keeps the aligned 32-byte sector (4 rows) of its last fetch in registers; scan and fast-forward steps that
 // stay inside it, and the very common case of both ends sitting in the same rows, cost no new request.
 template <typename IdxT, int KIND, int LAYOUT, bool SECTOR = false>
-__global__ void __launch_bounds__(PML3_THREADS, SECTOR ? 3 : 1)
+__global__ void __launch_bounds__(PML3_THREADS, SECTOR ? 3 : 5)
 movi_bs_kernel2(const DevIndex ix, const QueryArgs q) {
     __shared__ uint8_t s_code[256];
     __shared__ uint32_t s_idb[LAYOUT == LAYOUT_B6 ? IDB_SMEM : 1];

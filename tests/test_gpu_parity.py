@@ -334,3 +334,25 @@ def test_matching_lengths_saturate_at_65535(structures, index_dirs, ref_seq, typ
         c, p = ms.query_backward_search(bases, offsets)
         c2, p2 = orc.query_count(bases, offsets, threads=0)
         assert np.array_equal(c, c2) and np.array_equal(p, p2) and p[0] == 0 and c[0] >= 1
+
+
+@pytest.mark.parametrize("sep", [False, True])
+def test_device_row_format_round_trips_to_the_file_format(structures, index_dirs, sep):
+    """Upload permutes the bit fields of the regular-thresholds rows into the device format (threshold mask per read character,
+    character at the top of the word); movi_gpu_index_export_rows must give back the file's rows bit for bit."""
+    import ctypes as C
+    from movi_b200 import HostIndex
+    d = index_dirs[("regular-thresholds", sep)]
+    hix = HostIndex(d)
+    r = hix.r
+    file_rows = np.ctypeslib.as_array(C.cast(hix.desc.rows, C.POINTER(C.c_uint32)), shape=(r, 2)).copy()
+    got = structures[("regular-thresholds", sep)].export_rows()
+    assert got.shape == (r, 2)
+    assert np.array_equal(got[:, 0], file_rows[:, 0])
+    diff = np.nonzero(got[:, 1] != file_rows[:, 1])[0]
+    # the only freedom: threshold bits of rows whose character lies outside the four query characters ('$', '%')
+    for i in diff:
+        c = (int(file_rows[i, 1]) >> 13) & 7
+        assert i == hix.end_bwt_idx or (sep and c == 0) or c >= 4 + (1 if sep else 0), (int(i), hex(int(file_rows[i, 1])), hex(int(got[i, 1])))
+        assert (int(got[i, 1]) ^ int(file_rows[i, 1])) & ~((1 << 11) | (1 << 12) | (1 << 27)) == 0
+    assert len(diff) <= 16
