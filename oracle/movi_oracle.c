@@ -355,8 +355,41 @@ static int reposition_thresholds(const movi_oracle_index* ix, uint64_t* idx, uin
 
 static inline uint16_t clamp16(uint64_t v) { return v > 65535 ? 65535 : (uint16_t)v; }   /* move_query.hpp:26-38 */
 
+/* reposition_randomly, move_structure_query.cpp:604-688 (--rpml; the "random" direction is the half of the run the offset
+ * lies in -- the call to the random generator is commented out in the reference, :607-608).  Returns 1 = up, 0 = down. */
+static int reposition_randomly(const movi_oracle_index* ix, uint64_t* idx, uint64_t offset, unsigned char r_char) {
+    const uint64_t saved = *idx;
+    int dir = offset * 2 < row_n(ix, *idx) ? 1 : 0;                                   /* :608 */
+    if (*idx == ix->r - 1) dir = 1;                                                   /* :616-618 */
+    if (*idx == 0) dir = 0;                                                           /* :619-621 */
+    int up;
+    if ((dir == 1 && *idx > 0) || *idx == ix->r - 1) {                                /* :623 */
+        up = 1;
+        *idx = reposition_up(ix, saved, r_char);
+        if (*idx >= ix->r) {                                                          /* :634-649 */
+            up = 0;
+            *idx = reposition_down(ix, saved, r_char);
+            if (*idx == ix->r) return fail("[reposition randomly] Neither up or down repositioning works.");
+        }
+    } else {
+        up = 0;
+        *idx = reposition_down(ix, saved, r_char);
+        if (*idx >= ix->r) {                                                          /* :661-674 */
+            up = 1;
+            *idx = reposition_up(ix, saved, r_char);
+            if (*idx == ix->r) return fail("[reposition randomly] Neither up or down repositioning works.");
+        }
+    }
+    if (*idx >= ix->r || raw_char(ix, *idx) != r_char) return fail("[reposition randomly] This should never happen.");
+    return up;
+}
+
+static int query_pml_impl(const movi_oracle_index* ix, const char* read, int64_t len, uint16_t* out, int rpml);
 /* query_pml, move_structure_query.cpp:234-474 (multi-class / logs / SA branches are off) */
-int movi_oracle_query_pml(const movi_oracle_index* ix, const char* read, int64_t len, uint16_t* out) {
+int movi_oracle_query_pml(const movi_oracle_index* ix, const char* read, int64_t len, uint16_t* out) { return query_pml_impl(ix, read, len, out, 0); }
+/* the same with --rpml: Case 2 repositions with reposition_randomly (:304-311) */
+int movi_oracle_query_rpml(const movi_oracle_index* ix, const char* read, int64_t len, uint16_t* out) { return query_pml_impl(ix, read, len, out, 1); }
+static int query_pml_impl(const movi_oracle_index* ix, const char* read, int64_t len, uint16_t* out, int rpml) {
     int64_t pos = len - 1;
     uint64_t idx = ix->r - 1;
     uint64_t offset = row_n(ix, idx) - 1;
@@ -370,7 +403,7 @@ int movi_oracle_query_pml(const movi_oracle_index* ix, const char* read, int64_t
         } else if (row_ch == (int)rc) {
             match_len += 1;
         } else {
-            int up = reposition_thresholds(ix, &idx, offset, rc);
+            int up = rpml ? reposition_randomly(ix, &idx, offset, rc) : reposition_thresholds(ix, &idx, offset, rc);
             if (up < 0) return -1;
             match_len = 0;
             offset = up ? row_n(ix, idx) - 1 : 0;
@@ -478,6 +511,7 @@ int movi_oracle_query_ml_batch(const movi_oracle_index* ix, int kind, const char
         int64_t L = (int64_t)(offsets[i + 1] - offsets[i]);
         int rc;
         if (kind == 0) rc = movi_oracle_query_pml(ix, bases + offsets[i], L, out + offsets[i]);
+        else if (kind == 2) rc = movi_oracle_query_rpml(ix, bases + offsets[i], L, out + offsets[i]);
         else rc = movi_oracle_query_zml(ix, bases + offsets[i], L, out + offsets[i]) == L ? 0 : -1;
         if (rc) {
             #pragma omp atomic write

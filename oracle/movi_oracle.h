@@ -46,6 +46,8 @@ int64_t movi_oracle_lf_move(const movi_oracle_index* ix, uint64_t* offset, uint6
 /* PML of one read (reference query_pml).  out[k] is the k-th value produced, i.e. out[0]
  * belongs to the LAST base.  Returns 0, or <0 when the reference would have thrown. */
 int movi_oracle_query_pml(const movi_oracle_index* ix, const char* read, int64_t len, uint16_t* out);
+/* --rpml: PML with reposition_randomly (move_structure_query.cpp:604-688) instead of the thresholds */
+int movi_oracle_query_rpml(const movi_oracle_index* ix, const char* read, int64_t len, uint16_t* out);
 /* ZML of one read (reference query_zml); same orientation. Returns number of values written
  * (== len for every read the reference handles without UB) or <0. */
 int64_t movi_oracle_query_zml(const movi_oracle_index* ix, const char* read, int64_t len, uint16_t* out);
@@ -55,7 +57,7 @@ int movi_oracle_query_count(const movi_oracle_index* ix, const char* read, int64
                             uint64_t* count, int32_t* pos_on_r);
 
 /* Batch forms over concatenated reads (read i = bases[offsets[i] .. offsets[i+1]) ), OpenMP over
- * reads with `threads` threads (<=0: all).  kind: 0 = PML, 1 = ZML.  out uses the same offsets. */
+ * reads with `threads` threads (<=0: all).  kind: 0 = PML, 1 = ZML, 2 = PML with --rpml.  out uses the same offsets. */
 int movi_oracle_query_ml_batch(const movi_oracle_index* ix, int kind, const char* bases,
                                const uint64_t* offsets, uint64_t n_reads, uint16_t* out, int threads);
 int movi_oracle_query_count_batch(const movi_oracle_index* ix, const char* bases,

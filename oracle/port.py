@@ -113,6 +113,10 @@ class OracleIndex:
     def query_zml(self, bases, offsets, threads=1):
         return self._ml(1, bases, offsets, threads)
 
+    def query_rpml(self, bases, offsets, threads=1):
+        """--rpml: PML with the offset-based repositioning instead of the thresholds."""
+        return self._ml(2, bases, offsets, threads)
+
     def query_count(self, bases, offsets, threads=1):
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
