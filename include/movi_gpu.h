@@ -83,6 +83,9 @@ typedef struct movi_gpu_ctx movi_gpu_ctx;
 
 /* Query flags */
 #define MOVI_GPU_FLAG_NONE 0u
+/* PML entry points (query_pml, _pml_device, _classify, _ml8): `movi query --rpml`, i.e. reposition with reposition_randomly
+ * (src/move_structure_query.cpp:604-688, selected at :304-311) instead of the thresholds.  Ignored by ZML / count. */
+#define MOVI_GPU_FLAG_RPML 1u
 
 /* Device-resident row layouts (chosen at upload). */
 #define MOVI_GPU_LAYOUT_AUTO     0   /* EXPANDED8 when it fits in free HBM, else COMPACT where the mode has one */

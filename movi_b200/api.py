@@ -19,6 +19,9 @@ def device_count():
     return N.gpu_lib().movi_gpu_device_count()
 
 
+FLAG_RPML = 1          # MOVI_GPU_FLAG_RPML (include/movi_gpu.h)
+
+
 class HostIndex:
     """index.movi opened on the host (MoveStructure::deserialize, reference src/move_structure_io.cpp:471-511)."""
 
@@ -155,11 +158,12 @@ class MoveStructure:
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         return bases, offsets, len(offsets) - 1
 
-    def query_pml(self, bases, offsets, out=None):
+    def query_pml(self, bases, offsets, out=None, rpml=False):
+        """rpml=True: `movi query --rpml` (reposition_randomly instead of the thresholds)."""
         bases, offsets, n = self._prep(bases, offsets)
         if out is None:
             out = np.empty(int(offsets[-1]) if n >= 0 and len(offsets) else 0, dtype=np.uint16)
-        self._check(self._L.movi_gpu_query_pml(self._ctx, _ptr(bases), _ptr(offsets), max(n, 0), 0, _ptr(out)))
+        self._check(self._L.movi_gpu_query_pml(self._ctx, _ptr(bases), _ptr(offsets), max(n, 0), FLAG_RPML if rpml else 0, _ptr(out)))
         return out
 
     def query_classify(self, bases, offsets, bin_width, max_value_thr, zml=False, want_ml=False):
@@ -210,8 +214,8 @@ class MoveStructure:
     def query_pml_ptr(self, bases_ptr, offsets_ptr, n_reads, out_ptr):
         self._check(self._L.movi_gpu_query_pml(self._ctx, bases_ptr, offsets_ptr, n_reads, 0, out_ptr))
 
-    def query_pml_device(self, d_bases, d_offsets, n_reads, d_out, stream=0):
-        self._check(self._L.movi_gpu_query_pml_device(self._ctx, d_bases, d_offsets, n_reads, 0, d_out, stream))
+    def query_pml_device(self, d_bases, d_offsets, n_reads, d_out, stream=0, rpml=False):
+        self._check(self._L.movi_gpu_query_pml_device(self._ctx, d_bases, d_offsets, n_reads, FLAG_RPML if rpml else 0, d_out, stream))
 
     def query_zml_device(self, d_bases, d_offsets, n_reads, d_out, stream=0):
         self._check(self._L.movi_gpu_query_zml_device(self._ctx, d_bases, d_offsets, n_reads, 0, d_out, stream))

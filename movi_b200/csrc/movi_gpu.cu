@@ -74,6 +74,7 @@ struct movi_gpu_ctx {
     // exactly that: gpurun_out/trace_e2e.log of round 1); kernels rotate over st_k so that consecutive slices overlap
     cudaStream_t st_in = nullptr, st_out = nullptr, st_k[NKS] = {nullptr, nullptr, nullptr, nullptr};
     uint64_t launches = 0;
+    uint32_t call_flags = 0;          // MOVI_GPU_FLAG_* of the entry point that is running
     // options
     int64_t pml_variant = 5;          // 0/1: branchy kernel (2-byte / 16-byte stores); 2/3: convergent kernel (+/- L2 hints); 4: convergent + sector staging in smem; 5: 4 with a leaner loop + evict_first on the streamed data (pml_kernel4.cuh); 6: 5 without those hints; 7: 5 with the sector-cached row fetch; 8: batched service rings (pml_kernel5.cuh)
     int64_t pml_sector = -1;          // sector-cached row fetch: -1 by table size (> 512 MB) and batch size, 0 off, 1 on
@@ -237,6 +238,7 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
     } while (0)
     if (kind == Q_PML) {
         const int64_t variant = ctx->ix.layout != LAYOUT_R8 ? std::max<int64_t>(ctx->pml_variant, 4) : ctx->pml_variant;   // the compact layouts exist for variants 4 / 5 only
+        if ((qa.flags & MOVI_GPU_FLAG_RPML) && variant < 5) return fail(ctx, MOVI_GPU_ERR_ARG, "MOVI_GPU_FLAG_RPML needs pml_variant >= 5");
         if (variant == 0) { if (wide) LAUNCH((movi_pml_kernel<unsigned long long, 0>)); else LAUNCH((movi_pml_kernel<uint32_t, 0>)); }
         else if (variant == 1) { if (wide) LAUNCH((movi_pml_kernel<unsigned long long, 1>)); else LAUNCH((movi_pml_kernel<uint32_t, 1>)); }
         else if (variant == 2) { if (wide) LAUNCH((movi_pml_kernel2<unsigned long long, true>)); else LAUNCH((movi_pml_kernel2<uint32_t, true>)); }
@@ -245,6 +247,7 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
             // 6 blocks/SM (40 registers) measured fastest on both L2-sized (c2) and HBM-resident (8-64 GB) tables -- the
             // latter are bound by the memory system's random-request rate, not by exposed latency (profiles/r01_big_tables.jsonl)
             const bool b6 = ctx->ix.layout == LAYOUT_B6, t3 = ctx->ix.layout == LAYOUT_T3;
+            const bool rpml = (qa.flags & MOVI_GPU_FLAG_RPML) != 0;            // --rpml exists for the default kernel family only
             // tables far beyond the L2 are bound by the request rate of the memory system, not by issue: there the kernel keeps
             // the last fetched 32-byte sector in registers (variant 7; "pml_sector" -1 = by table size, 0 / 1 = off / on)
             // (measured, profiles/r01_big_tables.jsonl: 8 and 32 GB tables 1.2 -> 2.2-2.5e10 bases/s; the 124 MB c2 table -27 %;
@@ -253,7 +256,11 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
                                  ctx->ix.r * sizeof(uint2) > (512ull << 20) && qa.n_reads >= (1u << 17)));
             const bool sector = variant == 7 || (variant == 5 && (ctx->pml_sector == 1 || (ctx->pml_sector < 0 &&
                                 ctx->ix.r * sizeof(uint2) > (512ull << 20) && qa.n_reads >= (1u << 17))));
-#define PML3(IDX, SEPV) do { if (variant == 8) { \
+#define PML3(IDX, SEPV) do { if (rpml) { \
+                                 if (t3) LAUNCH((movi_pml_kernel4<IDX, SEPV, 5, LAYOUT_T3, true, false, true>)); \
+                                 else if (b6) LAUNCH((movi_pml_kernel4<IDX, SEPV, 6, LAYOUT_B6, true, false, true>)); \
+                                 else LAUNCH((movi_pml_kernel4<IDX, SEPV, 6, LAYOUT_R8, true, false, true>)); } \
+                             else if (variant == 8) { \
                                  if (t3) LAUNCH((movi_pml_kernel5<IDX, SEPV, 5, LAYOUT_T3>)); \
                                  else if (b6) LAUNCH((movi_pml_kernel5<IDX, SEPV, 6, LAYOUT_B6>)); \
                                  else if (sector8) LAUNCH((movi_pml_kernel5<IDX, SEPV, 5, LAYOUT_R8, true>)); \
@@ -318,6 +325,7 @@ int device_query(movi_gpu_ctx* ctx, Kind kind, const char* d_bases, const uint64
     qa.counter = d_counter;
     qa.status = ctx->d_status;
     qa.ld_mode = (uint32_t)ctx->row_ld_mode;
+    qa.flags = kind == Q_PML ? ctx->call_flags : 0u;
     qa.keep_frac = ctx->row_keep_pct >= 100 ? 1.0f : (float)ctx->row_keep_pct / 100.0f;
     return launch_query(ctx, kind, qa, st);
 }
@@ -816,16 +824,21 @@ int movi_gpu_index_export_rows(movi_gpu_ctx* ctx, uint64_t first, uint64_t count
     return rc;
 }
 
+// the flags of the call in progress travel in the context (one call at a time per context)
+struct CallFlags { movi_gpu_ctx* c; CallFlags(movi_gpu_ctx* ctx, uint32_t f) : c(ctx) { if (c) c->call_flags = f; } ~CallFlags() { if (c) c->call_flags = 0; } };
+
 int movi_gpu_query_pml(movi_gpu_ctx* ctx, const char* bases, const uint64_t* read_offsets, uint64_t n_reads,
-                       uint32_t, uint16_t* out_ml) {
+                       uint32_t flags, uint16_t* out_ml) {
     if (!ctx) return MOVI_GPU_ERR_ARG;
+    CallFlags cf(ctx, flags);
     if (n_reads && !out_ml) return fail(ctx, MOVI_GPU_ERR_ARG, "null output buffer");
     return host_query(ctx, Q_PML, bases, read_offsets, n_reads, out_ml, nullptr, nullptr);
 }
-int movi_gpu_query_classify(movi_gpu_ctx* ctx, int zml, const char* bases, const uint64_t* read_offsets, uint64_t n_reads, uint32_t,
+int movi_gpu_query_classify(movi_gpu_ctx* ctx, int zml, const char* bases, const uint64_t* read_offsets, uint64_t n_reads, uint32_t flags,
                             uint32_t bin_width, uint32_t max_value_thr, uint32_t* out_bins_above, uint32_t* out_bins_below,
                             uint64_t* out_sum_max, uint16_t* out_ml) {
     if (!ctx) return MOVI_GPU_ERR_ARG;
+    CallFlags cf(ctx, flags);
     if (bin_width == 0) return fail(ctx, MOVI_GPU_ERR_ARG, "bin_width must be positive");
     if (n_reads && (!out_bins_above || !out_bins_below || !out_sum_max)) return fail(ctx, MOVI_GPU_ERR_ARG, "null output buffer");
     const Kind kind = zml ? Q_ZML : Q_PML;
@@ -835,8 +848,9 @@ int movi_gpu_query_classify(movi_gpu_ctx* ctx, int zml, const char* bases, const
     return host_query(ctx, kind, bases, read_offsets, n_reads, out_ml, nullptr, nullptr, &c);
 }
 
-int movi_gpu_query_ml8(movi_gpu_ctx* ctx, int zml, const char* bases, const uint64_t* read_offsets, uint64_t n_reads, uint32_t,
+int movi_gpu_query_ml8(movi_gpu_ctx* ctx, int zml, const char* bases, const uint64_t* read_offsets, uint64_t n_reads, uint32_t flags,
                        uint8_t* out_ml8) {
+    CallFlags cf(ctx, flags);
     const Kind kind = zml ? Q_ZML : Q_PML;
     int rc = check_query_ready(ctx, kind, n_reads);
     if (rc) return rc;
@@ -871,7 +885,8 @@ static unsigned long long* next_counter(movi_gpu_ctx* ctx) {
 }
 
 int movi_gpu_query_pml_device(movi_gpu_ctx* ctx, const char* d_bases, const uint64_t* d_read_offsets, uint64_t n_reads,
-                              uint32_t, uint16_t* d_out_ml, void* stream) {
+                              uint32_t flags, uint16_t* d_out_ml, void* stream) {
+    CallFlags cf(ctx, flags);
     int rc = check_query_ready(ctx, Q_PML, n_reads);
     if (rc) return rc;
     return device_query(ctx, Q_PML, d_bases, d_read_offsets, 0, n_reads, d_out_ml, nullptr, nullptr, next_counter(ctx), (cudaStream_t)stream);

@@ -33,6 +33,7 @@ struct QueryArgs {
     unsigned long long* counter;          // work-queue head (zeroed before launch)
     unsigned int* status;                 // sticky error bits
     uint32_t ld_mode;                     // row fetch cache recipe (pml_kernel2.cuh: ld_row)
+    uint32_t flags;                       // MOVI_GPU_FLAG_* of the call
     float keep_frac;                      // fraction of the row table whose fetches carry L2 evict_last (the rest: evict_first)
 };
 

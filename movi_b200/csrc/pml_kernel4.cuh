@@ -52,7 +52,13 @@ __device__ __forceinline__ uint4 ld_keep128(const uint4* p, unsigned long long p
 // (Tried and dropped: fetching the row with cp.async.cg into shared memory instead of a load through L1 -- 5x slower,
 //  profiles/r01_explore.jsonl "9:..."; and the row fetches need their L1: with the shared-memory carve-out at its maximum
 //  the same kernel runs 2.8x slower, which is also what limits the per-lane staging buffers to 32 + 32 bytes.)
-template <typename IdxT, bool SEP, int MINB, int LAYOUT, bool HINTS = true, bool SECTOR = false>
+// RPML: `movi query --rpml` -- Case 2 repositions with reposition_randomly (src/move_structure_query.cpp:604-688) instead of
+// the thresholds: up when the offset lies in the first half of the run (the reference's random draw is commented out, :607-608),
+// forced at the two ends of the table, and if the scan leaves the table without finding the character it starts again from
+// the same row in the other direction (:634-649, :661-674; states ST_UPF / ST_DOWNF = "already turned round").
+constexpr uint32_t ST_UPF = 5, ST_DOWNF = 6;
+
+template <typename IdxT, bool SEP, int MINB, int LAYOUT, bool HINTS = true, bool SECTOR = false, bool RPML = false>
 __global__ void __launch_bounds__(PML3_THREADS, MINB)
 movi_pml_kernel4(const DevIndex ix, const QueryArgs q) {
     __shared__ uint8_t s_code[256];
@@ -100,6 +106,7 @@ movi_pml_kernel4(const DevIndex ix, const QueryArgs q) {
     uint32_t tick = 0;
     uint4 sec_lo = make_uint4(0, 0, 0, 0), sec_hi = make_uint4(0, 0, 0, 0);   // SECTOR: rows 4*sec_base .. 4*sec_base + 3
     IdxT sec_base = ~(IdxT)0;
+    IdxT saved = 0;                                                           // RPML: the row the reposition started from
     for (;;) {
         // idle lanes are looked after every REFILL_EVERY-th iteration only: a finished lane waits <= 3 of the ~240
         // iterations of a 150-base read, and the other iterations skip the vote / queue bookkeeping
@@ -175,7 +182,7 @@ movi_pml_kernel4(const DevIndex ix, const QueryArgs q) {
         const uint32_t code = lds_u8(sa_code + lds_u8(sa_in + (rp & 31u)));
         const bool is_ff = (st == ST_FF);
         const bool is_scan = (st >= ST_UP);
-        const bool scan_up = (st == ST_UP);
+        const bool scan_up = RPML ? ((st & 1u) != 0u) : (st == ST_UP);           // (ST_UP = 3, ST_UPF = 5)
         const bool hit = (c == code);
         const bool ffmove = is_ff && (idx < r1) && (off >= n);            // fast_forward, move_structure.cpp:524-545
         const bool at_base = is_ff && !ffmove;
@@ -186,13 +193,13 @@ movi_pml_kernel4(const DevIndex ix, const QueryArgs q) {
 
         const uint32_t ai = code - sep;
         uint32_t thr = (LAYOUT == LAYOUT_R8) ? row_thr(y, ai, n) : row_thr_raw3(y, c - sep, ai, n);
-        if (base_mis & ((idx == end_idx) | (SEP & (c == 0)))) {            // '$' row / '%' rows: rare, skipped warp-wide
+        if (!RPML && base_mis & ((idx == end_idx) | (SEP & (c == 0)))) {            // '$' row / '%' rows: rare, skipped warp-wide
             thr = (idx == end_idx) ? s_end_thr[ai & 3u] : sep_threshold(ix, (unsigned long long)idx, ai);
         }
-        const bool down = off >= thr;
+        const bool down = RPML ? !((idx == r1) || (idx > 0 && off * 2u < n)) : (off >= thr);
         const bool mv_down = (scan_move && !scan_up) || (base_mis && down);
         const bool mv_up = (scan_move && scan_up) || (base_mis && !down);
-        const bool bad = (mv_up && idx == 0) || (mv_down && idx == r1);
+        bool bad = (mv_up && idx == 0) || (mv_down && idx == r1);
 
         ml = (at_base && hit) ? ml + 1 : (emit ? 0u : ml);
         off = ffmove ? off - n : (scan_hit ? (scan_up ? n - 1 : 0u) : off);
@@ -236,8 +243,16 @@ movi_pml_kernel4(const DevIndex ix, const QueryArgs q) {
             if (lf) lf_id = (IdxT)sampled_get_id(Rows3{ix.rows3, (unsigned long long)end_idx}, ix.tally, ix.tally_len, ix.tally_cp, ix.r,
                                                  (unsigned long long)end_idx, (unsigned long long)idx, c, &bad_id);
         }
+        if (RPML) saved = base_mis ? idx : saved;
         idx = lf ? lf_id : (ffmove || mv_down) ? idx + 1 : (mv_up ? idx - 1 : idx);
         st = fin ? ST_IDLE : lf ? ST_FF : base_mis ? (down ? ST_DOWN : ST_UP) : st;
+        if (RPML) {
+            if (bad && st <= ST_DOWN && (mv_up ? saved < r1 : saved > 0)) {     // first scan left the table: turn round
+                idx = mv_up ? saved + 1 : saved - 1;
+                st = mv_up ? ST_DOWNF : ST_UPF;
+                bad = false;
+            }
+        }
         if (bad || bad_id) { atomicOr(q.status, bad_id ? 2u : 1u); st = ST_IDLE; }
     }
 }

@@ -26,6 +26,7 @@ namespace {
 struct Options {
     std::string action, index_dir, read_file, out_file, bpf_file;
     std::string query = "pml";
+    bool rpml = false;            // --rpml: PML with random repositioning; names its outputs "rpml" (src/utils.cpp:47-52)
     bool classify = false, filter = false, invert = false, to_stdout = false, no_output = false, reverse = false, verbose = false;
     int ignore_illegal = 0, gpus = 1, device = 0, threads = 1, strands = 16;
     uint64_t bin_width = 150;     // include/movi_options.hpp default
@@ -36,7 +37,7 @@ struct Options {
 
 [[noreturn]] void usage_error(const std::string& m) {
     fprintf(stderr, "\033[31m\n\n[ERROR] %s\n\033[0m\n", m.c_str());
-    fprintf(stderr, "usage: movi-b200 query -i <index dir> -r <reads.fa|fq|-> [--pml|--zml|--count] [--classify|--filter [-v]]\n"
+    fprintf(stderr, "usage: movi-b200 query -i <index dir> -r <reads.fa|fq|-> [--pml [--rpml]|--zml|--count] [--classify|--filter [-v]]\n"
                     "                       [--stdout] [-o prefix] [--no-output] [--reverse] [--ignore-illegal-chars 1|2]\n"
                     "                       [--bin-width N] [--gpus N] [--device D] [--chunk-bases N] [-t N] [-s N] [-n]\n"
                     "       movi-b200 view --bpf <file.bpf>\n");
@@ -75,6 +76,7 @@ Options parse(int argc, char** argv) {
         else if (take_value(argc, argv, i, nullptr, "--bpf", v)) o.bpf_file = v;
         else if (take_value(argc, argv, i, nullptr, "--chunk-bases", v)) o.chunk_bases = std::max<uint64_t>(1, strtoull(v.c_str(), nullptr, 10));
         else if (a == "--pml") o.query = "pml";
+        else if (a == "--rpml") o.rpml = true;                                  // movi_parser.cpp:149,357
         else if (a == "--zml") o.query = "zml";
         else if (a == "--count") o.query = "count";
         else if (a == "--classify") o.classify = true;
@@ -165,7 +167,10 @@ int main(int argc, char** argv) {
     const int gpus = std::max(1, std::min(o.gpus, n_dev));
 
     uint64_t max_value_thr = 0;
-    if (o.classify && movi_host_nulldb_threshold(o.index_dir.c_str(), o.query.c_str(), &max_value_thr)) die(movi_host_last_error());
+    // query_type() of the reference (src/utils.cpp:47-66): names the outputs and the null database
+    const std::string qname = (o.query == "pml" && o.rpml) ? "rpml" : o.query;
+    const uint32_t qflags = (o.query == "pml" && o.rpml) ? MOVI_GPU_FLAG_RPML : MOVI_GPU_FLAG_NONE;
+    if (o.classify && movi_host_nulldb_threshold(o.index_dir.c_str(), qname.c_str(), &max_value_thr)) die(movi_host_last_error());
 
     // the input streams through in batches of --chunk-bases bases: batch k + 1 is parsed while the GPUs walk batch k
     auto fetch = [&]() { Fetched f; f.rc = movi_host_reader_next(reader, o.chunk_bases, &f.rd); if (f.rc) f.err = movi_host_last_error(); return f; };
@@ -193,7 +198,7 @@ int main(int argc, char** argv) {
     const bool need_ml = o.query != "count" && (!fused_classify || o.write_output_allowed());
 
     // ---- output sinks, routed like handle_pml_zml / handle_count (src/movi.cpp:23-76)
-    const std::string prefix = (o.out_file.empty() ? o.read_file + "." + type : o.out_file) + "." + o.query;   // utils.cpp:348-351
+    const std::string prefix = (o.out_file.empty() ? o.read_file + "." + type : o.out_file) + "." + qname;   // utils.cpp:348-351
     FILE* f_counts = nullptr; FILE* f_report = nullptr; int fd_bpf = -1;
     if (o.query == "count") {
         if (o.write_output_allowed() && !o.write_stdout_enabled()) {
@@ -202,7 +207,7 @@ int main(int argc, char** argv) {
         }
     } else {
         if (o.classify && !o.filter && !o.to_stdout) {          // <reads>.<type>.<q>.report (classifier.cpp:39-60)
-            f_report = fopen((o.read_file + "." + type + "." + o.query + ".report").c_str(), "w");
+            f_report = fopen((o.read_file + "." + type + "." + qname + ".report").c_str(), "w");
             if (!f_report) die("cannot open the report file");
         }
         if (o.write_output_allowed() && !o.write_stdout_enabled()) {
@@ -298,9 +303,9 @@ int main(int argc, char** argv) {
             int r;
             // offsets stay absolute: the entry points index bases / outputs by them
             if (fused_classify)
-                r = movi_gpu_query_classify(ctx[g], o.query == "zml", bases, offsets + i0, nr, 0, (uint32_t)o.bin_width, (uint32_t)max_value_thr,
+                r = movi_gpu_query_classify(ctx[g], o.query == "zml", bases, offsets + i0, nr, qflags, (uint32_t)o.bin_width, (uint32_t)max_value_thr,
                                             R.above.p + i0, R.below.p + i0, R.sum.p + i0, need_ml ? R.ml.p : nullptr);
-            else if (o.query == "pml") r = movi_gpu_query_pml(ctx[g], bases, offsets + i0, nr, 0, R.ml.p);
+            else if (o.query == "pml") r = movi_gpu_query_pml(ctx[g], bases, offsets + i0, nr, qflags, R.ml.p);
             else if (o.query == "zml") r = movi_gpu_query_zml(ctx[g], bases, offsets + i0, nr, 0, R.ml.p);
             else r = movi_gpu_query_count(ctx[g], bases, offsets + i0, nr, 0, R.counts.p + i0, R.pos.p + i0);
             if (r) res[g] = {r, movi_gpu_last_error(ctx[g])};

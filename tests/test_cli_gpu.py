@@ -125,3 +125,17 @@ def test_streaming_batches_give_the_same_files(cli, index_dirs, tmp_path):
     assert run(cli, "query", "-i", d, "-r", str(empty), "--pml", "--stdout") == ""
     run(cli, "query", "-i", d, "-r", str(empty), "--pml")
     assert len(open(str(empty) + ".regular-thresholds.pml.bpf", "rb").read()) == 12
+
+
+@pytest.mark.parametrize("typ", TYPES)
+def test_rpml_stdout_and_file_names(cli, index_dirs, typ, tmp_path):
+    """--rpml: the reference's output (tests/golden/make_golden_rpml.py) and its file naming (query_type() = "rpml")."""
+    for read_set in ("sample.fastq", "edge.fasta"):
+        out = run(cli, "query", "--index", index_dirs[(typ, False)], "--read", reads_path(read_set), "--pml", "--rpml", "--stdout")
+        assert out == expected_text(read_set, "rpml")
+    reads = tmp_path / "sample.fasta"
+    shutil.copy(reads_path("sample.fasta"), reads)
+    run(cli, "query", "-i", index_dirs[(typ, False)], "-r", str(reads), "--rpml")
+    bpf = "%s.%s.rpml.bpf" % (reads, typ)
+    assert os.path.exists(bpf)
+    assert run(cli, "view", "--bpf", bpf) == expected_text("sample.fasta", "rpml")

@@ -356,3 +356,43 @@ def test_device_row_format_round_trips_to_the_file_format(structures, index_dirs
         assert i == hix.end_bwt_idx or (sep and c == 0) or c >= 4 + (1 if sep else 0), (int(i), hex(int(file_rows[i, 1])), hex(int(got[i, 1])))
         assert (int(got[i, 1]) ^ int(file_rows[i, 1])) & ~((1 << 11) | (1 << 12) | (1 << 27)) == 0
     assert len(diff) <= 16
+
+
+@pytest.mark.parametrize("sep", [False, True])
+@pytest.mark.parametrize("typ", TYPES)
+def test_rpml_matches_reference_and_oracle(structures, index_dirs, read_sets, ref_seq, typ, sep):
+    """MOVI_GPU_FLAG_RPML = `movi query --rpml` (reposition_randomly): the reference's own output on every read set, the oracle
+    on 20 k ragged random reads; expanded and compact device layouts; host-buffer, device and byte-wide entry points."""
+    import torch
+    from movi_b200 import MoveStructure
+    from oracle.port import OracleIndex, pack_reads
+    ms = structures[(typ, sep)]
+    for read_set in READ_SETS:
+        rd = read_sets[read_set]
+        ml = ms.query_pml(rd.bases, rd.offsets, rpml=True)
+        assert ml_text(rd.ids(), rd.offsets, ml) == expected_text(read_set, "rpml", sep)
+    orc = OracleIndex(index_dirs[(typ, sep)])
+    bases, offsets = pack_reads(_random_reads(13, 20000, 600, ref_seq))
+    want = orc.query_rpml(bases, offsets, threads=0)
+    assert not np.array_equal(want, orc.query_pml(bases, offsets, threads=0))
+    assert np.array_equal(ms.query_pml(bases, offsets, rpml=True), want)
+    assert np.array_equal(ms.query_pml(bases, offsets), orc.query_pml(bases, offsets, threads=0))     # the flag does not stick
+    if typ != "regular-thresholds" and not sep:
+        compact = MoveStructure(index_dirs[(typ, sep)], layout=2)
+        try:
+            assert np.array_equal(compact.query_pml(bases, offsets, rpml=True), want)
+        finally:
+            compact.close()
+    dev = torch.device("cuda:0")
+    pad = np.zeros(64, np.uint8)
+    d_b = torch.from_numpy(np.concatenate([bases, pad])).to(dev)
+    d_o = torch.from_numpy(offsets.astype(np.int64)).to(dev)
+    d_out = torch.zeros(len(bases) + 64, dtype=torch.int16, device=dev)
+    ms.query_pml_device(d_b.data_ptr(), d_o.data_ptr(), len(offsets) - 1, d_out.data_ptr(), torch.cuda.current_stream().cuda_stream, rpml=True)
+    torch.cuda.synchronize()
+    ms.check_device_status()
+    assert np.array_equal(d_out[: len(bases)].cpu().numpy().view(np.uint16), want)
+    ms.set_option("pml_variant", 4)
+    from movi_b200 import MoviGpuError
+    with pytest.raises(MoviGpuError, match="RPML"):
+        ms.query_pml(bases, offsets, rpml=True)
