@@ -55,17 +55,17 @@ md += ["",
 "",
 "Reading the table:",
 "* **v1 -> v2**: the branchy state machine kept 12 of 32 lanes busy per issued instruction; predicate-driven transitions raise that to 26 and drop the register count to 32, but time barely moves because v1/v2 were DRAM-traffic bound: 74 B of DRAM read per base and 2.1x write amplification -- every lane touched its read bytes and its output 8 bytes at a time, tens of microseconds apart, while the row fetches turn the 126 MB L2 over every ~35 us, so every 64-byte atom of the two streams was fetched / written back several times.",
-"* **v4**: read bytes and results are staged per lane in shared memory and cross the memory system one aligned 32-byte sector at a time: DRAM read 11.1 -> 8.3 GB, write amplification 2.15x -> 1.1x, L2 hit 25 -> 34 %.  After that the kernel is ~2/3 instruction-issue bound (issue active 62 %, ~185 instructions per warp iteration, 1.59 iterations per base) and ~1/3 exposed row-fetch latency (long scoreboard on the first use of the row word: `r01_pml_v4_hot_sass.txt`).",
+"* **v4**: read bytes and results are staged per lane in shared memory and cross the memory system one aligned 32-byte sector at a time: DRAM read 11.1 -> 8.3 GB, write amplification 2.15x -> 1.1x, L2 hit 25 -> 34 %.  After that the kernel is ~2/3 instruction-issue bound (issue active 62 %, ~185 instructions per warp iteration, 1.59 iterations per base) and ~1/3 exposed row-fetch latency (long scoreboard on the first use of the row word: `r01_pml_v5_hot_sass.txt`).",
 "* **probe**: the practical ceiling of the memory system for independent random 8-byte loads over the same table: 1.24e11 loads/s, DRAM at 5.4 TB/s (83 % of the measured streaming peak) with a 29 % L2 hit rate -- the 124 MB table does not stay L2 resident (effective capacity for this pattern ~ 126 MB / 2 dies / half-filled 128-byte lines; an LRU simulation of the access trace gives the same ~30 % at 32 MB).",
 "* Physical floor for PML on this table: one 64-byte DRAM atom per base x (1 - L2 hit) ~ 45 B/base; the algorithmic accounting of SURVEY 8(d) is 32 B/base (`roofline.achieved`), the measured traffic is `roofline.traffic` (`pml_c2_traffic.json`).",
 "* Random-gather probe vs table size (`r01_probe.jsonl`, first GPU session): 64 MB 2.8e11 loads/s (L2), 1 GB 4.3e10, 8-32 GB 3.7e10, 96 GB 1.4e10 loads/s -- beyond ~0.25 GB the TLB reach, not DRAM, sets the ceiling for fully random row fetches; this is the number the human-scale (c4) configuration will be measured against.",
 "",
-"Files: `r01_launches_bench.csv` (launch list of `bench.py --steps 4 --warmup 3 --no-cpu-baseline`: every launch of the timed region is `movi_pml_kernel3`; the torch fill kernels are buffer set-up), `r01_pml_*_raw.csv` (ncu raw pages), `r01_pml_v4_hot_sass.txt` (per-instruction execution counts and stall samples of the hot loop), `r01_bench.json` / `r01_bench_reference_arm.json` (bench lines of the same session), `r01_explore.jsonl` (variant / launch-shape / L2-option sweeps)."]
+"Files: `r01_launches_bench.csv` (launch list of `bench.py --steps 4 --warmup 3 --no-cpu-baseline`: every launch of the timed region is `movi_pml_kernel3`; the torch fill kernels are buffer set-up), `r01_pml_*_raw.csv` (ncu raw pages), `r01_pml_v5_hot_sass.txt` (per-instruction execution counts and stall samples of the hot loop), `r01_bench.json` / `r01_bench_reference_arm.json` (bench lines of the same session), `r01_explore.jsonl` (variant / launch-shape / L2-option sweeps)."]
 open('profiles/r01_summary.md','w').write("\n".join(md)+"\n")
 for src,dst in (('gpurun_out/launches_b.csv','r01_launches_bench.csv'),('gpurun_out/prof_pml_raw.csv','r01_pml_v1_raw.csv'),('gpurun_out/prof_v2_raw.csv','r01_pml_v2_and_probe_raw.csv'),
                 ('gpurun_out/prof_v4_raw.csv','r01_pml_v4_first_raw.csv'),('gpurun_out/prof_pml_b_raw.csv','r01_pml_v4_bench_raw.csv'),('gpurun_out/bench_b.json','r01_bench.json'),
                 ('gpurun_out/bench_ref.json','r01_bench_reference_arm.json'),('gpurun_out/explore_pml.jsonl','r01_explore.jsonl'),('gpurun_out/explore.jsonl','r01_probe.jsonl')):
     if os.path.exists(src): shutil.copy(src, os.path.join('profiles',dst))
 hot = '/root/.claude/projects/-root-repo/015383a3-1bd8-42e1-b993-330841f1bdeb/tool-results/b0k74ti2o.txt'
-if os.path.exists(hot): shutil.copy(hot,'profiles/r01_pml_v4_hot_sass.txt')
+if os.path.exists(hot): shutil.copy(hot,'profiles/r01_pml_v5_hot_sass.txt')
 print(open('profiles/r01_summary.md').read()[:2500])
