@@ -91,7 +91,7 @@ struct movi_gpu_ctx {
                                       // bottleneck of the host path: small slices keep the pipeline ramp short)
     int64_t kernel_streams = 4;       // 1..NKS: slices whose kernels may run concurrently (sweep: profiles/r01_pipeline_sweep.jsonl)
     int64_t pipeline_slots = NBUF;    // 2..NBUF
-    int64_t size_grid_to_batch = 1;   // 0: always launch the full persistent grid
+    int64_t size_grid_to_batch = 1;   // 0: always launch the full persistent grid; k >= 1: a grid that gives every lane k reads of the batch
     // gather probe scratch
     uint2* d_probe = nullptr; uint64_t probe_bytes = 0;
     int64_t probe_vmm_align_mb = 0;   // > 0: allocate the probe table through the VMM API at this alignment
@@ -209,7 +209,8 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
     // a small batch (a pipeline slice) gets a grid sized to one read per lane instead of the whole machine: full warps
     // issue a quarter of the instructions of warps holding a handful of reads each, and leave SM room for the kernels of
     // the neighbouring slices
-    const uint64_t grid_cap = ctx->size_grid_to_batch ? std::max<uint64_t>(1, ((uint64_t)qa.n_reads + threads - 1) / threads) : ~0ull;
+    const uint64_t per_block = (uint64_t)threads * (uint64_t)std::max<int64_t>(1, ctx->size_grid_to_batch);
+    const uint64_t grid_cap = ctx->size_grid_to_batch ? std::max<uint64_t>(1, ((uint64_t)qa.n_reads + per_block - 1) / per_block) : ~0ull;
     const bool wide = ctx->ix.r > 0xFFFFFFF0ull || ctx->force_wide;   // 64-bit row indices (tables beyond 2^32 rows = 34 GB)
     // optional: keep the row table persisting in L2 (launch attribute; the carve-out is set in set_option)
     cudaLaunchAttribute attr[1];
@@ -577,7 +578,7 @@ int movi_gpu_set_option(movi_gpu_ctx* ctx, const char* key, int64_t value) {
     else if (k == "smem_carveout") { if (value < -1 || value > 100) return fail(ctx, MOVI_GPU_ERR_ARG, "smem_carveout: -1, 0..100"); ctx->smem_carveout = value; }
     else if (k == "kernel_streams") { if (value < 1 || value > NKS) return fail(ctx, MOVI_GPU_ERR_ARG, "kernel_streams: 1..4"); ctx->kernel_streams = value; }
     else if (k == "pipeline_slots") { if (value < 2 || value > NBUF) return fail(ctx, MOVI_GPU_ERR_ARG, "pipeline_slots: 2..8"); ctx->pipeline_slots = value; }
-    else if (k == "size_grid_to_batch") { ctx->size_grid_to_batch = value != 0; }
+    else if (k == "size_grid_to_batch") { if (value < 0 || value > 64) return fail(ctx, MOVI_GPU_ERR_ARG, "size_grid_to_batch: 0 (off) or reads per lane 1..64"); ctx->size_grid_to_batch = value; }
     else return fail(ctx, MOVI_GPU_ERR_ARG, "unknown option " + k);
     return MOVI_GPU_OK;
 }
