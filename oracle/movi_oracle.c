@@ -17,6 +17,7 @@
 #include <omp.h>
 #endif
 
+#define MODE_REGULAR 3              /* "regular": 8-byte rows without thresholds (utils.hpp:136), 12-bit lengths */
 #define MODE_REGULAR_THRESHOLDS 6
 #define MODE_SAMPLED_THRESHOLDS 7
 #define MODE_BLOCKED_THRESHOLDS 8
@@ -33,6 +34,7 @@ struct movi_oracle_index {
     int sigma;
     unsigned char alphabet[8];
     int separators;                 /* use_separator(): move_structure.cpp:547-552 */
+    int no_thresholds;              /* NO_THRESHOLDS modes (utils.hpp:146): PML repositions with reposition_randomly */
     uint8_t* rows;                  /* r * row_bytes, packed exactly as on disk */
     /* MODE 7 */
     uint32_t tally_checkpoints;
@@ -78,6 +80,7 @@ int movi_oracle_load(const char* path, movi_oracle_index** out) {
     memcpy(&ix->length, h + 16, 8); memcpy(&ix->r, h + 24, 8);
     memcpy(&ix->original_r, h + 32, 8); memcpy(&ix->end_bwt_idx, h + 40, 8);
     switch (ix->mode) {
+        case MODE_REGULAR:
         case MODE_REGULAR_THRESHOLDS: ix->row_bytes = 8; break;
         case MODE_BLOCKED_THRESHOLDS: ix->row_bytes = 6; break;
         case MODE_SAMPLED_THRESHOLDS: ix->row_bytes = 3; break;
@@ -95,6 +98,7 @@ int movi_oracle_load(const char* path, movi_oracle_index** out) {
     uint16_t nt_splitting; uint8_t constant;
     if (rd(f, &nt_splitting, 2) || rd(f, &constant, 1)) goto bad;
     ix->separators = (ix->alphabet[0] == SEPARATOR && ix->sigma == 5);
+    ix->no_thresholds = (ix->mode == MODE_REGULAR);            /* NO_THRESHOLDS, utils.hpp:146 */
     /* read_main_table, io.cpp:361-397 */
     ix->rows = (uint8_t*)malloc(ix->r * (size_t)ix->row_bytes + 16);
     if (!ix->rows || rd(f, ix->rows, ix->r * (size_t)ix->row_bytes)) goto bad;
@@ -123,8 +127,8 @@ int movi_oracle_load(const char* path, movi_oracle_index** out) {
         }
         if (rd(f, &ix->block_size, 8)) goto bad;
     }
-    /* read_separators_thresholds, io.cpp:415-433 */
-    if (ix->separators) {
+    /* read_separators_thresholds, io.cpp:415-433 (#if USE_THRESHOLDS, io.cpp:504-508) */
+    if (ix->separators && !ix->no_thresholds) {
         if (rd(f, &ix->sep_cnt, 8)) goto bad;
         ix->sep_thr = (uint16_t*)malloc(ix->sep_cnt * 8 + 8);
         if (rd(f, ix->sep_thr, ix->sep_cnt * 8)) goto bad;
@@ -167,6 +171,7 @@ static inline uint32_t ld32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); re
 static inline uint64_t row_n(const movi_oracle_index* ix, uint64_t i) {
     const uint8_t* p = ix->rows + i * (size_t)ix->row_bytes;
     switch (ix->mode) {
+        case 3: return ld16(p + 4) & 0xFFFu;                              /* n[0:11], move_row_configs.hpp:20-31 */
         case 6: return ld16(p + 4) & 0x7FFu;                              /* n[0:10] */
         case 8: return ld16(p + 2) & 0x3FFu;                              /* n[0:9] */
         default: return (uint64_t)p[0] | ((uint64_t)((p[2] >> 1) & 1) << 8); /* n | c[1]<<8 */
@@ -175,6 +180,7 @@ static inline uint64_t row_n(const movi_oracle_index* ix, uint64_t i) {
 static inline uint64_t row_offset(const movi_oracle_index* ix, uint64_t i) {
     const uint8_t* p = ix->rows + i * (size_t)ix->row_bytes;
     switch (ix->mode) {
+        case 3: return ld16(p + 6) & 0xFFFu;
         case 6: return ld16(p + 6) & 0x7FFu;
         case 8: return ld16(p + 4) & 0x3FFu;
         default: return (uint64_t)p[1] | ((uint64_t)(p[2] & 1) << 8);
@@ -183,6 +189,7 @@ static inline uint64_t row_offset(const movi_oracle_index* ix, uint64_t i) {
 static inline int row_c(const movi_oracle_index* ix, uint64_t i) {
     const uint8_t* p = ix->rows + i * (size_t)ix->row_bytes;
     switch (ix->mode) {
+        case 3:                                                           /* REGULAR_MODES share the getters, move_row.hpp:231-258 */
         case 6: return (ld16(p + 4) >> 13) & 7;
         case 8: return (ld16(p + 4) >> 10) & 7;
         default: return (p[2] >> 2) & 7;
@@ -199,7 +206,7 @@ static inline int row_thr_bit(const movi_oracle_index* ix, uint64_t i, int k) {
 /* the id FIELD of the row (MoveRow::get_id), not MoveStructure::get_id */
 static inline uint64_t row_id_field(const movi_oracle_index* ix, uint64_t i) {
     const uint8_t* p = ix->rows + i * (size_t)ix->row_bytes;
-    if (ix->mode == 6) return (uint64_t)ld32(p) | ((uint64_t)((ld16(p + 6) >> 12) & 0xF) << 32);
+    if (ix->mode == 6 || ix->mode == 3) return (uint64_t)ld32(p) | ((uint64_t)((ld16(p + 6) >> 12) & 0xF) << 32);
     /* MODE 8: id16 | n[10:15] << 16 (ID_SIG_BITS2 == 0) */
     return (uint64_t)ld16(p) | ((uint64_t)((ld16(p + 2) >> 10) & 0x3F) << 16);
 }
@@ -217,7 +224,7 @@ static inline uint64_t tally_get(const movi_oracle_index* ix, int c, uint64_t k)
 
 /* MoveStructure::get_id, move_structure.cpp:91-286 */
 static int get_id(const movi_oracle_index* ix, uint64_t idx, uint64_t* out) {
-    if (ix->mode == 6) { *out = row_id_field(ix, idx); return 0; }               /* :92-94 */
+    if (ix->mode == 6 || ix->mode == 3) { *out = row_id_field(ix, idx); return 0; }   /* :92-94 */
     if (ix->mode == 8) {                                                          /* :95-102 */
         if (idx != ix->end_bwt_idx) {
             uint64_t block = idx / ix->block_size;
@@ -390,6 +397,7 @@ int movi_oracle_query_pml(const movi_oracle_index* ix, const char* read, int64_t
 /* the same with --rpml: Case 2 repositions with reposition_randomly (:304-311) */
 int movi_oracle_query_rpml(const movi_oracle_index* ix, const char* read, int64_t len, uint16_t* out) { return query_pml_impl(ix, read, len, out, 1); }
 static int query_pml_impl(const movi_oracle_index* ix, const char* read, int64_t len, uint16_t* out, int rpml) {
+    if (ix->no_thresholds) rpml = 1;                           /* move_structure_query.cpp:308-311 */
     int64_t pos = len - 1;
     uint64_t idx = ix->r - 1;
     uint64_t offset = row_n(ix, idx) - 1;

@@ -52,6 +52,15 @@ def index_dirs(tmp_path_factory):
     return out
 
 
+@pytest.fixture(scope="session")
+def regular_index_dir(tmp_path_factory):
+    """The non-threshold "regular" index (MODE 3) built by the unmodified reference (tests/golden/make_golden_regular.py)."""
+    d = tmp_path_factory.mktemp("c1_regular")
+    with lzma.open(os.path.join(GOLD, "c1", "regular", "index.movi.xz")) as f:
+        (d / "index.movi").write_bytes(f.read())
+    return str(d)
+
+
 def expected_text(read_set, query, sep=False):
     name = "%s%s.%s.txt.xz" % (read_set, ".sep" if sep else "", query)
     with lzma.open(os.path.join(GOLD, "expected", name)) as f:
