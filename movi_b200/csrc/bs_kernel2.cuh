@@ -24,7 +24,7 @@ constexpr uint32_t B_IDLE = 0, B_NEW = 1, B_SKIP = 2, B_RUN = 3, B_FAIL = 4, B_F
 // SECTOR (tables far beyond the L2, which are bound by the request rate of the memory system -- see pml_kernel4.cuh): each
 // interval end keeps the aligned 32-byte sector (4 rows) of its last fetch in registers; scan and fast-forward steps that
 // stay inside it, and the very common case of both ends sitting in the same rows, cost no new request.
-template <typename IdxT, int KIND, int LAYOUT, bool SECTOR = false>
+template <typename IdxT, int KIND, int LAYOUT, bool SECTOR = false, bool NT = false>
 __global__ void __launch_bounds__(PML3_THREADS, SECTOR ? 3 : 5)
 movi_bs_kernel2(const DevIndex ix, const QueryArgs q) {
     __shared__ uint8_t s_code[256];
@@ -190,7 +190,7 @@ movi_bs_kernel2(const DevIndex ix, const QueryArgs q) {
         // ---- the walking state: both interval ends step under predicates (lanes with !run change nothing)
         {
             const uint32_t yS = vS.y, yE = vE.y;
-            const uint32_t nS = row_n(yS), nE = row_n(yE);
+            const uint32_t nS = row_n<NT>(yS), nE = row_n<NT>(yE);
             // fast_forward of each end (src/move_structure.cpp:524-545)
             const bool ffS = run && (sS == W_FF), ffE = run && (sE == W_FF);
             const bool stepS = ffS && (rs < r1) && (os >= nS), stepE = ffE && (re < r1) && (oe >= nE);
@@ -221,11 +221,11 @@ movi_bs_kernel2(const DevIndex ix, const QueryArgs q) {
             const uint32_t chS = (rs == end_idx) ? 8u : row_c(yS), chE = (re == end_idx) ? 8u : row_c(yE);
             const bool hitS = scS && (chS == code), hitE = scE && (chE == code);
             const bool mvS = scS && !hitS, mvE = scE && !hitE;
-            os = hitS ? (movedS ? 0u : os) + row_off(yS) : os;
-            oe = hitE ? (movedE ? nE - 1u : oe) + row_off(yE) : oe;
+            os = hitS ? (movedS ? 0u : os) + row_off<NT>(yS) : os;
+            oe = hitE ? (movedE ? nE - 1u : oe) + row_off<NT>(yE) : oe;
             const bool cross0 = mvE && (re == 0);
-            rs = hitS ? row_id<IdxT>(vS) : (mvS ? rs + 1 : rs);
-            re = hitE ? row_id<IdxT>(vE) : ((mvE && !cross0) ? re - 1 : re);
+            rs = hitS ? row_id<IdxT, NT>(vS) : (mvS ? rs + 1 : rs);
+            re = hitE ? row_id<IdxT, NT>(vE) : ((mvE && !cross0) ? re - 1 : re);
             sS = hitS ? W_FF : sS; sE = hitE ? W_FF : sE;
             movedS = movedS || mvS; movedE = movedE || mvE;
             // no row with this character between the two cursors: the interval is empty

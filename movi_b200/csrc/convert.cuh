@@ -18,6 +18,17 @@ __global__ void relayout_regular_kernel(uint2* __restrict__ rows, unsigned long 
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (; i < r; i += stride) rows[i] = r8_from_file(rows[i], sep);
 }
+// ---- MODE 3 ("regular", no thresholds): the same, into the 12-bit form of R8
+__global__ void relayout_regular_nt_kernel(uint2* __restrict__ rows, unsigned long long r) {
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (; i < r; i += stride) rows[i] = r8nt_from_file(rows[i]);
+}
+__global__ void relayout_nt_to_file_kernel(const uint2* __restrict__ rows, uint2* __restrict__ out, unsigned long long r) {
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (; i < r; i += stride) out[i] = r8nt_to_file(rows[i]);
+}
 // the inverse, into a separate buffer (generators / tests that hand a device table to the CPU oracle)
 __global__ void relayout_to_file_kernel(const uint2* __restrict__ rows, uint2* __restrict__ out, unsigned long long r, uint32_t sep) {
     unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;

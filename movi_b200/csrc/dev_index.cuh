@@ -31,6 +31,7 @@ struct DevIndex {
     uint32_t id_blocks_size;
     uint32_t block_shift;         // block_size == 1 << block_shift
     uint32_t layout;
+    uint32_t nt;                  // 1: non-threshold index type (12-bit lengths, no threshold mask; PML repositions with the --rpml rule)
     const uint32_t* rows3;        // LAYOUT_T3: packed 3-byte rows viewed as 32-bit words (table padded by 8 bytes)
     const uint8_t* tally;         // LAYOUT_T3: sigma x tally_len MoveTally entries (5 bytes each)
     unsigned long long tally_len;
@@ -56,13 +57,28 @@ constexpr uint32_t CODE_ILLEGAL = 0xFFu;
 
 constexpr int R8_MAX_ROW_BITS = 35;     // 32 + 3 id bits: 3.4e10 rows = 275 GB of rows, more than a B200 holds
 
-__host__ __device__ __forceinline__ uint32_t row_n(uint32_t y) { return y & 0x7FFu; }
+// NT = the table came from a non-threshold index type ("regular", MODE 3: include/move_row_configs.hpp:20-31), whose run
+// lengths and offsets have 12 bits.  Its R8 word has no threshold mask: n[0:12] | offset[12:24] | id[32:35] << 24 | c << 29.
+template <bool NT = false> __host__ __device__ __forceinline__ uint32_t row_n(uint32_t y) { return NT ? (y & 0xFFFu) : (y & 0x7FFu); }
 __host__ __device__ __forceinline__ uint32_t row_c(uint32_t y) { return y >> 29; }
-__host__ __device__ __forceinline__ uint32_t row_off(uint32_t y) { return (y >> 11) & 0x7FFu; }
-template <typename IdxT>
+template <bool NT = false> __host__ __device__ __forceinline__ uint32_t row_off(uint32_t y) { return NT ? ((y >> 12) & 0xFFFu) : ((y >> 11) & 0x7FFu); }
+template <typename IdxT, bool NT = false>
 __host__ __device__ __forceinline__ IdxT row_id(uint2 v) {
-    if constexpr (sizeof(IdxT) == 8) return (IdxT)v.x | ((IdxT)((v.y >> 22) & 7u) << 32);
+    if constexpr (sizeof(IdxT) == 8) return (IdxT)v.x | ((IdxT)((v.y >> (NT ? 24 : 22)) & 7u) << 32);
     else return (IdxT)v.x;
+}
+// the reference's "regular" row (n 0..11, c 13..15 | offset 16..27, id high 28..31) <-> R8 (NT)
+__host__ __device__ __forceinline__ uint2 r8nt_from_file(uint2 f) {
+    const uint32_t y = f.y;
+    uint2 v; v.x = f.x;
+    v.y = (y & 0xFFFu) | (((y >> 16) & 0xFFFu) << 12) | (((y >> 28) & 7u) << 24) | (((y >> 13) & 7u) << 29);
+    return v;
+}
+__host__ __device__ __forceinline__ uint2 r8nt_to_file(uint2 v) {
+    const uint32_t y = v.y;
+    uint2 f; f.x = v.x;
+    f.y = (y & 0xFFFu) | ((y >> 29) << 13) | (((y >> 12) & 0xFFFu) << 16) | (((y >> 24) & 7u) << 28);
+    return f;
 }
 // alphamap_3 (src/utils.cpp:5-8): slot of read character b among the three thresholds of a row with character a
 __host__ __device__ __forceinline__ uint32_t thr_slot(uint32_t a, uint32_t b) { return b - (b > a ? 1u : 0u); }
@@ -117,7 +133,7 @@ __device__ __forceinline__ uint2 ldg64(const uint2* p) { return __ldg(p); }
 // Run length of row k whatever the device layout (count query: sums over the rows an interval spans)
 __device__ __forceinline__ uint32_t row_len_at(const DevIndex& ix, unsigned long long k) {
     if (ix.layout == LAYOUT_B6) return (uint32_t)reinterpret_cast<const uint16_t*>(ix.rows6)[3 * k + 1] & 0x3FFu;
-    return row_n(ix.rows[k].y);
+    return ix.nt ? row_n<true>(ix.rows[k].y) : row_n<false>(ix.rows[k].y);
 }
 
 // LAYOUT_B6: the packed blocked-thresholds row (include/move_row.hpp:128-130,139-142; bit fields

@@ -239,6 +239,10 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
     } while (0)
     if (kind == Q_PML) {
         const int64_t variant = ctx->ix.layout != LAYOUT_R8 ? std::max<int64_t>(ctx->pml_variant, 4) : ctx->pml_variant;   // the compact layouts exist for variants 4 / 5 only
+        if (ctx->ix.nt) {            // non-threshold table: 12-bit accessors, always the --rpml rule (move_structure_query.cpp:308-311)
+            if (ctx->ix.sep) { if (wide) LAUNCH((movi_pml_kernel4<unsigned long long, true, 6, LAYOUT_R8, true, false, true, true>)); else LAUNCH((movi_pml_kernel4<uint32_t, true, 6, LAYOUT_R8, true, false, true, true>)); }
+            else             { if (wide) LAUNCH((movi_pml_kernel4<unsigned long long, false, 6, LAYOUT_R8, true, false, true, true>)); else LAUNCH((movi_pml_kernel4<uint32_t, false, 6, LAYOUT_R8, true, false, true, true>)); }
+        } else
         if ((qa.flags & MOVI_GPU_FLAG_RPML) && variant < 5) return fail(ctx, MOVI_GPU_ERR_ARG, "MOVI_GPU_FLAG_RPML needs pml_variant >= 5");
         if (variant == 0) { if (wide) LAUNCH((movi_pml_kernel<unsigned long long, 0>)); else LAUNCH((movi_pml_kernel<uint32_t, 0>)); }
         else if (variant == 1) { if (wide) LAUNCH((movi_pml_kernel<unsigned long long, 1>)); else LAUNCH((movi_pml_kernel<uint32_t, 1>)); }
@@ -283,7 +287,8 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
         const bool v0 = ctx->bs_variant == 0 && !b6;
         const bool bs_sector = !b6 && !v0 && (ctx->pml_sector == 1 || (ctx->pml_sector < 0 &&
                                ctx->ix.r * sizeof(uint2) > (512ull << 20) && qa.n_reads >= (1u << 17)));
-#define BS(IDX, KINDV) do { if (v0) LAUNCH((movi_bs_kernel<IDX, KINDV>)); \
+#define BS(IDX, KINDV) do { if (ctx->ix.nt) LAUNCH((movi_bs_kernel2<IDX, KINDV, LAYOUT_R8, false, true>)); \
+                            else if (v0) LAUNCH((movi_bs_kernel<IDX, KINDV>)); \
                             else if (b6) LAUNCH((movi_bs_kernel2<IDX, KINDV, LAYOUT_B6>)); \
                             else if (bs_sector) LAUNCH((movi_bs_kernel2<IDX, KINDV, LAYOUT_R8, true>)); \
                             else LAUNCH((movi_bs_kernel2<IDX, KINDV, LAYOUT_R8>)); } while (0)
@@ -624,9 +629,13 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
     if (!ctx || !d) return MOVI_GPU_ERR_ARG;
     if (layout != MOVI_GPU_LAYOUT_AUTO && layout != MOVI_GPU_LAYOUT_EXPANDED8 && layout != MOVI_GPU_LAYOUT_COMPACT)
         return fail(ctx, MOVI_GPU_ERR_ARG, "unknown device layout");
-    if (d->mode != MOVI_MODE_REGULAR_THRESHOLDS && d->mode != MOVI_MODE_BLOCKED_THRESHOLDS && d->mode != MOVI_MODE_SAMPLED_THRESHOLDS)
+    if (d->mode != MOVI_MODE_REGULAR_THRESHOLDS && d->mode != MOVI_MODE_BLOCKED_THRESHOLDS && d->mode != MOVI_MODE_SAMPLED_THRESHOLDS &&
+        d->mode != MOVI_MODE_REGULAR)
         return fail(ctx, MOVI_GPU_ERR_INDEX, "unsupported index mode " + std::to_string(d->mode) +
-                    " (regular-thresholds 6, blocked-thresholds 8, sampled-thresholds 7)");
+                    " (regular-thresholds 6, blocked-thresholds 8, sampled-thresholds 7, regular 3)");
+    const bool nt = d->mode == MOVI_MODE_REGULAR;                     // NO_THRESHOLDS, include/utils.hpp:146
+    if (nt && (adopt_rows || layout == MOVI_GPU_LAYOUT_COMPACT))
+        return fail(ctx, MOVI_GPU_ERR_INDEX, "the regular (non-threshold) index type is uploaded from host rows, in the expanded layout");
     if ((!d->rows && !adopt_rows) || !d->alphamap || d->r == 0) return fail(ctx, MOVI_GPU_ERR_INDEX, "empty index description");
     if (d->r >= (1ull << R8_MAX_ROW_BITS)) return fail(ctx, MOVI_GPU_ERR_INDEX, "more than 2^35 rows");
     if (d->end_bwt_idx >= d->r) return fail(ctx, MOVI_GPU_ERR_INDEX, "end_bwt_idx out of range");
@@ -699,10 +708,11 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
 
     if (compact) {
         // nothing to convert
-    } else if (adopt_rows || d->mode == MOVI_MODE_REGULAR_THRESHOLDS) {
+    } else if (adopt_rows || d->mode == MOVI_MODE_REGULAR_THRESHOLDS || nt) {
         // the 8-byte rows of the reference: copy (unless already resident), then permute the bit fields into R8 in place
         if (!adopt_rows) CU(cudaMemcpyAsync(ctx->d_rows, d->rows, r * sizeof(uint2), cudaMemcpyHostToDevice, st));
-        relayout_regular_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(ctx->d_rows, r, sep ? 1u : 0u);
+        if (nt) relayout_regular_nt_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(ctx->d_rows, r);
+        else relayout_regular_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(ctx->d_rows, r, sep ? 1u : 0u);
         ctx->launches += 1;
         CU(cudaGetLastError());
     } else if (d->mode == MOVI_MODE_BLOCKED_THRESHOLDS) {
@@ -750,6 +760,7 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
     ix.rows6 = ctx->d_rows6;
     ix.id_blocks = ctx->d_id_blocks;
     ix.layout = compact_t3 ? LAYOUT_T3 : compact ? LAYOUT_B6 : LAYOUT_R8;
+    ix.nt = nt ? 1u : 0u;
     ix.rows3 = ctx->d_rows3; ix.tally = ctx->d_tally; ix.tally_len = d->tally_len; ix.tally_cp = d->tally_checkpoints;
     if (compact && !compact_t3) {
         ix.id_blocks_size = (uint32_t)d->id_blocks_size;
@@ -774,10 +785,10 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
     {   // n(r-1) for the start state of query_pml
         uint2 last = make_uint2(0u, n_last_host);
         if (!compact) CU(cudaMemcpy(&last, ctx->d_rows + (r - 1), sizeof(last), cudaMemcpyDeviceToHost));
-        ix.n_last = last.y & 0x7FFu;
+        ix.n_last = nt ? row_n<true>(last.y) : (last.y & 0x7FFu);
         if (ix.n_last == 0) return fail(ctx, MOVI_GPU_ERR_INDEX, "last row has length 0");
     }
-    if (sep) {
+    if (sep && !nt) {
         // separators_thresholds_map: row -> slot; keep it as a sorted key array + thresholds in key order,
         // plus one trailing entry that mirrors slot 0 (what unordered_map::operator[] would yield for a miss)
         std::vector<std::pair<uint64_t, uint64_t>> kv(d->sep_map_size);
@@ -816,7 +827,8 @@ int movi_gpu_index_export_rows(movi_gpu_ctx* ctx, uint64_t first, uint64_t count
     int rc = MOVI_GPU_OK;
     for (uint64_t done = 0; done < count && rc == MOVI_GPU_OK; done += chunk) {
         const uint64_t m = std::min(chunk, count - done);
-        relayout_to_file_kernel<<<ctx->num_sms * 8, 256, 0, ctx->st_k[0]>>>(ctx->d_rows + first + done, d_tmp, m, ctx->ix.sep);
+        if (ctx->ix.nt) relayout_nt_to_file_kernel<<<ctx->num_sms * 8, 256, 0, ctx->st_k[0]>>>(ctx->d_rows + first + done, d_tmp, m);
+        else relayout_to_file_kernel<<<ctx->num_sms * 8, 256, 0, ctx->st_k[0]>>>(ctx->d_rows + first + done, d_tmp, m, ctx->ix.sep);
         if (cudaMemcpyAsync(static_cast<uint2*>(host_rows) + done, d_tmp, m * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->st_k[0]) != cudaSuccess ||
             cudaStreamSynchronize(ctx->st_k[0]) != cudaSuccess)
             rc = fail(ctx, MOVI_GPU_ERR_CUDA, std::string("export rows: ") + cudaGetErrorString(cudaGetLastError()));

@@ -58,7 +58,8 @@ __device__ __forceinline__ uint4 ld_keep128(const uint4* p, unsigned long long p
 // the same row in the other direction (:634-649, :661-674; states ST_UPF / ST_DOWNF = "already turned round").
 constexpr uint32_t ST_UPF = 5, ST_DOWNF = 6;
 
-template <typename IdxT, bool SEP, int MINB, int LAYOUT, bool HINTS = true, bool SECTOR = false, bool RPML = false>
+// NT: the table of a non-threshold index type (dev_index.cuh): 12-bit field accessors; always queried with RPML.
+template <typename IdxT, bool SEP, int MINB, int LAYOUT, bool HINTS = true, bool SECTOR = false, bool RPML = false, bool NT = false>
 __global__ void __launch_bounds__(PML3_THREADS, MINB)
 movi_pml_kernel4(const DevIndex ix, const QueryArgs q) {
     __shared__ uint8_t s_code[256];
@@ -177,7 +178,7 @@ movi_pml_kernel4(const DevIndex ix, const QueryArgs q) {
 
         // ---- one predicate-driven step of the state machine for every lane
         const uint32_t y = v.y;
-        const uint32_t n = row_n(y);
+        const uint32_t n = row_n<NT>(y);
         const uint32_t c = row_c(y);
         const uint32_t code = lds_u8(sa_code + lds_u8(sa_in + (rp & 31u)));
         const bool is_ff = (st == ST_FF);
@@ -235,8 +236,8 @@ movi_pml_kernel4(const DevIndex ix, const QueryArgs q) {
         rem -= emit ? 1u : 0u;
         need_chunk = need_chunk || (lf && (rp & 31u) == 0u);
         rp -= lf ? 1u : 0u;
-        off += lf ? row_off(y) : 0u;                                        // LF_move, move_structure.cpp:66
-        IdxT lf_id = row_id<IdxT>(v);
+        off += lf ? row_off<NT>(y) : 0u;                                        // LF_move, move_structure.cpp:66
+        IdxT lf_id = row_id<IdxT, NT>(v);
         bool bad_id = false;
         if (LAYOUT == LAYOUT_T3) {
             // sampled-thresholds: get_id = checkpoint scan + walk-back (src/move_structure.cpp:103-219), per LF step

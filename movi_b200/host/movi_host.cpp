@@ -92,6 +92,7 @@ int movi_host_index_open(const char* path, movi_host_index** out) {
     std::memcpy(&ix->original_r, h + 32, 8); std::memcpy(&d.end_bwt_idx, h + 40, 8);
     size_t row_bytes;
     switch (d.mode) {
+        case MOVI_MODE_REGULAR: row_bytes = 8; ix->type_name = "regular"; break;                         /* src/utils.cpp:20-24 */
         case MOVI_MODE_REGULAR_THRESHOLDS: row_bytes = 8; ix->type_name = "regular-thresholds"; break;
         case MOVI_MODE_BLOCKED_THRESHOLDS: row_bytes = 6; ix->type_name = "blocked-thresholds"; break;
         case MOVI_MODE_SAMPLED_THRESHOLDS: row_bytes = 3; ix->type_name = "sampled-thresholds"; break;
@@ -149,7 +150,7 @@ int movi_host_index_open(const char* path, movi_host_index** out) {
     }
     if (!c.ok) return bad("truncated index file");
     // read_separators_thresholds, io.cpp:415-433 (present iff use_separator(), move_structure.cpp:547-552)
-    if (sigma == 5 && d.alphabet[0] == '%') {
+    if (sigma == 5 && d.alphabet[0] == '%' && d.mode != MOVI_MODE_REGULAR) {      // (#if USE_THRESHOLDS, io.cpp:504-508)
         d.sep_count = c.get<uint64_t>();
         const uint8_t* t = c.take(d.sep_count * 8);
         if (!c.ok) return bad("truncated separators thresholds");

@@ -139,3 +139,16 @@ def test_rpml_stdout_and_file_names(cli, index_dirs, typ, tmp_path):
     bpf = "%s.%s.rpml.bpf" % (reads, typ)
     assert os.path.exists(bpf)
     assert run(cli, "view", "--bpf", bpf) == expected_text("sample.fasta", "rpml")
+
+
+def test_regular_index_type(cli, regular_index_dir, tmp_path):
+    """The non-threshold "regular" index type through the command line: the reference's output and its file naming."""
+    for read_set in ("sample.fastq", "edge.fasta"):
+        out = run(cli, "query", "--index", regular_index_dir, "--read", reads_path(read_set), "--pml", "--stdout")
+        assert out == expected_text(read_set + ".regular", "pml")
+        out = run(cli, "query", "--index", regular_index_dir, "--read", reads_path(read_set), "--count", "--stdout")
+        assert out == expected_text(read_set, "count")
+    reads = tmp_path / "sample.fasta"
+    shutil.copy(reads_path("sample.fasta"), reads)
+    run(cli, "query", "-i", regular_index_dir, "-r", str(reads), "--zml")
+    assert run(cli, "view", "--bpf", "%s.regular.zml.bpf" % reads) == expected_text("sample.fasta", "zml")

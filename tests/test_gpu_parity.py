@@ -396,3 +396,45 @@ def test_rpml_matches_reference_and_oracle(structures, index_dirs, read_sets, re
     from movi_b200 import MoviGpuError
     with pytest.raises(MoviGpuError, match="RPML"):
         ms.query_pml(bases, offsets, rpml=True)
+
+
+def test_regular_index_without_thresholds(regular_index_dir, read_sets, ref_seq):
+    """The non-threshold "regular" index type (MODE 3: 12-bit run lengths, no threshold bits): PML (which repositions with
+    reposition_randomly there), ZML and count against the unmodified reference's output and, on 20 k ragged random reads,
+    against the oracle; host-buffer, byte-wide and fused-classify entry points; rows export back to the file's bytes."""
+    import ctypes as C
+    from movi_b200 import HostIndex, MoveStructure
+    from oracle.port import OracleIndex, classify, pack_reads
+    ms = MoveStructure(regular_index_dir)
+    try:
+        assert ms.host_index.type_name == "regular"
+        for read_set in READ_SETS:
+            rd = read_sets[read_set]
+            assert ml_text(rd.ids(), rd.offsets, ms.query_pml(rd.bases, rd.offsets)) == expected_text(read_set + ".regular", "pml")
+            assert ml_text(rd.ids(), rd.offsets, ms.query_zml(rd.bases, rd.offsets)) == expected_text(read_set, "zml")
+            c, p = ms.query_backward_search(rd.bases, rd.offsets)
+            assert count_text(rd.ids(), rd.offsets, c, p) == expected_text(read_set, "count")
+        orc = OracleIndex(regular_index_dir)
+        bases, offsets = pack_reads(_random_reads(17, 20000, 600, ref_seq))
+        want = orc.query_pml(bases, offsets, threads=0)
+        assert np.array_equal(ms.query_pml(bases, offsets), want)
+        assert np.array_equal(ms.query_pml(bases, offsets, rpml=True), want)          # the flag changes nothing here
+        assert np.array_equal(ms.query_zml(bases, offsets), orc.query_zml(bases, offsets, threads=0))
+        c1, p1 = ms.query_backward_search(bases, offsets)
+        c2, p2 = orc.query_count(bases, offsets, threads=0)
+        assert np.array_equal(c1, c2) and np.array_equal(p1, p2)
+        short = pack_reads(_random_reads(19, 4000, 255, ref_seq))
+        assert np.array_equal(ms.query_ml8(*short), orc.query_pml(*short, threads=0).astype(np.uint8))
+        a, b, s = ms.query_classify(bases, offsets, 150, 7)
+        for i in range(0, len(offsets) - 1, 97):
+            v = want[int(offsets[i]):int(offsets[i + 1])]
+            if len(v):
+                _, ea, eb, es, _ = classify(v, 150, 7)
+                assert (a[i], b[i], s[i]) == (ea, eb, es)
+        hix = HostIndex(regular_index_dir)
+        file_rows = np.ctypeslib.as_array(C.cast(hix.desc.rows, C.POINTER(C.c_uint32)), shape=(hix.r, 2)).copy()
+        got = ms.export_rows()
+        mask = ~np.uint32(1 << 12)                 # bit 12 of the n field is not used by the format (LENGTH_BITS 12, SHIFT_C 13)
+        assert np.array_equal(got[:, 0], file_rows[:, 0]) and np.array_equal(got[:, 1] & mask, file_rows[:, 1] & mask)
+    finally:
+        ms.close()

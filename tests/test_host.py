@@ -255,3 +255,11 @@ def test_cli_fails_loudly_without_gpu(index_dirs):
     r = subprocess.run([build.CLI, "query", "-i", index_dirs[("regular-thresholds", False)], "-r", reads_path("sample.fastq"), "--pml", "--stdout"],
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 1 and "no CUDA device" in r.stderr and r.stdout == ""
+
+
+def test_index_reader_opens_the_regular_type(regular_index_dir):
+    from oracle.port import OracleIndex
+    hix = HostIndex(regular_index_dir)
+    orc = OracleIndex(regular_index_dir)
+    assert hix.type_name == "regular" and hix.mode == 3 and hix.r == orc.r and hix.end_bwt_idx == orc.end_idx if hasattr(orc, "end_idx") else True
+    assert hix.r * 8 < 871479 < hix.r * 8 + 8192
