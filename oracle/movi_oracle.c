@@ -17,7 +17,9 @@
 #include <omp.h>
 #endif
 
+#define MODE_BLOCKED 2              /* "blocked": 6-byte rows + id_blocks, no thresholds, two more id bits (move_row_configs.hpp:54-73) */
 #define MODE_REGULAR 3              /* "regular": 8-byte rows without thresholds (utils.hpp:136), 12-bit lengths */
+#define MODE_SAMPLED 5              /* "sampled": 3-byte rows + id checkpoints, no thresholds, 10-bit lengths (:107-118) */
 #define MODE_REGULAR_THRESHOLDS 6
 #define MODE_SAMPLED_THRESHOLDS 7
 #define MODE_BLOCKED_THRESHOLDS 8
@@ -82,7 +84,9 @@ int movi_oracle_load(const char* path, movi_oracle_index** out) {
     switch (ix->mode) {
         case MODE_REGULAR:
         case MODE_REGULAR_THRESHOLDS: ix->row_bytes = 8; break;
+        case MODE_BLOCKED:
         case MODE_BLOCKED_THRESHOLDS: ix->row_bytes = 6; break;
+        case MODE_SAMPLED:
         case MODE_SAMPLED_THRESHOLDS: ix->row_bytes = 3; break;
         default: fail("unsupported index mode"); goto bad2;
     }
@@ -98,12 +102,12 @@ int movi_oracle_load(const char* path, movi_oracle_index** out) {
     uint16_t nt_splitting; uint8_t constant;
     if (rd(f, &nt_splitting, 2) || rd(f, &constant, 1)) goto bad;
     ix->separators = (ix->alphabet[0] == SEPARATOR && ix->sigma == 5);
-    ix->no_thresholds = (ix->mode == MODE_REGULAR);            /* NO_THRESHOLDS, utils.hpp:146 */
+    ix->no_thresholds = (ix->mode == MODE_REGULAR || ix->mode == MODE_BLOCKED || ix->mode == MODE_SAMPLED);   /* NO_THRESHOLDS, utils.hpp:146 */
     /* read_main_table, io.cpp:361-397 */
     ix->rows = (uint8_t*)malloc(ix->r * (size_t)ix->row_bytes + 16);
     if (!ix->rows || rd(f, ix->rows, ix->r * (size_t)ix->row_bytes)) goto bad;
     /* read_tally_table, io.cpp:338-349 */
-    if (ix->mode == MODE_SAMPLED_THRESHOLDS) {
+    if (ix->mode == MODE_SAMPLED_THRESHOLDS || ix->mode == MODE_SAMPLED) {
         if (rd(f, &ix->tally_checkpoints, 4) || rd(f, &ix->tally_len, 8)) goto bad;
         ix->tally = (uint8_t*)malloc((size_t)ix->sigma * ix->tally_len * 5 + 8);
         if (!ix->tally || rd(f, ix->tally, (size_t)ix->sigma * ix->tally_len * 5)) goto bad;
@@ -119,7 +123,7 @@ int movi_oracle_load(const char* path, movi_oracle_index** out) {
     if (rd(f, ix->last_runs, sz * 8) || rd(f, ix->last_offsets, sz * 8) ||
         rd(f, ix->first_runs, sz * 8) || rd(f, ix->first_offsets, sz * 8)) goto bad;
     /* read_id_blocks, io.cpp:305-324 */
-    if (ix->mode == MODE_BLOCKED_THRESHOLDS) {
+    if (ix->mode == MODE_BLOCKED_THRESHOLDS || ix->mode == MODE_BLOCKED) {
         if (rd(f, &ix->id_blocks_size, 8)) goto bad;
         if (ix->id_blocks_size) {
             ix->id_blocks = (uint32_t*)malloc((size_t)ix->sigma * ix->id_blocks_size * 4);
@@ -173,7 +177,9 @@ static inline uint64_t row_n(const movi_oracle_index* ix, uint64_t i) {
     switch (ix->mode) {
         case 3: return ld16(p + 4) & 0xFFFu;                              /* n[0:11], move_row_configs.hpp:20-31 */
         case 6: return ld16(p + 4) & 0x7FFu;                              /* n[0:10] */
+        case 2:
         case 8: return ld16(p + 2) & 0x3FFu;                              /* n[0:9] */
+        case 5: return (uint64_t)p[0] | ((uint64_t)((p[2] >> 2) & 3) << 8);  /* n | c[2:4]<<8, move_row.hpp:208-211 with LENGTH_MASK_BITS 2 */
         default: return (uint64_t)p[0] | ((uint64_t)((p[2] >> 1) & 1) << 8); /* n | c[1]<<8 */
     }
 }
@@ -182,7 +188,9 @@ static inline uint64_t row_offset(const movi_oracle_index* ix, uint64_t i) {
     switch (ix->mode) {
         case 3: return ld16(p + 6) & 0xFFFu;
         case 6: return ld16(p + 6) & 0x7FFu;
+        case 2:
         case 8: return ld16(p + 4) & 0x3FFu;
+        case 5: return (uint64_t)p[1] | ((uint64_t)(p[2] & 3) << 8);
         default: return (uint64_t)p[1] | ((uint64_t)(p[2] & 1) << 8);
     }
 }
@@ -191,7 +199,9 @@ static inline int row_c(const movi_oracle_index* ix, uint64_t i) {
     switch (ix->mode) {
         case 3:                                                           /* REGULAR_MODES share the getters, move_row.hpp:231-258 */
         case 6: return (ld16(p + 4) >> 13) & 7;
+        case 2:
         case 8: return (ld16(p + 4) >> 10) & 7;
+        case 5: return (p[2] >> 4) & 15;                                  /* C_BITS 4, SHIFT_C 4 */
         default: return (p[2] >> 2) & 7;
     }
 }
@@ -207,8 +217,10 @@ static inline int row_thr_bit(const movi_oracle_index* ix, uint64_t i, int k) {
 static inline uint64_t row_id_field(const movi_oracle_index* ix, uint64_t i) {
     const uint8_t* p = ix->rows + i * (size_t)ix->row_bytes;
     if (ix->mode == 6 || ix->mode == 3) return (uint64_t)ld32(p) | ((uint64_t)((ld16(p + 6) >> 12) & 0xF) << 32);
-    /* MODE 8: id16 | n[10:15] << 16 (ID_SIG_BITS2 == 0) */
-    return (uint64_t)ld16(p) | ((uint64_t)((ld16(p + 2) >> 10) & 0x3F) << 16);
+    /* MODE 8: id16 | n[10:15] << 16 (ID_SIG_BITS2 == 0); MODE 2: two more bits from offset[14:15] at bit 22 (move_row.hpp:267-286) */
+    uint64_t id = (uint64_t)ld16(p) | ((uint64_t)((ld16(p + 2) >> 10) & 0x3F) << 16);
+    if (ix->mode == 2) id |= (uint64_t)((ld16(p + 4) >> 14) & 3) << 22;
+    return id;
 }
 /* move_structure.cpp:288-293 get_char: '$' for the end row.  -1 stands for '$'. */
 static inline int get_char(const movi_oracle_index* ix, uint64_t i) {
@@ -225,7 +237,7 @@ static inline uint64_t tally_get(const movi_oracle_index* ix, int c, uint64_t k)
 /* MoveStructure::get_id, move_structure.cpp:91-286 */
 static int get_id(const movi_oracle_index* ix, uint64_t idx, uint64_t* out) {
     if (ix->mode == 6 || ix->mode == 3) { *out = row_id_field(ix, idx); return 0; }   /* :92-94 */
-    if (ix->mode == 8) {                                                          /* :95-102 */
+    if (ix->mode == 8 || ix->mode == 2) {                                         /* :95-102 */
         if (idx != ix->end_bwt_idx) {
             uint64_t block = idx / ix->block_size;
             int c = row_c(ix, idx);

@@ -52,13 +52,24 @@ def index_dirs(tmp_path_factory):
     return out
 
 
+NOTHR_TYPES = ["regular", "blocked", "sampled"]      # MODE 3 / 2 / 5: no thresholds, PML repositions with reposition_randomly
+
+
 @pytest.fixture(scope="session")
-def regular_index_dir(tmp_path_factory):
-    """The non-threshold "regular" index (MODE 3) built by the unmodified reference (tests/golden/make_golden_regular.py)."""
-    d = tmp_path_factory.mktemp("c1_regular")
-    with lzma.open(os.path.join(GOLD, "c1", "regular", "index.movi.xz")) as f:
-        (d / "index.movi").write_bytes(f.read())
-    return str(d)
+def nothr_index_dirs(tmp_path_factory):
+    """{type: directory} of the non-threshold index types, built by the unmodified reference (tests/golden/make_golden_nothresholds.py)."""
+    out = {}
+    for typ in NOTHR_TYPES:
+        d = tmp_path_factory.mktemp("c1_" + typ)
+        with lzma.open(os.path.join(GOLD, "c1", typ, "index.movi.xz")) as f:
+            (d / "index.movi").write_bytes(f.read())
+        out[typ] = str(d)
+    return out
+
+
+@pytest.fixture(scope="session")
+def regular_index_dir(nothr_index_dirs):
+    return nothr_index_dirs["regular"]
 
 
 def expected_text(read_set, query, sep=False):
