@@ -46,7 +46,9 @@ enum {
 };
 
 /* Index modes = the reference's compile-time MODE (include/utils.hpp:133-147). */
-#define MOVI_MODE_REGULAR            3   /* 8-byte rows, no thresholds (12-bit lengths); PML repositions with the --rpml rule */
+#define MOVI_MODE_BLOCKED            2   /* 6-byte rows + id_blocks, no thresholds; PML repositions with the --rpml rule */
+#define MOVI_MODE_REGULAR            3   /* 8-byte rows, no thresholds (12-bit lengths); the same */
+#define MOVI_MODE_SAMPLED            5   /* 3-byte rows + id checkpoints, no thresholds; the same (PML only) */
 #define MOVI_MODE_REGULAR_THRESHOLDS 6   /* 8-byte rows  */
 #define MOVI_MODE_SAMPLED_THRESHOLDS 7   /* 3-byte rows + id checkpoints ("tally") */
 #define MOVI_MODE_BLOCKED_THRESHOLDS 8   /* 6-byte rows + id_blocks */

@@ -37,7 +37,7 @@ __global__ void relayout_to_file_kernel(const uint2* __restrict__ rows, uint2* _
 }
 
 __global__ void convert_blocked_kernel(const uint16_t* __restrict__ raw, uint2* __restrict__ out,
-                                       unsigned long long r, unsigned long long end_idx, uint32_t sep,
+                                       unsigned long long r, unsigned long long end_idx, uint32_t sep, uint32_t nothr,
                                        const uint32_t* __restrict__ id_blocks, unsigned long long id_blocks_size,
                                        unsigned long long block_size, const unsigned long long* __restrict__ first_runs) {
     unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
@@ -47,8 +47,11 @@ __global__ void convert_blocked_kernel(const uint16_t* __restrict__ raw, uint2* 
         const uint32_t n = f_n & 0x3FFu;
         const uint32_t off = f_off & 0x3FFu;
         const uint32_t c = (f_off >> 10) & 7u;
-        const uint32_t thr = (f_off >> 13) & 7u;                       // thresholds #0..#2 = offset bits 13..15
+        // MODE 8: thresholds #0..#2 = offset bits 13..15.  MODE 2 ("blocked", no thresholds): offset bits 14..15 are two more
+        // id bits (include/move_row.hpp:267-286, move_row_configs.hpp:54-73)
+        const uint32_t thr = nothr ? 0u : (f_off >> 13) & 7u;
         unsigned long long id = (unsigned long long)f_id | ((unsigned long long)((f_n >> 10) & 0x3Fu) << 16);
+        if (nothr) id |= (unsigned long long)((f_off >> 14) & 3u) << 22;
         if (i != end_idx) id += (unsigned long long)id_blocks[c * id_blocks_size + i / block_size] + first_runs[c + 1];
         out[i] = make_r8(id, n, off, c, thr, sep);
     }
@@ -56,19 +59,19 @@ __global__ void convert_blocked_kernel(const uint16_t* __restrict__ raw, uint2* 
 
 // ---- MODE 7 -> R8: one thread per row runs sampled_get_id (dev_index.cuh) on the packed table
 __global__ void convert_sampled_kernel(const uint32_t* __restrict__ raw_words, uint2* __restrict__ out,
-                                       unsigned long long r, unsigned long long end_idx, uint32_t sep,
+                                       unsigned long long r, unsigned long long end_idx, uint32_t sep, uint32_t nothr,
                                        const uint8_t* __restrict__ tally, unsigned long long tally_len, uint32_t cp,
                                        unsigned int* __restrict__ status) {
-    const Rows3 R{raw_words, end_idx};
+    const Rows3 R{raw_words, end_idx, nothr};
     unsigned long long idx = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (; idx < r; idx += stride) {
         const uint32_t x = R.raw(idx);
-        const uint32_t ci = Rows3::c_of(x);
+        const uint32_t ci = R.dc(x);
         bool bad = false;
         const unsigned long long id = sampled_get_id(R, tally, tally_len, cp, r, end_idx, idx, ci, &bad);
         if (bad) atomicOr(status, 2u);
-        out[idx] = make_r8(id, Rows3::n_of(x), Rows3::off_of(x), ci, Rows3::thr_of(x), sep);
+        out[idx] = make_r8(id, R.dn(x), R.doff(x), ci, nothr ? 0u : Rows3::thr_of(x), sep);
     }
 }
 

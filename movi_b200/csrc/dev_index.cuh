@@ -173,6 +173,8 @@ __device__ __forceinline__ uint32_t sep_threshold(const DevIndex& ix, unsigned l
 struct Rows3 {              // the packed table read through aligned 32-bit words (two loads per row)
     const uint32_t* w;
     unsigned long long end_idx;
+    uint32_t nothr = 0;     // 1: MODE 5 "sampled" (no thresholds): two length bits and a 4-bit character in the third byte
+                            //    (include/move_row_configs.hpp:107-118) instead of one and three + thresholds (:120-136)
     __device__ __forceinline__ uint32_t raw(unsigned long long i) const {
         const unsigned long long a = 3ull * i;
         const uint32_t* p = w + (a >> 2);
@@ -182,10 +184,13 @@ struct Rows3 {              // the packed table read through aligned 32-bit word
     static __device__ __forceinline__ uint32_t off_of(uint32_t x) { return ((x >> 8) & 0xFFu) | (((x >> 16) & 1u) << 8); }
     static __device__ __forceinline__ uint32_t c_of(uint32_t x) { return (x >> 18) & 7u; }
     static __device__ __forceinline__ uint32_t thr_of(uint32_t x) { return (x >> 21) & 7u; }
-    __device__ __forceinline__ uint32_t n(unsigned long long i) const { return n_of(raw(i)); }
-    __device__ __forceinline__ uint32_t off(unsigned long long i) const { return off_of(raw(i)); }
-    // get_char (src/move_structure.cpp:288-293): '$' (here 8) for the end row
-    __device__ __forceinline__ uint32_t ch(unsigned long long i) const { return i == end_idx ? 8u : c_of(raw(i)); }
+    __device__ __forceinline__ uint32_t dn(uint32_t x) const { return nothr ? ((x & 0xFFu) | (((x >> 18) & 3u) << 8)) : n_of(x); }
+    __device__ __forceinline__ uint32_t doff(uint32_t x) const { return nothr ? (((x >> 8) & 0xFFu) | (((x >> 16) & 3u) << 8)) : off_of(x); }
+    __device__ __forceinline__ uint32_t dc(uint32_t x) const { return nothr ? ((x >> 20) & 15u) : c_of(x); }
+    __device__ __forceinline__ uint32_t n(unsigned long long i) const { return dn(raw(i)); }
+    __device__ __forceinline__ uint32_t off(unsigned long long i) const { return doff(raw(i)); }
+    // get_char (src/move_structure.cpp:288-293): '$' (here 16) for the end row
+    __device__ __forceinline__ uint32_t ch(unsigned long long i) const { return i == end_idx ? 16u : dc(raw(i)); }
 };
 
 __device__ __forceinline__ unsigned long long tally_get(const uint8_t* tally, unsigned long long tally_len, uint32_t c, unsigned long long k) {

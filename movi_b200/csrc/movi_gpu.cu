@@ -74,6 +74,7 @@ struct movi_gpu_ctx {
     // exactly that: gpurun_out/trace_e2e.log of round 1); kernels rotate over st_k so that consecutive slices overlap
     cudaStream_t st_in = nullptr, st_out = nullptr, st_k[NKS] = {nullptr, nullptr, nullptr, nullptr};
     uint64_t launches = 0;
+    bool always_rpml = false;         // non-threshold index type: every PML query repositions with the --rpml rule
     uint32_t call_flags = 0;          // MOVI_GPU_FLAG_* of the entry point that is running
     // options
     int64_t pml_variant = 5;          // 0/1: branchy kernel (2-byte / 16-byte stores); 2/3: convergent kernel (+/- L2 hints); 4: convergent + sector staging in smem; 5: 4 with a leaner loop + evict_first on the streamed data (pml_kernel4.cuh); 6: 5 without those hints; 7: 5 with the sector-cached row fetch; 8: batched service rings (pml_kernel5.cuh)
@@ -306,7 +307,7 @@ int check_query_ready(movi_gpu_ctx* ctx, Kind kind, uint64_t n_reads) {
     if (!ctx) return MOVI_GPU_ERR_ARG;
     if (!ctx->has_index) return fail(ctx, MOVI_GPU_ERR_INDEX, "no index uploaded");
     if (n_reads >= 0xFFFFFFF0ull) return fail(ctx, MOVI_GPU_ERR_ARG, "too many reads in one device call (limit 2^32 - 16)");
-    if (kind != Q_PML && ctx->mode == MOVI_MODE_SAMPLED_THRESHOLDS)
+    if (kind != Q_PML && (ctx->mode == MOVI_MODE_SAMPLED_THRESHOLDS || ctx->mode == MOVI_MODE_SAMPLED))
         // reference src/movi.cpp:228-233
         return fail(ctx, MOVI_GPU_ERR_INDEX, "This query type is not suppported by the sampled modes yet.");
     return MOVI_GPU_OK;
@@ -331,7 +332,7 @@ int device_query(movi_gpu_ctx* ctx, Kind kind, const char* d_bases, const uint64
     qa.counter = d_counter;
     qa.status = ctx->d_status;
     qa.ld_mode = (uint32_t)ctx->row_ld_mode;
-    qa.flags = kind == Q_PML ? ctx->call_flags : 0u;
+    qa.flags = kind == Q_PML ? (ctx->call_flags | (ctx->always_rpml ? MOVI_GPU_FLAG_RPML : 0u)) : 0u;
     qa.keep_frac = ctx->row_keep_pct >= 100 ? 1.0f : (float)ctx->row_keep_pct / 100.0f;
     return launch_query(ctx, kind, qa, st);
 }
@@ -630,21 +631,26 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
     if (layout != MOVI_GPU_LAYOUT_AUTO && layout != MOVI_GPU_LAYOUT_EXPANDED8 && layout != MOVI_GPU_LAYOUT_COMPACT)
         return fail(ctx, MOVI_GPU_ERR_ARG, "unknown device layout");
     if (d->mode != MOVI_MODE_REGULAR_THRESHOLDS && d->mode != MOVI_MODE_BLOCKED_THRESHOLDS && d->mode != MOVI_MODE_SAMPLED_THRESHOLDS &&
-        d->mode != MOVI_MODE_REGULAR)
+        d->mode != MOVI_MODE_REGULAR && d->mode != MOVI_MODE_BLOCKED && d->mode != MOVI_MODE_SAMPLED)
         return fail(ctx, MOVI_GPU_ERR_INDEX, "unsupported index mode " + std::to_string(d->mode) +
-                    " (regular-thresholds 6, blocked-thresholds 8, sampled-thresholds 7, regular 3)");
-    const bool nt = d->mode == MOVI_MODE_REGULAR;                     // NO_THRESHOLDS, include/utils.hpp:146
-    if (nt && (adopt_rows || layout == MOVI_GPU_LAYOUT_COMPACT))
-        return fail(ctx, MOVI_GPU_ERR_INDEX, "the regular (non-threshold) index type is uploaded from host rows, in the expanded layout");
+                    " (regular-thresholds 6, blocked-thresholds 8, sampled-thresholds 7, regular 3, blocked 2, sampled 5)");
+    // NO_THRESHOLDS (include/utils.hpp:146): PML always repositions with the --rpml rule.  "regular" also has 12-bit lengths
+    // (its own form of the device row, flag nt); "blocked" and "sampled" fit the ordinary one with an empty threshold mask.
+    const bool no_thr = d->mode == MOVI_MODE_REGULAR || d->mode == MOVI_MODE_BLOCKED || d->mode == MOVI_MODE_SAMPLED;
+    const bool nt = d->mode == MOVI_MODE_REGULAR;
+    const bool blocked = d->mode == MOVI_MODE_BLOCKED_THRESHOLDS || d->mode == MOVI_MODE_BLOCKED;
+    const bool sampled = d->mode == MOVI_MODE_SAMPLED_THRESHOLDS || d->mode == MOVI_MODE_SAMPLED;
+    if (no_thr && (adopt_rows || layout == MOVI_GPU_LAYOUT_COMPACT))
+        return fail(ctx, MOVI_GPU_ERR_INDEX, "the non-threshold index types are uploaded from host rows, in the expanded layout");
     if ((!d->rows && !adopt_rows) || !d->alphamap || d->r == 0) return fail(ctx, MOVI_GPU_ERR_INDEX, "empty index description");
     if (d->r >= (1ull << R8_MAX_ROW_BITS)) return fail(ctx, MOVI_GPU_ERR_INDEX, "more than 2^35 rows");
     if (d->end_bwt_idx >= d->r) return fail(ctx, MOVI_GPU_ERR_INDEX, "end_bwt_idx out of range");
     const bool sep = (d->sigma == 5 && d->alphabet[0] == '%');       // use_separator(), src/move_structure.cpp:547-552
     if (!sep && (d->sigma < 1 || d->sigma > 4))
         return fail(ctx, MOVI_GPU_ERR_INDEX, "alphabet must have at most 4 characters, or be \"%ACGT\" with separators");
-    if (d->mode == MOVI_MODE_BLOCKED_THRESHOLDS && (!d->id_blocks || d->block_size == 0 || d->id_blocks_size < (d->r + d->block_size - 1) / d->block_size))
+    if (blocked && (!d->id_blocks || d->block_size == 0 || d->id_blocks_size < (d->r + d->block_size - 1) / d->block_size))
         return fail(ctx, MOVI_GPU_ERR_INDEX, "blocked-thresholds index without a consistent id_blocks table");
-    if (d->mode == MOVI_MODE_SAMPLED_THRESHOLDS && (!d->tally_ids || d->tally_checkpoints == 0 || d->tally_len < d->r / d->tally_checkpoints + 1))
+    if (sampled && (!d->tally_ids || d->tally_checkpoints == 0 || d->tally_len < d->r / d->tally_checkpoints + 1))
         return fail(ctx, MOVI_GPU_ERR_INDEX, "sampled-thresholds index without a consistent id checkpoint table");
     if (sep && d->sep_count && (!d->separators_thresholds || (d->sep_map_size && !d->separators_map)))
         return fail(ctx, MOVI_GPU_ERR_INDEX, "separators index without its thresholds table");
@@ -715,7 +721,7 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
         else relayout_regular_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(ctx->d_rows, r, sep ? 1u : 0u);
         ctx->launches += 1;
         CU(cudaGetLastError());
-    } else if (d->mode == MOVI_MODE_BLOCKED_THRESHOLDS) {
+    } else if (blocked) {
         Scratch s_raw, s_blocks, s_first;
         CU(cudaMalloc(&s_raw.p, r * 6 + 8));
         CU(cudaMalloc(&s_blocks.p, (size_t)d->sigma * d->id_blocks_size * sizeof(uint32_t)));
@@ -725,7 +731,7 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
         CU(cudaMemcpyAsync(d_raw, d->rows, r * 6, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_blocks, d->id_blocks, (size_t)d->sigma * d->id_blocks_size * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_first, d->first_runs, 8 * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
-        convert_blocked_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(d_raw, ctx->d_rows, r, d->end_bwt_idx, sep ? 1u : 0u, d_blocks, d->id_blocks_size,
+        convert_blocked_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(d_raw, ctx->d_rows, r, d->end_bwt_idx, sep ? 1u : 0u, no_thr ? 1u : 0u, d_blocks, d->id_blocks_size,
                                                                d->block_size, d_first);
         ctx->launches += 1;
         CU(cudaStreamSynchronize(st));
@@ -741,7 +747,7 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
         CU(cudaMemcpyAsync(d_raw, d->rows, r * 3, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_tally, d->tally_ids, tally_bytes, cudaMemcpyHostToDevice, st));
         CU(cudaMemsetAsync(ctx->d_status, 0, sizeof(unsigned int), st));
-        convert_sampled_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_raw), ctx->d_rows, r, d->end_bwt_idx, sep ? 1u : 0u, d_tally, d->tally_len,
+        convert_sampled_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_raw), ctx->d_rows, r, d->end_bwt_idx, sep ? 1u : 0u, no_thr ? 1u : 0u, d_tally, d->tally_len,
                                                                d->tally_checkpoints, ctx->d_status);
         ctx->launches += 1;
         unsigned int status = 0;
@@ -788,7 +794,7 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
         ix.n_last = nt ? row_n<true>(last.y) : (last.y & 0x7FFu);
         if (ix.n_last == 0) return fail(ctx, MOVI_GPU_ERR_INDEX, "last row has length 0");
     }
-    if (sep && !nt) {
+    if (sep && !no_thr) {
         // separators_thresholds_map: row -> slot; keep it as a sorted key array + thresholds in key order,
         // plus one trailing entry that mirrors slot 0 (what unordered_map::operator[] would yield for a miss)
         std::vector<std::pair<uint64_t, uint64_t>> kv(d->sep_map_size);
@@ -811,6 +817,7 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
     }
     CU(cudaStreamSynchronize(st));
     ctx->mode = d->mode;
+    ctx->always_rpml = no_thr;
     ctx->has_index = true;
     rollback.done = true;
     return MOVI_GPU_OK;

@@ -157,7 +157,7 @@ int main(int argc, char** argv) {
     MoviGpuIndexDesc desc;
     movi_host_index_desc(hix, &desc);
     const std::string type = movi_host_index_type_name(hix);
-    if (desc.mode == MOVI_MODE_SAMPLED_THRESHOLDS && o.query != "pml")     // src/movi.cpp:228-233
+    if ((desc.mode == MOVI_MODE_SAMPLED_THRESHOLDS || desc.mode == MOVI_MODE_SAMPLED) && o.query != "pml")     // src/movi.cpp:228-233
         die("This query type is not suppported by the sampled modes yet.");
     movi_host_reader* reader = nullptr;
     if (movi_host_reader_open(o.read_file.c_str(), o.reverse ? 1 : 0, &reader)) die(movi_host_last_error());

@@ -94,6 +94,8 @@ int movi_host_index_open(const char* path, movi_host_index** out) {
     switch (d.mode) {
         case MOVI_MODE_REGULAR: row_bytes = 8; ix->type_name = "regular"; break;                         /* src/utils.cpp:20-24 */
         case MOVI_MODE_REGULAR_THRESHOLDS: row_bytes = 8; ix->type_name = "regular-thresholds"; break;
+        case MOVI_MODE_BLOCKED: row_bytes = 6; ix->type_name = "blocked"; break;
+        case MOVI_MODE_SAMPLED: row_bytes = 3; ix->type_name = "sampled"; break;
         case MOVI_MODE_BLOCKED_THRESHOLDS: row_bytes = 6; ix->type_name = "blocked-thresholds"; break;
         case MOVI_MODE_SAMPLED_THRESHOLDS: row_bytes = 3; ix->type_name = "sampled-thresholds"; break;
         default: return bad("Index mode " + std::to_string(d.mode) + " is not supported by the GPU query path "
@@ -118,7 +120,7 @@ int movi_host_index_open(const char* path, movi_host_index** out) {
     d.rows = c.take(d.r * row_bytes);
     if (!d.rows) return bad("truncated row table");
     // read_tally_table, io.cpp:338-349
-    if (d.mode == MOVI_MODE_SAMPLED_THRESHOLDS) {
+    if (d.mode == MOVI_MODE_SAMPLED_THRESHOLDS || d.mode == MOVI_MODE_SAMPLED) {
         d.tally_checkpoints = c.get<uint32_t>();
         d.tally_len = c.get<uint64_t>();
         d.tally_ids = c.take((size_t)sigma * d.tally_len * 5);
@@ -139,7 +141,7 @@ int movi_host_index_open(const char* path, movi_host_index** out) {
     for (uint64_t k = 0; k < k1; k++) d.first_runs[k] = c.get<uint64_t>();
     for (uint64_t k = 0; k < k1; k++) d.first_offsets[k] = c.get<uint64_t>();
     // read_id_blocks, io.cpp:305-324
-    if (d.mode == MOVI_MODE_BLOCKED_THRESHOLDS) {
+    if (d.mode == MOVI_MODE_BLOCKED_THRESHOLDS || d.mode == MOVI_MODE_BLOCKED) {
         d.id_blocks_size = c.get<uint64_t>();
         const uint8_t* b = c.take((size_t)sigma * d.id_blocks_size * 4);
         if (!b && d.id_blocks_size) return bad("truncated id_blocks");
@@ -150,7 +152,8 @@ int movi_host_index_open(const char* path, movi_host_index** out) {
     }
     if (!c.ok) return bad("truncated index file");
     // read_separators_thresholds, io.cpp:415-433 (present iff use_separator(), move_structure.cpp:547-552)
-    if (sigma == 5 && d.alphabet[0] == '%' && d.mode != MOVI_MODE_REGULAR) {      // (#if USE_THRESHOLDS, io.cpp:504-508)
+    const bool no_thresholds = d.mode == MOVI_MODE_REGULAR || d.mode == MOVI_MODE_BLOCKED || d.mode == MOVI_MODE_SAMPLED;
+    if (sigma == 5 && d.alphabet[0] == '%' && !no_thresholds) {                    // (#if USE_THRESHOLDS, io.cpp:504-508)
         d.sep_count = c.get<uint64_t>();
         const uint8_t* t = c.take(d.sep_count * 8);
         if (!c.ok) return bad("truncated separators thresholds");

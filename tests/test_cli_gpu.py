@@ -141,14 +141,17 @@ def test_rpml_stdout_and_file_names(cli, index_dirs, typ, tmp_path):
     assert run(cli, "view", "--bpf", bpf) == expected_text("sample.fasta", "rpml")
 
 
-def test_regular_index_type(cli, regular_index_dir, tmp_path):
-    """The non-threshold "regular" index type through the command line: the reference's output and its file naming."""
+@pytest.mark.parametrize("typ", ["regular", "blocked", "sampled"])
+def test_index_types_without_thresholds(cli, nothr_index_dirs, tmp_path, typ):
+    """The non-threshold index types through the command line: the reference's output and its file naming."""
+    d = nothr_index_dirs[typ]
     for read_set in ("sample.fastq", "edge.fasta"):
-        out = run(cli, "query", "--index", regular_index_dir, "--read", reads_path(read_set), "--pml", "--stdout")
-        assert out == expected_text(read_set + ".regular", "pml")
-        out = run(cli, "query", "--index", regular_index_dir, "--read", reads_path(read_set), "--count", "--stdout")
-        assert out == expected_text(read_set, "count")
+        out = run(cli, "query", "--index", d, "--read", reads_path(read_set), "--pml", "--stdout")
+        assert out == expected_text("%s.%s" % (read_set, typ), "pml")
+        if typ != "sampled":
+            out = run(cli, "query", "--index", d, "--read", reads_path(read_set), "--count", "--stdout")
+            assert out == expected_text(read_set, "count")
     reads = tmp_path / "sample.fasta"
     shutil.copy(reads_path("sample.fasta"), reads)
-    run(cli, "query", "-i", regular_index_dir, "-r", str(reads), "--zml")
-    assert run(cli, "view", "--bpf", "%s.regular.zml.bpf" % reads) == expected_text("sample.fasta", "zml")
+    run(cli, "query", "-i", d, "-r", str(reads), "--pml")
+    assert run(cli, "view", "--bpf", "%s.%s.pml.bpf" % (reads, typ)) == expected_text("sample.fasta." + typ, "pml")

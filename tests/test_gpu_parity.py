@@ -398,31 +398,39 @@ def test_rpml_matches_reference_and_oracle(structures, index_dirs, read_sets, re
         ms.query_pml(bases, offsets, rpml=True)
 
 
-def test_regular_index_without_thresholds(regular_index_dir, read_sets, ref_seq):
-    """The non-threshold "regular" index type (MODE 3: 12-bit run lengths, no threshold bits): PML (which repositions with
-    reposition_randomly there), ZML and count against the unmodified reference's output and, on 20 k ragged random reads,
-    against the oracle; host-buffer, byte-wide and fused-classify entry points; rows export back to the file's bytes."""
+@pytest.mark.parametrize("typ", ["regular", "blocked", "sampled"])
+def test_index_types_without_thresholds(nothr_index_dirs, read_sets, ref_seq, typ):
+    """The non-threshold index types (MODE 3 "regular": 12-bit run lengths; MODE 2 "blocked": id_blocks + two more id bits;
+    MODE 5 "sampled": id checkpoints, 10-bit lengths, 4-bit character): PML (which repositions with reposition_randomly there),
+    ZML and count against the unmodified reference's output and, on 20 k ragged random reads, against the oracle; host-buffer,
+    byte-wide and fused-classify entry points; for "regular" the rows export back to the file's bytes."""
     import ctypes as C
-    from movi_b200 import HostIndex, MoveStructure
+    from movi_b200 import HostIndex, MoveStructure, MoviGpuError
     from oracle.port import OracleIndex, classify, pack_reads
-    ms = MoveStructure(regular_index_dir)
+    d = nothr_index_dirs[typ]
+    ms = MoveStructure(d)
     try:
-        assert ms.host_index.type_name == "regular"
+        assert ms.host_index.type_name == typ
         for read_set in READ_SETS:
             rd = read_sets[read_set]
-            assert ml_text(rd.ids(), rd.offsets, ms.query_pml(rd.bases, rd.offsets)) == expected_text(read_set + ".regular", "pml")
-            assert ml_text(rd.ids(), rd.offsets, ms.query_zml(rd.bases, rd.offsets)) == expected_text(read_set, "zml")
-            c, p = ms.query_backward_search(rd.bases, rd.offsets)
-            assert count_text(rd.ids(), rd.offsets, c, p) == expected_text(read_set, "count")
-        orc = OracleIndex(regular_index_dir)
+            assert ml_text(rd.ids(), rd.offsets, ms.query_pml(rd.bases, rd.offsets)) == expected_text("%s.%s" % (read_set, typ), "pml")
+            if typ != "sampled":
+                assert ml_text(rd.ids(), rd.offsets, ms.query_zml(rd.bases, rd.offsets)) == expected_text(read_set, "zml")
+                c, p = ms.query_backward_search(rd.bases, rd.offsets)
+                assert count_text(rd.ids(), rd.offsets, c, p) == expected_text(read_set, "count")
+        orc = OracleIndex(d)
         bases, offsets = pack_reads(_random_reads(17, 20000, 600, ref_seq))
         want = orc.query_pml(bases, offsets, threads=0)
         assert np.array_equal(ms.query_pml(bases, offsets), want)
         assert np.array_equal(ms.query_pml(bases, offsets, rpml=True), want)          # the flag changes nothing here
-        assert np.array_equal(ms.query_zml(bases, offsets), orc.query_zml(bases, offsets, threads=0))
-        c1, p1 = ms.query_backward_search(bases, offsets)
-        c2, p2 = orc.query_count(bases, offsets, threads=0)
-        assert np.array_equal(c1, c2) and np.array_equal(p1, p2)
+        if typ != "sampled":
+            assert np.array_equal(ms.query_zml(bases, offsets), orc.query_zml(bases, offsets, threads=0))
+            c1, p1 = ms.query_backward_search(bases, offsets)
+            c2, p2 = orc.query_count(bases, offsets, threads=0)
+            assert np.array_equal(c1, c2) and np.array_equal(p1, p2)
+        else:
+            with pytest.raises(MoviGpuError, match="not suppported by the sampled modes"):
+                ms.query_zml(bases, offsets)
         short = pack_reads(_random_reads(19, 4000, 255, ref_seq))
         assert np.array_equal(ms.query_ml8(*short), orc.query_pml(*short, threads=0).astype(np.uint8))
         a, b, s = ms.query_classify(bases, offsets, 150, 7)
@@ -431,10 +439,11 @@ def test_regular_index_without_thresholds(regular_index_dir, read_sets, ref_seq)
             if len(v):
                 _, ea, eb, es, _ = classify(v, 150, 7)
                 assert (a[i], b[i], s[i]) == (ea, eb, es)
-        hix = HostIndex(regular_index_dir)
-        file_rows = np.ctypeslib.as_array(C.cast(hix.desc.rows, C.POINTER(C.c_uint32)), shape=(hix.r, 2)).copy()
-        got = ms.export_rows()
-        mask = ~np.uint32(1 << 12)                 # bit 12 of the n field is not used by the format (LENGTH_BITS 12, SHIFT_C 13)
-        assert np.array_equal(got[:, 0], file_rows[:, 0]) and np.array_equal(got[:, 1] & mask, file_rows[:, 1] & mask)
+        if typ == "regular":
+            hix = HostIndex(d)
+            file_rows = np.ctypeslib.as_array(C.cast(hix.desc.rows, C.POINTER(C.c_uint32)), shape=(hix.r, 2)).copy()
+            got = ms.export_rows()
+            mask = ~np.uint32(1 << 12)                 # bit 12 of the n field is not used by the format (LENGTH_BITS 12, SHIFT_C 13)
+            assert np.array_equal(got[:, 0], file_rows[:, 0]) and np.array_equal(got[:, 1] & mask, file_rows[:, 1] & mask)
     finally:
         ms.close()

@@ -257,9 +257,11 @@ def test_cli_fails_loudly_without_gpu(index_dirs):
     assert r.returncode == 1 and "no CUDA device" in r.stderr and r.stdout == ""
 
 
-def test_index_reader_opens_the_regular_type(regular_index_dir):
+def test_index_reader_opens_the_types_without_thresholds(nothr_index_dirs):
     from oracle.port import OracleIndex
-    hix = HostIndex(regular_index_dir)
-    orc = OracleIndex(regular_index_dir)
-    assert hix.type_name == "regular" and hix.mode == 3 and hix.r == orc.r and hix.end_bwt_idx == orc.end_idx if hasattr(orc, "end_idx") else True
-    assert hix.r * 8 < 871479 < hix.r * 8 + 8192
+    for typ, mode, row_bytes in (("regular", 3, 8), ("blocked", 2, 6), ("sampled", 5, 3)):
+        hix = HostIndex(nothr_index_dirs[typ])
+        orc = OracleIndex(nothr_index_dirs[typ])
+        assert hix.type_name == typ and hix.mode == mode and hix.r == orc.r
+        size = os.path.getsize(os.path.join(nothr_index_dirs[typ], "index.movi"))
+        assert hix.r * row_bytes < size
