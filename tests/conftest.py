@@ -57,19 +57,22 @@ NOTHR_TYPES = ["regular", "blocked", "sampled"]      # MODE 3 / 2 / 5: no thresh
 
 @pytest.fixture(scope="session")
 def nothr_index_dirs(tmp_path_factory):
-    """{type: directory} of the non-threshold index types, built by the unmodified reference (tests/golden/make_golden_nothresholds.py)."""
+    """{(type, sep): directory} of the non-threshold index types, built by the unmodified reference
+    (tests/golden/make_golden_nothresholds.py)."""
     out = {}
     for typ in NOTHR_TYPES:
-        d = tmp_path_factory.mktemp("c1_" + typ)
-        with lzma.open(os.path.join(GOLD, "c1", typ, "index.movi.xz")) as f:
-            (d / "index.movi").write_bytes(f.read())
-        out[typ] = str(d)
+        for sep in (False, True):
+            tag = typ + (".sep" if sep else "")
+            d = tmp_path_factory.mktemp("c1_" + tag)
+            with lzma.open(os.path.join(GOLD, "c1", tag, "index.movi.xz")) as f:
+                (d / "index.movi").write_bytes(f.read())
+            out[(typ, sep)] = str(d)
     return out
 
 
 @pytest.fixture(scope="session")
 def regular_index_dir(nothr_index_dirs):
-    return nothr_index_dirs["regular"]
+    return nothr_index_dirs[("regular", False)]
 
 
 def expected_text(read_set, query, sep=False):

@@ -144,7 +144,7 @@ def test_rpml_stdout_and_file_names(cli, index_dirs, typ, tmp_path):
 @pytest.mark.parametrize("typ", ["regular", "blocked", "sampled"])
 def test_index_types_without_thresholds(cli, nothr_index_dirs, tmp_path, typ):
     """The non-threshold index types through the command line: the reference's output and its file naming."""
-    d = nothr_index_dirs[typ]
+    d = nothr_index_dirs[(typ, False)]
     for read_set in ("sample.fastq", "edge.fasta"):
         out = run(cli, "query", "--index", d, "--read", reads_path(read_set), "--pml", "--stdout")
         assert out == expected_text("%s.%s" % (read_set, typ), "pml")

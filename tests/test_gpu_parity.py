@@ -398,8 +398,9 @@ def test_rpml_matches_reference_and_oracle(structures, index_dirs, read_sets, re
         ms.query_pml(bases, offsets, rpml=True)
 
 
+@pytest.mark.parametrize("sep", [False, True])
 @pytest.mark.parametrize("typ", ["regular", "blocked", "sampled"])
-def test_index_types_without_thresholds(nothr_index_dirs, read_sets, ref_seq, typ):
+def test_index_types_without_thresholds(nothr_index_dirs, read_sets, ref_seq, typ, sep):
     """The non-threshold index types (MODE 3 "regular": 12-bit run lengths; MODE 2 "blocked": id_blocks + two more id bits;
     MODE 5 "sampled": id checkpoints, 10-bit lengths, 4-bit character): PML (which repositions with reposition_randomly there),
     ZML and count against the unmodified reference's output and, on 20 k ragged random reads, against the oracle; host-buffer,
@@ -407,17 +408,17 @@ def test_index_types_without_thresholds(nothr_index_dirs, read_sets, ref_seq, ty
     import ctypes as C
     from movi_b200 import HostIndex, MoveStructure, MoviGpuError
     from oracle.port import OracleIndex, classify, pack_reads
-    d = nothr_index_dirs[typ]
+    d = nothr_index_dirs[(typ, sep)]
     ms = MoveStructure(d)
     try:
         assert ms.host_index.type_name == typ
         for read_set in READ_SETS:
             rd = read_sets[read_set]
-            assert ml_text(rd.ids(), rd.offsets, ms.query_pml(rd.bases, rd.offsets)) == expected_text("%s.%s" % (read_set, typ), "pml")
+            assert ml_text(rd.ids(), rd.offsets, ms.query_pml(rd.bases, rd.offsets)) == expected_text("%s.%s" % (read_set, typ), "pml", sep)
             if typ != "sampled":
-                assert ml_text(rd.ids(), rd.offsets, ms.query_zml(rd.bases, rd.offsets)) == expected_text(read_set, "zml")
+                assert ml_text(rd.ids(), rd.offsets, ms.query_zml(rd.bases, rd.offsets)) == expected_text(read_set, "zml", sep)
                 c, p = ms.query_backward_search(rd.bases, rd.offsets)
-                assert count_text(rd.ids(), rd.offsets, c, p) == expected_text(read_set, "count")
+                assert count_text(rd.ids(), rd.offsets, c, p) == expected_text(read_set, "count", sep)
         orc = OracleIndex(d)
         bases, offsets = pack_reads(_random_reads(17, 20000, 600, ref_seq))
         want = orc.query_pml(bases, offsets, threads=0)

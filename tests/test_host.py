@@ -260,8 +260,10 @@ def test_cli_fails_loudly_without_gpu(index_dirs):
 def test_index_reader_opens_the_types_without_thresholds(nothr_index_dirs):
     from oracle.port import OracleIndex
     for typ, mode, row_bytes in (("regular", 3, 8), ("blocked", 2, 6), ("sampled", 5, 3)):
-        hix = HostIndex(nothr_index_dirs[typ])
-        orc = OracleIndex(nothr_index_dirs[typ])
-        assert hix.type_name == typ and hix.mode == mode and hix.r == orc.r
-        size = os.path.getsize(os.path.join(nothr_index_dirs[typ], "index.movi"))
-        assert hix.r * row_bytes < size
+        for sep in (False, True):
+            hix = HostIndex(nothr_index_dirs[(typ, sep)])
+            orc = OracleIndex(nothr_index_dirs[(typ, sep)])
+            assert hix.type_name == typ and hix.mode == mode and hix.r == orc.r
+            assert hix.alphabet == (b"%ACGT" if sep else b"ACGT")
+            size = os.path.getsize(os.path.join(nothr_index_dirs[(typ, sep)], "index.movi"))
+            assert hix.r * row_bytes < size
