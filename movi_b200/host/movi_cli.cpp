@@ -74,6 +74,11 @@ Options parse(int argc, char** argv) {
         else if (take_value(argc, argv, i, nullptr, "--gpus", v)) o.gpus = atoi(v.c_str());
         else if (take_value(argc, argv, i, nullptr, "--device", v)) o.device = atoi(v.c_str());
         else if (take_value(argc, argv, i, nullptr, "--bpf", v)) o.bpf_file = v;
+        // ftab seeds a backward search with the interval of its first k bases (src/move_structure_search.cpp:203-293): an
+        // accelerator with identical results (the stepwise search reaches the same interval and emits the same 0..k-2), so
+        // the flags are accepted and the table is not needed
+        else if (take_value(argc, argv, i, nullptr, "--ftab-k", v)) { }
+        else if (a == "--multi-ftab") { }
         else if (take_value(argc, argv, i, nullptr, "--chunk-bases", v)) o.chunk_bases = std::max<uint64_t>(1, strtoull(v.c_str(), nullptr, 10));
         else if (a == "--pml") o.query = "pml";
         else if (a == "--rpml") o.rpml = true;                                  // movi_parser.cpp:149,357

@@ -155,3 +155,13 @@ def test_index_types_without_thresholds(cli, nothr_index_dirs, tmp_path, typ):
     shutil.copy(reads_path("sample.fasta"), reads)
     run(cli, "query", "-i", d, "-r", str(reads), "--pml")
     assert run(cli, "view", "--bpf", "%s.%s.pml.bpf" % (reads, typ)) == expected_text("sample.fasta." + typ, "pml")
+
+
+def test_ftab_flags_are_accepted(cli, index_dirs):
+    """--ftab-k seeds the backward search from a k-mer table in the reference: an accelerator with identical results (checked with
+    the unmodified reference: `query --zml/--count --ftab-k 6` after `movi ftab --ftab-k 6` prints byte-identical output on
+    synth300.fasta and edge.fasta).  The flags are accepted; no table is needed."""
+    d = index_dirs[("blocked-thresholds", False)]
+    for q in ("zml", "count"):
+        out = run(cli, "query", "-i", d, "-r", reads_path("edge.fasta"), "--" + q, "--ftab-k", "6", "--multi-ftab", "--stdout")
+        assert out == expected_text("edge.fasta", q)
