@@ -66,16 +66,16 @@ typedef struct MoviGpuIndexDesc {
     const uint64_t* alphamap;            /* 256 entries, 256 == not in the alphabet (src/move_structure_build.cpp:428-447) */
     uint64_t end_bwt_idx_thresholds[4];  /* src/move_structure_io.cpp:147 */
     uint64_t first_runs[8], first_offsets[8], last_runs[8], last_offsets[8];   /* sigma+1 used; io.cpp:269-287 */
-    /* MODE 8 (src/move_structure_io.cpp:305-324) */
+    /* MODE 8 and 2 (src/move_structure_io.cpp:305-324) */
     const uint32_t* id_blocks;           /* sigma * id_blocks_size, character major */
     uint64_t id_blocks_size;
     uint64_t block_size;
-    /* MODE 7 (src/move_structure_io.cpp:338-349) */
+    /* MODE 7 and 5 (src/move_structure_io.cpp:338-349) */
     const void* tally_ids;               /* sigma * tally_len MoveTally {u32 right; u8 left}, 5 bytes each */
     uint64_t tally_len;
     uint32_t tally_checkpoints;
     uint32_t reserved0;
-    /* separators (src/move_structure_io.cpp:415-433); zero / NULL when the index has none */
+    /* separators (src/move_structure_io.cpp:415-433); zero / NULL when the index has none (the non-threshold modes never do) */
     const uint16_t* separators_thresholds;   /* sep_count * 4 (ThresholdsRow) */
     uint64_t sep_count;
     const uint64_t* separators_map;          /* sep_map_size pairs (row, slot) in any order */
