@@ -178,8 +178,8 @@ int  movi_gpu_classify_device(movi_gpu_ctx* ctx, const uint16_t* d_ml, const uin
 
 /* Introspection for benchmarks: kernels launched by this context so far, name and time of the last one. */
 uint64_t movi_gpu_launch_count(const movi_gpu_ctx* ctx);
-/* Tuning knobs (benchmarks / profiling / tests): "pml_variant", "blocks_per_sm", "threads_per_block", "batch_bases",
- * "force_wide" (64-bit row indices on small tables), "row_ld_mode", "l2_persist_mb", "l2_fetch_granularity";
+/* Tuning knobs (benchmarks / profiling / tests): "pml_sector" (-1 by table size / 0 / 1: sector-cached row fetch),
+ * "blocks_per_sm", "threads_per_block", "force_wide" (64-bit row indices on small tables), "smem_carveout";
  * host-buffer pipeline: "batch_bases" (bases per slice), "pipeline_slots" (2..8 slices in flight), "kernel_streams"
  * (1..4 slices walking concurrently), "size_grid_to_batch" (k >= 1: a small batch gets a grid of k reads per lane; 1 measured best). */
 int  movi_gpu_set_option(movi_gpu_ctx* ctx, const char* key, int64_t value);

@@ -166,14 +166,14 @@ class MoveStructure:
         self._check(self._L.movi_gpu_query_pml(self._ctx, _ptr(bases), _ptr(offsets), max(n, 0), FLAG_RPML if rpml else 0, _ptr(out)))
         return out
 
-    def query_classify(self, bases, offsets, bin_width, max_value_thr, zml=False, want_ml=False):
+    def query_classify(self, bases, offsets, bin_width, max_value_thr, zml=False, want_ml=False, rpml=False):
         """PML (or ZML) + binary classification on the device -> (bins_above, bins_below, sum_max[, ml])."""
         bases, offsets, n = self._prep(bases, offsets)
         n = max(n, 0)
         above, below = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
         total = np.zeros(n, np.uint64)
         ml = np.empty(int(offsets[-1]) if len(offsets) else 0, dtype=np.uint16) if want_ml else None
-        self._check(self._L.movi_gpu_query_classify(self._ctx, int(zml), _ptr(bases), _ptr(offsets), n, 0, bin_width, max_value_thr,
+        self._check(self._L.movi_gpu_query_classify(self._ctx, int(zml), _ptr(bases), _ptr(offsets), n, FLAG_RPML if rpml else 0, bin_width, max_value_thr,
                                                     _ptr(above), _ptr(below), _ptr(total), _ptr(ml) if want_ml else None))
         return (above, below, total, ml) if want_ml else (above, below, total)
 
@@ -185,12 +185,12 @@ class MoveStructure:
         self._check(self._L.movi_gpu_index_export_rows(self._ctx, first, count, _ptr(out)))
         return out
 
-    def query_ml8(self, bases, offsets, zml=False, out=None):
+    def query_ml8(self, bases, offsets, zml=False, out=None, rpml=False):
         """PML (or ZML) of a batch of reads of at most 255 bases, returned as uint8 (half the copy-back of query_pml)."""
         bases, offsets, n = self._prep(bases, offsets)
         if out is None:
             out = np.empty(int(offsets[-1]) if len(offsets) else 0, dtype=np.uint8)
-        self._check(self._L.movi_gpu_query_ml8(self._ctx, int(zml), _ptr(bases), _ptr(offsets), max(n, 0), 0, _ptr(out)))
+        self._check(self._L.movi_gpu_query_ml8(self._ctx, int(zml), _ptr(bases), _ptr(offsets), max(n, 0), FLAG_RPML if rpml else 0, _ptr(out)))
         return out
 
     def query_zml(self, bases, offsets, out=None):
@@ -211,8 +211,8 @@ class MoveStructure:
     query_count = query_backward_search
 
     # ---- raw pointer forms (host pinned or device pointers as ints)
-    def query_pml_ptr(self, bases_ptr, offsets_ptr, n_reads, out_ptr):
-        self._check(self._L.movi_gpu_query_pml(self._ctx, bases_ptr, offsets_ptr, n_reads, 0, out_ptr))
+    def query_pml_ptr(self, bases_ptr, offsets_ptr, n_reads, out_ptr, rpml=False):
+        self._check(self._L.movi_gpu_query_pml(self._ctx, bases_ptr, offsets_ptr, n_reads, FLAG_RPML if rpml else 0, out_ptr))
 
     def query_pml_device(self, d_bases, d_offsets, n_reads, d_out, stream=0, rpml=False):
         self._check(self._L.movi_gpu_query_pml_device(self._ctx, d_bases, d_offsets, n_reads, FLAG_RPML if rpml else 0, d_out, stream))

@@ -15,15 +15,11 @@
 #include <vector>
 
 #include "bs_kernel.cuh"
-#include "bs_kernel2.cuh"
 #include "convert.cuh"
 #include "dev_index.cuh"
+#include "kernel_common.cuh"
 #include "misc_kernels.cuh"
 #include "pml_kernel.cuh"
-#include "pml_kernel2.cuh"
-#include "pml_kernel3.cuh"
-#include "pml_kernel4.cuh"
-#include "pml_kernel5.cuh"
 
 using namespace movi;
 
@@ -50,7 +46,6 @@ struct Staging {                              // one pipeline slot
 struct movi_gpu_ctx {
     int device = 0;
     int num_sms = 0;
-    int64_t max_persist_bytes = 0, max_window_bytes = 0;
     std::string err;
     // index
     bool has_index = false;
@@ -77,15 +72,9 @@ struct movi_gpu_ctx {
     bool always_rpml = false;         // non-threshold index type: every PML query repositions with the --rpml rule
     uint32_t call_flags = 0;          // MOVI_GPU_FLAG_* of the entry point that is running
     // options
-    int64_t pml_variant = 5;          // 0/1: branchy kernel (2-byte / 16-byte stores); 2/3: convergent kernel (+/- L2 hints); 4: convergent + sector staging in smem; 5: 4 with a leaner loop + evict_first on the streamed data (pml_kernel4.cuh); 6: 5 without those hints; 7: 5 with the sector-cached row fetch; 8: batched service rings (pml_kernel5.cuh)
     int64_t pml_sector = -1;          // sector-cached row fetch: -1 by table size (> 512 MB) and batch size, 0 off, 1 on
-    int64_t row_keep_pct = 100;       // percent of the row table fetched with L2 evict_last (the rest evict_first); exploration
     int64_t smem_carveout = -1;       // >= 0: preferred shared-memory carve-out of the query kernels, percent of the maximum (exploration)
-    int64_t l2_persist_mb = 0;        // > 0: mark the row table persisting in L2 (access policy window) for query launches
-    int64_t l2_fetch_granularity = 0; // 0: leave the device default; 32 / 64 / 128: cudaLimitMaxL2FetchGranularity
-    int64_t bs_variant = 1;           // count / ZML kernel: 0 = branch-per-state (bs_kernel.cuh), 1 = convergent + sector staging
     int64_t force_wide = 0;           // tests: run the 64-bit-index instantiations on a small table
-    int64_t row_ld_mode = 0;          // cache recipe of the row fetch (pml_kernel2.cuh: ld_row)
     int64_t blocks_per_sm = 0;        // 0: occupancy query
     int64_t threads_per_block = 256;
     int64_t batch_bases = 12ll << 20; // bases per pipeline slice in the host-buffer entry points (D2H of the results is the
@@ -213,20 +202,6 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
     const uint64_t per_block = (uint64_t)threads * (uint64_t)std::max<int64_t>(1, ctx->size_grid_to_batch);
     const uint64_t grid_cap = ctx->size_grid_to_batch ? std::max<uint64_t>(1, ((uint64_t)qa.n_reads + per_block - 1) / per_block) : ~0ull;
     const bool wide = ctx->ix.r > 0xFFFFFFF0ull || ctx->force_wide;   // 64-bit row indices (tables beyond 2^32 rows = 34 GB)
-    // optional: keep the row table persisting in L2 (launch attribute; the carve-out is set in set_option)
-    cudaLaunchAttribute attr[1];
-    int n_attr = 0;
-    if (ctx->l2_persist_mb > 0) {
-        const size_t table = (size_t)ctx->ix.r * sizeof(uint2);
-        const size_t win = std::min<size_t>(table, (size_t)ctx->max_window_bytes);
-        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-        attr[0].val.accessPolicyWindow.base_ptr = (void*)ctx->d_rows;
-        attr[0].val.accessPolicyWindow.num_bytes = win;
-        attr[0].val.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)(ctx->l2_persist_mb << 20) / (double)win);
-        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        n_attr = 1;
-    }
 #define LAUNCH(KERNEL)                                                            \
     do {                                                                          \
         auto k_ = KERNEL;                                                         \
@@ -235,64 +210,37 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
         cfg_.gridDim = dim3((unsigned)std::min<uint64_t>((uint64_t)blocks_for(ctx, k_, threads), grid_cap)); \
         cfg_.blockDim = dim3((unsigned)threads);                                  \
         cfg_.stream = st;                                                         \
-        cfg_.attrs = attr; cfg_.numAttrs = n_attr;                                \
         CU(cudaLaunchKernelEx(&cfg_, k_, ctx->ix, qa));                           \
     } while (0)
+    // tables far beyond the L2 are bound by the request rate of the memory system, not by issue: there the kernels keep the
+    // last fetched 32-byte sector in registers ("pml_sector" -1 = by table size, 0 / 1 = off / on)
+    // (measured, profiles/r01_big_tables.jsonl: 8 and 32 GB tables 1.2 -> 2.2-2.5e10 bases/s; the 124 MB c2 table -27 %;
+    //  a batch of few long reads, which leaves most lanes empty and is latency bound, -10 %: those keep the plain fetch)
+    const bool b6 = ctx->ix.layout == LAYOUT_B6, t3 = ctx->ix.layout == LAYOUT_T3;
+    const bool sector = !b6 && !t3 && !ctx->ix.nt && (ctx->pml_sector == 1 || (ctx->pml_sector < 0 &&
+                        ctx->ix.r * sizeof(uint2) > (512ull << 20) && qa.n_reads >= (1u << 17)));
     if (kind == Q_PML) {
-        const int64_t variant = ctx->ix.layout != LAYOUT_R8 ? std::max<int64_t>(ctx->pml_variant, 4) : ctx->pml_variant;   // the compact layouts exist for variants 4 / 5 only
-        if (ctx->ix.nt) {            // non-threshold table: 12-bit accessors, always the --rpml rule (move_structure_query.cpp:308-311)
-            if (ctx->ix.sep) { if (wide) LAUNCH((movi_pml_kernel4<unsigned long long, true, 6, LAYOUT_R8, true, false, true, true>)); else LAUNCH((movi_pml_kernel4<uint32_t, true, 6, LAYOUT_R8, true, false, true, true>)); }
-            else             { if (wide) LAUNCH((movi_pml_kernel4<unsigned long long, false, 6, LAYOUT_R8, true, false, true, true>)); else LAUNCH((movi_pml_kernel4<uint32_t, false, 6, LAYOUT_R8, true, false, true, true>)); }
-        } else
-        if ((qa.flags & MOVI_GPU_FLAG_RPML) && variant < 5) return fail(ctx, MOVI_GPU_ERR_ARG, "MOVI_GPU_FLAG_RPML needs pml_variant >= 5");
-        if (variant == 0) { if (wide) LAUNCH((movi_pml_kernel<unsigned long long, 0>)); else LAUNCH((movi_pml_kernel<uint32_t, 0>)); }
-        else if (variant == 1) { if (wide) LAUNCH((movi_pml_kernel<unsigned long long, 1>)); else LAUNCH((movi_pml_kernel<uint32_t, 1>)); }
-        else if (variant == 2) { if (wide) LAUNCH((movi_pml_kernel2<unsigned long long, true>)); else LAUNCH((movi_pml_kernel2<uint32_t, true>)); }
-        else if (variant == 3) { if (wide) LAUNCH((movi_pml_kernel2<unsigned long long, false>)); else LAUNCH((movi_pml_kernel2<uint32_t, false>)); }
-        else {
-            // 6 blocks/SM (40 registers) measured fastest on both L2-sized (c2) and HBM-resident (8-64 GB) tables -- the
-            // latter are bound by the memory system's random-request rate, not by exposed latency (profiles/r01_big_tables.jsonl)
-            const bool b6 = ctx->ix.layout == LAYOUT_B6, t3 = ctx->ix.layout == LAYOUT_T3;
-            const bool rpml = (qa.flags & MOVI_GPU_FLAG_RPML) != 0;            // --rpml exists for the default kernel family only
-            // tables far beyond the L2 are bound by the request rate of the memory system, not by issue: there the kernel keeps
-            // the last fetched 32-byte sector in registers (variant 7; "pml_sector" -1 = by table size, 0 / 1 = off / on)
-            // (measured, profiles/r01_big_tables.jsonl: 8 and 32 GB tables 1.2 -> 2.2-2.5e10 bases/s; the 124 MB c2 table -27 %;
-            //  a batch of few long reads, which leaves most lanes empty and is latency bound, -10 %: those keep the plain fetch)
-            const bool sector8 = variant == 8 && (ctx->pml_sector == 1 || (ctx->pml_sector < 0 &&
-                                 ctx->ix.r * sizeof(uint2) > (512ull << 20) && qa.n_reads >= (1u << 17)));
-            const bool sector = variant == 7 || (variant == 5 && (ctx->pml_sector == 1 || (ctx->pml_sector < 0 &&
-                                ctx->ix.r * sizeof(uint2) > (512ull << 20) && qa.n_reads >= (1u << 17))));
-#define PML3(IDX, SEPV) do { if (rpml) { \
-                                 if (t3) LAUNCH((movi_pml_kernel4<IDX, SEPV, 5, LAYOUT_T3, true, false, true>)); \
-                                 else if (b6) LAUNCH((movi_pml_kernel4<IDX, SEPV, 6, LAYOUT_B6, true, false, true>)); \
-                                 else LAUNCH((movi_pml_kernel4<IDX, SEPV, 6, LAYOUT_R8, true, false, true>)); } \
-                             else if (variant == 8) { \
-                                 if (t3) LAUNCH((movi_pml_kernel5<IDX, SEPV, 5, LAYOUT_T3>)); \
-                                 else if (b6) LAUNCH((movi_pml_kernel5<IDX, SEPV, 6, LAYOUT_B6>)); \
-                                 else if (sector8) LAUNCH((movi_pml_kernel5<IDX, SEPV, 5, LAYOUT_R8, true>)); \
-                                 else LAUNCH((movi_pml_kernel5<IDX, SEPV, 6, LAYOUT_R8>)); } \
-                             else if (variant == 6 && !t3 && !b6) LAUNCH((movi_pml_kernel4<IDX, SEPV, 6, LAYOUT_R8, false>)); \
-                             else if (sector && !t3 && !b6) LAUNCH((movi_pml_kernel4<IDX, SEPV, 5, LAYOUT_R8, true, true>)); \
-                             else if (variant >= 5) { \
-                                 if (t3) LAUNCH((movi_pml_kernel4<IDX, SEPV, 5, LAYOUT_T3>)); \
-                                 else if (b6) LAUNCH((movi_pml_kernel4<IDX, SEPV, 6, LAYOUT_B6>)); else LAUNCH((movi_pml_kernel4<IDX, SEPV, 6, LAYOUT_R8>)); \
-                             } else { \
-                                 if (t3) LAUNCH((movi_pml_kernel3<IDX, SEPV, 5, LAYOUT_T3>)); \
-                                 else if (b6) LAUNCH((movi_pml_kernel3<IDX, SEPV, 6, LAYOUT_B6>)); else LAUNCH((movi_pml_kernel3<IDX, SEPV, 6, LAYOUT_R8>)); } } while (0)
-            if (ctx->ix.sep) { if (wide) PML3(unsigned long long, true); else PML3(uint32_t, true); }
-            else             { if (wide) PML3(unsigned long long, false); else PML3(uint32_t, false); }
-#undef PML3
-        }
+        // 6 blocks/SM (40 registers) measured fastest on both L2-sized (c2) and HBM-resident (8-64 GB) tables
+        const bool rpml = (qa.flags & MOVI_GPU_FLAG_RPML) != 0;
+#define PML(IDX, SEPV) do { \
+            if (ctx->ix.nt) LAUNCH((movi_pml_kernel<IDX, SEPV, 6, LAYOUT_R8, false, true, true>));   /* non-threshold table: 12-bit accessors, always the --rpml rule (move_structure_query.cpp:308-311) */ \
+            else if (rpml) { \
+                if (t3) LAUNCH((movi_pml_kernel<IDX, SEPV, 5, LAYOUT_T3, false, true>)); \
+                else if (b6) LAUNCH((movi_pml_kernel<IDX, SEPV, 6, LAYOUT_B6, false, true>)); \
+                else LAUNCH((movi_pml_kernel<IDX, SEPV, 6, LAYOUT_R8, false, true>)); } \
+            else if (t3) LAUNCH((movi_pml_kernel<IDX, SEPV, 5, LAYOUT_T3>)); \
+            else if (b6) LAUNCH((movi_pml_kernel<IDX, SEPV, 6, LAYOUT_B6>)); \
+            else if (sector && ctx->blocks_per_sm >= 6) LAUNCH((movi_pml_kernel<IDX, SEPV, 6, LAYOUT_R8, true>)); \
+            else if (sector) LAUNCH((movi_pml_kernel<IDX, SEPV, 5, LAYOUT_R8, true>)); \
+            else LAUNCH((movi_pml_kernel<IDX, SEPV, 6, LAYOUT_R8>)); } while (0)
+        if (ctx->ix.sep) { if (wide) PML(unsigned long long, true); else PML(uint32_t, true); }
+        else             { if (wide) PML(unsigned long long, false); else PML(uint32_t, false); }
+#undef PML
     } else {
-        const bool b6 = ctx->ix.layout == LAYOUT_B6;
-        const bool v0 = ctx->bs_variant == 0 && !b6;
-        const bool bs_sector = !b6 && !v0 && (ctx->pml_sector == 1 || (ctx->pml_sector < 0 &&
-                               ctx->ix.r * sizeof(uint2) > (512ull << 20) && qa.n_reads >= (1u << 17)));
-#define BS(IDX, KINDV) do { if (ctx->ix.nt) LAUNCH((movi_bs_kernel2<IDX, KINDV, LAYOUT_R8, false, true>)); \
-                            else if (v0) LAUNCH((movi_bs_kernel<IDX, KINDV>)); \
-                            else if (b6) LAUNCH((movi_bs_kernel2<IDX, KINDV, LAYOUT_B6>)); \
-                            else if (bs_sector) LAUNCH((movi_bs_kernel2<IDX, KINDV, LAYOUT_R8, true>)); \
-                            else LAUNCH((movi_bs_kernel2<IDX, KINDV, LAYOUT_R8>)); } while (0)
+#define BS(IDX, KINDV) do { if (ctx->ix.nt) LAUNCH((movi_bs_kernel<IDX, KINDV, LAYOUT_R8, false, true>)); \
+                            else if (b6) LAUNCH((movi_bs_kernel<IDX, KINDV, LAYOUT_B6>)); \
+                            else if (sector) LAUNCH((movi_bs_kernel<IDX, KINDV, LAYOUT_R8, true>)); \
+                            else LAUNCH((movi_bs_kernel<IDX, KINDV, LAYOUT_R8>)); } while (0)
         if (kind == Q_ZML) { if (wide) BS(unsigned long long, KIND_ZML); else BS(uint32_t, KIND_ZML); }
         else               { if (wide) BS(unsigned long long, KIND_COUNT); else BS(uint32_t, KIND_COUNT); }
 #undef BS
@@ -331,9 +279,7 @@ int device_query(movi_gpu_ctx* ctx, Kind kind, const char* d_bases, const uint64
     qa.out_pos = d_pos;
     qa.counter = d_counter;
     qa.status = ctx->d_status;
-    qa.ld_mode = (uint32_t)ctx->row_ld_mode;
     qa.flags = kind == Q_PML ? (ctx->call_flags | (ctx->always_rpml ? MOVI_GPU_FLAG_RPML : 0u)) : 0u;
-    qa.keep_frac = ctx->row_keep_pct >= 100 ? 1.0f : (float)ctx->row_keep_pct / 100.0f;
     return launch_query(ctx, kind, qa, st);
 }
 
@@ -499,8 +445,6 @@ int movi_gpu_create(int device, movi_gpu_ctx** out) {
     movi_gpu_ctx* c = new movi_gpu_ctx();
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
-    c->max_persist_bytes = prop.persistingL2CacheMaxSize;
-    c->max_window_bytes = prop.accessPolicyMaxWindowSize;
     ctx = c;
     cudaError_t e2 = cudaMalloc(&c->d_status, sizeof(unsigned int));
     if (e2 == cudaSuccess) e2 = cudaMemset(c->d_status, 0, sizeof(unsigned int));
@@ -554,25 +498,8 @@ uint64_t movi_gpu_launch_count(const movi_gpu_ctx* ctx) { return ctx ? ctx->laun
 int movi_gpu_set_option(movi_gpu_ctx* ctx, const char* key, int64_t value) {
     if (!ctx || !key) return MOVI_GPU_ERR_ARG;
     const std::string k(key);
-    if (k == "pml_variant") { if (value < 0 || value > 8) return fail(ctx, MOVI_GPU_ERR_ARG, "pml_variant: 0..8"); ctx->pml_variant = value; }
+    if (k == "force_wide") { ctx->force_wide = value ? 1 : 0; }
     else if (k == "probe_vmm_align_mb") { if (value < 0 || value > 4096) return fail(ctx, MOVI_GPU_ERR_ARG, "probe_vmm_align_mb: 0..4096"); ctx->probe_vmm_align_mb = value; }
-    else if (k == "bs_variant") { if (value < 0 || value > 1) return fail(ctx, MOVI_GPU_ERR_ARG, "bs_variant: 0 or 1"); ctx->bs_variant = value; }
-    else if (k == "force_wide") { ctx->force_wide = value ? 1 : 0; }
-    else if (k == "row_ld_mode") { if (value < 0 || value > 7) return fail(ctx, MOVI_GPU_ERR_ARG, "row_ld_mode: 0..7"); ctx->row_ld_mode = value; }
-    else if (k == "l2_persist_mb") {
-        if (value < 0) return fail(ctx, MOVI_GPU_ERR_ARG, "l2_persist_mb: >= 0");
-        CU(cudaSetDevice(ctx->device));
-        const int64_t capped = std::min<int64_t>(value, ctx->max_persist_bytes >> 20);
-        CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)capped << 20));
-        if (capped == 0) cudaCtxResetPersistingL2Cache();
-        ctx->l2_persist_mb = capped;
-    }
-    else if (k == "l2_fetch_granularity") {
-        if (value != 32 && value != 64 && value != 128) return fail(ctx, MOVI_GPU_ERR_ARG, "l2_fetch_granularity: 32, 64 or 128");
-        CU(cudaSetDevice(ctx->device));
-        CU(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
-        ctx->l2_fetch_granularity = value;
-    }
     else if (k == "blocks_per_sm") { if (value < 0 || value > 32) return fail(ctx, MOVI_GPU_ERR_ARG, "blocks_per_sm: 0..32"); ctx->blocks_per_sm = value; }
     else if (k == "threads_per_block") {
         if (value < 32 || value > 256 || value % 32) return fail(ctx, MOVI_GPU_ERR_ARG, "threads_per_block: multiple of 32 in [32, 256]");
@@ -580,7 +507,6 @@ int movi_gpu_set_option(movi_gpu_ctx* ctx, const char* key, int64_t value) {
     }
     else if (k == "batch_bases") { if (value < (1 << 16)) return fail(ctx, MOVI_GPU_ERR_ARG, "batch_bases: >= 65536"); ctx->batch_bases = value; }
     else if (k == "pml_sector") { if (value < -1 || value > 1) return fail(ctx, MOVI_GPU_ERR_ARG, "pml_sector: -1 (by table size), 0, 1"); ctx->pml_sector = value; }
-    else if (k == "row_keep_pct") { if (value < 0 || value > 100) return fail(ctx, MOVI_GPU_ERR_ARG, "row_keep_pct: 0..100"); ctx->row_keep_pct = value; }
     else if (k == "smem_carveout") { if (value < -1 || value > 100) return fail(ctx, MOVI_GPU_ERR_ARG, "smem_carveout: -1, 0..100"); ctx->smem_carveout = value; }
     else if (k == "kernel_streams") { if (value < 1 || value > NKS) return fail(ctx, MOVI_GPU_ERR_ARG, "kernel_streams: 1..4"); ctx->kernel_streams = value; }
     else if (k == "pipeline_slots") { if (value < 2 || value > NBUF) return fail(ctx, MOVI_GPU_ERR_ARG, "pipeline_slots: 2..8"); ctx->pipeline_slots = value; }
@@ -591,7 +517,6 @@ int movi_gpu_set_option(movi_gpu_ctx* ctx, const char* key, int64_t value) {
 int64_t movi_gpu_get_option(const movi_gpu_ctx* ctx, const char* key) {
     if (!ctx || !key) return -1;
     const std::string k(key);
-    if (k == "pml_variant") return ctx->pml_variant;
     if (k == "blocks_per_sm") return ctx->blocks_per_sm;
     if (k == "threads_per_block") return ctx->threads_per_block;
     if (k == "batch_bases") return ctx->batch_bases;
@@ -600,16 +525,7 @@ int64_t movi_gpu_get_option(const movi_gpu_ctx* ctx, const char* key) {
     if (k == "pipeline_slots") return ctx->pipeline_slots;
     if (k == "size_grid_to_batch") return ctx->size_grid_to_batch;
     if (k == "num_sms") return ctx->num_sms;
-    if (k == "row_ld_mode") return ctx->row_ld_mode;
     if (k == "force_wide") return ctx->force_wide;
-    if (k == "bs_variant") return ctx->bs_variant;
-    if (k == "l2_persist_mb") return ctx->l2_persist_mb;
-    if (k == "l2_persist_max_mb") return ctx->max_persist_bytes >> 20;
-    if (k == "l2_fetch_granularity") {
-        size_t v = 0;
-        if (cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity) != cudaSuccess) { cudaGetLastError(); return -1; }
-        return (int64_t)v;
-    }
     return -1;
 }
 

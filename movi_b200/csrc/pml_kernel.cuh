@@ -1,196 +1,234 @@
-// pml_kernel.cuh -- pseudo-matching lengths: many reads per warp, one read per lane.
+// pml_kernel.cuh -- pseudo-matching lengths: one read per lane, a persistent grid, one row fetch per warp iteration.
 //
-// Restates, for a whole batch at once, the per-base loop of MoveStructure::query_pml
-// (src/move_structure_query.cpp:234-474): compare the row character with the read base, on a
-// mismatch reposition with the threshold bit (reposition_thresholds :513-601, reposition_up/down
-// :188-232), emit the matching length (MoveQuery::add_ml, include/move_query.hpp:26-38), then
+// Restates, for a whole batch at once, the per-base loop of MoveStructure::query_pml (src/move_structure_query.cpp:234-474):
+// compare the row character with the read base, on a mismatch reposition with the threshold bit (reposition_thresholds
+// :513-601, reposition_up/down :188-232), emit the matching length (MoveQuery::add_ml, include/move_query.hpp:26-38), then
 // LF_move (src/move_structure.cpp:59-87) with fast_forward (:524-545).
 //
-// Design (B200): the walk is a chain of dependent random 8-byte row fetches, so throughput comes from
-// the number of independent reads in flight, not from any one read.  Every lane owns one read and runs a
-// small state machine whose every iteration issues EXACTLY ONE row fetch for all lanes together:
-//     ST_FF    row just reached by an LF jump or a fast-forward step: if offset >= n, step to the next
-//              row (costs an iteration); otherwise process the next base against this row in place
-//     ST_UP/ST_DOWN  scanning for the nearest row with the read's character after a mismatch
-//     ST_NEW   fetch the read's [start, end) offsets (uses the same load slot as the row fetch)
-// so fast-forward and reposition scans of one lane never stall the other 31 lanes (the CPU reference
-// hides the same latency with 16 "strands" per thread and software prefetch,
-// src/read_processor.cpp:641-730).  Finished lanes refill from a warp-local queue that is topped up
-// from one global atomic counter in chunks, so reads of unequal length stay load balanced.
+// The walk is a chain of dependent random row fetches, so throughput comes from the number of independent reads in flight.
+// Every lane owns one read and runs a small state machine whose every iteration issues exactly one row fetch for all lanes:
+//     ST_FF        row reached by an LF jump or a fast-forward step: offset >= n ? step to idx + 1 : process the base here
+//     ST_UP/DOWN   scanning for the nearest row with the read's character after a mismatch
+// so the fast-forward / reposition scan of one lane never stalls the other 31 (the CPU reference hides the same latency with
+// 16 "strands" per thread and software prefetch, src/read_processor.cpp:641-730).  All transitions are predicates / selects:
+// one instruction stream per warp.  Finished lanes refill from a warp-local queue topped up from one global atomic (guided
+// self-scheduling), a read is started inside that rarely taken branch.  Streaming: each lane stages its read bytes one
+// aligned 32-byte sector at a time with cp.async (behind a warp vote) and its results 16 at a time in shared memory, written
+// with two 16-byte stores, so every sector of the two streams crosses the memory system once.  History of the formulations
+// that led here (branch-per-state, register-buffered output, batched service rings, ...): git log + profiles/r01_explore.jsonl.
 #pragma once
-#include "dev_index.cuh"
+#include "kernel_common.cuh"
 
 namespace movi {
 
-struct QueryArgs {
-    const uint8_t* bases;                 // 8-byte aligned; read i = bases[offsets[i]-origin .. offsets[i+1]-origin)
-    const unsigned long long* offsets;    // n_reads + 1
-    unsigned long long origin;            // subtracted from every offset
-    uint32_t n_reads;
-    uint16_t* out_ml;                     // PML / ZML values at the same (offset - origin) positions
-    unsigned long long* out_count;        // count query
-    int32_t* out_pos;                     // count query
-    unsigned long long* counter;          // work-queue head (zeroed before launch)
-    unsigned int* status;                 // sticky error bits
-    uint32_t ld_mode;                     // row fetch cache recipe (pml_kernel2.cuh: ld_row)
-    uint32_t flags;                       // MOVI_GPU_FLAG_* of the call
-    float keep_frac;                      // fraction of the row table whose fetches carry L2 evict_last (the rest: evict_first)
-};
+// SECTOR: keep the aligned 32-byte sector (4 rows) of the last row fetch in registers and serve fast-forward / scan steps
+// that stay inside it from there.  Costs ~10 instructions per iteration, saves ~20 % of the row requests: a loss on
+// L2-sized tables (issue bound), a gain on tables far beyond the L2, which are bound by the request rate of the memory
+// system (profiles/r01_big_tables.jsonl) -- selected by table size in movi_gpu.cu.
+// (Tried and dropped: fetching the row with cp.async.cg into shared memory instead of a load through L1 -- 5x slower,
+//  profiles/r01_explore.jsonl "9:..."; and the row fetches need their L1: with the shared-memory carve-out at its maximum
+//  the same kernel runs 2.8x slower, which is also what limits the per-lane staging buffers to 32 + 32 bytes.)
+// RPML: `movi query --rpml` -- Case 2 repositions with reposition_randomly (src/move_structure_query.cpp:604-688) instead of
+// the thresholds: up when the offset lies in the first half of the run (the reference's random draw is commented out, :607-608),
+// forced at the two ends of the table, and if the scan leaves the table without finding the character it starts again from
+// the same row in the other direction (:634-649, :661-674; states ST_UPF / ST_DOWNF = "already turned round").
+constexpr uint32_t ST_UPF = 5, ST_DOWNF = 6;
 
-constexpr uint32_t ST_IDLE = 0, ST_NEW = 1, ST_FF = 2, ST_UP = 3, ST_DOWN = 4;
-constexpr uint32_t QUEUE_CHUNK = 32;      // reads taken from the global counter per warp refill (small: short tail)
-constexpr unsigned FULL = 0xffffffffu;
-
-// Register-buffered output (OUTV == 1): the last `pend` (< 8) pushed values sit in the top `pend`
-// 16-bit positions of (b0..b3); write them to out[op - pend + 1 .. op] with 2-byte stores.  Only used
-// for the ragged head / tail group of a read; full groups go out as one 16-byte store.
-__device__ __forceinline__ void flush_partial(uint16_t* out, uint32_t op, uint32_t pend,
-                                              uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
-    for (uint32_t t = 0; t < pend; t++) {
-        const uint32_t pos = 8u - pend + t;
-        const uint32_t ws = pos >> 1;
-        const uint32_t w = ws == 0 ? b0 : ws == 1 ? b1 : ws == 2 ? b2 : b3;
-        out[op - pend + 1 + t] = (uint16_t)((pos & 1u) ? (w >> 16) : (w & 0xFFFFu));
-    }
-}
-
-// OUTV: 0 = one 2-byte store per base, 1 = 8 values buffered in registers, 16-byte stores
-template <typename IdxT, int OUTV>
-__global__ void __launch_bounds__(256)
+// NT: the table of a non-threshold index type (dev_index.cuh): 12-bit field accessors; always queried with RPML.
+template <typename IdxT, bool SEP, int MINB, int LAYOUT, bool SECTOR = false, bool RPML = false, bool NT = false>
+__global__ void __launch_bounds__(QUERY_THREADS, MINB)
 movi_pml_kernel(const DevIndex ix, const QueryArgs q) {
     __shared__ uint8_t s_code[256];
     __shared__ uint32_t s_end_thr[4];
+    __shared__ uint32_t s_idb[LAYOUT == LAYOUT_B6 ? IDB_SMEM : 1];
+    __shared__ unsigned long long s_first[8];
+    const uint32_t idb_n = ix.id_blocks_size * ix.sigma;
+    const bool idb_in_smem = LAYOUT == LAYOUT_B6 && idb_n <= IDB_SMEM;
+    if (LAYOUT == LAYOUT_B6) {
+        if (idb_in_smem) for (uint32_t i = threadIdx.x; i < idb_n; i += blockDim.x) s_idb[i] = ix.id_blocks[i];
+        if (threadIdx.x < 8) s_first[threadIdx.x] = ix.first_runs[threadIdx.x];
+    }
+    const uint32_t* const idb = idb_in_smem ? s_idb : ix.id_blocks;
+    __shared__ __align__(32) uint8_t s_in[QUERY_THREADS * 32];      // per lane: the 32-byte sector of its read that holds bases[rp]
+    __shared__ __align__(32) uint16_t s_out[QUERY_THREADS * 16];    // per lane: the 32-byte sector of its output being filled
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_code[i] = ix.code_of[i];
     if (threadIdx.x < 4) s_end_thr[threadIdx.x] = ix.end_thr[threadIdx.x];
     __syncthreads();
 
+    const unsigned long long pol_keep = policy_evict_last();
+    const unsigned long long pol_stream = policy_evict_first();
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     const IdxT r1 = (IdxT)(ix.r - 1);
     const IdxT end_idx = (IdxT)ix.end_idx;
     const uint2* __restrict__ rows = ix.rows;
-    const uint2* __restrict__ bases8 = reinterpret_cast<const uint2*>(q.bases);
-    const uint32_t sep = ix.sep;
+    const uint8_t* __restrict__ bases = q.bases;
+    const uint2* __restrict__ offs8 = reinterpret_cast<const uint2*>(q.offsets);
+    uint16_t* const out_slot = s_out + threadIdx.x * 16;              // (generic pointer: only the rare ragged flush uses it)
+    const uint32_t sa_in = smem_addr(s_in) + threadIdx.x * 32u;       // shared-window addresses of this lane's slots
+    const uint32_t sa_out = smem_addr(s_out) + threadIdx.x * 32u;
+    const uint32_t sa_code = smem_addr(s_code);
+    constexpr uint32_t sep = SEP ? 1u : 0u;
+    constexpr uint32_t REFILL_EVERY = 4;
     const uint32_t n_reads = q.n_reads;
 
-    uint32_t q_next = 0, q_end = 0;
-    bool exhausted = false;                 // warp uniform
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t q_next = 0, q_end = 0, chunk = min(QUEUE_CHUNK, max(1u, n_reads / (2u * n_warps)));
+    bool exhausted = false;
     uint32_t st = ST_IDLE;
-    IdxT idx = 0;                           // row index; read index while ST_NEW
-    uint32_t off = 0, ml = 0;
-    uint32_t rp = 0, op = 0, rem = 0;       // next base to read, next output slot, bases left
-    uint32_t clo = 0, chi = 0;              // the 8 read bytes that contain bases[rp]
+    IdxT idx = 0;
+    uint32_t off = 0, ml = 0, rp = 0, op = 0, rem = 0, pend = 0;
     bool need_chunk = false;
-    uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0, pend = 0;   // OUTV==1: output shift register (8 x u16) + fill count
 
+    uint32_t tick = 0;
+    uint4 sec_lo = make_uint4(0, 0, 0, 0), sec_hi = make_uint4(0, 0, 0, 0);   // SECTOR: rows 4*sec_base .. 4*sec_base + 3
+    IdxT sec_base = ~(IdxT)0;
+    IdxT saved = 0;                                                           // RPML: the row the reposition started from
     for (;;) {
-        // ---- hand reads to idle lanes (warp-aggregated; one global atomic per QUEUE_CHUNK reads)
-        const bool want = (st == ST_IDLE) && !exhausted;
-        const unsigned m = __ballot_sync(FULL, want);
+        // idle lanes are looked after every REFILL_EVERY-th iteration only: a finished lane waits <= 3 of the ~240
+        // iterations of a 150-base read, and the other iterations skip the vote / queue bookkeeping
+        const bool service = (tick++ & (REFILL_EVERY - 1u)) == 0u;
+        const bool want = service && (st == ST_IDLE) && !exhausted;
+        const unsigned m = service ? __ballot_sync(FULL, want) : 0u;
         if (m) {
             if (q_next == q_end) {
+                // guided self-scheduling: take 32 reads per refill while plenty remain, fewer as the batch drains, so that
+                // no warp sits on a private backlog while the lanes of other warps have already gone idle
                 unsigned long long b = 0;
-                if (lane == 0) b = atomicAdd(q.counter, (unsigned long long)QUEUE_CHUNK);
+                if (lane == 0) b = atomicAdd(q.counter, (unsigned long long)chunk);
                 b = __shfl_sync(FULL, b, 0);
                 q_next = b < n_reads ? (uint32_t)b : n_reads;
-                q_end = b + QUEUE_CHUNK < n_reads ? (uint32_t)(b + QUEUE_CHUNK) : n_reads;
+                q_end = b + chunk < n_reads ? (uint32_t)(b + chunk) : n_reads;
                 if (q_next == q_end) exhausted = true;
+                const uint32_t left = n_reads - q_end;
+                chunk = min(QUEUE_CHUNK, max(1u, left / (2u * n_warps)));
             }
             const uint32_t avail = q_end - q_next;
             const uint32_t rank = __popc(m & lt_mask);
-            if (want && rank < avail) { idx = (IdxT)(q_next + rank); st = ST_NEW; }
+            if (want && rank < avail) {                                   // start a read (query_pml :237-240)
+                const uint32_t ri = q_next + rank;
+                const uint2 a = ldg64(offs8 + ri), b = ldg64(offs8 + ri + 1);
+                const unsigned long long s = (((unsigned long long)a.y << 32) | a.x) - q.origin;
+                const unsigned long long e = (((unsigned long long)b.y << 32) | b.x) - q.origin;
+                rem = (uint32_t)(e - s);
+                rp = (uint32_t)e - 1; op = (uint32_t)s;
+                idx = r1; off = ix.n_last - 1; ml = 0; pend = 0;
+                st = rem ? ST_FF : ST_IDLE;                                // (an empty read leaves the lane idle: it asks again)
+                need_chunk = true;
+            }
             const uint32_t cnt = __popc(m);
             q_next += cnt < avail ? cnt : avail;
         }
-        if (exhausted && __all_sync(FULL, st == ST_IDLE)) break;
+        if (service && exhausted && __all_sync(FULL, st == ST_IDLE)) break;
 
-        // ---- the two load slots of this iteration
-        uint2 v = make_uint2(0u, 0u), w = make_uint2(0u, 0u);
-        if (st != ST_IDLE) {
-            const uint2* a = (st == ST_NEW) ? reinterpret_cast<const uint2*>(q.offsets + idx) : rows + idx;
-            v = ldg64(a);
-            if (st == ST_NEW || need_chunk) {
-                const uint2* b = (st == ST_NEW) ? reinterpret_cast<const uint2*>(q.offsets + idx + 1) : bases8 + (rp >> 3);
-                w = ldg64(b);
+        // ---- loads: row fetch for every walking lane; a lane that ran out of staged read bytes pulls the next sector
+        const bool proc = (st != ST_IDLE);
+        // (lanes that are not walking fetch row 0: harmless and keeps the fetch out of a divergent branch)
+        const IdxT fidx = proc ? idx : (IdxT)0;
+        uint2 v;
+        if (LAYOUT == LAYOUT_R8 && SECTOR) {
+            const IdxT fb = fidx >> 2;
+            if (proc && fb != sec_base) {
+                const uint4* sp = reinterpret_cast<const uint4*>(rows) + 2 * (size_t)fb;
+                ld_keep256(sp, pol_keep, sec_lo, sec_hi);
+                sec_base = fb;
             }
+            const uint4 h = (fidx & 2) ? sec_hi : sec_lo;
+            v = (fidx & 1) ? make_uint2(h.z, h.w) : make_uint2(h.x, h.y);
+        }
+        else if (LAYOUT == LAYOUT_R8) v = ld_keep(rows + fidx, pol_keep);
+        else if (LAYOUT == LAYOUT_B6) v = fetch_row_b6<IdxT>(ix.rows6, fidx, end_idx, idb, ix.id_blocks_size, ix.block_shift, s_first);
+        else {              // LAYOUT_T3: the 3-byte row without its destination id (resolved below, only when an LF step needs it)
+            const uint32_t x = Rows3{ix.rows3, (unsigned long long)end_idx}.raw((unsigned long long)fidx);
+            v = make_r8_raw3(0, Rows3::n_of(x), Rows3::off_of(x), Rows3::c_of(x), Rows3::thr_of(x));
+        }
+        if (__any_sync(FULL, proc && need_chunk)) {
+            if (proc && need_chunk) {
+                const uint8_t* src = bases + (rp & ~31u);
+                cp_async16_stream(sa_in, src, pol_stream); cp_async16_stream(sa_in + 16u, src + 16, pol_stream);
+            }
+            cp_async_wait_all();
+            need_chunk = need_chunk && !proc;
         }
 
-        if (st == ST_NEW) {
-            const unsigned long long s = ((unsigned long long)v.y << 32 | v.x) - q.origin;
-            const unsigned long long e = ((unsigned long long)w.y << 32 | w.x) - q.origin;
-            const uint32_t len = (uint32_t)(e - s);
-            if (len == 0) {
-                st = ST_IDLE;
-            } else {
-                // query_pml :237-240: start at the last row, last offset
-                rp = (uint32_t)e - 1; op = (uint32_t)s; rem = len;
-                idx = r1; off = ix.n_last - 1; ml = 0;
-                st = ST_FF; need_chunk = true; pend = 0;
-            }
-        } else if (st != ST_IDLE) {
-            if (need_chunk) { clo = w.x; chi = w.y; need_chunk = false; }
-            const uint32_t y = v.y;
-            const uint32_t n = row_n(y);
-            bool at_base = true;
-            if (st == ST_FF && idx < r1 && off >= n) {       // fast_forward, one row per iteration
-                off -= n; idx += 1; at_base = false;
-            }
-            if (at_base) {
-                const uint32_t c = row_c(y);
-                const uint32_t byte = __byte_perm(clo, chi, rp & 7u) & 0xFFu;
-                const uint32_t code = s_code[byte];
-                bool emit = false, bad = false;
-                if (st == ST_FF) {
-                    if (code == CODE_ILLEGAL) { ml = 0; emit = true; }          // :278-284
-                    else if (c == code) { ml += 1; emit = true; }               // :285-296 (Case 1)
-                    else {                                                      // :297-350 (Case 2)
-                        uint32_t thr;
-                        const uint32_t ai = code - sep;
-                        if (idx == end_idx) thr = s_end_thr[ai & 3u];
-                        else if (sep && c == 0) thr = sep_threshold(ix, (unsigned long long)idx, ai);
-                        else thr = row_thr(y, ai, n);                                        // get_thresholds
-                        if (off >= thr) { if (idx == r1) bad = true; else { idx += 1; st = ST_DOWN; } }
-                        else            { if (idx == 0)  bad = true; else { idx -= 1; st = ST_UP; } }
-                    }
-                } else if (c == code) {                                         // scan hit: :313-327
-                    off = (st == ST_UP) ? n - 1 : 0u; ml = 0; emit = true;
-                } else if (st == ST_UP) {
-                    if (idx == 0) bad = true; else idx -= 1;
+        // ---- one predicate-driven step of the state machine for every lane
+        const uint32_t y = v.y;
+        const uint32_t n = row_n<NT>(y);
+        const uint32_t c = row_c(y);
+        const uint32_t code = lds_u8(sa_code + lds_u8(sa_in + (rp & 31u)));
+        const bool is_ff = (st == ST_FF);
+        const bool is_scan = (st >= ST_UP);
+        const bool scan_up = RPML ? ((st & 1u) != 0u) : (st == ST_UP);           // (ST_UP = 3, ST_UPF = 5)
+        const bool hit = (c == code);
+        const bool ffmove = is_ff && (idx < r1) && (off >= n);            // fast_forward, move_structure.cpp:524-545
+        const bool at_base = is_ff && !ffmove;
+        const bool base_mis = at_base && !hit && (code != CODE_ILLEGAL);   // Case 2, query.cpp:297-350
+        const bool scan_hit = is_scan && hit;
+        const bool scan_move = is_scan && !hit;
+        const bool emit = (at_base && !base_mis) || scan_hit;
+
+        const uint32_t ai = code - sep;
+        uint32_t thr = (LAYOUT == LAYOUT_R8) ? row_thr(y, ai, n) : row_thr_raw3(y, c - sep, ai, n);
+        if (!RPML && base_mis & ((idx == end_idx) | (SEP & (c == 0)))) {            // '$' row / '%' rows: rare, skipped warp-wide
+            thr = (idx == end_idx) ? s_end_thr[ai & 3u] : sep_threshold(ix, (unsigned long long)idx, ai);
+        }
+        const bool down = RPML ? !((idx == r1) || (idx > 0 && off * 2u < n)) : (off >= thr);
+        const bool mv_down = (scan_move && !scan_up) || (base_mis && down);
+        const bool mv_up = (scan_move && scan_up) || (base_mis && !down);
+        bool bad = (mv_up && idx == 0) || (mv_down && idx == r1);
+
+        ml = (at_base && hit) ? ml + 1 : (emit ? 0u : ml);
+        off = ffmove ? off - n : (scan_hit ? (scan_up ? n - 1 : 0u) : off);
+
+        const bool fin = emit && (rem == 1u);
+        const bool lf = emit && !fin;
+        if (emit) {
+            sts_u16(sa_out + 2u * (op & 15u), ml < 65535u ? ml : 65535u);  // add_ml clamp
+            pend += 1;
+            if ((op & 15u) == 15u || fin) {
+                uint16_t* g = q.out_ml + (op & ~15u);
+                if (pend == 16u) {
+                    const uint4 lo = lds_128(sa_out);
+                    const uint4 hi = lds_128(sa_out + 16u);
+                    st_stream128(g, lo, pol_stream); st_stream128(g + 8, hi, pol_stream);
                 } else {
-                    if (idx == r1) bad = true; else idx += 1;
+                    // ragged head / tail of a read: only our own slots [lo, hi] of the sector, widest aligned pieces first
+                    uint32_t lo = (op & 15u) + 1u - pend;
+                    const uint32_t hi1 = (op & 15u) + 1u;                  // one past the last slot
+                    if ((lo & 1u) && lo < hi1) { g[lo] = out_slot[lo]; lo += 1; }
+                    if ((lo & 2u) && lo + 2 <= hi1) { *reinterpret_cast<uint32_t*>(g + lo) = *reinterpret_cast<const uint32_t*>(out_slot + lo); lo += 2; }
+                    if ((lo & 4u) && lo + 4 <= hi1) { *reinterpret_cast<uint2*>(g + lo) = *reinterpret_cast<const uint2*>(out_slot + lo); lo += 4; }
+                    if (lo + 8 <= hi1) { *reinterpret_cast<uint4*>(g + lo) = *reinterpret_cast<const uint4*>(out_slot + lo); lo += 8; }
+                    if (lo + 4 <= hi1) { *reinterpret_cast<uint2*>(g + lo) = *reinterpret_cast<const uint2*>(out_slot + lo); lo += 4; }
+                    if (lo + 2 <= hi1) { *reinterpret_cast<uint32_t*>(g + lo) = *reinterpret_cast<const uint32_t*>(out_slot + lo); lo += 2; }
+                    if (lo < hi1) g[lo] = out_slot[lo];
                 }
-                if (bad) {            // reference: reposition returned r -> "This should not happen"
-                    atomicOr(q.status, 1u);
-                    st = ST_IDLE;
-                }
-                if (emit) {
-                    const uint32_t val = ml < 65535u ? ml : 65535u;             // add_ml clamp
-                    if (OUTV == 0) {
-                        q.out_ml[op] = (uint16_t)val;
-                    } else {
-                        // shift register: the newest value enters at the top; after 8 pushes the oldest is at bit 0
-                        b0 = __funnelshift_r(b0, b1, 16); b1 = __funnelshift_r(b1, b2, 16);
-                        b2 = __funnelshift_r(b2, b3, 16); b3 = (b3 >> 16) | (val << 16);
-                        pend += 1;
-                        if ((op & 7u) == 7u || rem == 1u) {
-                            if (pend == 8u) *reinterpret_cast<uint4*>(q.out_ml + (op & ~7u)) = make_uint4(b0, b1, b2, b3);
-                            else flush_partial(q.out_ml, op, pend, b0, b1, b2, b3);
-                            pend = 0;
-                        }
-                    }
-                    op += 1; rem -= 1;
-                    if (rem == 0) {
-                        st = ST_IDLE;
-                    } else {
-                        if ((rp & 7u) == 0) need_chunk = true;
-                        rp -= 1;
-                        off += row_off(y);                                      // LF_move :66
-                        idx = row_id<IdxT>(v);
-                        st = ST_FF;
-                    }
-                }
+                pend = 0;
             }
         }
+        op += emit ? 1u : 0u;
+        rem -= emit ? 1u : 0u;
+        need_chunk = need_chunk || (lf && (rp & 31u) == 0u);
+        rp -= lf ? 1u : 0u;
+        off += lf ? row_off<NT>(y) : 0u;                                        // LF_move, move_structure.cpp:66
+        IdxT lf_id = row_id<IdxT, NT>(v);
+        bool bad_id = false;
+        if (LAYOUT == LAYOUT_T3) {
+            // sampled-thresholds: get_id = checkpoint scan + walk-back (src/move_structure.cpp:103-219), per LF step
+            if (lf) lf_id = (IdxT)sampled_get_id(Rows3{ix.rows3, (unsigned long long)end_idx}, ix.tally, ix.tally_len, ix.tally_cp, ix.r,
+                                                 (unsigned long long)end_idx, (unsigned long long)idx, c, &bad_id);
+        }
+        if (RPML) saved = base_mis ? idx : saved;
+        idx = lf ? lf_id : (ffmove || mv_down) ? idx + 1 : (mv_up ? idx - 1 : idx);
+        st = fin ? ST_IDLE : lf ? ST_FF : base_mis ? (down ? ST_DOWN : ST_UP) : st;
+        if (RPML) {
+            if (bad && st <= ST_DOWN && (mv_up ? saved < r1 : saved > 0)) {     // first scan left the table: turn round
+                idx = mv_up ? saved + 1 : saved - 1;
+                st = mv_up ? ST_DOWNF : ST_UPF;
+                bad = false;
+            }
+        }
+        if (bad || bad_id) { atomicOr(q.status, bad_id ? 2u : 1u); st = ST_IDLE; }
     }
 }
 

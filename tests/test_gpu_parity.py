@@ -32,21 +32,21 @@ def _default_kernels_after_each_test(structures):
     """Tests that walk through the kernel variants leave the shared contexts on the library's defaults."""
     if not _DEFAULTS:
         ms = next(iter(structures.values()))
-        _DEFAULTS.update(pml_variant=ms.get_option("pml_variant"), bs_variant=ms.get_option("bs_variant"))
+        _DEFAULTS.update(pml_sector=ms.get_option("pml_sector"))
     yield
     for ms in structures.values():
         for k, v in _DEFAULTS.items():
             ms.set_option(k, v)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("sector", [0, 1])       # plain row fetch / the sector-cached fetch tables beyond the L2 get
 @pytest.mark.parametrize("sep", [False, True])
 @pytest.mark.parametrize("typ", TYPES)
 @pytest.mark.parametrize("read_set", READ_SETS)
-def test_pml_matches_reference(structures, read_sets, typ, read_set, sep, variant):
+def test_pml_matches_reference(structures, read_sets, typ, read_set, sep, sector):
     rd = read_sets[read_set]
     ms = structures[(typ, sep)]
-    ms.set_option("pml_variant", variant)
+    ms.set_option("pml_sector", sector)
     ml = ms.query_pml(rd.bases, rd.offsets)
     assert ml_text(rd.ids(), rd.offsets, ml) == expected_text(read_set, "pml", sep)
 
@@ -117,15 +117,16 @@ def test_random_reads_vs_oracle(structures, index_dirs, ref_seq, typ, sep):
     bases, offsets = pack_reads(reads)
     orc = OracleIndex(index_dirs[(typ, sep)])
     ms = structures[(typ, sep)]
-    for variant in (0, 1, 2, 3, 4, 5, 6, 7, 8):
-        ms.set_option("pml_variant", variant)
-        assert np.array_equal(ms.query_pml(bases, offsets), orc.query_pml(bases, offsets, threads=0))
+    want = orc.query_pml(bases, offsets, threads=0)
+    for sector in (0, 1):
+        ms.set_option("pml_sector", sector)
+        assert np.array_equal(ms.query_pml(bases, offsets), want)
+    ms.set_option("pml_sector", -1)
     if typ != "sampled-thresholds":
         # (reads of length 0 are outside the reference's domain for zml/count -- it indexes R[-1]; both sides emit nothing / 0)
         want_z = orc.query_zml(bases, offsets, threads=0)
         c2, p2 = orc.query_count(bases, offsets, threads=0)
-        for bs_variant, sector in ((0, -1), (1, -1), (1, 1)):      # (1, 1): the sector-cached form big tables use
-            ms.set_option("bs_variant", bs_variant)
+        for sector in (0, 1):      # 1: the sector-cached form big tables use
             ms.set_option("pml_sector", sector)
             try:
                 assert np.array_equal(ms.query_zml(bases, offsets), want_z)
@@ -324,8 +325,8 @@ def test_matching_lengths_saturate_at_65535(structures, index_dirs, ref_seq, typ
     orc = OracleIndex(index_dirs[(typ, False)])
     want = orc.query_pml(bases, offsets, threads=0)
     assert want.max() == 65535 and (want == 65535).sum() > 5000
-    for variant in (4, 5, 7, 8):
-        ms.set_option("pml_variant", variant)
+    for sector in (0, 1):
+        ms.set_option("pml_sector", sector)
         assert np.array_equal(ms.query_pml(bases, offsets), want)
     if typ != "sampled-thresholds":
         want_z = orc.query_zml(bases, offsets, threads=0)
@@ -392,10 +393,14 @@ def test_rpml_matches_reference_and_oracle(structures, index_dirs, read_sets, re
     torch.cuda.synchronize()
     ms.check_device_status()
     assert np.array_equal(d_out[: len(bases)].cpu().numpy().view(np.uint16), want)
-    ms.set_option("pml_variant", 4)
-    from movi_b200 import MoviGpuError
-    with pytest.raises(MoviGpuError, match="RPML"):
-        ms.query_pml(bases, offsets, rpml=True)
+    # the fused-classify and byte-wide entry points take the flag as well
+    from oracle.port import classify
+    a, b, s = ms.query_classify(bases, offsets, 150, 7, rpml=True)
+    for i in range(0, len(offsets) - 1, 211):
+        v = want[int(offsets[i]):int(offsets[i + 1])]
+        if len(v):
+            _, ea, eb, es, _ = classify(v, 150, 7)
+            assert (a[i], b[i], s[i]) == (ea, eb, es)
 
 
 @pytest.mark.parametrize("sep", [False, True])
@@ -412,6 +417,10 @@ def test_index_types_without_thresholds(nothr_index_dirs, read_sets, ref_seq, ty
     ms = MoveStructure(d)
     try:
         assert ms.host_index.type_name == typ
+        rd0 = read_sets["sample.fastq"]
+        l0 = ms.launch_count
+        ms.query_pml(rd0.bases, rd0.offsets)
+        assert ms.launch_count == l0 + 1          # exactly one kernel per PML call (one pipeline slice)
         for read_set in READ_SETS:
             rd = read_sets[read_set]
             assert ml_text(rd.ids(), rd.offsets, ms.query_pml(rd.bases, rd.offsets)) == expected_text("%s.%s" % (read_set, typ), "pml", sep)
