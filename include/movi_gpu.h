@@ -158,16 +158,18 @@ int  movi_gpu_query_count(movi_gpu_ctx* ctx, const char* bases, const uint64_t* 
 /* Same queries on DEVICE buffers (already resident in HBM), enqueued on `cuda_stream` (a cudaStream_t,
  * NULL = default stream) without synchronising: for callers that pipeline their own copies.
  * d_bases and d_out_ml must be 32-byte aligned and d_bases readable up to the next multiple of 32 bytes (the
- * kernels move whole aligned 32-byte sectors); read_offsets are relative to d_bases; total bases per call < 2^32.
- * d_out_ml has read_offsets[n_reads] entries. */
+ * kernels move whole aligned 32-byte sectors); read_offsets are relative to d_bases; total bases per call < 2^32 (a
+ * larger batch is refused: the kernels flag it and movi_gpu_check_device_status returns MOVI_GPU_ERR_ARG; the host-buffer
+ * entry points slice such batches themselves).  d_out_ml has read_offsets[n_reads] entries.  At most 64 *_device calls
+ * of one context may be in flight at a time (each takes one of a ring of 64 work counters). */
 int  movi_gpu_query_pml_device(movi_gpu_ctx* ctx, const char* d_bases, const uint64_t* d_read_offsets, uint64_t n_reads,
                                uint32_t flags, uint16_t* d_out_ml, void* cuda_stream);
 int  movi_gpu_query_zml_device(movi_gpu_ctx* ctx, const char* d_bases, const uint64_t* d_read_offsets, uint64_t n_reads,
                                uint32_t flags, uint16_t* d_out_ml, void* cuda_stream);
 int  movi_gpu_query_count_device(movi_gpu_ctx* ctx, const char* d_bases, const uint64_t* d_read_offsets, uint64_t n_reads,
                                  uint32_t flags, uint64_t* d_out_count, int32_t* d_out_pos_on_r, void* cuda_stream);
-/* After a *_device call has completed (caller synchronised the stream): MOVI_GPU_OK, or
- * MOVI_GPU_ERR_QUERY if any read hit a "should not happen" state.  Clears the flag. */
+/* After a *_device call has completed (caller synchronised the stream): MOVI_GPU_OK, MOVI_GPU_ERR_ARG for a batch of
+ * 2^32 bases or more, or MOVI_GPU_ERR_QUERY if any read hit a "should not happen" state.  Clears the flag. */
 int  movi_gpu_check_device_status(movi_gpu_ctx* ctx);
 
 /* Binary classification on the device from PMLs already in HBM (Classifier::classify, src/classifier.cpp:99-143):

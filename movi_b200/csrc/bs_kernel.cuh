@@ -111,7 +111,8 @@ movi_bs_kernel(const DevIndex ix, const QueryArgs q) {
                 const unsigned long long s = (((unsigned long long)a.y << 32) | a.x) - q.origin;
                 const unsigned long long e = (((unsigned long long)b.y << 32) | b.x) - q.origin;
                 start = (uint32_t)s; op = (uint32_t)s; m = 0; pend = 0; inscan = false;
-                if (e == s) {                       // empty read: outside the reference's domain (it indexes R[-1])
+                if (e >> 32) atomicOr(q.status, 4u);   // per-read cursors are 32-bit: a device call holds < 2^32 bases
+                if (e == s || (e >> 32)) {          // empty read: outside the reference's domain (it indexes R[-1])
                     if (KIND == KIND_COUNT) { q.out_count[ri] = 0; q.out_pos[ri] = 0; }
                     pst = B_IDLE;
                 } else {

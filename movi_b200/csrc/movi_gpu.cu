@@ -846,6 +846,8 @@ int movi_gpu_check_device_status(movi_gpu_ctx* ctx) {
     CU(cudaMemcpy(&status, ctx->d_status, sizeof(status), cudaMemcpyDeviceToHost));
     if (status) {
         CU(cudaMemset(ctx->d_status, 0, sizeof(unsigned int)));
+        if (status & 4u)
+            return fail(ctx, MOVI_GPU_ERR_ARG, "a *_device call was given 2^32 or more bases: split the batch (the host-buffer entry points do)");
         return fail(ctx, MOVI_GPU_ERR_QUERY, (status & 2u)
                     ? "[get id - tally mode] The offset in the destination run should be always smaller than the length of that run. "
                       "(the reference throws here, src/move_structure.cpp:196-199)"

@@ -111,6 +111,7 @@ movi_pml_kernel(const DevIndex ix, const QueryArgs q) {
                 const unsigned long long s = (((unsigned long long)a.y << 32) | a.x) - q.origin;
                 const unsigned long long e = (((unsigned long long)b.y << 32) | b.x) - q.origin;
                 rem = (uint32_t)(e - s);
+                if (e >> 32) { atomicOr(q.status, 4u); rem = 0; }          // per-read cursors are 32-bit: a device call holds < 2^32 bases
                 rp = (uint32_t)e - 1; op = (uint32_t)s;
                 idx = r1; off = ix.n_last - 1; ml = 0; pend = 0;
                 st = rem ? ST_FF : ST_IDLE;                                // (an empty read leaves the lane idle: it asks again)

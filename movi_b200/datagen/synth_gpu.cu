@@ -166,6 +166,56 @@ __global__ void make_reads(Gen g, const uint2* __restrict__ rows, uint8_t* __res
     }
 }
 
+// Reads that behave like reads of a real pangenome index: the generator runs the QUERY's own walk (query_pml, reference
+// src/move_structure_query.cpp:234-350) and writes down the characters it meets.  Where it decides on a substitution it picks a
+// different character and repositions exactly as the query will (threshold bit -> up / down, scan to the nearest run of that
+// character, :513-601), then carries on from there -- so after every error the read keeps matching along the new path and
+// its PMLs climb again, as they do after a SNP on a suffix-sorted index (whose thresholds are LCP-guided).  With plain
+// LF-walk reads (make_reads above) a read never re-synchronises on a random table: its first error leaves the walk on an
+// unrelated path and the rest of the read runs in the worst-case reposition regime.  The first `lead` processed bases are
+// uniform random: they scatter the walks, which all start at the last row like every query, over the whole table.
+__global__ void make_reads_resync(Gen g, const uint2* __restrict__ rows, uint8_t* __restrict__ bases, u64 n_reads, uint32_t len,
+                                  uint32_t sub_per_1024, uint32_t rand_every, uint32_t lead, u64 read_seed) {
+    u64 t = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    const char ACGT[4] = {'A', 'C', 'G', 'T'};
+    const u64 r1 = g.r - 1;
+    const uint32_t n_last = movi::row_n(rows[r1].y);
+    for (; t < n_reads; t += stride) {
+        u64 h = mix(t * 0xD1B54A32D192ED03ULL + g.seed + 99 + read_seed * 0x9E3779B97F4A7C15ULL);
+        u64 idx = r1;
+        uint32_t off = n_last - 1;
+        uint8_t* out = bases + t * (u64)len;
+        const bool rnd = rand_every && (t % rand_every == rand_every - 1);
+        for (uint32_t k = 0; k < len; k++) {
+            h = mix(h + k);
+            uint2 v = rows[idx];
+            const uint32_t c = movi::row_c(v.y) & 3u;         // the '$' row decodes as alphabet[0] in PML
+            uint32_t e = c;
+            if (rnd || k < lead) e = (uint32_t)((h >> 12) & 3u);
+            else if ((h & 1023u) < sub_per_1024) e = (c + 1u + (uint32_t)((h >> 12) % 3u)) & 3u;
+            if (e != c) {
+                const uint32_t n = movi::row_n(v.y);
+                const uint32_t thr = (idx == g.end_idx) ? 0u : ((v.y >> e) & (1u << 25)) ? n : 0u;     // row_thr of dev_index.cuh
+                const bool down = off >= thr;
+                u64 j = idx; bool found = false; uint2 w = v;
+                for (uint32_t s = 0; s < 4096; s++) {
+                    if (down ? j == r1 : j == 0) break;
+                    j = down ? j + 1 : j - 1;
+                    w = rows[j];
+                    if ((movi::row_c(w.y) & 7u) == e) { found = true; break; }
+                }
+                if (found) { idx = j; v = w; off = down ? 0u : movi::row_n(w.y) - 1u; }
+                else e = c;                                   // the scan would leave the table: keep the matching character
+            }
+            out[len - 1 - k] = (uint8_t)ACGT[e];
+            off += movi::row_off(v.y);                        // LF_move + fast_forward (src/move_structure.cpp:59-87, 524-545)
+            idx = movi::row_id<u64>(v);
+            for (;;) { const uint32_t n = movi::row_n(rows[idx].y); if (idx < r1 && off >= n) { off -= n; idx++; } else break; }
+        }
+    }
+}
+
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fprintf(stderr, "synth_gpu: %s: %s\n", #call, cudaGetErrorString(e_)); return 2; } } while (0)
 
 }  // namespace
@@ -228,6 +278,17 @@ int movi_synth_reads(const void* d_rows, uint64_t r, uint64_t seed, void* d_base
                      uint32_t sub_per_1024, uint32_t rand_every) {
     Gen g{r, mix(seed) % (r / 2) + r / 4, seed, 0};   // the walk only reads the finished rows
     make_reads<<<148 * 8, 128>>>(g, static_cast<const uint2*>(d_rows), static_cast<uint8_t*>(d_bases), n_reads, len, sub_per_1024, rand_every);
+    CK(cudaDeviceSynchronize());
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// The same with reads that re-synchronise after every error (make_reads_resync); read_seed selects the batch.
+int movi_synth_reads_resync(const void* d_rows, uint64_t r, uint64_t seed, void* d_bases, uint64_t n_reads, uint32_t len,
+                            uint32_t sub_per_1024, uint32_t rand_every, uint32_t lead, uint64_t read_seed) {
+    Gen g{r, mix(seed) % (r / 2) + r / 4, seed, 0};
+    make_reads_resync<<<148 * 16, 128>>>(g, static_cast<const uint2*>(d_rows), static_cast<uint8_t*>(d_bases), n_reads, len, sub_per_1024,
+                                         rand_every, lead, read_seed);
     CK(cudaDeviceSynchronize());
     CK(cudaGetLastError());
     return 0;

@@ -1,7 +1,5 @@
 """Python side of datagen/synth_gpu.cu: human-scale synthetic move tables built directly in HBM (bench data, not product)."""
 import ctypes as C
-import os
-import struct
 
 import numpy as np
 
@@ -22,6 +20,9 @@ def lib():
         L.movi_synth_index.restype = C.c_int
         L.movi_synth_reads.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
         L.movi_synth_reads.restype = C.c_int
+        L.movi_synth_reads_resync.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
+                                              C.c_uint32, C.c_uint64]
+        L.movi_synth_reads_resync.restype = C.c_int
         _lib = L
     return _lib
 
@@ -53,27 +54,26 @@ class SyntheticStructure(MoveStructure):
         if rc != 0:
             raise RuntimeError("movi_synth_reads failed")
 
-    def write_index_file(self, directory):
-        """index.movi (regular-thresholds) of this table, for the CPU oracle / the reference (small tables only)."""
-        rows = np.empty(self.r * 2, dtype=np.uint32)
-        self._check(self._L.movi_gpu_index_export_rows(self._ctx, 0, self.r, rows.ctypes.data))   # back in the reference's row format
+    def make_reads_resync(self, d_bases_ptr, n_reads, read_len, sub_per_1024=51, rand_every=10, lead=24, read_seed=0):
+        """Reads written down by the query's own walk: after each substitution the generator repositions the way the query will,
+        so the read keeps matching along the new path (PMLs recover after an error, as on a suffix-sorted index)."""
+        rc = lib().movi_synth_reads_resync(self.device_rows, self.r, self.seed, d_bases_ptr, n_reads, read_len, sub_per_1024, rand_every,
+                                           lead, read_seed)
+        if rc != 0:
+            raise RuntimeError("movi_synth_reads_resync failed")
+
+    def write_index_file(self, directory, chunk_rows=1 << 27):
+        """index.movi (regular-thresholds) of this table, for the CPU oracle / the unmodified reference.  The rows come back from
+        HBM in the reference's row format 1 GB at a time, so a table of any size costs no more host memory than that."""
+        from .index_file import write_regular_thresholds
         d = self.desc
-        os.makedirs(directory, exist_ok=True)
-        alphamap = np.full(256, 256, dtype=np.uint64)
-        for k, ch in enumerate(b"ACGT"):
-            alphamap[ch] = k
-        with open(os.path.join(directory, "index.movi"), "wb") as f:
-            h = bytearray(48)
-            struct.pack_into("<IBBBb", h, 0, 0x4D4F5649, 2, 0, 0, 6)
-            struct.pack_into("<QQQQ", h, 16, self.n, self.r, self.r, d.end_bwt_idx)
-            f.write(h)
-            f.write(struct.pack("<4Q", *d.end_bwt_idx_thresholds)); f.write(b"\0" * 64)
-            f.write(struct.pack("<Q", 256)); f.write(alphamap.tobytes())
-            f.write(struct.pack("<Q", 4)); f.write(b"ACGT"); f.write(struct.pack("<HB", 0, 0))
-            f.write(rows.tobytes())
-            f.write(struct.pack("<QQQ", 0, 0, 0))
-            f.write(struct.pack("<Q4Q", 4, 0, 0, 0, 0))          # counts: not used by the query path
-            f.write(struct.pack("<Q", 5))
-            for arr in (d.last_runs, d.last_offsets, d.first_runs, d.first_offsets):
-                f.write(struct.pack("<5Q", *arr[:5]))
-        return directory
+
+        def chunks():
+            for first in range(0, self.r, chunk_rows):
+                m = min(chunk_rows, self.r - first)
+                rows = np.empty(m * 2, dtype=np.uint32)
+                self._check(self._L.movi_gpu_index_export_rows(self._ctx, first, m, rows.ctypes.data))
+                yield rows
+
+        return write_regular_thresholds(directory, self.n, self.r, d.end_bwt_idx, list(d.end_bwt_idx_thresholds), chunks(),
+                                        d.last_runs, d.last_offsets, d.first_runs, d.first_offsets)

@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -38,6 +39,7 @@ struct movi_oracle_index {
     int separators;                 /* use_separator(): move_structure.cpp:547-552 */
     int no_thresholds;              /* NO_THRESHOLDS modes (utils.hpp:146): PML repositions with reposition_randomly */
     uint8_t* rows;                  /* r * row_bytes, packed exactly as on disk */
+    void* map; size_t map_len;      /* row tables beyond 1 GiB are mapped from the file instead of copied (human-scale bench tables) */
     /* MODE 7 */
     uint32_t tally_checkpoints;
     uint64_t tally_len;
@@ -104,8 +106,21 @@ int movi_oracle_load(const char* path, movi_oracle_index** out) {
     ix->separators = (ix->alphabet[0] == SEPARATOR && ix->sigma == 5);
     ix->no_thresholds = (ix->mode == MODE_REGULAR || ix->mode == MODE_BLOCKED || ix->mode == MODE_SAMPLED);   /* NO_THRESHOLDS, utils.hpp:146 */
     /* read_main_table, io.cpp:361-397 */
-    ix->rows = (uint8_t*)malloc(ix->r * (size_t)ix->row_bytes + 16);
-    if (!ix->rows || rd(f, ix->rows, ix->r * (size_t)ix->row_bytes)) goto bad;
+    {
+        const size_t table = ix->r * (size_t)ix->row_bytes;
+        if (table > ((size_t)1 << 30)) {
+            const long at = ftell(f);
+            if (at < 0) goto bad;
+            ix->map_len = (size_t)at + table;
+            ix->map = mmap(NULL, ix->map_len, PROT_READ, MAP_PRIVATE, fileno(f), 0);
+            if (ix->map == MAP_FAILED) { ix->map = NULL; goto bad; }
+            ix->rows = (uint8_t*)ix->map + at;
+            if (fseek(f, (long)table, SEEK_CUR)) goto bad;
+        } else {
+            ix->rows = (uint8_t*)malloc(table + 16);
+            if (!ix->rows || rd(f, ix->rows, table)) goto bad;
+        }
+    }
     /* read_tally_table, io.cpp:338-349 */
     if (ix->mode == MODE_SAMPLED_THRESHOLDS || ix->mode == MODE_SAMPLED) {
         if (rd(f, &ix->tally_checkpoints, 4) || rd(f, &ix->tally_len, 8)) goto bad;
@@ -154,7 +169,8 @@ bad2:
 
 void movi_oracle_free(movi_oracle_index* ix) {
     if (!ix) return;
-    free(ix->rows); free(ix->tally); free(ix->id_blocks); free(ix->sep_thr); free(ix->sep_map);
+    if (ix->map) munmap(ix->map, ix->map_len); else free(ix->rows);
+    free(ix->tally); free(ix->id_blocks); free(ix->sep_thr); free(ix->sep_map);
     free(ix);
 }
 

@@ -59,3 +59,44 @@ def test_synthetic_pangenome_is_seeded_and_shaped():
     assert len(bases) == 500 * 150 and offsets[-1] == len(bases) and set(np.unique(bases)) <= set(b"ACGT")
     b2, _ = synth.make_reads(haps, 500, 150)
     assert np.array_equal(bases, b2)
+
+
+def test_synthetic_index_writer_is_read_by_the_reference_and_the_oracle(index_dirs, tmp_path):
+    """datagen/index_file.py writes the index.movi of tables synthesised in HBM (bench workload c4).  Here it re-writes the
+    reference-built c1 index from its parsed fields: the unmodified reference (when compiled here) and the oracle must give
+    the same PML / ZML / count output on the re-written file as on the original."""
+    import ctypes as C
+    from movi_b200 import HostIndex
+    from movi_b200.datagen.index_file import write_regular_thresholds
+    from oracle.port import OracleIndex, pack_reads
+    src = index_dirs[("regular-thresholds", False)]
+    hix = HostIndex(src)
+    d = hix.desc
+    rows = np.ctypeslib.as_array(C.cast(d.rows, C.POINTER(C.c_uint32)), shape=(hix.r * 2,)).copy()
+    half = (hix.r // 2) * 2
+    out = write_regular_thresholds(str(tmp_path / "rewritten"), hix.n, hix.r, hix.end_bwt_idx, list(d.end_bwt_idx_thresholds),
+                                   [rows[:half], rows[half:]], d.last_runs, d.last_offsets, d.first_runs, d.first_offsets,
+                                   original_r=hix.original_r)
+    reads = os.path.join(GOLD, "reads", "synth300.fasta")
+    a, b = OracleIndex(src), OracleIndex(out)
+    from movi_b200 import Reads
+    rd = Reads(reads)
+    assert np.array_equal(a.query_pml(rd.bases, rd.offsets), b.query_pml(rd.bases, rd.offsets))
+    assert np.array_equal(a.query_zml(rd.bases, rd.offsets), b.query_zml(rd.bases, rd.offsets))
+    ca, cb = a.query_count(rd.bases, rd.offsets), b.query_count(rd.bases, rd.offsets)
+    assert np.array_equal(ca[0], cb[0]) and np.array_equal(ca[1], cb[1])
+    ref_bin = os.path.join(os.path.dirname(GOLD), "..", "oracle", "_ref", "movi-regular-thresholds")
+    if not os.path.exists(ref_bin):
+        pytest.skip("oracle/_ref not built here")
+    for q in ("--pml", "--zml", "--count"):
+        outs = []
+        for idx in (src, out):
+            r = subprocess.run([ref_bin, "query", "--index", idx, "--read", reads, q, "--stdout", "--no-prefetch", "-t1"],
+                               stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+            assert r.returncode == 0
+            outs.append(r.stdout)
+        assert outs[0] == outs[1] and len(outs[0]) > 1000
+        # the multithreaded prefetch path (what the bench's CPU arm runs) loads it as well
+        r = subprocess.run([ref_bin, "query", "--index", out, "--read", reads, q, "--no-output", "-t", "4", "-s", "16"],
+                           stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+        assert r.returncode == 0 and b"processing the reads" in r.stderr
