@@ -155,6 +155,20 @@ int  movi_gpu_query_zml(movi_gpu_ctx* ctx, const char* bases, const uint64_t* re
 int  movi_gpu_query_count(movi_gpu_ctx* ctx, const char* bases, const uint64_t* read_offsets, uint64_t n_reads,
                           uint32_t flags, uint64_t* out_count, int32_t* out_pos_on_r);
 
+/* PML (zml = 0) or ZML (zml = 1) with DEVICE-SIDE .bpf EMISSION: out_image receives the records
+ *     { u16 id_len; char id[id_len]; u64 L; u16 ml[L] }
+ * of the batch back to back -- exactly the bytes output_base_stats / output_binary (src/utils.cpp:202-246) append to
+ * <prefix>.pml.bpf after the 12-byte BPFHeader (include/utils.hpp:64-86) -- assembled on the GPU per pipeline slice, so the host
+ * does one write() per batch and no per-read work.  ids = the read ids concatenated (the reference's id rule: through and
+ * including the first blank, src/batch_loader.cpp:117-119), id_offsets = n_reads + 1 prefix offsets into it.
+ * movi_gpu_bpf_image_bytes = 10 * n + id bytes + 2 * bases: the size out_image must have. */
+uint64_t movi_gpu_bpf_image_bytes(const uint64_t* read_offsets, const uint64_t* id_offsets, uint64_t n_reads);
+int  movi_gpu_query_bpf(movi_gpu_ctx* ctx, int zml, const char* bases, const uint64_t* read_offsets, uint64_t n_reads, uint32_t flags,
+                        const char* ids, const uint64_t* id_offsets, uint8_t* out_image, uint64_t image_capacity);
+/* The assembly alone on device buffers (d_ml as written by a *_device query: d_read_offsets relative to it). */
+int  movi_gpu_bpf_assemble_device(movi_gpu_ctx* ctx, const uint16_t* d_ml, const uint64_t* d_read_offsets, uint64_t n_reads,
+                                  const char* d_ids, const uint64_t* d_id_offsets, uint8_t* d_image, void* cuda_stream);
+
 /* Same queries on DEVICE buffers (already resident in HBM), enqueued on `cuda_stream` (a cudaStream_t,
  * NULL = default stream) without synchronising: for callers that pipeline their own copies.
  * d_bases and d_out_ml must be 32-byte aligned and d_bases readable up to the next multiple of 32 bytes (the

@@ -40,11 +40,17 @@ int  movi_host_reads_load(const char* path, int reverse, movi_host_reads** out);
  * The file stays memory-mapped, so inputs larger than RAM stream through. */
 int  movi_host_reader_open(const char* path, int reverse, movi_host_reader** out);
 int  movi_host_reader_next(movi_host_reader* r, uint64_t max_bases, movi_host_reads** out);
+/* The reference's loadBatch(input, num_bases, min_number_of_reads) (src/batch_loader.cpp:26-75): the batch grows until it
+ * holds max_bases bases AND min_reads reads -- a GPU wants one read per lane in flight however long the reads are -- but never
+ * beyond cap_bases bases (0 = no cap; the bound on host memory per batch). */
+int  movi_host_reader_next_reads(movi_host_reader* r, uint64_t max_bases, uint64_t min_reads, uint64_t cap_bases, movi_host_reads** out);
 void movi_host_reader_close(movi_host_reader* r);
 uint64_t movi_host_reads_count(const movi_host_reads* rd);
 const char* movi_host_reads_bases(const movi_host_reads* rd);          /* concatenated */
 const uint64_t* movi_host_reads_offsets(const movi_host_reads* rd);    /* count + 1 */
 const char* movi_host_reads_id(const movi_host_reads* rd, uint64_t i, uint32_t* len);
+const char* movi_host_reads_ids(const movi_host_reads* rd);             /* the ids concatenated ... */
+const uint64_t* movi_host_reads_id_offsets(const movi_host_reads* rd);  /* ... and their count + 1 offsets (movi_gpu_query_bpf takes both) */
 void movi_host_reads_free(movi_host_reads* rd);
 
 /* movi.<q>.nulldb -> Classifier::initialize_report_file's threshold: max(percentile, 3) + 1
@@ -57,6 +63,8 @@ int  movi_host_write_bpf(const char* file, const movi_host_reads* rd, const uint
 /* the same file written batch by batch: begin returns the descriptor (-1 on error) after writing the header */
 int  movi_host_bpf_begin(const char* file);
 int  movi_host_bpf_append(int fd, const movi_host_reads* rd, const uint16_t* ml);
+/* Append records already assembled on the device (movi_gpu_query_bpf): one image per batch, written by several threads at once. */
+int  movi_host_bpf_append_image(int fd, const uint8_t* image, uint64_t bytes);
 int  movi_host_bpf_end(int fd);
 int  movi_host_write_ml_text(int fd, const movi_host_reads* rd, const uint16_t* ml);                /* --stdout form */
 int  movi_host_write_counts(int fd, const movi_host_reads* rd, const uint64_t* counts, const int32_t* pos_on_r);   /* src/utils.cpp:248-256 */

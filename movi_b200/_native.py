@@ -44,6 +44,9 @@ GPU_SYMBOLS = {
     "movi_gpu_query_ml8": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]),
     "movi_gpu_query_classify": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "movi_gpu_bpf_image_bytes": (C.c_uint64, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "movi_gpu_query_bpf": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "movi_gpu_bpf_assemble_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "movi_gpu_query_zml": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]),
     "movi_gpu_query_count": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
     "movi_gpu_query_pml_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
@@ -79,6 +82,10 @@ HOST_SYMBOLS = {
     "movi_host_reads_free": (None, [C.c_void_p]),
     "movi_host_nulldb_threshold": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_uint64)]),
     "movi_host_write_bpf": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p]),
+    "movi_host_reads_ids": (C.c_void_p, [C.c_void_p]),
+    "movi_host_reads_id_offsets": (C.c_void_p, [C.c_void_p]),
+    "movi_host_bpf_append_image": (C.c_int, [C.c_int, C.c_void_p, C.c_uint64]),
+    "movi_host_reader_next_reads": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]),
     "movi_host_bpf_begin": (C.c_int, [C.c_char_p]),
     "movi_host_bpf_append": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
     "movi_host_bpf_end": (C.c_int, [C.c_int]),

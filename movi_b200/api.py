@@ -69,6 +69,15 @@ class Reads:
         b = L.movi_host_reads_bases(self._h)
         self.bases = np.ctypeslib.as_array(C.cast(b, N.u8p), shape=(total,)).copy() if total else np.zeros(0, np.uint8)
 
+    @property
+    def id_blob(self):
+        """(ids uint8[total], id_offsets uint64[count + 1]): the read ids concatenated, as movi_gpu_query_bpf takes them."""
+        L = N.host_lib()
+        off = np.ctypeslib.as_array(C.cast(L.movi_host_reads_id_offsets(self._h), N.u64p), shape=(self.count + 1,)).copy()
+        total = int(off[-1])
+        blob = np.ctypeslib.as_array(C.cast(L.movi_host_reads_ids(self._h), N.u8p), shape=(total,)).copy() if total else np.zeros(0, np.uint8)
+        return blob, off
+
     def id(self, i):
         n = C.c_uint32()
         p = N.host_lib().movi_host_reads_id(self._h, i, C.byref(n))
@@ -192,6 +201,19 @@ class MoveStructure:
             out = np.empty(int(offsets[-1]) if len(offsets) else 0, dtype=np.uint8)
         self._check(self._L.movi_gpu_query_ml8(self._ctx, int(zml), _ptr(bases), _ptr(offsets), max(n, 0), FLAG_RPML if rpml else 0, _ptr(out)))
         return out
+
+    def query_bpf(self, bases, offsets, ids, id_offsets, zml=False, rpml=False):
+        """PML (or ZML) with the .bpf records assembled on the device -> uint8 image = the bytes the reference appends to
+        <prefix>.pml.bpf after the 12-byte header (src/utils.cpp:202-246)."""
+        bases, offsets, n = self._prep(bases, offsets)
+        ids = np.ascontiguousarray(ids, dtype=np.uint8)
+        id_offsets = np.ascontiguousarray(id_offsets, dtype=np.uint64)
+        n = max(n, 0)
+        size = self._L.movi_gpu_bpf_image_bytes(_ptr(offsets), _ptr(id_offsets), n) if n else 0
+        image = np.empty(size, dtype=np.uint8)
+        self._check(self._L.movi_gpu_query_bpf(self._ctx, int(zml), _ptr(bases), _ptr(offsets), n, FLAG_RPML if rpml else 0,
+                                               _ptr(ids), _ptr(id_offsets), _ptr(image), size))
+        return image
 
     def query_zml(self, bases, offsets, out=None):
         bases, offsets, n = self._prep(bases, offsets)

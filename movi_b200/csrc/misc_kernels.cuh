@@ -34,6 +34,51 @@ __global__ void classify_kernel(const uint16_t* __restrict__ ml, const unsigned 
     }
 }
 
+// Device-side .bpf emission (output_base_stats, binary branch: reference src/utils.cpp:202-246): the records
+//     { u16 id_len; char id[id_len]; u64 L; u16 ml[L] }
+// of reads [0, n_reads) back to back, i.e. exactly the bytes the reference appends to <prefix>.pml.bpf after the 12-byte BPFHeader.
+// No scan is needed for the record positions: id_offsets and read offsets are prefix sums already, so record i starts at byte
+// 10 * i + (id_offsets[i] - id_offsets[0]) + 2 * (offsets[i] - offsets[0]).  One warp per read.  The payload lands at an
+// arbitrary byte address (odd when id_len is odd): interior 4-byte words of the destination are assembled from the two aligned
+// source words that hold their bytes (funnel shift), the edges of a record go byte by byte.
+__global__ void bpf_assemble_kernel(const uint16_t* __restrict__ ml, const unsigned long long* __restrict__ offsets, unsigned long long origin,
+                                    unsigned long long n_reads, const uint8_t* __restrict__ ids, const unsigned long long* __restrict__ id_offsets,
+                                    uint8_t* __restrict__ image) {
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned long long w = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    const unsigned long long off0 = offsets[0], id0 = id_offsets[0];
+    for (; w < n_reads; w += n_warps) {
+        const unsigned long long s = offsets[w], L = offsets[w + 1] - s;
+        const unsigned long long ia = id_offsets[w];
+        const uint32_t idl = (uint32_t)(id_offsets[w + 1] - ia);
+        uint8_t* rec = image + 10ull * w + (ia - id0) + 2ull * (s - off0);
+        for (uint32_t b = lane; b < 10u + idl; b += 32u) {                      // u16 id_len | id | u64 L
+            uint8_t v;
+            if (b < 2u) v = (uint8_t)(idl >> (8u * b));
+            else if (b < 2u + idl) v = ids[ia - id0 + (b - 2u)];
+            else v = (uint8_t)(L >> (8u * (b - 2u - idl)));
+            rec[b] = v;
+        }
+        uint8_t* pay = rec + 10u + idl;                                         // 2 * L bytes of matching lengths
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(ml + (s - origin));
+        const unsigned long long nbytes = 2ull * L;
+        const unsigned long long head = min((unsigned long long)((4u - ((uintptr_t)pay & 3u)) & 3u), nbytes);   // bytes up to the first aligned word
+        const unsigned long long words = (nbytes - head) >> 2;
+        const unsigned long long tail0 = head + (words << 2);
+        if (lane < head) pay[lane] = src[lane];
+        if (lane < nbytes - tail0) pay[tail0 + lane] = src[tail0 + lane];
+        uint32_t* dst = reinterpret_cast<uint32_t*>(pay + head);
+        const uint8_t* sp = src + head;                                         // source of the first aligned word; sp + 4k for word k
+        const uint32_t sh = 8u * (uint32_t)((uintptr_t)sp & 3u);
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>((uintptr_t)sp & ~(uintptr_t)3);
+        for (unsigned long long k = lane; k < words; k += 32u) {
+            const uint32_t lo = sw[k], hi = sh ? sw[k + 1] : 0u;                // (hi stays inside the ml buffer: it is padded by 64 bytes)
+            dst[k] = __funnelshift_r(lo, hi, sh);
+        }
+    }
+}
+
 // u16 -> u8 re-pack of a slice of matching lengths (movi_gpu_query_ml8: every read of the batch is <= 255 bases, so no
 // value can exceed 255; clamped anyway).  16 values per thread: two 16-byte loads, one 16-byte store.
 __global__ void narrow_ml_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, unsigned long long n_groups) {

@@ -37,6 +37,9 @@ struct Staging {                              // one pipeline slot
     uint8_t* d_ml8 = nullptr; size_t ml8_cap = 0;                       // movi_gpu_query_ml8: the slice's lengths as bytes
     unsigned long long* d_count = nullptr; int32_t* d_pos = nullptr; size_t count_cap = 0;
     uint32_t* d_above = nullptr; uint32_t* d_below = nullptr; unsigned long long* d_sum = nullptr; size_t cls_cap = 0;
+    uint8_t* d_ids = nullptr; size_t ids_cap = 0;                       // movi_gpu_query_bpf: the slice's read ids,
+    unsigned long long* d_id_offsets = nullptr; size_t id_offsets_cap = 0;   // their offsets,
+    uint8_t* d_image = nullptr; size_t image_cap = 0;                   // and its .bpf records
     unsigned long long* d_counter = nullptr;
     bool busy = false;
 };
@@ -297,9 +300,15 @@ int grow(movi_gpu_ctx* ctx, T*& p, size_t& cap, size_t need) {
 // Host-buffer entry point: split the batch into slices of ~batch_bases, run them through a 3-deep
 // pipeline (H2D on slot stream, kernel, D2H), results land directly in the caller's buffers.
 struct ClassifyOut { uint32_t bin_width = 0, thr = 0; uint32_t* above = nullptr; uint32_t* below = nullptr; uint64_t* sum = nullptr; };
+struct BpfOut { const char* ids = nullptr; const uint64_t* id_offsets = nullptr; uint8_t* image = nullptr; };
+// byte position of read i's record in the .bpf image of a batch (both offset arrays are prefix sums)
+inline uint64_t bpf_record_at(const uint64_t* offsets, const uint64_t* id_offsets, uint64_t i) {
+    return 10ull * i + (id_offsets[i] - id_offsets[0]) + 2ull * (offsets[i] - offsets[0]);
+}
 
 int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* offsets, uint64_t n_reads,
-               uint16_t* out_ml, uint64_t* out_count, int32_t* out_pos, const ClassifyOut* cls = nullptr, uint8_t* out_ml8 = nullptr) {
+               uint16_t* out_ml, uint64_t* out_count, int32_t* out_pos, const ClassifyOut* cls = nullptr, uint8_t* out_ml8 = nullptr,
+               const BpfOut* bpf = nullptr) {
     int rc = check_query_ready(ctx, kind, 0);
     if (rc) return rc;
     if (n_reads == 0) return MOVI_GPU_OK;
@@ -310,7 +319,13 @@ int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* 
 
     const int n_slots = (int)std::min<int64_t>(std::max<int64_t>(ctx->pipeline_slots, 2), NBUF);
     const int n_ks = (int)std::min<int64_t>(std::max<int64_t>(ctx->kernel_streams, 1), NKS);
-    const uint64_t max_bases = (uint64_t)std::max<int64_t>(ctx->batch_bases, 1 << 16);
+    // a slice holds batch_bases bases, or -- reads longer than ~200 bases -- as many reads as one of the n_ks concurrently
+    // walking slices has lanes: a read is one dependent chain, so a slice of few long reads would take the full walk latency
+    // of a read however small it is (12 M bases = 1200 reads of 10 kbp: 4.7 s per 4.1e9-base batch instead of 0.3 s)
+    const uint64_t lanes = (uint64_t)ctx->num_sms * 6u * (uint64_t)ctx->threads_per_block;
+    const uint64_t avg_len = std::max<uint64_t>(1, (offsets[n_reads] - offsets[0]) / n_reads);
+    const uint64_t max_bases = std::min<uint64_t>(std::max<uint64_t>((uint64_t)std::max<int64_t>(ctx->batch_bases, 1 << 16),
+                                                                     avg_len * (lanes / (uint64_t)n_ks)), 1ull << 30);
     // MOVI_GPU_TRACE=1: per-slice device timeline (ms since the first copy was enqueued) on stderr -- a debugging aid for
     // the copy / kernel overlap of this pipeline, off the product path
     static const bool trace = getenv("MOVI_GPU_TRACE") != nullptr;
@@ -348,6 +363,15 @@ int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* 
             if ((rc = grow(ctx, S.d_ml, S.ml_cap, nb + shift + 64))) return rc;
         }
         if (out_ml8 && (rc = grow(ctx, S.d_ml8, S.ml8_cap, nb + shift + 64))) return rc;
+        uint64_t img0 = 0, img_bytes = 0, id_bytes = 0;
+        if (bpf) {
+            img0 = bpf_record_at(offsets, bpf->id_offsets, i0);
+            img_bytes = bpf_record_at(offsets, bpf->id_offsets, i1) - img0;
+            id_bytes = bpf->id_offsets[i1] - bpf->id_offsets[i0];
+            if ((rc = grow(ctx, S.d_ids, S.ids_cap, id_bytes + 16))) return rc;
+            if ((rc = grow(ctx, S.d_id_offsets, S.id_offsets_cap, nr + 1))) return rc;
+            if ((rc = grow(ctx, S.d_image, S.image_cap, img_bytes + 16))) return rc;
+        }
         if (cls) {
             size_t c1 = S.cls_cap, c2 = S.cls_cap;
             if ((rc = grow(ctx, S.d_above, S.cls_cap, nr))) return rc;
@@ -358,6 +382,10 @@ int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* 
         mark(ctx->st_in);
         CU(cudaMemcpyAsync(S.d_bases + shift, bases + o0, nb, cudaMemcpyHostToDevice, ctx->st_in));
         CU(cudaMemcpyAsync(S.d_offsets, offsets + i0, (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->st_in));
+        if (bpf) {
+            CU(cudaMemcpyAsync(S.d_ids, bpf->ids + bpf->id_offsets[i0], id_bytes, cudaMemcpyHostToDevice, ctx->st_in));
+            CU(cudaMemcpyAsync(S.d_id_offsets, bpf->id_offsets + i0, (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->st_in));
+        }
         CU(cudaEventRecord(S.in_done, ctx->st_in));
         mark(ctx->st_in);
         // walk
@@ -380,6 +408,13 @@ int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* 
             ctx->launches += 1;
             CU(cudaGetLastError());
         }
+        if (bpf) {
+            // the slice's .bpf records assembled where the lengths sit: one copy back, no per-read work on the host
+            const unsigned blocks = (unsigned)std::min<uint64_t>((nr * 32 + 255) / 256, (uint64_t)ctx->num_sms * 16);
+            bpf_assemble_kernel<<<blocks, 256, 0, kst>>>(S.d_ml, S.d_offsets, o0 - shift, nr, S.d_ids, S.d_id_offsets, S.d_image);
+            ctx->launches += 1;
+            CU(cudaGetLastError());
+        }
         CU(cudaEventRecord(S.k_done, kst));
         mark(kst);
         // out
@@ -395,6 +430,7 @@ int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* 
             }
             if (out_ml) CU(cudaMemcpyAsync(out_ml + o0, S.d_ml + shift, nb * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->st_out));
             if (out_ml8) CU(cudaMemcpyAsync(out_ml8 + o0, S.d_ml8 + shift, nb, cudaMemcpyDeviceToHost, ctx->st_out));
+            if (bpf) CU(cudaMemcpyAsync(bpf->image + (img0 - bpf_record_at(offsets, bpf->id_offsets, 0)), S.d_image, img_bytes, cudaMemcpyDeviceToHost, ctx->st_out));
         }
         CU(cudaEventRecord(S.out_done, ctx->st_out));
         mark(ctx->st_out);
@@ -476,6 +512,7 @@ int movi_gpu_destroy(movi_gpu_ctx* ctx) {
         Staging& S = ctx->slot[k];
         cudaFree(S.d_bases); cudaFree(S.d_offsets); cudaFree(S.d_ml); cudaFree(S.d_ml8); cudaFree(S.d_count); cudaFree(S.d_pos); cudaFree(S.d_counter);
         cudaFree(S.d_above); cudaFree(S.d_below); cudaFree(S.d_sum);
+        cudaFree(S.d_ids); cudaFree(S.d_id_offsets); cudaFree(S.d_image);
         if (S.in_done) cudaEventDestroy(S.in_done);
         if (S.k_done) cudaEventDestroy(S.k_done);
         if (S.out_done) cudaEventDestroy(S.out_done);
@@ -795,6 +832,41 @@ int movi_gpu_query_ml8(movi_gpu_ctx* ctx, int zml, const char* bases, const uint
     for (uint64_t i = 0; i < n_reads; i++) longest = std::max(longest, read_offsets[i + 1] - read_offsets[i]);
     if (longest > 255) return fail(ctx, MOVI_GPU_ERR_ARG, "movi_gpu_query_ml8: a read is longer than 255 bases (its lengths may not fit one byte); use the 16-bit entry points");
     return host_query(ctx, kind, bases, read_offsets, n_reads, nullptr, nullptr, nullptr, nullptr, out_ml8);
+}
+
+uint64_t movi_gpu_bpf_image_bytes(const uint64_t* read_offsets, const uint64_t* id_offsets, uint64_t n_reads) {
+    if (!read_offsets || !id_offsets) return 0;
+    return bpf_record_at(read_offsets, id_offsets, n_reads);
+}
+
+int movi_gpu_query_bpf(movi_gpu_ctx* ctx, int zml, const char* bases, const uint64_t* read_offsets, uint64_t n_reads, uint32_t flags,
+                       const char* ids, const uint64_t* id_offsets, uint8_t* out_image, uint64_t image_capacity) {
+    if (!ctx) return MOVI_GPU_ERR_ARG;
+    CallFlags cf(ctx, flags);
+    const Kind kind = zml ? Q_ZML : Q_PML;
+    int rc = check_query_ready(ctx, kind, 0);
+    if (rc) return rc;
+    if (n_reads == 0) return MOVI_GPU_OK;
+    if (!read_offsets || !ids || !id_offsets || !out_image) return fail(ctx, MOVI_GPU_ERR_ARG, "null buffer");
+    for (uint64_t i = 0; i < n_reads; i++)
+        if (id_offsets[i + 1] - id_offsets[i] > 0xFFFFull) return fail(ctx, MOVI_GPU_ERR_ARG, "a read id is longer than 65535 bytes (the .bpf record holds its length in 16 bits)");
+    if (movi_gpu_bpf_image_bytes(read_offsets, id_offsets, n_reads) > image_capacity) return fail(ctx, MOVI_GPU_ERR_ARG, "the .bpf image buffer is too small");
+    BpfOut b; b.ids = ids; b.id_offsets = id_offsets; b.image = out_image;
+    return host_query(ctx, kind, bases, read_offsets, n_reads, nullptr, nullptr, nullptr, nullptr, nullptr, &b);
+}
+
+int movi_gpu_bpf_assemble_device(movi_gpu_ctx* ctx, const uint16_t* d_ml, const uint64_t* d_read_offsets, uint64_t n_reads,
+                                 const char* d_ids, const uint64_t* d_id_offsets, uint8_t* d_image, void* stream) {
+    if (!ctx) return MOVI_GPU_ERR_ARG;
+    if (n_reads == 0) return MOVI_GPU_OK;
+    if (!d_ml || !d_read_offsets || !d_ids || !d_id_offsets || !d_image) return fail(ctx, MOVI_GPU_ERR_ARG, "null buffer");
+    const unsigned blocks = (unsigned)std::min<uint64_t>((n_reads * 32 + 255) / 256, (uint64_t)ctx->num_sms * 16);
+    bpf_assemble_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_ml, reinterpret_cast<const unsigned long long*>(d_read_offsets), 0ull, n_reads,
+                                                                  reinterpret_cast<const uint8_t*>(d_ids),
+                                                                  reinterpret_cast<const unsigned long long*>(d_id_offsets), d_image);
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    return MOVI_GPU_OK;
 }
 
 int movi_gpu_query_zml(movi_gpu_ctx* ctx, const char* bases, const uint64_t* read_offsets, uint64_t n_reads,

@@ -31,6 +31,8 @@ struct Options {
     int ignore_illegal = 0, gpus = 1, device = 0, threads = 1, strands = 16;
     uint64_t bin_width = 150;     // include/movi_options.hpp default
     uint64_t chunk_bases = 1ull << 26;   // bases per batch of the streaming loop (host memory: ~10 bytes per base of a batch)
+    uint64_t chunk_reads = 0;            // reads per batch at least: 0 = 2.3e5 per GPU (one read per lane in flight, however long the reads)
+    uint64_t max_chunk_bases = 1ull << 31;   // ... but never more bases than this per batch (pinned results: 2 x 2 bytes per base)
     bool write_output_allowed() const { return !no_output && !filter; }          // movi_options.hpp:70
     bool write_stdout_enabled() const { return to_stdout && !classify; }         // movi_options.hpp:71
 };
@@ -39,7 +41,8 @@ struct Options {
     fprintf(stderr, "\033[31m\n\n[ERROR] %s\n\033[0m\n", m.c_str());
     fprintf(stderr, "usage: movi-b200 query -i <index dir> -r <reads.fa|fq|-> [--pml [--rpml]|--zml|--count] [--classify|--filter [-v]]\n"
                     "                       [--stdout] [-o prefix] [--no-output] [--reverse] [--ignore-illegal-chars 1|2]\n"
-                    "                       [--bin-width N] [--gpus N] [--device D] [--chunk-bases N] [-t N] [-s N] [-n]\n"
+                    "                       [--bin-width N] [--gpus N] [--device D] [--chunk-bases N] [--chunk-reads N] [--max-chunk-bases N]\n"
+                    "                       [-t N] [-s N] [-n]\n"
                     "       movi-b200 view --bpf <file.bpf>\n");
     exit(1);
 }
@@ -80,6 +83,8 @@ Options parse(int argc, char** argv) {
         else if (take_value(argc, argv, i, nullptr, "--ftab-k", v)) { }
         else if (a == "--multi-ftab") { }
         else if (take_value(argc, argv, i, nullptr, "--chunk-bases", v)) o.chunk_bases = std::max<uint64_t>(1, strtoull(v.c_str(), nullptr, 10));
+        else if (take_value(argc, argv, i, nullptr, "--chunk-reads", v)) o.chunk_reads = strtoull(v.c_str(), nullptr, 10);
+        else if (take_value(argc, argv, i, nullptr, "--max-chunk-bases", v)) o.max_chunk_bases = std::max<uint64_t>(1, strtoull(v.c_str(), nullptr, 10));
         else if (a == "--pml") o.query = "pml";
         else if (a == "--rpml") o.rpml = true;                                  // movi_parser.cpp:149,357
         else if (a == "--zml") o.query = "zml";
@@ -144,6 +149,7 @@ struct Results {
     movi_host_reads* rd = nullptr;
     PinnedBuf<uint16_t> ml; PinnedBuf<uint64_t> counts; PinnedBuf<int32_t> pos;
     PinnedBuf<uint32_t> above, below; PinnedBuf<uint64_t> sum;
+    PinnedBuf<uint8_t> image; uint64_t image_bytes = 0;     // the batch's .bpf records, assembled on the GPUs
 };
 
 void die(const std::string& m) { fprintf(stderr, "\033[31m\n\n[ERROR] %s\n\033[0m", m.c_str()); exit(1); }
@@ -178,7 +184,16 @@ int main(int argc, char** argv) {
     if (o.classify && movi_host_nulldb_threshold(o.index_dir.c_str(), qname.c_str(), &max_value_thr)) die(movi_host_last_error());
 
     // the input streams through in batches of --chunk-bases bases: batch k + 1 is parsed while the GPUs walk batch k
-    auto fetch = [&]() { Fetched f; f.rc = movi_host_reader_next(reader, o.chunk_bases, &f.rd); if (f.rc) f.err = movi_host_last_error(); return f; };
+    // (the reference's batches: loadBatch(input, num_bases, min_number_of_reads), src/movi.cpp:281-284.)  A batch holds at least
+    // one read per GPU lane -- 227 k per B200 -- so that long reads fill the machine too: a batch of 2^26 bases is 447 k reads of
+    // 150 bp but only 6.7 k reads of 10 kbp, and a read's walk is one dependent chain whatever the GPU count.
+    const uint64_t min_reads = o.chunk_reads ? o.chunk_reads : 230000ull * (uint64_t)gpus;
+    auto fetch = [&]() {
+        Fetched f;
+        f.rc = movi_host_reader_next_reads(reader, o.chunk_bases, min_reads, std::max(o.max_chunk_bases, o.chunk_bases), &f.rd);
+        if (f.rc) f.err = movi_host_last_error();
+        return f;
+    };
     std::future<Fetched> ahead = std::async(std::launch::async, fetch);
 
     // one context per GPU, index replicated (uploaded while the first batch is being parsed)
@@ -200,7 +215,10 @@ int main(int argc, char** argv) {
     // With --classify / --filter the binning runs on the device (movi_gpu_query_classify); the matching lengths only come
     // back when something needs them (the .bpf file next to a --classify report; never for --filter or --no-output).
     const bool fused_classify = o.classify && o.query != "count";
-    const bool need_ml = o.query != "count" && (!fused_classify || o.write_output_allowed());
+    // A .bpf file as the only consumer of the lengths: its records are assembled on the device (movi_gpu_query_bpf) and the
+    // writer appends one image per batch (output_base_stats / output_binary, src/utils.cpp:202-246).
+    const bool device_bpf = o.query != "count" && !fused_classify && o.write_output_allowed() && !o.write_stdout_enabled();
+    const bool need_ml = o.query != "count" && !device_bpf && (!fused_classify || o.write_output_allowed());
 
     // ---- output sinks, routed like handle_pml_zml / handle_count (src/movi.cpp:23-76)
     const std::string prefix = (o.out_file.empty() ? o.read_file + "." + type : o.out_file) + "." + qname;   // utils.cpp:348-351
@@ -254,6 +272,7 @@ int main(int argc, char** argv) {
             }
             if (!rc && o.write_output_allowed()) {
                 if (o.write_stdout_enabled()) rc = movi_host_write_ml_text(STDOUT_FILENO, rd, R.ml.p);
+                else if (device_bpf) rc = movi_host_bpf_append_image(fd_bpf, R.image.p, R.image_bytes);
                 else rc = movi_host_bpf_append(fd_bpf, rd, R.ml.p);
             }
         }
@@ -290,6 +309,12 @@ int main(int argc, char** argv) {
         bool ok = true;
         if (o.query == "count") ok = R.counts.need(n_reads) && R.pos.need(n_reads);
         else if (need_ml) ok = R.ml.need(n_bases);
+        const char* ids = movi_host_reads_ids(rd);
+        const uint64_t* id_offsets = movi_host_reads_id_offsets(rd);
+        if (device_bpf) {
+            R.image_bytes = n_reads ? movi_gpu_bpf_image_bytes(offsets, id_offsets, n_reads) : 0;
+            ok = ok && R.image.need(R.image_bytes);
+        }
         if (ok && fused_classify) ok = R.above.need(n_reads) && R.below.need(n_reads) && R.sum.need(n_reads);
         if (!ok) die("cannot allocate pinned host memory for the results of a batch (try a smaller --chunk-bases)");
 
@@ -310,6 +335,10 @@ int main(int argc, char** argv) {
             if (fused_classify)
                 r = movi_gpu_query_classify(ctx[g], o.query == "zml", bases, offsets + i0, nr, qflags, (uint32_t)o.bin_width, (uint32_t)max_value_thr,
                                             R.above.p + i0, R.below.p + i0, R.sum.p + i0, need_ml ? R.ml.p : nullptr);
+            else if (device_bpf) {
+                const uint64_t at = movi_gpu_bpf_image_bytes(offsets, id_offsets, i0);       // where read i0's record starts in the image
+                r = movi_gpu_query_bpf(ctx[g], o.query == "zml", bases, offsets + i0, nr, qflags, ids, id_offsets + i0, R.image.p + at, R.image_bytes - at);
+            }
             else if (o.query == "pml") r = movi_gpu_query_pml(ctx[g], bases, offsets + i0, nr, qflags, R.ml.p);
             else if (o.query == "zml") r = movi_gpu_query_zml(ctx[g], bases, offsets + i0, nr, 0, R.ml.p);
             else r = movi_gpu_query_count(ctx[g], bases, offsets + i0, nr, 0, R.counts.p + i0, R.pos.p + i0);

@@ -457,3 +457,47 @@ def test_index_types_without_thresholds(nothr_index_dirs, read_sets, ref_seq, ty
             assert np.array_equal(got[:, 0], file_rows[:, 0]) and np.array_equal(got[:, 1] & mask, file_rows[:, 1] & mask)
     finally:
         ms.close()
+
+
+@pytest.mark.parametrize("typ", ["regular-thresholds", "sampled-thresholds"])
+def test_device_side_bpf_records(structures, read_sets, ref_seq, tmp_path, typ):
+    """movi_gpu_query_bpf: the .bpf records {u16 id_len; id; u64 L; u16 ml[L]} assembled on the device equal, byte for byte, what
+    the host writer produces from the same matching lengths (= the reference's file, tests/test_cli_gpu.py) -- every read set
+    (odd and even id lengths, 1-base reads), one slice and many tiny slices, PML and ZML, and the device-only entry point."""
+    import torch
+    from movi_b200 import _native as N
+    ms = structures[(typ, False)]
+    H = N.host_lib()
+    old = ms.get_option("batch_bases")
+    for read_set in READ_SETS:
+        rd = read_sets[read_set]
+        ids, id_off = rd.id_blob
+        for zml in ((False,) if typ == "sampled-thresholds" else (False, True)):
+            ml = ms.query_zml(rd.bases, rd.offsets) if zml else ms.query_pml(rd.bases, rd.offsets)
+            f = str(tmp_path / ("%s.%d.bpf" % (read_set, zml)))
+            assert H.movi_host_write_bpf(f.encode(), rd._h, ml.ctypes.data) == 0
+            want = open(f, "rb").read()[12:]
+            for batch in (old, 65536):
+                ms.set_option("batch_bases", batch)
+                try:
+                    got = ms.query_bpf(rd.bases, rd.offsets, ids, id_off, zml=zml)
+                finally:
+                    ms.set_option("batch_bases", old)
+                assert got.tobytes() == want, (read_set, zml, batch)
+    # device-only form on torch buffers
+    rd = read_sets["synth300.fasta"]
+    ids, id_off = rd.id_blob
+    dev = torch.device("cuda:0")
+    ml = ms.query_pml(rd.bases, rd.offsets)
+    d_ml = torch.from_numpy(np.concatenate([ml, np.zeros(64, np.uint16)]).view(np.int16)).to(dev)
+    d_off = torch.from_numpy(rd.offsets.astype(np.int64)).to(dev)
+    d_ids = torch.from_numpy(np.concatenate([ids, np.zeros(16, np.uint8)])).to(dev)
+    d_ido = torch.from_numpy(id_off.astype(np.int64)).to(dev)
+    size = 10 * rd.count + int(id_off[-1]) + 2 * int(rd.offsets[-1])
+    d_img = torch.zeros(size + 16, dtype=torch.uint8, device=dev)
+    ms._check(ms._L.movi_gpu_bpf_assemble_device(ms._ctx, d_ml.data_ptr(), d_off.data_ptr(), rd.count, d_ids.data_ptr(), d_ido.data_ptr(),
+                                                 d_img.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    f = str(tmp_path / "dev.bpf")
+    assert H.movi_host_write_bpf(f.encode(), rd._h, ml.ctypes.data) == 0
+    assert d_img[:size].cpu().numpy().tobytes() == open(f, "rb").read()[12:]
