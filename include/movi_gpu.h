@@ -169,6 +169,28 @@ int  movi_gpu_query_bpf(movi_gpu_ctx* ctx, int zml, const char* bases, const uin
 int  movi_gpu_bpf_assemble_device(movi_gpu_ctx* ctx, const uint16_t* d_ml, const uint64_t* d_read_offsets, uint64_t n_reads,
                                   const char* d_ids, const uint64_t* d_id_offsets, uint8_t* d_image, void* cuda_stream);
 
+/* DEVICE-SIDE INGEST: a chunk of a FASTA / FASTQ read file (raw bytes, starting at a record boundary; < 4 GiB) is copied to the GPU
+ * and parsed there -- BatchLoader::loadBatch + grabNextRead, src/batch_loader.cpp:26-143: multi-line FASTA, four-line FASTQ,
+ * trailing white space dropped, ids through and including their first blank -- walked (PML or ZML) and, when out_image is not
+ * NULL, returned as the .bpf records of its reads (as movi_gpu_query_bpf).  final_chunk = 0: the chunk ends somewhere inside the
+ * file; its last, possibly incomplete record is left to the next chunk: res->consumed_bytes says where that one starts.
+ * res->parse_flags != 0 (MOVI_GPU_PARSE_*): the chunk holds something the reference rejects or stops at; nothing was queried and
+ * the caller should hand the input to the host parser (movi_host_reader_*), which reproduces the reference's behaviour. */
+typedef struct MoviGpuChunkResult {
+    uint64_t n_reads, n_bases, id_bytes, consumed_bytes, image_bytes;
+    uint32_t parse_flags, reserved;
+} MoviGpuChunkResult;
+#define MOVI_GPU_PARSE_BAD_HEADER   1u   /* a record does not start with '>' / '@' */
+#define MOVI_GPU_PARSE_NO_ID        2u   /* "header line is missing an id" */
+#define MOVI_GPU_PARSE_EMPTY_HEADER 4u   /* an empty line where a header is due: the reference stops reading there */
+#define MOVI_GPU_PARSE_OVERFLOW     8u   /* an id longer than 65535 bytes */
+int  movi_gpu_query_file_chunk(movi_gpu_ctx* ctx, int zml, const char* raw, uint64_t n_bytes, int fastq, int final_chunk, uint32_t flags,
+                               uint8_t* out_image, uint64_t image_capacity, MoviGpuChunkResult* res);
+/* The parse alone, results copied back to the host (tests, tools). */
+int  movi_gpu_parse_chunk(movi_gpu_ctx* ctx, const char* raw, uint64_t n_bytes, int fastq, int final_chunk,
+                          char* out_bases, uint64_t bases_capacity, uint64_t* out_offsets, char* out_ids, uint64_t ids_capacity,
+                          uint64_t* out_id_offsets, uint64_t reads_capacity, MoviGpuChunkResult* res);
+
 /* Same queries on DEVICE buffers (already resident in HBM), enqueued on `cuda_stream` (a cudaStream_t,
  * NULL = default stream) without synchronising: for callers that pipeline their own copies.
  * d_bases and d_out_ml must be 32-byte aligned and d_bases readable up to the next multiple of 32 bytes (the

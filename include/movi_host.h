@@ -44,6 +44,13 @@ int  movi_host_reader_next(movi_host_reader* r, uint64_t max_bases, movi_host_re
  * holds max_bases bases AND min_reads reads -- a GPU wants one read per lane in flight however long the reads are -- but never
  * beyond cap_bases bases (0 = no cap; the bound on host memory per batch). */
 int  movi_host_reader_next_reads(movi_host_reader* r, uint64_t max_bases, uint64_t min_reads, uint64_t cap_bases, movi_host_reads** out);
+/* The whole input as the reader holds it (memory-mapped file / slurped stdin / inflated gzip) and its format: what the device-side
+ * ingest (movi_gpu_query_file_chunk) is fed from.  The pointer stays valid until movi_host_reader_close. */
+int  movi_host_reader_raw(const movi_host_reader* r, const char** data, uint64_t* size, int* fastq);
+/* First record boundary at or after `from` (the offset of a '>' / '@' that starts a record; `size` if there is none): FASTA = a
+ * line starting with '>'; FASTQ = a line starting with '@' whose next-but-one line starts with '+' (a quality line may start
+ * with '@' too, but then the line two further down is a sequence, never a '+' line). */
+uint64_t movi_host_record_boundary(const char* data, uint64_t size, uint64_t from, int fastq);
 void movi_host_reader_close(movi_host_reader* r);
 uint64_t movi_host_reads_count(const movi_host_reads* rd);
 const char* movi_host_reads_bases(const movi_host_reads* rd);          /* concatenated */

@@ -11,6 +11,11 @@ from . import build as _build
 u8p, u16p, u32p, u64p, i32p = (C.POINTER(t) for t in (C.c_uint8, C.c_uint16, C.c_uint32, C.c_uint64, C.c_int32))
 
 
+class MoviGpuChunkResult(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("n_bases", C.c_uint64), ("id_bytes", C.c_uint64), ("consumed_bytes", C.c_uint64),
+                ("image_bytes", C.c_uint64), ("parse_flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 class MoviGpuIndexDesc(C.Structure):
     _fields_ = [
         ("mode", C.c_int32), ("sigma", C.c_uint32),
@@ -47,6 +52,10 @@ GPU_SYMBOLS = {
     "movi_gpu_bpf_image_bytes": (C.c_uint64, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "movi_gpu_query_bpf": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     "movi_gpu_bpf_assemble_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "movi_gpu_query_file_chunk": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_uint64,
+                                            C.POINTER(MoviGpuChunkResult)]),
+    "movi_gpu_parse_chunk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
+                                       C.c_void_p, C.c_uint64, C.POINTER(MoviGpuChunkResult)]),
     "movi_gpu_query_zml": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]),
     "movi_gpu_query_count": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
     "movi_gpu_query_pml_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
@@ -86,6 +95,8 @@ HOST_SYMBOLS = {
     "movi_host_reads_id_offsets": (C.c_void_p, [C.c_void_p]),
     "movi_host_bpf_append_image": (C.c_int, [C.c_int, C.c_void_p, C.c_uint64]),
     "movi_host_reader_next_reads": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "movi_host_reader_raw": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
+    "movi_host_record_boundary": (C.c_uint64, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int]),
     "movi_host_bpf_begin": (C.c_int, [C.c_char_p]),
     "movi_host_bpf_append": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
     "movi_host_bpf_end": (C.c_int, [C.c_int]),

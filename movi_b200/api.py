@@ -215,6 +215,30 @@ class MoveStructure:
                                                _ptr(ids), _ptr(id_offsets), _ptr(image), size))
         return image
 
+    def parse_chunk(self, raw, fastq, final=True):
+        """A chunk of FASTA / FASTQ bytes parsed on the device -> (bases, offsets, ids, id_offsets, consumed_bytes, parse_flags)."""
+        raw = np.frombuffer(raw, dtype=np.uint8) if not isinstance(raw, np.ndarray) else raw
+        n = len(raw)
+        bases, ids = np.zeros(n + 1, np.uint8), np.zeros(n + 1, np.uint8)
+        offsets, id_offsets = np.zeros(n // 2 + 2, np.uint64), np.zeros(n // 2 + 2, np.uint64)
+        res = N.MoviGpuChunkResult()
+        self._check(self._L.movi_gpu_parse_chunk(self._ctx, _ptr(raw) if n else None, n, int(fastq), int(final), _ptr(bases), n + 1, _ptr(offsets),
+                                                 _ptr(ids), n + 1, _ptr(id_offsets), n // 2 + 1, C.byref(res)))
+        k = int(res.n_reads)
+        return (bases[: int(res.n_bases)], offsets[: k + 1], ids[: int(res.id_bytes)], id_offsets[: k + 1], int(res.consumed_bytes),
+                int(res.parse_flags))
+
+    def query_file_chunk(self, raw, fastq, final=True, zml=False, rpml=False, want_image=True):
+        """File bytes in, .bpf records out: parse + walk + record assembly on the device -> (image uint8[], result struct)."""
+        raw = np.frombuffer(raw, dtype=np.uint8) if not isinstance(raw, np.ndarray) else raw
+        n = len(raw)
+        cap = 3 * n + 64
+        image = np.zeros(cap if want_image else 1, np.uint8)
+        res = N.MoviGpuChunkResult()
+        self._check(self._L.movi_gpu_query_file_chunk(self._ctx, int(zml), _ptr(raw) if n else None, n, int(fastq), int(final),
+                                                      FLAG_RPML if rpml else 0, _ptr(image) if want_image else None, cap, C.byref(res)))
+        return image[: int(res.image_bytes)] if want_image else None, res
+
     def query_zml(self, bases, offsets, out=None):
         bases, offsets, n = self._prep(bases, offsets)
         if out is None:

@@ -44,10 +44,13 @@ __device__ __forceinline__ uint4 ld_keep128(const uint4* p, unsigned long long p
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
     return v;
 }
-// one aligned 32-byte sector (4 rows) in ONE request: a 256-bit load (sm_100+)
+// one aligned 32-byte sector (4 rows) in ONE request: a 256-bit load (sm_100+).  L2::64B: on a miss the L2 of this part brings in
+// the whole 128-byte line (4 sectors) by default, whatever the width of the load -- 4.0 DRAM sectors per random load measured on a
+// 36 GB table, 2.0 with this qualifier (profiles/r02_load_flavours_ncu.csv; cudaLimitMaxL2FetchGranularity changes nothing).  This
+// fetch serves tables far beyond the L2, where the other sectors of the line are never used before they are evicted.
 __device__ __forceinline__ void ld_keep256(const void* p, unsigned long long pol, uint4& lo, uint4& hi) {
     unsigned long long a, b, c, d;
-    asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
+    asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
                  : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p), "l"(pol));
     lo = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
     hi = make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)d, (uint32_t)(d >> 32));

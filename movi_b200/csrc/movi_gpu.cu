@@ -19,6 +19,7 @@
 #include "dev_index.cuh"
 #include "kernel_common.cuh"
 #include "misc_kernels.cuh"
+#include "parse_kernels.cuh"
 #include "pml_kernel.cuh"
 
 using namespace movi;
@@ -77,6 +78,7 @@ struct movi_gpu_ctx {
     // options
     int64_t pml_sector = -1;          // sector-cached row fetch: -1 by table size (> 512 MB) and batch size, 0 off, 1 on
     int64_t smem_carveout = -1;       // >= 0: preferred shared-memory carve-out of the query kernels, percent of the maximum (exploration)
+    int64_t out_stage = 32;           // sector-cached PML kernel: matching lengths staged per lane before a flush (16 or 32)
     int64_t force_wide = 0;           // tests: run the 64-bit-index instantiations on a small table
     int64_t blocks_per_sm = 0;        // 0: occupancy query
     int64_t threads_per_block = 256;
@@ -85,6 +87,19 @@ struct movi_gpu_ctx {
     int64_t kernel_streams = 4;       // 1..NKS: slices whose kernels may run concurrently (sweep: profiles/r01_pipeline_sweep.jsonl)
     int64_t pipeline_slots = NBUF;    // 2..NBUF
     int64_t size_grid_to_batch = 1;   // 0: always launch the full persistent grid; k >= 1: a grid that gives every lane k reads of the batch
+    // device-side ingest (movi_gpu_query_file_chunk): raw chunk, parse scratch, parsed reads, lengths, .bpf image
+    uint8_t* p_raw = nullptr; size_t p_raw_cap = 0;
+    uint32_t* p_tile = nullptr; size_t p_tile_cap = 0;
+    uint32_t* p_nlpos = nullptr; size_t p_nlpos_cap = 0;
+    LineInfo* p_lines = nullptr; size_t p_lines_cap = 0;
+    Sum3* p_ltile = nullptr; size_t p_ltile_cap = 0;
+    ParseResult* p_res = nullptr;                      // + one Sum3 + one u32 behind it
+    uint8_t* p_bases = nullptr; size_t p_bases_cap = 0;
+    unsigned long long* p_offsets = nullptr; size_t p_offsets_cap = 0;
+    uint8_t* p_ids = nullptr; size_t p_ids_cap = 0;
+    unsigned long long* p_id_offsets = nullptr; size_t p_id_offsets_cap = 0;
+    uint16_t* p_ml = nullptr; size_t p_ml_cap = 0;
+    uint8_t* p_image = nullptr; size_t p_image_cap = 0;
     // gather probe scratch
     uint2* d_probe = nullptr; uint64_t probe_bytes = 0;
     int64_t probe_vmm_align_mb = 0;   // > 0: allocate the probe table through the VMM API at this alignment
@@ -155,10 +170,13 @@ void vmm_free(VmmBlock* b) {
 }
 
 template <typename K>
-int blocks_for(movi_gpu_ctx* ctx, K kernel, int threads) {
+int blocks_for(movi_gpu_ctx* ctx, K kernel, int threads, int cap_per_sm = 0) {
     int per_sm = 0;
     if (ctx->blocks_per_sm > 0) per_sm = (int)ctx->blocks_per_sm;
-    else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    else {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+        if (cap_per_sm > 0) per_sm = std::min(per_sm, cap_per_sm);
+    }
     return per_sm * ctx->num_sms;
 }
 
@@ -210,7 +228,7 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
         auto k_ = KERNEL;                                                         \
         if (ctx->smem_carveout >= 0) cudaFuncSetAttribute(k_, cudaFuncAttributePreferredSharedMemoryCarveout, (int)ctx->smem_carveout); \
         cudaLaunchConfig_t cfg_ = {};                                             \
-        cfg_.gridDim = dim3((unsigned)std::min<uint64_t>((uint64_t)blocks_for(ctx, k_, threads), grid_cap)); \
+        cfg_.gridDim = dim3((unsigned)std::min<uint64_t>((uint64_t)blocks_for(ctx, k_, threads, sm_cap), grid_cap)); \
         cfg_.blockDim = dim3((unsigned)threads);                                  \
         cfg_.stream = st;                                                         \
         CU(cudaLaunchKernelEx(&cfg_, k_, ctx->ix, qa));                           \
@@ -220,10 +238,14 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
     // (measured, profiles/r01_big_tables.jsonl: 8 and 32 GB tables 1.2 -> 2.2-2.5e10 bases/s; the 124 MB c2 table -27 %;
     //  a batch of few long reads, which leaves most lanes empty and is latency bound, -10 %: those keep the plain fetch)
     const bool b6 = ctx->ix.layout == LAYOUT_B6, t3 = ctx->ix.layout == LAYOUT_T3;
+    int sm_cap = 0;                     // resident blocks per SM at most (0 = what the registers allow)
     const bool sector = !b6 && !t3 && !ctx->ix.nt && (ctx->pml_sector == 1 || (ctx->pml_sector < 0 &&
                         ctx->ix.r * sizeof(uint2) > (512ull << 20) && qa.n_reads >= (1u << 17)));
     if (kind == Q_PML) {
-        // 6 blocks/SM (40 registers) measured fastest on both L2-sized (c2) and HBM-resident (8-64 GB) tables
+        if (sector) sm_cap = 4;
+        // 6 blocks/SM (40 registers) measured fastest on L2-sized tables (c2); the sector-cached kernel of HBM-resident tables runs
+        // 4 blocks/SM: those tables are bound by the request rate of the memory system, and fewer walks in flight queue less
+        // (36.8 GB table, 4.1e9 bases: 180 ms at 4 blocks/SM, 195 ms at 5, 193 ms at 3 -- profiles/r02_sweep_c4.jsonl)
         const bool rpml = (qa.flags & MOVI_GPU_FLAG_RPML) != 0;
 #define PML(IDX, SEPV) do { \
             if (ctx->ix.nt) LAUNCH((movi_pml_kernel<IDX, SEPV, 6, LAYOUT_R8, false, true, true>));   /* non-threshold table: 12-bit accessors, always the --rpml rule (move_structure_query.cpp:308-311) */ \
@@ -233,8 +255,8 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
                 else LAUNCH((movi_pml_kernel<IDX, SEPV, 6, LAYOUT_R8, false, true>)); } \
             else if (t3) LAUNCH((movi_pml_kernel<IDX, SEPV, 5, LAYOUT_T3>)); \
             else if (b6) LAUNCH((movi_pml_kernel<IDX, SEPV, 6, LAYOUT_B6>)); \
-            else if (sector && ctx->blocks_per_sm >= 6) LAUNCH((movi_pml_kernel<IDX, SEPV, 6, LAYOUT_R8, true>)); \
-            else if (sector) LAUNCH((movi_pml_kernel<IDX, SEPV, 5, LAYOUT_R8, true>)); \
+            else if (sector && ctx->out_stage == 16) LAUNCH((movi_pml_kernel<IDX, SEPV, 4, LAYOUT_R8, true>)); \
+            else if (sector) LAUNCH((movi_pml_kernel<IDX, SEPV, 4, LAYOUT_R8, true, false, false, 32>)); \
             else LAUNCH((movi_pml_kernel<IDX, SEPV, 6, LAYOUT_R8>)); } while (0)
         if (ctx->ix.sep) { if (wide) PML(unsigned long long, true); else PML(uint32_t, true); }
         else             { if (wide) PML(unsigned long long, false); else PML(uint32_t, false); }
@@ -520,6 +542,8 @@ int movi_gpu_destroy(movi_gpu_ctx* ctx) {
     if (ctx->st_in) cudaStreamDestroy(ctx->st_in);
     if (ctx->st_out) cudaStreamDestroy(ctx->st_out);
     for (int k = 0; k < NKS; k++) if (ctx->st_k[k]) cudaStreamDestroy(ctx->st_k[k]);
+    cudaFree(ctx->p_raw); cudaFree(ctx->p_tile); cudaFree(ctx->p_nlpos); cudaFree(ctx->p_lines); cudaFree(ctx->p_ltile); cudaFree(ctx->p_res);
+    cudaFree(ctx->p_bases); cudaFree(ctx->p_offsets); cudaFree(ctx->p_ids); cudaFree(ctx->p_id_offsets); cudaFree(ctx->p_ml); cudaFree(ctx->p_image);
     cudaFree(ctx->d_status); cudaFree(ctx->d_counters);
     if (ctx->probe_vmm[0]) { VmmBlock b; b.ptr = ctx->probe_vmm[0]; b.size = ctx->probe_vmm[1]; b.handle = ctx->probe_vmm[2]; vmm_free(&b); }
     else cudaFree(ctx->d_probe);
@@ -536,6 +560,7 @@ int movi_gpu_set_option(movi_gpu_ctx* ctx, const char* key, int64_t value) {
     if (!ctx || !key) return MOVI_GPU_ERR_ARG;
     const std::string k(key);
     if (k == "force_wide") { ctx->force_wide = value ? 1 : 0; }
+    else if (k == "out_stage") { if (value != 16 && value != 32) return fail(ctx, MOVI_GPU_ERR_ARG, "out_stage: 16 or 32"); ctx->out_stage = value; }
     else if (k == "probe_vmm_align_mb") { if (value < 0 || value > 4096) return fail(ctx, MOVI_GPU_ERR_ARG, "probe_vmm_align_mb: 0..4096"); ctx->probe_vmm_align_mb = value; }
     else if (k == "blocks_per_sm") { if (value < 0 || value > 32) return fail(ctx, MOVI_GPU_ERR_ARG, "blocks_per_sm: 0..32"); ctx->blocks_per_sm = value; }
     else if (k == "threads_per_block") {
@@ -563,6 +588,7 @@ int64_t movi_gpu_get_option(const movi_gpu_ctx* ctx, const char* key) {
     if (k == "size_grid_to_batch") return ctx->size_grid_to_batch;
     if (k == "num_sms") return ctx->num_sms;
     if (k == "force_wide") return ctx->force_wide;
+    if (k == "out_stage") return ctx->out_stage;
     return -1;
 }
 
@@ -890,6 +916,132 @@ static unsigned long long* next_counter(movi_gpu_ctx* ctx) {
     unsigned long long* p = ctx->d_counters + (ctx->counter_slot & 63u);
     ctx->counter_slot++;
     return p;
+}
+
+// ---- device-side ingest: a chunk of a FASTA / FASTQ file (starting at a record boundary) parsed in HBM (parse_kernels.cuh)
+namespace {
+struct ParsedChunk { ParseResult r{}; };
+
+// raw chunk (host memory) -> ctx->p_bases / p_offsets / p_ids / p_id_offsets on the device; synchronises `st`
+int parse_chunk(movi_gpu_ctx* ctx, const char* raw, uint64_t n, int fastq, int final_chunk, cudaStream_t st, ParseResult* out) {
+    std::memset(out, 0, sizeof *out);
+    if (n >= 0xFFFFFF00ull) return fail(ctx, MOVI_GPU_ERR_ARG, "a file chunk must be smaller than 4 GiB");
+    int rc;
+    if (!ctx->p_res) CU(cudaMalloc(&ctx->p_res, sizeof(ParseResult) + sizeof(Sum3) + 16));
+    Sum3* d_total = reinterpret_cast<Sum3*>(ctx->p_res + 1);
+    uint32_t* d_nl_total = reinterpret_cast<uint32_t*>(d_total + 1);
+    CU(cudaMemsetAsync(ctx->p_res, 0, sizeof(ParseResult) + sizeof(Sum3) + 16, st));
+    if (n == 0) { CU(cudaStreamSynchronize(st)); return MOVI_GPU_OK; }
+    if ((rc = grow(ctx, ctx->p_raw, ctx->p_raw_cap, n + 64))) return rc;
+    CU(cudaMemcpyAsync(ctx->p_raw, raw, n, cudaMemcpyHostToDevice, st));
+    const uint64_t n_tiles = (n + PARSE_TILE - 1) / PARSE_TILE;
+    if ((rc = grow(ctx, ctx->p_tile, ctx->p_tile_cap, n_tiles + 1))) return rc;
+    parse_count_newlines<<<(unsigned)n_tiles, 256, 0, st>>>(ctx->p_raw, n, ctx->p_tile);
+    parse_scan_u32<<<1, 1024, 0, st>>>(ctx->p_tile, n_tiles, d_nl_total);
+    uint32_t n_nl = 0;
+    CU(cudaMemcpyAsync(&n_nl, d_nl_total, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    ctx->launches += 2;
+    // lines: every '\n'-terminated one, plus -- in the last chunk of a file -- a final line without '\n'
+    const uint32_t n_lines = n_nl + ((final_chunk && raw[n - 1] != '\n') ? 1u : 0u);
+    if (n_lines == 0) return MOVI_GPU_OK;               // no complete line yet: nothing consumed
+    if ((rc = grow(ctx, ctx->p_nlpos, ctx->p_nlpos_cap, (size_t)n_nl + 2))) return rc;
+    if ((rc = grow(ctx, ctx->p_lines, ctx->p_lines_cap, (size_t)n_lines + 1))) return rc;
+    const uint32_t l_tiles = (n_lines + LINE_TILE - 1) / LINE_TILE;
+    if ((rc = grow(ctx, ctx->p_ltile, ctx->p_ltile_cap, (size_t)l_tiles + 1))) return rc;
+    parse_fill_newlines<<<(unsigned)n_tiles, 256, 0, st>>>(ctx->p_raw, n, ctx->p_tile, ctx->p_nlpos);
+    parse_classify_lines<<<(n_lines + 255) / 256, 256, 0, st>>>(ctx->p_raw, n, ctx->p_nlpos, n_nl, n_lines, fastq, ctx->p_lines, ctx->p_res);
+    parse_line_tile_sums<<<l_tiles, LINE_TILE, 0, st>>>(ctx->p_lines, n_lines, ctx->p_ltile);
+    parse_scan_tiles<<<1, 32, 0, st>>>(ctx->p_ltile, l_tiles, d_total);
+    Sum3 total{};
+    ParseResult pr{};
+    CU(cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&pr, ctx->p_res, sizeof pr, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    ctx->launches += 4;
+    out->flags = pr.flags; out->n_lines = n_lines;
+    if (pr.flags) return MOVI_GPU_OK;                   // the caller hands the file to the host parser
+    uint32_t n_keep;
+    if (fastq) n_keep = n_lines / 4;                    // records whose four lines are all there (a truncated last record is dropped)
+    else n_keep = final_chunk ? total.recs : (total.recs ? total.recs - 1 : 0);   // the last record may continue in the next chunk
+    if ((rc = grow(ctx, ctx->p_bases, ctx->p_bases_cap, (size_t)total.bases + 96))) return rc;
+    if ((rc = grow(ctx, ctx->p_offsets, ctx->p_offsets_cap, (size_t)total.recs + 2))) return rc;
+    if ((rc = grow(ctx, ctx->p_ids, ctx->p_ids_cap, (size_t)total.ids + 16))) return rc;
+    if ((rc = grow(ctx, ctx->p_id_offsets, ctx->p_id_offsets_cap, (size_t)total.recs + 2))) return rc;
+    parse_apply<<<l_tiles, LINE_TILE, 0, st>>>(ctx->p_raw, ctx->p_lines, n_lines, ctx->p_ltile, n_keep, ctx->p_bases, ctx->p_offsets, ctx->p_ids,
+                                               ctx->p_id_offsets, ctx->p_res, 0);
+    // every record kept: totals from the grand totals; what is consumed ends after the last complete line
+    parse_finish<<<1, 32, 0, st>>>(d_total, n_keep, final_chunk ? n : 0ull, ctx->p_offsets, ctx->p_id_offsets, ctx->p_res);
+    CU(cudaMemcpyAsync(&pr, ctx->p_res, sizeof pr, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    ctx->launches += 2;
+    if (!final_chunk && n_keep == total.recs) {
+        // (FASTQ whose last complete record ends exactly at the last newline of the chunk) consumed = one past that newline
+        uint32_t last_nl = 0;
+        CU(cudaMemcpy(&last_nl, ctx->p_nlpos + (n_nl - 1), 4, cudaMemcpyDeviceToHost));
+        pr.consumed = fastq ? (uint64_t)last_nl + 1 : 0;
+        if (fastq && (n_lines & 3u)) return fail(ctx, MOVI_GPU_ERR_QUERY, "internal: FASTQ chunk accounting");
+    }
+    *out = pr;
+    out->n_lines = n_lines;
+    return MOVI_GPU_OK;
+}
+}  // namespace
+
+extern "C" int movi_gpu_parse_chunk(movi_gpu_ctx* ctx, const char* raw, uint64_t n_bytes, int fastq, int final_chunk,
+                                    char* out_bases, uint64_t bases_capacity, uint64_t* out_offsets, char* out_ids, uint64_t ids_capacity,
+                                    uint64_t* out_id_offsets, uint64_t reads_capacity, MoviGpuChunkResult* res) {
+    if (!ctx || !res || (n_bytes && !raw)) return MOVI_GPU_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    ParseResult pr;
+    int rc = parse_chunk(ctx, raw, n_bytes, fastq, final_chunk, ctx->st_k[0], &pr);
+    if (rc) return rc;
+    res->n_reads = pr.n_reads; res->n_bases = pr.n_bases; res->id_bytes = pr.id_bytes; res->consumed_bytes = pr.consumed;
+    res->image_bytes = 0; res->parse_flags = pr.flags;
+    if (pr.flags || pr.n_reads == 0) return MOVI_GPU_OK;
+    if (pr.n_bases > bases_capacity || pr.id_bytes > ids_capacity || pr.n_reads > reads_capacity) return fail(ctx, MOVI_GPU_ERR_ARG, "output buffers too small for the parsed chunk");
+    CU(cudaMemcpy(out_bases, ctx->p_bases, pr.n_bases, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out_offsets, ctx->p_offsets, (pr.n_reads + 1) * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out_ids, ctx->p_ids, pr.id_bytes, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out_id_offsets, ctx->p_id_offsets, (pr.n_reads + 1) * 8, cudaMemcpyDeviceToHost));
+    return MOVI_GPU_OK;
+}
+
+extern "C" int movi_gpu_query_file_chunk(movi_gpu_ctx* ctx, int zml, const char* raw, uint64_t n_bytes, int fastq, int final_chunk, uint32_t flags,
+                                         uint8_t* out_image, uint64_t image_capacity, MoviGpuChunkResult* res) {
+    if (!ctx || !res || (n_bytes && !raw)) return MOVI_GPU_ERR_ARG;
+    CallFlags cf(ctx, flags);
+    const Kind kind = zml ? Q_ZML : Q_PML;
+    int rc = check_query_ready(ctx, kind, 0);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->st_k[0];
+    ParseResult pr;
+    if ((rc = parse_chunk(ctx, raw, n_bytes, fastq, final_chunk, st, &pr))) return rc;
+    res->n_reads = pr.n_reads; res->n_bases = pr.n_bases; res->id_bytes = pr.id_bytes; res->consumed_bytes = pr.consumed;
+    res->parse_flags = pr.flags;
+    res->image_bytes = pr.flags ? 0 : 10ull * pr.n_reads + pr.id_bytes + 2ull * pr.n_bases;
+    if (pr.flags || pr.n_reads == 0) return MOVI_GPU_OK;
+    if (out_image && res->image_bytes > image_capacity) return fail(ctx, MOVI_GPU_ERR_NOMEM, "the .bpf image buffer is too small for this chunk");
+    if ((rc = grow(ctx, ctx->p_ml, ctx->p_ml_cap, (size_t)pr.n_bases + 96))) return rc;
+    CU(cudaMemsetAsync(ctx->d_status, 0, sizeof(unsigned int), st));
+    CU(cudaMemsetAsync(ctx->p_bases + pr.n_bases, 0, 64, st));
+    rc = device_query(ctx, kind, reinterpret_cast<const char*>(ctx->p_bases), reinterpret_cast<const uint64_t*>(ctx->p_offsets), 0, pr.n_reads,
+                      ctx->p_ml, nullptr, nullptr, next_counter(ctx), st);
+    if (rc) return rc;
+    if (out_image) {
+        if ((rc = grow(ctx, ctx->p_image, ctx->p_image_cap, (size_t)res->image_bytes + 16))) return rc;
+        const unsigned blocks = (unsigned)std::min<uint64_t>((pr.n_reads * 32 + 255) / 256, (uint64_t)ctx->num_sms * 16);
+        bpf_assemble_kernel<<<blocks, 256, 0, st>>>(ctx->p_ml, ctx->p_offsets, 0ull, pr.n_reads, ctx->p_ids, ctx->p_id_offsets, ctx->p_image);
+        ctx->launches += 1;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(out_image, ctx->p_image, res->image_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    return movi_gpu_check_device_status(ctx);
 }
 
 int movi_gpu_query_pml_device(movi_gpu_ctx* ctx, const char* d_bases, const uint64_t* d_read_offsets, uint64_t n_reads,

@@ -35,7 +35,10 @@ namespace movi {
 constexpr uint32_t ST_UPF = 5, ST_DOWNF = 6;
 
 // NT: the table of a non-threshold index type (dev_index.cuh): 12-bit field accessors; always queried with RPML.
-template <typename IdxT, bool SEP, int MINB, int LAYOUT, bool SECTOR = false, bool RPML = false, bool NT = false>
+// OUTW: matching lengths staged per lane before they are written (16 = one 32-byte sector, 32 = one 64-byte DRAM atom).  Tables
+// far beyond the L2 turn the whole L2 over between two flushes of a lane, so a 32-byte flush reaches DRAM as a partial atom;
+// with 32 values the write is a whole atom and there are half as many of them (the request rate is what bounds such tables).
+template <typename IdxT, bool SEP, int MINB, int LAYOUT, bool SECTOR = false, bool RPML = false, bool NT = false, int OUTW = 16>
 __global__ void __launch_bounds__(QUERY_THREADS, MINB)
 movi_pml_kernel(const DevIndex ix, const QueryArgs q) {
     __shared__ uint8_t s_code[256];
@@ -50,7 +53,7 @@ movi_pml_kernel(const DevIndex ix, const QueryArgs q) {
     }
     const uint32_t* const idb = idb_in_smem ? s_idb : ix.id_blocks;
     __shared__ __align__(32) uint8_t s_in[QUERY_THREADS * 32];      // per lane: the 32-byte sector of its read that holds bases[rp]
-    __shared__ __align__(32) uint16_t s_out[QUERY_THREADS * 16];    // per lane: the 32-byte sector of its output being filled
+    __shared__ __align__(32) uint16_t s_out[QUERY_THREADS * OUTW];  // per lane: the sector (OUTW = 16) / atom (32) of its output being filled
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_code[i] = ix.code_of[i];
     if (threadIdx.x < 4) s_end_thr[threadIdx.x] = ix.end_thr[threadIdx.x];
     __syncthreads();
@@ -64,9 +67,10 @@ movi_pml_kernel(const DevIndex ix, const QueryArgs q) {
     const uint2* __restrict__ rows = ix.rows;
     const uint8_t* __restrict__ bases = q.bases;
     const uint2* __restrict__ offs8 = reinterpret_cast<const uint2*>(q.offsets);
-    uint16_t* const out_slot = s_out + threadIdx.x * 16;              // (generic pointer: only the rare ragged flush uses it)
+    uint16_t* const out_slot = s_out + threadIdx.x * OUTW;            // (generic pointer: only the rare ragged flush uses it)
+    constexpr uint32_t OM = OUTW - 1;
     const uint32_t sa_in = smem_addr(s_in) + threadIdx.x * 32u;       // shared-window addresses of this lane's slots
-    const uint32_t sa_out = smem_addr(s_out) + threadIdx.x * 32u;
+    const uint32_t sa_out = smem_addr(s_out) + threadIdx.x * (2u * OUTW);
     const uint32_t sa_code = smem_addr(s_code);
     constexpr uint32_t sep = SEP ? 1u : 0u;
     constexpr uint32_t REFILL_EVERY = 4;
@@ -184,25 +188,23 @@ movi_pml_kernel(const DevIndex ix, const QueryArgs q) {
         const bool fin = emit && (rem == 1u);
         const bool lf = emit && !fin;
         if (emit) {
-            sts_u16(sa_out + 2u * (op & 15u), ml < 65535u ? ml : 65535u);  // add_ml clamp
+            sts_u16(sa_out + 2u * (op & OM), ml < 65535u ? ml : 65535u);   // add_ml clamp
             pend += 1;
-            if ((op & 15u) == 15u || fin) {
-                uint16_t* g = q.out_ml + (op & ~15u);
-                if (pend == 16u) {
-                    const uint4 lo = lds_128(sa_out);
-                    const uint4 hi = lds_128(sa_out + 16u);
-                    st_stream128(g, lo, pol_stream); st_stream128(g + 8, hi, pol_stream);
+            if ((op & OM) == OM || fin) {
+                uint16_t* g = q.out_ml + (op & ~OM);
+                if (pend == (uint32_t)OUTW) {
+#pragma unroll
+                    for (uint32_t k = 0; k < (uint32_t)OUTW / 8u; k++) st_stream128(g + 8u * k, lds_128(sa_out + 16u * k), pol_stream);
                 } else {
-                    // ragged head / tail of a read: only our own slots [lo, hi] of the sector, widest aligned pieces first
-                    uint32_t lo = (op & 15u) + 1u - pend;
-                    const uint32_t hi1 = (op & 15u) + 1u;                  // one past the last slot
-                    if ((lo & 1u) && lo < hi1) { g[lo] = out_slot[lo]; lo += 1; }
-                    if ((lo & 2u) && lo + 2 <= hi1) { *reinterpret_cast<uint32_t*>(g + lo) = *reinterpret_cast<const uint32_t*>(out_slot + lo); lo += 2; }
-                    if ((lo & 4u) && lo + 4 <= hi1) { *reinterpret_cast<uint2*>(g + lo) = *reinterpret_cast<const uint2*>(out_slot + lo); lo += 4; }
-                    if (lo + 8 <= hi1) { *reinterpret_cast<uint4*>(g + lo) = *reinterpret_cast<const uint4*>(out_slot + lo); lo += 8; }
-                    if (lo + 4 <= hi1) { *reinterpret_cast<uint2*>(g + lo) = *reinterpret_cast<const uint2*>(out_slot + lo); lo += 4; }
-                    if (lo + 2 <= hi1) { *reinterpret_cast<uint32_t*>(g + lo) = *reinterpret_cast<const uint32_t*>(out_slot + lo); lo += 2; }
-                    if (lo < hi1) g[lo] = out_slot[lo];
+                    // ragged head / tail of a read: only our own slots [lo, hi1) of the staged group, widest aligned pieces first
+                    uint32_t lo = (op & OM) + 1u - pend;
+                    const uint32_t hi1 = (op & OM) + 1u;                   // one past the last slot
+                    while (lo < hi1) {
+                        if (!(lo & 7u) && lo + 8u <= hi1) { *reinterpret_cast<uint4*>(g + lo) = *reinterpret_cast<const uint4*>(out_slot + lo); lo += 8u; }
+                        else if (!(lo & 3u) && lo + 4u <= hi1) { *reinterpret_cast<uint2*>(g + lo) = *reinterpret_cast<const uint2*>(out_slot + lo); lo += 4u; }
+                        else if (!(lo & 1u) && lo + 2u <= hi1) { *reinterpret_cast<uint32_t*>(g + lo) = *reinterpret_cast<const uint32_t*>(out_slot + lo); lo += 2u; }
+                        else { g[lo] = out_slot[lo]; lo += 1u; }
+                    }
                 }
                 pend = 0;
             }

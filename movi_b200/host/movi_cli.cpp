@@ -8,11 +8,14 @@
 // `movi-b200 view --bpf F` prints a .bpf file like the reference's view action (src/movi.cpp:402-503).
 #include <unistd.h>
 
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <future>
+#include <mutex>
 #include <random>
 #include <string>
 #include <thread>
@@ -33,6 +36,8 @@ struct Options {
     uint64_t chunk_bases = 1ull << 26;   // bases per batch of the streaming loop (host memory: ~10 bytes per base of a batch)
     uint64_t chunk_reads = 0;            // reads per batch at least: 0 = 2.3e5 per GPU (one read per lane in flight, however long the reads)
     uint64_t max_chunk_bases = 1ull << 31;   // ... but never more bases than this per batch (pinned results: 2 x 2 bytes per base)
+    uint64_t chunk_bytes = 256ull << 20;     // device-side ingest: file bytes per chunk (grows by itself when reads are long)
+    bool host_parse = false;                 // --host-parse: never use the device-side ingest
     bool write_output_allowed() const { return !no_output && !filter; }          // movi_options.hpp:70
     bool write_stdout_enabled() const { return to_stdout && !classify; }         // movi_options.hpp:71
 };
@@ -42,6 +47,7 @@ struct Options {
     fprintf(stderr, "usage: movi-b200 query -i <index dir> -r <reads.fa|fq|-> [--pml [--rpml]|--zml|--count] [--classify|--filter [-v]]\n"
                     "                       [--stdout] [-o prefix] [--no-output] [--reverse] [--ignore-illegal-chars 1|2]\n"
                     "                       [--bin-width N] [--gpus N] [--device D] [--chunk-bases N] [--chunk-reads N] [--max-chunk-bases N]\n"
+                    "                       [--chunk-bytes N] [--host-parse]\n"
                     "                       [-t N] [-s N] [-n]\n"
                     "       movi-b200 view --bpf <file.bpf>\n");
     exit(1);
@@ -84,6 +90,8 @@ Options parse(int argc, char** argv) {
         else if (a == "--multi-ftab") { }
         else if (take_value(argc, argv, i, nullptr, "--chunk-bases", v)) o.chunk_bases = std::max<uint64_t>(1, strtoull(v.c_str(), nullptr, 10));
         else if (take_value(argc, argv, i, nullptr, "--chunk-reads", v)) o.chunk_reads = strtoull(v.c_str(), nullptr, 10);
+        else if (take_value(argc, argv, i, nullptr, "--chunk-bytes", v)) o.chunk_bytes = std::max<uint64_t>(4096, strtoull(v.c_str(), nullptr, 10));
+        else if (a == "--host-parse") o.host_parse = true;
         else if (take_value(argc, argv, i, nullptr, "--max-chunk-bases", v)) o.max_chunk_bases = std::max<uint64_t>(1, strtoull(v.c_str(), nullptr, 10));
         else if (a == "--pml") o.query = "pml";
         else if (a == "--rpml") o.rpml = true;                                  // movi_parser.cpp:149,357
@@ -152,6 +160,94 @@ struct Results {
     PinnedBuf<uint8_t> image; uint64_t image_bytes = 0;     // the batch's .bpf records, assembled on the GPUs
 };
 
+// ---- device-side ingest path: file bytes -> GPU (parse, walk, .bpf records) -> file.  The host only finds record boundaries
+// near the chunk ends, copies nothing and formats nothing: chunk k goes to GPU k mod G, the images are appended in chunk order by
+// a writer thread (several positional writes at once).  Returns 0 when the whole input went through, 1 when the input holds
+// something the reference rejects or stops at (nothing has been written then: the caller runs the host parser, which reproduces
+// the reference's behaviour), -1 on errors (message in `err`).
+struct IngestStats { uint64_t reads = 0, bases = 0, chunks = 0; };
+
+int run_device_ingest(const Options& o, const std::vector<movi_gpu_ctx*>& ctx, const char* data, uint64_t size, int fastq, bool zml,
+                      uint32_t qflags, int fd_bpf, IngestStats* stats, std::string* err) {
+    const int G = (int)ctx.size();
+    struct Slot { PinnedBuf<uint8_t> image; uint64_t bytes = 0, seq = ~0ull; bool full = false; };
+    std::vector<Slot> slots((size_t)G * 2);
+    std::mutex mu;
+    std::condition_variable cv;
+    uint64_t next_begin = 0, next_seq = 0, write_seq = 0, chunk_bytes = o.chunk_bytes;
+    std::atomic<int> status{0};                    // 0 running / ok, 1 fall back, -1 error
+    const bool want_image = fd_bpf >= 0;
+
+    auto worker = [&](int g) {
+        for (int turn = 0;; turn++) {
+            Slot& S = slots[(size_t)g * 2 + (turn & 1)];
+            uint64_t begin, end, seq;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return !S.full || status != 0; });          // the writer has emptied this slot
+                if (status != 0 || next_begin >= size) return;
+                begin = next_begin;
+                end = begin + chunk_bytes >= size ? size : movi_host_record_boundary(data, size, begin + chunk_bytes, fastq);
+                next_begin = end; seq = next_seq++;
+            }
+            MoviGpuChunkResult res{};
+            for (;;) {
+                const uint64_t cap = want_image ? std::max<uint64_t>(S.image.cap, (end - begin) * 5 / 2 + (16u << 20)) : 0;
+                if (want_image && !S.image.need(cap)) { *err = "cannot allocate pinned host memory for a chunk's records (try a smaller --chunk-bytes)"; status = -1; cv.notify_all(); return; }
+                const int rc = movi_gpu_query_file_chunk(ctx[g], zml ? 1 : 0, data + begin, end - begin, fastq, 1, qflags,
+                                                         want_image ? S.image.p : nullptr, want_image ? S.image.cap : 0, &res);
+                if (rc == MOVI_GPU_ERR_NOMEM && want_image && res.image_bytes > S.image.cap) {      // many tiny records: grow and retry
+                    if (!S.image.need(res.image_bytes + (1u << 20))) { *err = "cannot allocate pinned host memory"; status = -1; cv.notify_all(); return; }
+                    continue;
+                }
+                if (rc) { std::lock_guard<std::mutex> lk(mu); *err = movi_gpu_last_error(ctx[g]); status = -1; cv.notify_all(); return; }
+                break;
+            }
+            std::lock_guard<std::mutex> lk(mu);
+            if (res.parse_flags || res.consumed_bytes != end - begin) { if (status == 0) status = 1; cv.notify_all(); return; }
+            S.bytes = res.image_bytes; S.seq = seq; S.full = true;
+            stats->reads += res.n_reads; stats->bases += res.n_bases; stats->chunks += 1;
+            // a chunk should hold a read per lane of its GPU: long reads get bigger chunks (the table rows are random gathers,
+            // only the number of walks in flight hides their latency)
+            if (res.n_reads < 230000 && chunk_bytes < (3ull << 30)) chunk_bytes = std::min<uint64_t>(chunk_bytes * 2, 3ull << 30);
+            cv.notify_all();
+        }
+    };
+    auto writer = [&]() {
+        for (;;) {
+            Slot* S = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] {
+                    S = nullptr;
+                    if (status != 0) return true;
+                    for (auto& s : slots) if (s.full && s.seq == write_seq) { S = &s; return true; }
+                    return next_begin >= size && write_seq == next_seq;        // every chunk handed out has been written
+                });
+                if (status != 0 || !S) return;
+            }
+            if (want_image && S->bytes && movi_host_bpf_append_image(fd_bpf, S->image.p, S->bytes)) {
+                std::lock_guard<std::mutex> lk(mu);
+                *err = movi_host_last_error(); status = -1; cv.notify_all();
+                return;
+            }
+            std::lock_guard<std::mutex> lk(mu);
+            S->full = false; write_seq += 1;
+            cv.notify_all();
+        }
+    };
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; g++) th.emplace_back(worker, g);
+    std::thread wt(writer);
+    for (auto& t : th) t.join();
+    {   // workers are done: let the writer drain (or stop on failure)
+        std::lock_guard<std::mutex> lk(mu);
+        cv.notify_all();
+    }
+    wt.join();
+    return status;        // 1: the caller starts over with the host parser (and a fresh output file)
+}
+
 void die(const std::string& m) { fprintf(stderr, "\033[31m\n\n[ERROR] %s\n\033[0m", m.c_str()); exit(1); }
 
 }  // namespace
@@ -194,7 +290,12 @@ int main(int argc, char** argv) {
         if (f.rc) f.err = movi_host_last_error();
         return f;
     };
-    std::future<Fetched> ahead = std::async(std::launch::async, fetch);
+    // Device-side ingest: when all that is wanted of a PML / ZML query is its .bpf file (or nothing: --no-output), the file
+    // bytes go to the GPUs as they are and come back as .bpf records (run_device_ingest).
+    const bool ingest_on_device = !o.host_parse && (o.query == "pml" || o.query == "zml") && !o.classify && !o.reverse && o.ignore_illegal == 0 &&
+                                  !o.write_stdout_enabled() && !(o.to_stdout && o.write_output_allowed());
+    std::future<Fetched> ahead;
+    if (!ingest_on_device) ahead = std::async(std::launch::async, fetch);
 
     // one context per GPU, index replicated (uploaded while the first batch is being parsed)
     std::vector<movi_gpu_ctx*> ctx(gpus, nullptr);
@@ -237,6 +338,31 @@ int main(int argc, char** argv) {
             fd_bpf = movi_host_bpf_begin((prefix + ".bpf").c_str());
             if (fd_bpf < 0) die(movi_host_last_error());
         }
+    }
+
+    if (ingest_on_device) {
+        const char* data = nullptr; uint64_t size = 0; int fastq = 0;
+        movi_host_reader_raw(reader, &data, &size, &fastq);
+        IngestStats st; std::string err;
+        const int rc = run_device_ingest(o, ctx, data, size, fastq, o.query == "zml", qflags, fd_bpf, &st, &err);
+        if (rc < 0) die(err);
+        if (rc == 0) {
+            auto t_q1 = std::chrono::steady_clock::now();
+            if (o.verbose)
+                fprintf(stderr, "[INFO] index loaded + uploaded in %.3f s; %llu chunk(s) ingested, queried on %d GPU(s) and written in %.3f s: %llu reads / %llu bases (device-side ingest)\n",
+                        std::chrono::duration<double>(t_q0 - t_load0).count(), (unsigned long long)st.chunks, gpus,
+                        std::chrono::duration<double>(t_q1 - t_q0).count(), (unsigned long long)st.reads, (unsigned long long)st.bases);
+            if (fd_bpf >= 0 && movi_host_bpf_end(fd_bpf)) die(movi_host_last_error());
+            fflush(stdout); fflush(stderr);
+            _exit(0);
+        }
+        // the input holds something the reference rejects or stops at: start over with the host parser, which reproduces that
+        if (fd_bpf >= 0) {
+            movi_host_bpf_end(fd_bpf);
+            fd_bpf = movi_host_bpf_begin((prefix + ".bpf").c_str());
+            if (fd_bpf < 0) die(movi_host_last_error());
+        }
+        ahead = std::async(std::launch::async, fetch);
     }
 
     // Three stages run side by side: the parser thread reads batch k + 1, the GPUs walk batch k, the writer thread appends

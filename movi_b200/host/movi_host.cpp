@@ -286,6 +286,37 @@ int movi_host_reader_open(const char* path, int reverse, movi_host_reader** out)
 
 void movi_host_reader_close(movi_host_reader* r) { delete r; }
 
+int movi_host_reader_raw(const movi_host_reader* r, const char** data, uint64_t* size, int* fastq) {
+    if (!r || !data || !size) return fail("null argument");
+    *data = r->data; *size = r->size;
+    if (fastq) *fastq = r->fastq ? 1 : 0;
+    return 0;
+}
+
+uint64_t movi_host_record_boundary(const char* data, uint64_t size, uint64_t from, int fastq) {
+    if (!data || from >= size) return size;
+    const char* end = data + size;
+    const char* p = data + from;
+    if (from > 0 && p[-1] != '\n') {                      // move to the next line start
+        p = static_cast<const char*>(memchr(p, '\n', (size_t)(end - p)));
+        if (!p) return size;
+        p++;
+    }
+    while (p < end) {
+        if (!fastq) { if (*p == '>') return (uint64_t)(p - data); }
+        else if (*p == '@') {
+            const char* l1 = static_cast<const char*>(memchr(p, '\n', (size_t)(end - p)));
+            const char* l2 = l1 ? static_cast<const char*>(memchr(l1 + 1, '\n', (size_t)(end - l1 - 1))) : nullptr;
+            if (l2 && l2 + 1 < end && l2[1] == '+') return (uint64_t)(p - data);
+            if (!l2 || l2 + 1 >= end) return size;        // not enough lines left for another record
+        }
+        p = static_cast<const char*>(memchr(p, '\n', (size_t)(end - p)));
+        if (!p) return size;
+        p++;
+    }
+    return size;
+}
+
 // Whole records until the batch holds max_bases bases (at least one record); *out = NULL once the input is exhausted.
 int movi_host_reader_next(movi_host_reader* r, uint64_t max_bases, movi_host_reads** out) {
     return movi_host_reader_next_reads(r, max_bases, 0, 0, out);

@@ -165,3 +165,45 @@ def test_ftab_flags_are_accepted(cli, index_dirs):
     for q in ("zml", "count"):
         out = run(cli, "query", "-i", d, "-r", reads_path("edge.fasta"), "--" + q, "--ftab-k", "6", "--multi-ftab", "--stdout")
         assert out == expected_text("edge.fasta", q)
+
+
+@pytest.mark.parametrize("typ", ["regular-thresholds", "blocked-thresholds"])
+def test_device_side_ingest_bpf_files(cli, index_dirs, tmp_path, typ):
+    """`movi-b200 query --pml` whose only output is the .bpf file: the read file's bytes go to the GPU as they are (parse + walk +
+    record assembly there).  Whatever the chunking, and with the host parser instead (--host-parse), the file is the same, and
+    its lengths are the reference's."""
+    d = index_dirs[(typ, False)]
+    for read_set in READ_SETS:
+        for q in ("pml", "zml"):
+            files = {}
+            for name, extra in (("device", []), ("tiny chunks", ["--chunk-bytes", "4096"]), ("host", ["--host-parse"])):
+                reads = tmp_path / ("%s.%s" % (name.replace(" ", "_"), read_set))
+                shutil.copy(reads_path(read_set), reads)
+                run(cli, "query", "-i", d, "-r", str(reads), "--" + q, *extra)
+                bpf = "%s.%s.%s.bpf" % (reads, typ, q)
+                files[name] = open(bpf, "rb").read()
+                if name == "device":
+                    assert run(cli, "view", "--bpf", bpf) == expected_text(read_set, q)
+            assert files["device"][:10] == files["host"][:10] and files["device"][12:] == files["host"][12:]
+            assert files["device"] == files["tiny chunks"]
+    # --no-output goes through the same path and writes nothing
+    reads = tmp_path / "quiet.fasta"
+    shutil.copy(reads_path("synth300.fasta"), reads)
+    run(cli, "query", "-i", d, "-r", str(reads), "--pml", "--no-output")
+    assert not os.path.exists("%s.%s.pml.bpf" % (reads, typ))
+
+
+def test_device_side_ingest_hands_odd_inputs_to_the_host_parser(cli, index_dirs, tmp_path):
+    """An empty line where a FASTQ header is due ends the input in the reference; the device-side ingest flags it and the host
+    parser takes over from the start: same file as with --host-parse."""
+    d = index_dirs[("regular-thresholds", False)]
+    text = open(reads_path("sample.fastq"), "rb").read()
+    lines = text.split(b"\n")
+    odd = b"\n".join(lines[:8]) + b"\n\n" + b"\n".join(lines[8:])
+    out = {}
+    for name, extra in (("device", []), ("host", ["--host-parse"])):
+        reads = tmp_path / (name + ".fastq")
+        reads.write_bytes(odd)
+        run(cli, "query", "-i", d, "-r", str(reads), "--pml", *extra)
+        out[name] = open("%s.regular-thresholds.pml.bpf" % reads, "rb").read()
+    assert out["device"][12:] == out["host"][12:] and len(out["host"]) > 12

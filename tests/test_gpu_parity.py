@@ -501,3 +501,82 @@ def test_device_side_bpf_records(structures, read_sets, ref_seq, tmp_path, typ):
     f = str(tmp_path / "dev.bpf")
     assert H.movi_host_write_bpf(f.encode(), rd._h, ml.ctypes.data) == 0
     assert d_img[:size].cpu().numpy().tobytes() == open(f, "rb").read()[12:]
+
+
+def _variants(text):
+    """The same records in other dresses: CRLF line ends, no final newline, sequences folded to 37 columns (FASTA only)."""
+    out = {"as is": text, "crlf": text.replace(b"\n", b"\r\n"), "no final newline": text.rstrip(b"\n")}
+    if text[:1] == b">":
+        folded = []
+        for rec in text.split(b">")[1:]:
+            head, _, seq = rec.partition(b"\n")
+            seq = seq.replace(b"\n", b"")
+            folded.append(b">" + head + b"\n" + b"".join(seq[i:i + 37] + b" \t\n" for i in range(0, len(seq), 37)))
+        out["folded"] = b"".join(folded)
+    return out
+
+
+@pytest.mark.parametrize("read_set", READ_SETS)
+def test_device_side_ingest_matches_the_host_parser(structures, read_set, tmp_path):
+    """movi_gpu_parse_chunk (FASTA / FASTQ parsed on the device) against movi_host_reads_load (the restatement of the reference's
+    BatchLoader): whole files, and files cut into two chunks at many byte positions -- the first chunk leaves its last record to
+    the second one."""
+    from movi_b200 import Reads
+    ms = structures[("regular-thresholds", False)]
+    text = open(reads_path(read_set), "rb").read()
+    fastq = text[:1] == b"@"
+    for name, t in _variants(text).items():
+        f = tmp_path / "v.fa"
+        f.write_bytes(t)
+        want = Reads(str(f))
+        wids, wido = want.id_blob
+        bases, offsets, ids, ido, consumed, flags = ms.parse_chunk(t, fastq, final=True)
+        assert flags == 0, name
+        assert np.array_equal(offsets, want.offsets) and np.array_equal(bases, want.bases), name
+        assert np.array_equal(ido, wido) and np.array_equal(ids, wids), name
+        rng = np.random.default_rng(len(t))
+        cuts = sorted(set(int(c) for c in rng.integers(0, len(t), 24)) | {0, 1, len(t) - 1, len(t)})
+        for c in cuts:
+            b1, o1, i1, io1, used, fl = ms.parse_chunk(t[:c], fastq, final=False)
+            assert fl == 0 and used <= c
+            b2, o2, i2, io2, used2, fl2 = ms.parse_chunk(t[used:], fastq, final=True)
+            assert fl2 == 0, (name, c)
+            n1 = len(o1) - 1 if len(o1) else 0
+            got_b = np.concatenate([b1, b2])
+            got_o = np.concatenate([o1[:n1], o2 + (o1[n1] if len(o1) else 0)]) if len(o2) else o1
+            got_i = np.concatenate([i1, i2])
+            got_io = np.concatenate([io1[:n1], io2 + (io1[n1] if len(io1) else 0)]) if len(io2) else io1
+            assert np.array_equal(got_o, want.offsets) and np.array_equal(got_b, want.bases), (name, c)
+            assert np.array_equal(got_io, wido) and np.array_equal(got_i, wids), (name, c)
+
+
+def test_device_side_ingest_flags_what_the_reference_rejects(structures):
+    ms = structures[("regular-thresholds", False)]
+    assert ms.parse_chunk(b"ACGT\n>a\nAC\n", False)[5] & 1                 # does not start with '>'
+    assert ms.parse_chunk(b"@a\nAC\n+\nII\nxx\nAC\n+\nII\n", True)[5] & 1    # FASTQ record not starting with '@'
+    assert ms.parse_chunk(b">a\nAC\n>\nGG\n", False)[5] & 2                # header without an id
+    assert ms.parse_chunk(b"@a\nAC\n+\nII\n\n", True)[5] & 4               # empty line where a header is due
+    assert ms.parse_chunk(b"", False) [5] == 0
+
+
+def test_file_bytes_to_bpf_records_on_the_device(structures, read_sets, tmp_path):
+    """movi_gpu_query_file_chunk: raw file bytes in, .bpf records out, nothing but two copies on the host path."""
+    from movi_b200 import _native as N
+    H = N.host_lib()
+    for typ in ("regular-thresholds", "blocked-thresholds"):
+        ms = structures[(typ, False)]
+        for read_set in READ_SETS:
+            rd = read_sets[read_set]
+            text = open(reads_path(read_set), "rb").read()
+            for zml in (False, True):
+                ml = ms.query_zml(rd.bases, rd.offsets) if zml else ms.query_pml(rd.bases, rd.offsets)
+                f = str(tmp_path / "w.bpf")
+                assert H.movi_host_write_bpf(f.encode(), rd._h, ml.ctypes.data) == 0
+                want = open(f, "rb").read()[12:]
+                image, res = ms.query_file_chunk(text, text[:1] == b"@", final=True, zml=zml)
+                assert res.parse_flags == 0 and res.n_reads == rd.count and res.consumed_bytes == len(text)
+                assert image.tobytes() == want, (typ, read_set, zml)
+                # two chunks
+                image1, r1 = ms.query_file_chunk(text[: len(text) // 2], text[:1] == b"@", final=False, zml=zml)
+                image2, r2 = ms.query_file_chunk(text[r1.consumed_bytes:], text[:1] == b"@", final=True, zml=zml)
+                assert image1.tobytes() + image2.tobytes() == want

@@ -46,9 +46,12 @@ def sweep(ms, tag, d_b, d_o, n_reads, n_bases, kinds, settings, extra=None):
     st = torch.cuda.current_stream().cuda_stream
     first = {}
     for kind in kinds:
-        for sector, bps in settings:
+        for setting in settings:
+            sector, bps = setting[0], setting[1]
+            out_stage = setting[2] if len(setting) > 2 else 32
             ms.set_option("pml_sector", sector)
             ms.set_option("blocks_per_sm", bps)
+            ms.set_option("out_stage", out_stage)
             if kind == "pml":
                 fn = lambda: ms.query_pml_device(d_b.data_ptr(), d_o.data_ptr(), n_reads, d_out.data_ptr(), st)
             elif kind == "zml":
@@ -63,7 +66,7 @@ def sweep(ms, tag, d_b, d_o, n_reads, n_bases, kinds, settings, extra=None):
                 same = bool(torch.equal(first[kind], res))
             else:
                 first[kind] = res
-            rec = {"kind": kind, "tag": tag, "pml_sector": sector, "blocks_per_sm": bps, "n_reads": n_reads, "n_bases": n_bases,
+            rec = {"kind": kind, "tag": tag, "pml_sector": sector, "blocks_per_sm": bps, "out_stage": out_stage, "n_reads": n_reads, "n_bases": n_bases,
                    "ms": round(t, 3), "Gbases_per_s": round(n_bases / t / 1e6, 2), "same_as_first": same}
             if extra:
                 rec.update(extra)
@@ -103,10 +106,17 @@ def main():
         ms = SyntheticStructure(r, seed=44, profile=profile)
         n_bases = n_reads * L
         d_b = torch.zeros(n_bases + 64, dtype=torch.uint8, device=dev)
-        ms.make_reads(d_b.data_ptr(), n_reads, L, 5, 50)
+        resync = os.environ.get("MOVI_SWEEP_RESYNC", "1") == "1"
+        if resync:
+            ms.make_reads_resync(d_b.data_ptr(), n_reads, L, 51, 10, 24, read_seed=3)      # the c4 read mix of bench.py
+        else:
+            ms.make_reads(d_b.data_ptr(), n_reads, L, 5, 50)
         d_o = torch.arange(n_reads + 1, dtype=torch.int64, device=dev) * L
-        sweep(ms, "synth %.0fGB p%d %dx%d" % (gb, profile, n_reads, L), d_b, d_o, n_reads, n_bases, sys.argv[6:] or ["pml"],
-              [(0, 0), (1, 0), (1, 6), (1, 4)], {"n_over_r": round(ms.n / r, 1)})
+        settings = [(1, 0, 32), (1, 0, 16), (1, 4, 32), (1, 4, 16), (1, 3, 32), (0, 0, 16)]
+        if os.environ.get("MOVI_SWEEP_ONE"):
+            settings = [(1, 0, 32)]
+        sweep(ms, "synth %.0fGB p%d %dx%d %s" % (gb, profile, n_reads, L, "resync" if resync else "lfwalk"), d_b, d_o, n_reads, n_bases,
+              sys.argv[6:] or ["pml"], settings, {"n_over_r": round(ms.n / r, 1)})
         ms.close()
 
 

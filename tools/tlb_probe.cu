@@ -49,6 +49,44 @@ __global__ void gather(const u64* __restrict__ t, u64 n_words, u64 slice_words, 
     if (acc == 0x1234567ull) *sink = acc;
 }
 
+// Load flavours of the 32-byte sector fetch (what does each one make the L2 bring in from DRAM?  run under ncu and read
+// dram__bytes_read per launch): 0 = 8-byte __ldg; 1 = 256-bit load, no hints; 2 = 256-bit + L1::evict_last + L2 evict_last policy
+// (the query kernels' fetch); 3 = 2 + L2::64B prefetch size; 4 = two 128-bit loads + the same hints; 5 = 256-bit L1::no_allocate;
+// 6 = 256-bit with an L2 evict_first policy; 7 = 8-byte load with the hints of 2; 8 = 256-bit ld.global.cg (no .nc);
+// 9 = 256-bit + L2 evict_normal policy; 10 = 8-byte + L2::64B; 11 = 256-bit L2::128B
+template <int F>
+__global__ void flavour(const u64* __restrict__ t, u64 n_words, unsigned steps, u64* sink) {
+    u64 x = mix64(blockIdx.x * (u64)blockDim.x + threadIdx.x + 0x9E3779B97F4A7C15ULL);
+    u64 pol_last, pol_first, pol_normal;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_normal));
+    u64 acc = 0;
+    for (unsigned s = 0; s < steps; s++) {
+        const u64 i = __umul64hi(x, n_words) & ~3ull;          // aligned 32-byte sector
+        const u64* p = t + i;
+        u64 a = 0, b = 0, c = 0, d = 0;
+        if (F == 0) a = __ldg(p);
+        if (F == 1) asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+        if (F == 2) asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p), "l"(pol_last));
+        if (F == 3) asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4], %5;" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p), "l"(pol_last));
+        if (F == 4) {
+            asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.v2.u64 {%0,%1}, [%2], %3;" : "=l"(a), "=l"(b) : "l"(p), "l"(pol_last));
+            asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.v2.u64 {%0,%1}, [%2], %3;" : "=l"(c), "=l"(d) : "l"(p + 2), "l"(pol_last));
+        }
+        if (F == 5) asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+        if (F == 6) asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p), "l"(pol_first));
+        if (F == 7) asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(a) : "l"(p), "l"(pol_last));
+        if (F == 8) asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+        if (F == 9) asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p), "l"(pol_normal));
+        if (F == 10) asm volatile("ld.global.nc.L2::64B.u64 %0, [%1];" : "=l"(a) : "l"(p));
+        if (F == 11) asm volatile("ld.global.nc.L2::128B.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+        acc += a ^ b ^ c ^ d;
+        x = x * 6364136223846793005ULL + 1442695040888963407ULL;
+    }
+    if (acc == 0x1234567ull) *sink = acc;
+}
+
 __global__ void atomics(u64* counters, unsigned n, unsigned steps, u64* sink) {
     u64 x = mix64(blockIdx.x * (u64)blockDim.x + threadIdx.x + 77);
     u64 acc = 0;
@@ -112,6 +150,14 @@ int main(int argc, char** argv) {
             mode = 3; slice_words = (u64)(atof(m.c_str() + 7) * (1 << 20)) / 8;
             if (slice_words * 148 > n_words) { printf("{\"mode\": \"%s\", \"skipped\": \"table too small\"}\n", m.c_str()); continue; }
         }
+        else if (m.rfind("gran:", 0) == 0) {           // cudaLimitMaxL2FetchGranularity for the launches that follow
+            const size_t g = (size_t)atoi(m.c_str() + 5); size_t now = 0;
+            cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g);
+            cudaDeviceGetLimit(&now, cudaLimitMaxL2FetchGranularity);
+            printf("{\"mode\": \"%s\", \"set\": \"%s\", \"now\": %zu}\n", m.c_str(), cudaGetErrorString(e), now);
+            continue;
+        }
+        else if (m.rfind("flavour:", 0) == 0) { mode = 100 + atoi(m.c_str() + 8); }
         else if (m.rfind("atomic:", 0) == 0) { mode = 4; nq = (unsigned)atoi(m.c_str() + 7); }
         else if (m.rfind("queue:", 0) == 0) { mode = 5; nq = (unsigned)atoi(m.c_str() + 6); }
         else if (m.rfind("queueagg:", 0) == 0) { mode = 6; nq = (unsigned)atoi(m.c_str() + 9); }
@@ -126,9 +172,21 @@ int main(int argc, char** argv) {
                 case 4: atomics<<<blocks, threads>>>(t, nq, st, sink); break;
                 case 5: queue_push<false><<<blocks, threads>>>(t, reinterpret_cast<uint4*>(t + 16 * 4096), nq, cap, st, sink); break;
                 case 6: queue_push<true><<<blocks, threads>>>(t, reinterpret_cast<uint4*>(t + 16 * 4096), nq, cap, st, sink); break;
+                case 100: flavour<0><<<blocks, threads>>>(t, n_words, st, sink); break;
+                case 101: flavour<1><<<blocks, threads>>>(t, n_words, st, sink); break;
+                case 102: flavour<2><<<blocks, threads>>>(t, n_words, st, sink); break;
+                case 103: flavour<3><<<blocks, threads>>>(t, n_words, st, sink); break;
+                case 104: flavour<4><<<blocks, threads>>>(t, n_words, st, sink); break;
+                case 105: flavour<5><<<blocks, threads>>>(t, n_words, st, sink); break;
+                case 106: flavour<6><<<blocks, threads>>>(t, n_words, st, sink); break;
+                case 107: flavour<7><<<blocks, threads>>>(t, n_words, st, sink); break;
+                case 108: flavour<8><<<blocks, threads>>>(t, n_words, st, sink); break;
+                case 109: flavour<9><<<blocks, threads>>>(t, n_words, st, sink); break;
+                case 110: flavour<10><<<blocks, threads>>>(t, n_words, st, sink); break;
+                case 111: flavour<11><<<blocks, threads>>>(t, n_words, st, sink); break;
             }
         };
-        if (mode >= 4) CK(cudaMemset(t, 0, 16 * 4096 * 8));
+        if (mode >= 4 && mode < 100) CK(cudaMemset(t, 0, 16 * 4096 * 8));
         run(steps / 8);
         CK(cudaEventRecord(e0));
         run(steps);
@@ -140,7 +198,7 @@ int main(int argc, char** argv) {
         printf("{\"kind\": \"tlb_probe\", \"table_gb\": %.2f, \"mode\": \"%s\", \"ms\": %.3f, \"steps_per_s\": %.4g, \"loads_per_s\": %.4g}\n",
                gb, m.c_str(), ms, ops / (ms * 1e-3), ops * per_step / (ms * 1e-3));
         fflush(stdout);
-        if (mode >= 4) { fill<<<148 * 8, 256>>>(t, n_words); CK(cudaDeviceSynchronize()); }
+        if (mode >= 4 && mode < 100) { fill<<<148 * 8, 256>>>(t, n_words); CK(cudaDeviceSynchronize()); }
     }
     return 0;
 }
