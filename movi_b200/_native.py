@@ -54,6 +54,8 @@ GPU_SYMBOLS = {
     "movi_gpu_bpf_assemble_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "movi_gpu_query_file_chunk": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_uint64,
                                             C.POINTER(MoviGpuChunkResult)]),
+    "movi_gpu_file_chunk_parse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(MoviGpuChunkResult)]),
+    "movi_gpu_file_chunk_query": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_uint64, C.c_int, C.c_uint64]),
     "movi_gpu_parse_chunk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
                                        C.c_void_p, C.c_uint64, C.POINTER(MoviGpuChunkResult)]),
     "movi_gpu_query_zml": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]),

@@ -75,6 +75,28 @@ __global__ void convert_sampled_kernel(const uint32_t* __restrict__ raw_words, u
     }
 }
 
+// ---- MODE 7 -> T4 (dev_index.cuh): the 3-byte row + the walk-back distance of its destination id from the checkpoint entry
+__global__ void convert_sampled_t4_kernel(const uint32_t* __restrict__ raw_words, uint32_t* __restrict__ out, unsigned long long r,
+                                          unsigned long long end_idx, const uint8_t* __restrict__ tally, unsigned long long tally_len, uint32_t cp,
+                                          unsigned int* __restrict__ status) {
+    const Rows3 R{raw_words, end_idx, 0u};
+    unsigned long long idx = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (; idx < r; idx += stride) {
+        const uint32_t x = R.raw(idx);
+        const uint32_t ci = Rows3::c_of(x);
+        bool bad = false;
+        uint32_t d = 0;
+        if (idx != end_idx) {
+            const unsigned long long id = sampled_get_id(R, tally, tally_len, cp, r, end_idx, idx, ci, &bad);
+            const unsigned long long from = tally_get(tally, tally_len, ci, t4_tally_slot(idx, r, tally_len, cp));
+            d = (from >= id && from - id < T4_FAR) ? (uint32_t)(from - id) : T4_FAR;
+        }
+        if (bad) atomicOr(status, 2u);
+        out[idx] = Rows4::pack(Rows3::n_of(x), Rows3::off_of(x), ci, Rows3::thr_of(x), d);
+    }
+}
+
 // ---- sampled prefix sums of run lengths (for MoveInterval::count in O(1): include/move_intervals.hpp:47-58)
 // pass 1: group sums (one u32 per 2^PREFIX_SHIFT rows) and per-block totals
 constexpr int SCAN_BLOCK = 1024;

@@ -22,7 +22,7 @@ namespace movi {
 
 constexpr int LAYOUT_R8 = 0;      // 8-byte rows, full destination id in the row
 constexpr int LAYOUT_B6 = 1;      // the reference's blocked-thresholds rows as they are on disk: 6 bytes per row + id_blocks
-constexpr int LAYOUT_T3 = 2;      // the reference's sampled-thresholds rows as they are on disk: 3 bytes per row + id checkpoints
+constexpr int LAYOUT_T4 = 2;      // sampled-thresholds: 4 bytes per row (the 3-byte row + its walk-back distance) + the id checkpoints
 
 struct DevIndex {
     const uint2* rows;            // LAYOUT_R8: R8 rows
@@ -32,8 +32,8 @@ struct DevIndex {
     uint32_t block_shift;         // block_size == 1 << block_shift
     uint32_t layout;
     uint32_t nt;                  // 1: non-threshold index type (12-bit lengths, no threshold mask; PML repositions with the --rpml rule)
-    const uint32_t* rows3;        // LAYOUT_T3: packed 3-byte rows viewed as 32-bit words (table padded by 8 bytes)
-    const uint8_t* tally;         // LAYOUT_T3: sigma x tally_len MoveTally entries (5 bytes each)
+    const uint32_t* rows4;        // LAYOUT_T4: one 32-bit word per row (Rows4 below)
+    const uint8_t* tally;         // LAYOUT_T4: sigma x tally_len MoveTally entries (5 bytes each), 4-byte aligned, padded by 8 bytes
     unsigned long long tally_len;
     uint32_t tally_cp;            // id checkpoint interval (tally_checkpoints)
     unsigned long long r;
@@ -230,6 +230,63 @@ __device__ __forceinline__ unsigned long long sampled_get_id(const R& rows, cons
         if (rows_until >= nn) { rows_until -= nn; id -= 1; } else rows_until = 0;
     }
     return id;
+}
+
+
+// ---- LAYOUT_T4: the memory-constrained device form of a sampled-thresholds index.  One aligned 32-bit word per row:
+//     n[0:9) | offset[9:18) | c[18:21) | thresholds #0..#2 [21:24) | d[24:32)
+// The first 24 bits are the reference's 3-byte row (include/move_row_configs.hpp:120-136) regrouped; d is computed once per row
+// at upload: MoveStructure::get_id for TALLY_MODES (src/move_structure.cpp:103-219) ends in "the id sampled at the next
+// checkpoint, minus the rows walked back from it", so
+//     get_id(idx) = tally_ids[c][k(idx)] - d(idx),   k = idx / cp  at a checkpoint row, the last entry for the last row, idx / cp + 1 otherwise
+// and the per-step scan of up to `cp` rows + walk-back (20 + ~5 dependent row reads) becomes one 5-byte table read.  d = 255 marks
+// the rare row whose distance does not fit: there the full procedure runs on the resident rows.  4 + 5 * sigma / cp bytes per row
+// (5 with four characters and checkpoints every 20 rows) against 8 for the expanded layout.
+struct Rows4 {
+    const uint32_t* w;
+    unsigned long long end_idx;
+    static __host__ __device__ __forceinline__ uint32_t pack(uint32_t n, uint32_t off, uint32_t c, uint32_t thr, uint32_t d) {
+        return (n & 0x1FFu) | ((off & 0x1FFu) << 9) | ((c & 7u) << 18) | ((thr & 7u) << 21) | (d << 24);
+    }
+    static __device__ __forceinline__ uint32_t n_of(uint32_t x) { return x & 0x1FFu; }
+    static __device__ __forceinline__ uint32_t off_of(uint32_t x) { return (x >> 9) & 0x1FFu; }
+    static __device__ __forceinline__ uint32_t c_of(uint32_t x) { return (x >> 18) & 7u; }
+    static __device__ __forceinline__ uint32_t thr_of(uint32_t x) { return (x >> 21) & 7u; }
+    static __device__ __forceinline__ uint32_t d_of(uint32_t x) { return x >> 24; }
+    __device__ __forceinline__ uint32_t n(unsigned long long i) const { return n_of(__ldg(w + i)); }
+    __device__ __forceinline__ uint32_t off(unsigned long long i) const { return off_of(__ldg(w + i)); }
+    __device__ __forceinline__ uint32_t ch(unsigned long long i) const { return i == end_idx ? 16u : c_of(__ldg(w + i)); }
+};
+constexpr uint32_t T4_FAR = 255u;
+
+// one MoveTally entry through two aligned 32-bit loads (the table is 4-byte aligned and padded)
+__device__ __forceinline__ unsigned long long tally_get_w(const uint8_t* tally, unsigned long long tally_len, uint32_t c, unsigned long long k) {
+    const unsigned long long a = (c * tally_len + k) * 5ull;
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(tally) + (a >> 2);
+    const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1);
+    const uint32_t lo = __funnelshift_r(w0, w1, (uint32_t)(a & 3u) * 8u);
+    const uint32_t hi = (w1 >> ((uint32_t)((a + 4u) & 3u) * 8u)) & 0xFFu;
+    return (unsigned long long)lo | ((unsigned long long)hi << 32);
+}
+// which checkpoint entry get_id starts from (src/move_structure.cpp:114-139)
+__device__ __forceinline__ unsigned long long t4_tally_slot(unsigned long long idx, unsigned long long r, unsigned long long tally_len, uint32_t cp) {
+    if (idx == r - 1) return tally_len - 1;
+    const unsigned long long q = idx / cp;
+    return idx - q * cp == 0 ? q : q + 1;
+}
+template <typename IdxT>
+__device__ __forceinline__ IdxT t4_get_id(const DevIndex& ix, IdxT idx, IdxT end_idx, uint32_t x, bool* bad) {
+    if (idx == end_idx) return 0;                                                                    // :106-108
+    const uint32_t c = Rows4::c_of(x), d = Rows4::d_of(x);
+    if (d == T4_FAR)
+        return (IdxT)sampled_get_id(Rows4{ix.rows4, (unsigned long long)end_idx}, ix.tally, ix.tally_len, ix.tally_cp, ix.r,
+                                    (unsigned long long)end_idx, (unsigned long long)idx, c, bad);
+    IdxT k;
+    if (sizeof(IdxT) == 4) {             // 32-bit division: tables below 2^32 rows
+        const uint32_t i32 = (uint32_t)idx, q = i32 / ix.tally_cp;
+        k = (i32 == (uint32_t)(ix.r - 1)) ? (IdxT)(ix.tally_len - 1) : (IdxT)(i32 - q * ix.tally_cp == 0 ? q : q + 1);
+    } else k = (IdxT)t4_tally_slot((unsigned long long)idx, ix.r, ix.tally_len, ix.tally_cp);
+    return (IdxT)(tally_get_w(ix.tally, ix.tally_len, c, (unsigned long long)k) - d);
 }
 
 }  // namespace movi

@@ -6,12 +6,14 @@
 #include "../../include/movi_gpu.h"
 
 #include <cuda.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "bs_kernel.cuh"
@@ -57,7 +59,7 @@ struct movi_gpu_ctx {
     uint2* d_rows = nullptr;
     uint32_t* d_rows6 = nullptr;      // LAYOUT_B6: packed blocked-thresholds rows
     uint32_t* d_id_blocks = nullptr;
-    uint32_t* d_rows3 = nullptr;      // LAYOUT_T3: packed sampled-thresholds rows
+    uint32_t* d_rows4 = nullptr;      // LAYOUT_T4: sampled-thresholds rows, 4 bytes each (row + walk-back distance)
     uint8_t* d_tally = nullptr;
     unsigned long long* d_sep_keys = nullptr; uint16_t* d_sep_vals = nullptr;
     unsigned long long* d_prefix = nullptr;
@@ -100,6 +102,10 @@ struct movi_gpu_ctx {
     unsigned long long* p_id_offsets = nullptr; size_t p_id_offsets_cap = 0;
     uint16_t* p_ml = nullptr; size_t p_ml_cap = 0;
     uint8_t* p_image = nullptr; size_t p_image_cap = 0;
+    ParseResult p_last{};                              // result of the last movi_gpu_file_chunk_parse (what _query works on)
+    // pinned staging ring for copies from / to pageable memory and files (a file mapping is pageable by nature)
+    uint8_t* pin[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t pin_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // gather probe scratch
     uint2* d_probe = nullptr; uint64_t probe_bytes = 0;
     int64_t probe_vmm_align_mb = 0;   // > 0: allocate the probe table through the VMM API at this alignment
@@ -184,7 +190,7 @@ void free_index(movi_gpu_ctx* ctx) {
     cudaFree(ctx->d_rows); ctx->d_rows = nullptr;
     cudaFree(ctx->d_rows6); ctx->d_rows6 = nullptr;
     cudaFree(ctx->d_id_blocks); ctx->d_id_blocks = nullptr;
-    cudaFree(ctx->d_rows3); ctx->d_rows3 = nullptr;
+    cudaFree(ctx->d_rows4); ctx->d_rows4 = nullptr;
     cudaFree(ctx->d_tally); ctx->d_tally = nullptr;
     cudaFree(ctx->d_sep_keys); ctx->d_sep_keys = nullptr;
     cudaFree(ctx->d_sep_vals); ctx->d_sep_vals = nullptr;
@@ -237,7 +243,7 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
     // last fetched 32-byte sector in registers ("pml_sector" -1 = by table size, 0 / 1 = off / on)
     // (measured, profiles/r01_big_tables.jsonl: 8 and 32 GB tables 1.2 -> 2.2-2.5e10 bases/s; the 124 MB c2 table -27 %;
     //  a batch of few long reads, which leaves most lanes empty and is latency bound, -10 %: those keep the plain fetch)
-    const bool b6 = ctx->ix.layout == LAYOUT_B6, t3 = ctx->ix.layout == LAYOUT_T3;
+    const bool b6 = ctx->ix.layout == LAYOUT_B6, t3 = ctx->ix.layout == LAYOUT_T4;
     int sm_cap = 0;                     // resident blocks per SM at most (0 = what the registers allow)
     const bool sector = !b6 && !t3 && !ctx->ix.nt && (ctx->pml_sector == 1 || (ctx->pml_sector < 0 &&
                         ctx->ix.r * sizeof(uint2) > (512ull << 20) && qa.n_reads >= (1u << 17)));
@@ -250,10 +256,10 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
 #define PML(IDX, SEPV) do { \
             if (ctx->ix.nt) LAUNCH((movi_pml_kernel<IDX, SEPV, 6, LAYOUT_R8, false, true, true>));   /* non-threshold table: 12-bit accessors, always the --rpml rule (move_structure_query.cpp:308-311) */ \
             else if (rpml) { \
-                if (t3) LAUNCH((movi_pml_kernel<IDX, SEPV, 5, LAYOUT_T3, false, true>)); \
+                if (t3) LAUNCH((movi_pml_kernel<IDX, SEPV, 5, LAYOUT_T4, false, true>)); \
                 else if (b6) LAUNCH((movi_pml_kernel<IDX, SEPV, 6, LAYOUT_B6, false, true>)); \
                 else LAUNCH((movi_pml_kernel<IDX, SEPV, 6, LAYOUT_R8, false, true>)); } \
-            else if (t3) LAUNCH((movi_pml_kernel<IDX, SEPV, 5, LAYOUT_T3>)); \
+            else if (t3) LAUNCH((movi_pml_kernel<IDX, SEPV, 5, LAYOUT_T4>)); \
             else if (b6) LAUNCH((movi_pml_kernel<IDX, SEPV, 6, LAYOUT_B6>)); \
             else if (sector && ctx->out_stage == 16) LAUNCH((movi_pml_kernel<IDX, SEPV, 4, LAYOUT_R8, true>)); \
             else if (sector) LAUNCH((movi_pml_kernel<IDX, SEPV, 4, LAYOUT_R8, true, false, false, 32>)); \
@@ -542,6 +548,7 @@ int movi_gpu_destroy(movi_gpu_ctx* ctx) {
     if (ctx->st_in) cudaStreamDestroy(ctx->st_in);
     if (ctx->st_out) cudaStreamDestroy(ctx->st_out);
     for (int k = 0; k < NKS; k++) if (ctx->st_k[k]) cudaStreamDestroy(ctx->st_k[k]);
+    for (int k = 0; k < 4; k++) { if (ctx->pin[k]) cudaFreeHost(ctx->pin[k]); if (ctx->pin_ev[k]) cudaEventDestroy(ctx->pin_ev[k]); }
     cudaFree(ctx->p_raw); cudaFree(ctx->p_tile); cudaFree(ctx->p_nlpos); cudaFree(ctx->p_lines); cudaFree(ctx->p_ltile); cudaFree(ctx->p_res);
     cudaFree(ctx->p_bases); cudaFree(ctx->p_offsets); cudaFree(ctx->p_ids); cudaFree(ctx->p_id_offsets); cudaFree(ctx->p_ml); cudaFree(ctx->p_image);
     cudaFree(ctx->d_status); cudaFree(ctx->d_counters);
@@ -665,13 +672,31 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
     uint32_t n_last_host = 0;
     const bool compact_t3 = compact && d->mode == MOVI_MODE_SAMPLED_THRESHOLDS;
     if (compact_t3) {
+        // T4 (dev_index.cuh): the 3-byte rows go up as they are, one pass adds every row's walk-back distance
         const size_t tally_bytes = (size_t)d->sigma * d->tally_len * 5;
-        CU(cudaMalloc(&ctx->d_rows3, r * 3 + 16));
-        CU(cudaMemsetAsync(reinterpret_cast<uint8_t*>(ctx->d_rows3) + r * 3, 0, 16, st));
-        CU(cudaMemcpyAsync(ctx->d_rows3, d->rows, r * 3, cudaMemcpyHostToDevice, st));
-        CU(cudaMalloc(&ctx->d_tally, tally_bytes + 8));
+        Scratch s_raw;
+        CU(cudaMalloc(&s_raw.p, r * 3 + 16));
+        uint8_t* d_raw = static_cast<uint8_t*>(s_raw.p);
+        CU(cudaMemsetAsync(d_raw + r * 3, 0, 16, st));
+        CU(cudaMemcpyAsync(d_raw, d->rows, r * 3, cudaMemcpyHostToDevice, st));
+        CU(cudaMalloc(&ctx->d_rows4, (r + 4) * 4));
+        CU(cudaMemsetAsync(ctx->d_rows4 + r, 0, 16, st));
+        CU(cudaMalloc(&ctx->d_tally, tally_bytes + 16));
+        CU(cudaMemsetAsync(ctx->d_tally + tally_bytes, 0, 16, st));
         CU(cudaMemcpyAsync(ctx->d_tally, d->tally_ids, tally_bytes, cudaMemcpyHostToDevice, st));
-        ctx->index_bytes = r * 3 + 16 + tally_bytes + 8;
+        CU(cudaMemsetAsync(ctx->d_status, 0, sizeof(unsigned int), st));
+        convert_sampled_t4_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_raw), ctx->d_rows4, r, d->end_bwt_idx, ctx->d_tally,
+                                                                  d->tally_len, d->tally_checkpoints, ctx->d_status);
+        ctx->launches += 1;
+        unsigned int status = 0;
+        CU(cudaMemcpyAsync(&status, ctx->d_status, sizeof(status), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        CU(cudaGetLastError());
+        if (status) {
+            CU(cudaMemset(ctx->d_status, 0, sizeof(unsigned int)));
+            return fail(ctx, MOVI_GPU_ERR_INDEX, "[get id - tally mode] The offset in the destination run should be always smaller than the length of that run.");
+        }
+        ctx->index_bytes = (r + 4) * 4 + tally_bytes + 16;
         const uint8_t* lastp = static_cast<const uint8_t*>(d->rows) + (r - 1) * 3;
         n_last_host = (uint32_t)lastp[0] | (((uint32_t)lastp[2] >> 1) & 1u) << 8;
     } else if (compact) {
@@ -744,9 +769,9 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
     ix.rows = ctx->d_rows;
     ix.rows6 = ctx->d_rows6;
     ix.id_blocks = ctx->d_id_blocks;
-    ix.layout = compact_t3 ? LAYOUT_T3 : compact ? LAYOUT_B6 : LAYOUT_R8;
+    ix.layout = compact_t3 ? LAYOUT_T4 : compact ? LAYOUT_B6 : LAYOUT_R8;
     ix.nt = nt ? 1u : 0u;
-    ix.rows3 = ctx->d_rows3; ix.tally = ctx->d_tally; ix.tally_len = d->tally_len; ix.tally_cp = d->tally_checkpoints;
+    ix.rows4 = ctx->d_rows4; ix.tally = ctx->d_tally; ix.tally_len = d->tally_len; ix.tally_cp = d->tally_checkpoints;
     if (compact && !compact_t3) {
         ix.id_blocks_size = (uint32_t)d->id_blocks_size;
         ix.block_shift = 0;
@@ -918,9 +943,80 @@ static unsigned long long* next_counter(movi_gpu_ctx* ctx) {
     return p;
 }
 
-// ---- device-side ingest: a chunk of a FASTA / FASTQ file (starting at a record boundary) parsed in HBM (parse_kernels.cuh)
+}  // extern "C" (the helpers below are C++)
+
 namespace {
-struct ParsedChunk { ParseResult r{}; };
+// ---- staged copies: pageable host memory (a memory-mapped file, a std::vector) and file descriptors on one side, HBM on the other.
+// cudaMemcpyAsync on pageable memory is staged by the driver through one thread at ~6 GB/s and blocks; here the pieces go through
+// a ring of four pinned buffers, filled / drained by a few host threads while the previous pieces are on the wire.
+constexpr size_t PIN_PIECE = 32u << 20;
+constexpr int PIN_THREADS = 4;
+
+int ensure_pin_ring(movi_gpu_ctx* ctx) {
+    for (int k = 0; k < 4; k++) {
+        if (!ctx->pin[k]) CU(cudaHostAlloc(reinterpret_cast<void**>(&ctx->pin[k]), PIN_PIECE, cudaHostAllocDefault));
+        if (!ctx->pin_ev[k]) CU(cudaEventCreateWithFlags(&ctx->pin_ev[k], cudaEventDisableTiming));
+    }
+    return MOVI_GPU_OK;
+}
+bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+template <typename F> void in_parts(size_t n, F f) {          // f(begin, end) on PIN_THREADS threads
+    const int t = (int)std::min<size_t>(PIN_THREADS, (n + (4u << 20) - 1) / (4u << 20));
+    if (t <= 1) { f((size_t)0, n); return; }
+    std::vector<std::thread> th;
+    for (int k = 0; k < t; k++) th.emplace_back(f, n * k / t, n * (k + 1) / t);
+    for (auto& x : th) x.join();
+}
+int staged_h2d(movi_gpu_ctx* ctx, void* d_dst, const char* src, size_t n, cudaStream_t st) {
+    if (n == 0) return MOVI_GPU_OK;
+    if (is_pinned(src)) { CU(cudaMemcpyAsync(d_dst, src, n, cudaMemcpyHostToDevice, st)); return MOVI_GPU_OK; }
+    int rc = ensure_pin_ring(ctx);
+    if (rc) return rc;
+    size_t k = 0;
+    for (size_t off = 0; off < n; off += PIN_PIECE, k++) {
+        const size_t len = std::min(PIN_PIECE, n - off);
+        const int slot = (int)(k & 3);
+        if (k >= 4) CU(cudaEventSynchronize(ctx->pin_ev[slot]));
+        uint8_t* buf = ctx->pin[slot];
+        in_parts(len, [&](size_t b, size_t e) { std::memcpy(buf + b, src + off + b, e - b); });
+        CU(cudaMemcpyAsync(static_cast<uint8_t*>(d_dst) + off, buf, len, cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(ctx->pin_ev[slot], st));
+    }
+    return MOVI_GPU_OK;
+}
+// device -> host memory (dst != NULL) or -> file (fd >= 0, positional writes at file_off); returns when everything has landed
+int staged_d2h(movi_gpu_ctx* ctx, uint8_t* dst, int fd, uint64_t file_off, const uint8_t* d_src, size_t n, cudaStream_t st) {
+    if (n == 0) return MOVI_GPU_OK;
+    if (dst && fd < 0 && is_pinned(dst)) { CU(cudaMemcpyAsync(dst, d_src, n, cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); return MOVI_GPU_OK; }
+    int rc = ensure_pin_ring(ctx);
+    if (rc) return rc;
+    const size_t pieces = (n + PIN_PIECE - 1) / PIN_PIECE;
+    size_t issued = 0;
+    bool io_ok = true;
+    for (size_t done = 0; done < pieces; done++) {
+        for (; issued < pieces && issued - done < 4; issued++) {
+            const size_t off = issued * PIN_PIECE, len = std::min(PIN_PIECE, n - off);
+            CU(cudaMemcpyAsync(ctx->pin[issued & 3], d_src + off, len, cudaMemcpyDeviceToHost, st));
+            CU(cudaEventRecord(ctx->pin_ev[issued & 3], st));
+        }
+        CU(cudaEventSynchronize(ctx->pin_ev[done & 3]));
+        const size_t off = done * PIN_PIECE, len = std::min(PIN_PIECE, n - off);
+        const uint8_t* buf = ctx->pin[done & 3];
+        if (fd >= 0)
+            in_parts(len, [&](size_t b, size_t e) {
+                while (b < e) { const ssize_t w = pwrite(fd, buf + b, e - b, (off_t)(file_off + off + b)); if (w <= 0) { io_ok = false; return; } b += (size_t)w; }
+            });
+        if (dst) in_parts(len, [&](size_t b, size_t e) { std::memcpy(dst + off + b, buf + b, e - b); });
+    }
+    if (!io_ok) return fail(ctx, MOVI_GPU_ERR_ARG, "write failed: .bpf");
+    return MOVI_GPU_OK;
+}
+
+// ---- device-side ingest: a chunk of a FASTA / FASTQ file (starting at a record boundary) parsed in HBM (parse_kernels.cuh)
 
 // raw chunk (host memory) -> ctx->p_bases / p_offsets / p_ids / p_id_offsets on the device; synchronises `st`
 int parse_chunk(movi_gpu_ctx* ctx, const char* raw, uint64_t n, int fastq, int final_chunk, cudaStream_t st, ParseResult* out) {
@@ -933,7 +1029,7 @@ int parse_chunk(movi_gpu_ctx* ctx, const char* raw, uint64_t n, int fastq, int f
     CU(cudaMemsetAsync(ctx->p_res, 0, sizeof(ParseResult) + sizeof(Sum3) + 16, st));
     if (n == 0) { CU(cudaStreamSynchronize(st)); return MOVI_GPU_OK; }
     if ((rc = grow(ctx, ctx->p_raw, ctx->p_raw_cap, n + 64))) return rc;
-    CU(cudaMemcpyAsync(ctx->p_raw, raw, n, cudaMemcpyHostToDevice, st));
+    if ((rc = staged_h2d(ctx, ctx->p_raw, raw, n, st))) return rc;
     const uint64_t n_tiles = (n + PARSE_TILE - 1) / PARSE_TILE;
     if ((rc = grow(ctx, ctx->p_tile, ctx->p_tile_cap, n_tiles + 1))) return rc;
     parse_count_newlines<<<(unsigned)n_tiles, 256, 0, st>>>(ctx->p_raw, n, ctx->p_tile);
@@ -991,6 +1087,8 @@ int parse_chunk(movi_gpu_ctx* ctx, const char* raw, uint64_t n, int fastq, int f
 }
 }  // namespace
 
+extern "C" {
+
 extern "C" int movi_gpu_parse_chunk(movi_gpu_ctx* ctx, const char* raw, uint64_t n_bytes, int fastq, int final_chunk,
                                     char* out_bases, uint64_t bases_capacity, uint64_t* out_offsets, char* out_ids, uint64_t ids_capacity,
                                     uint64_t* out_id_offsets, uint64_t reads_capacity, MoviGpuChunkResult* res) {
@@ -1010,38 +1108,57 @@ extern "C" int movi_gpu_parse_chunk(movi_gpu_ctx* ctx, const char* raw, uint64_t
     return MOVI_GPU_OK;
 }
 
-extern "C" int movi_gpu_query_file_chunk(movi_gpu_ctx* ctx, int zml, const char* raw, uint64_t n_bytes, int fastq, int final_chunk, uint32_t flags,
-                                         uint8_t* out_image, uint64_t image_capacity, MoviGpuChunkResult* res) {
+extern "C" int movi_gpu_file_chunk_parse(movi_gpu_ctx* ctx, const char* raw, uint64_t n_bytes, int fastq, int final_chunk, MoviGpuChunkResult* res) {
     if (!ctx || !res || (n_bytes && !raw)) return MOVI_GPU_ERR_ARG;
+    if (!ctx->has_index) return fail(ctx, MOVI_GPU_ERR_INDEX, "no index uploaded");
+    CU(cudaSetDevice(ctx->device));
+    ParseResult pr;
+    ctx->p_last = ParseResult{};
+    int rc = parse_chunk(ctx, raw, n_bytes, fastq, final_chunk, ctx->st_k[0], &pr);
+    if (rc) return rc;
+    res->n_reads = pr.n_reads; res->n_bases = pr.n_bases; res->id_bytes = pr.id_bytes; res->consumed_bytes = pr.consumed;
+    res->parse_flags = pr.flags; res->reserved = 0;
+    res->image_bytes = pr.flags ? 0 : 10ull * pr.n_reads + pr.id_bytes + 2ull * pr.n_bases;
+    if (!pr.flags) ctx->p_last = pr;
+    return MOVI_GPU_OK;
+}
+
+extern "C" int movi_gpu_file_chunk_query(movi_gpu_ctx* ctx, int zml, uint32_t flags, uint8_t* out_image, uint64_t image_capacity, int out_fd,
+                                         uint64_t file_offset) {
+    if (!ctx) return MOVI_GPU_ERR_ARG;
     CallFlags cf(ctx, flags);
     const Kind kind = zml ? Q_ZML : Q_PML;
     int rc = check_query_ready(ctx, kind, 0);
     if (rc) return rc;
+    const ParseResult pr = ctx->p_last;
+    if (pr.n_reads == 0) return MOVI_GPU_OK;
+    const uint64_t image_bytes = 10ull * pr.n_reads + pr.id_bytes + 2ull * pr.n_bases;
+    if (out_image && image_bytes > image_capacity) return fail(ctx, MOVI_GPU_ERR_NOMEM, "the .bpf image buffer is too small for this chunk");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->st_k[0];
-    ParseResult pr;
-    if ((rc = parse_chunk(ctx, raw, n_bytes, fastq, final_chunk, st, &pr))) return rc;
-    res->n_reads = pr.n_reads; res->n_bases = pr.n_bases; res->id_bytes = pr.id_bytes; res->consumed_bytes = pr.consumed;
-    res->parse_flags = pr.flags;
-    res->image_bytes = pr.flags ? 0 : 10ull * pr.n_reads + pr.id_bytes + 2ull * pr.n_bases;
-    if (pr.flags || pr.n_reads == 0) return MOVI_GPU_OK;
-    if (out_image && res->image_bytes > image_capacity) return fail(ctx, MOVI_GPU_ERR_NOMEM, "the .bpf image buffer is too small for this chunk");
     if ((rc = grow(ctx, ctx->p_ml, ctx->p_ml_cap, (size_t)pr.n_bases + 96))) return rc;
     CU(cudaMemsetAsync(ctx->d_status, 0, sizeof(unsigned int), st));
     CU(cudaMemsetAsync(ctx->p_bases + pr.n_bases, 0, 64, st));
     rc = device_query(ctx, kind, reinterpret_cast<const char*>(ctx->p_bases), reinterpret_cast<const uint64_t*>(ctx->p_offsets), 0, pr.n_reads,
                       ctx->p_ml, nullptr, nullptr, next_counter(ctx), st);
     if (rc) return rc;
-    if (out_image) {
-        if ((rc = grow(ctx, ctx->p_image, ctx->p_image_cap, (size_t)res->image_bytes + 16))) return rc;
+    if (out_image || out_fd >= 0) {
+        if ((rc = grow(ctx, ctx->p_image, ctx->p_image_cap, (size_t)image_bytes + 16))) return rc;
         const unsigned blocks = (unsigned)std::min<uint64_t>((pr.n_reads * 32 + 255) / 256, (uint64_t)ctx->num_sms * 16);
         bpf_assemble_kernel<<<blocks, 256, 0, st>>>(ctx->p_ml, ctx->p_offsets, 0ull, pr.n_reads, ctx->p_ids, ctx->p_id_offsets, ctx->p_image);
         ctx->launches += 1;
         CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(out_image, ctx->p_image, res->image_bytes, cudaMemcpyDeviceToHost, st));
+        if ((rc = staged_d2h(ctx, out_image, out_fd, file_offset, ctx->p_image, image_bytes, st))) return rc;
     }
     CU(cudaStreamSynchronize(st));
     return movi_gpu_check_device_status(ctx);
+}
+
+extern "C" int movi_gpu_query_file_chunk(movi_gpu_ctx* ctx, int zml, const char* raw, uint64_t n_bytes, int fastq, int final_chunk, uint32_t flags,
+                                         uint8_t* out_image, uint64_t image_capacity, MoviGpuChunkResult* res) {
+    int rc = movi_gpu_file_chunk_parse(ctx, raw, n_bytes, fastq, final_chunk, res);
+    if (rc || res->parse_flags || res->n_reads == 0) return rc;
+    return movi_gpu_file_chunk_query(ctx, zml, flags, out_image, image_capacity, -1, 0);
 }
 
 int movi_gpu_query_pml_device(movi_gpu_ctx* ctx, const char* d_bases, const uint64_t* d_read_offsets, uint64_t n_reads,

@@ -131,6 +131,7 @@ movi_pml_kernel(const DevIndex ix, const QueryArgs q) {
         // (lanes that are not walking fetch row 0: harmless and keeps the fetch out of a divergent branch)
         const IdxT fidx = proc ? idx : (IdxT)0;
         uint2 v;
+        uint32_t x4 = 0;                                              // LAYOUT_T4: the row word (its top byte is needed at the LF step)
         if (LAYOUT == LAYOUT_R8 && SECTOR) {
             const IdxT fb = fidx >> 2;
             if (proc && fb != sec_base) {
@@ -143,9 +144,9 @@ movi_pml_kernel(const DevIndex ix, const QueryArgs q) {
         }
         else if (LAYOUT == LAYOUT_R8) v = ld_keep(rows + fidx, pol_keep);
         else if (LAYOUT == LAYOUT_B6) v = fetch_row_b6<IdxT>(ix.rows6, fidx, end_idx, idb, ix.id_blocks_size, ix.block_shift, s_first);
-        else {              // LAYOUT_T3: the 3-byte row without its destination id (resolved below, only when an LF step needs it)
-            const uint32_t x = Rows3{ix.rows3, (unsigned long long)end_idx}.raw((unsigned long long)fidx);
-            v = make_r8_raw3(0, Rows3::n_of(x), Rows3::off_of(x), Rows3::c_of(x), Rows3::thr_of(x));
+        else {              // LAYOUT_T4: the 4-byte row; its destination id is resolved below, only when an LF step needs it
+            asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(x4) : "l"(ix.rows4 + fidx), "l"(pol_keep));
+            v = make_r8_raw3(0, Rows4::n_of(x4), Rows4::off_of(x4), Rows4::c_of(x4), Rows4::thr_of(x4));
         }
         if (__any_sync(FULL, proc && need_chunk)) {
             if (proc && need_chunk) {
@@ -216,10 +217,9 @@ movi_pml_kernel(const DevIndex ix, const QueryArgs q) {
         off += lf ? row_off<NT>(y) : 0u;                                        // LF_move, move_structure.cpp:66
         IdxT lf_id = row_id<IdxT, NT>(v);
         bool bad_id = false;
-        if (LAYOUT == LAYOUT_T3) {
+        if (LAYOUT == LAYOUT_T4) {
             // sampled-thresholds: get_id = checkpoint scan + walk-back (src/move_structure.cpp:103-219), per LF step
-            if (lf) lf_id = (IdxT)sampled_get_id(Rows3{ix.rows3, (unsigned long long)end_idx}, ix.tally, ix.tally_len, ix.tally_cp, ix.r,
-                                                 (unsigned long long)end_idx, (unsigned long long)idx, c, &bad_id);
+            if (lf) lf_id = t4_get_id<IdxT>(ix, idx, end_idx, x4, &bad_id);
         }
         if (RPML) saved = base_mis ? idx : saved;
         idx = lf ? lf_id : (ffmove || mv_down) ? idx + 1 : (mv_up ? idx - 1 : idx);

@@ -161,91 +161,56 @@ struct Results {
 };
 
 // ---- device-side ingest path: file bytes -> GPU (parse, walk, .bpf records) -> file.  The host only finds record boundaries
-// near the chunk ends, copies nothing and formats nothing: chunk k goes to GPU k mod G, the images are appended in chunk order by
-// a writer thread (several positional writes at once).  Returns 0 when the whole input went through, 1 when the input holds
-// something the reference rejects or stops at (nothing has been written then: the caller runs the host parser, which reproduces
-// the reference's behaviour), -1 on errors (message in `err`).
+// near the chunk ends; it copies nothing into buffers of its own and formats nothing.  Chunk k goes to GPU k mod G (one host
+// thread per GPU): the chunk is parsed there, which tells the size of its records, so the chunks' places in the output file are
+// handed out in chunk order while the walks and the writes (positional, straight from the copy-back ring of the library:
+// movi_gpu_file_chunk_query) run side by side.  Returns 0 when the whole input went through, 1 when the input holds something the
+// reference rejects or stops at (the caller starts over with the host parser, which reproduces the reference's behaviour, and a
+// fresh output file), -1 on errors (message in `err`).
 struct IngestStats { uint64_t reads = 0, bases = 0, chunks = 0; };
 
 int run_device_ingest(const Options& o, const std::vector<movi_gpu_ctx*>& ctx, const char* data, uint64_t size, int fastq, bool zml,
                       uint32_t qflags, int fd_bpf, IngestStats* stats, std::string* err) {
     const int G = (int)ctx.size();
-    struct Slot { PinnedBuf<uint8_t> image; uint64_t bytes = 0, seq = ~0ull; bool full = false; };
-    std::vector<Slot> slots((size_t)G * 2);
     std::mutex mu;
     std::condition_variable cv;
-    uint64_t next_begin = 0, next_seq = 0, write_seq = 0, chunk_bytes = o.chunk_bytes;
-    std::atomic<int> status{0};                    // 0 running / ok, 1 fall back, -1 error
-    const bool want_image = fd_bpf >= 0;
+    uint64_t next_begin = 0, next_seq = 0, place_seq = 0, file_off = 12, chunk_bytes = o.chunk_bytes;     // 12: the BPFHeader
+    int status = 0;                                // 0 running / ok, 1 fall back, -1 error (under mu)
 
     auto worker = [&](int g) {
-        for (int turn = 0;; turn++) {
-            Slot& S = slots[(size_t)g * 2 + (turn & 1)];
+        for (;;) {
             uint64_t begin, end, seq;
             {
-                std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return !S.full || status != 0; });          // the writer has emptied this slot
+                std::lock_guard<std::mutex> lk(mu);
                 if (status != 0 || next_begin >= size) return;
                 begin = next_begin;
                 end = begin + chunk_bytes >= size ? size : movi_host_record_boundary(data, size, begin + chunk_bytes, fastq);
                 next_begin = end; seq = next_seq++;
             }
             MoviGpuChunkResult res{};
-            for (;;) {
-                const uint64_t cap = want_image ? std::max<uint64_t>(S.image.cap, (end - begin) * 5 / 2 + (16u << 20)) : 0;
-                if (want_image && !S.image.need(cap)) { *err = "cannot allocate pinned host memory for a chunk's records (try a smaller --chunk-bytes)"; status = -1; cv.notify_all(); return; }
-                const int rc = movi_gpu_query_file_chunk(ctx[g], zml ? 1 : 0, data + begin, end - begin, fastq, 1, qflags,
-                                                         want_image ? S.image.p : nullptr, want_image ? S.image.cap : 0, &res);
-                if (rc == MOVI_GPU_ERR_NOMEM && want_image && res.image_bytes > S.image.cap) {      // many tiny records: grow and retry
-                    if (!S.image.need(res.image_bytes + (1u << 20))) { *err = "cannot allocate pinned host memory"; status = -1; cv.notify_all(); return; }
-                    continue;
-                }
-                if (rc) { std::lock_guard<std::mutex> lk(mu); *err = movi_gpu_last_error(ctx[g]); status = -1; cv.notify_all(); return; }
-                break;
-            }
-            std::lock_guard<std::mutex> lk(mu);
-            if (res.parse_flags || res.consumed_bytes != end - begin) { if (status == 0) status = 1; cv.notify_all(); return; }
-            S.bytes = res.image_bytes; S.seq = seq; S.full = true;
-            stats->reads += res.n_reads; stats->bases += res.n_bases; stats->chunks += 1;
-            // a chunk should hold a read per lane of its GPU: long reads get bigger chunks (the table rows are random gathers,
-            // only the number of walks in flight hides their latency)
-            if (res.n_reads < 230000 && chunk_bytes < (3ull << 30)) chunk_bytes = std::min<uint64_t>(chunk_bytes * 2, 3ull << 30);
-            cv.notify_all();
-        }
-    };
-    auto writer = [&]() {
-        for (;;) {
-            Slot* S = nullptr;
+            int rc = movi_gpu_file_chunk_parse(ctx[g], data + begin, end - begin, fastq, 1, &res);
+            uint64_t my_off = 0;
             {
                 std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] {
-                    S = nullptr;
-                    if (status != 0) return true;
-                    for (auto& s : slots) if (s.full && s.seq == write_seq) { S = &s; return true; }
-                    return next_begin >= size && write_seq == next_seq;        // every chunk handed out has been written
-                });
-                if (status != 0 || !S) return;
+                if (rc) { if (status == 0) { *err = movi_gpu_last_error(ctx[g]); status = -1; } cv.notify_all(); return; }
+                if (res.parse_flags || res.consumed_bytes != end - begin) { if (status == 0) status = 1; cv.notify_all(); return; }
+                cv.wait(lk, [&] { return place_seq == seq || status != 0; });      // places in the file go out in chunk order
+                if (status != 0) return;
+                my_off = file_off; file_off += res.image_bytes; place_seq += 1;
+                stats->reads += res.n_reads; stats->bases += res.n_bases; stats->chunks += 1;
+                // a chunk should hold a read per lane of its GPU: long reads get bigger chunks (the table rows are random gathers,
+                // only the number of walks in flight hides their latency)
+                if (res.n_reads < 230000 && chunk_bytes < (3ull << 30)) chunk_bytes = std::min<uint64_t>(chunk_bytes * 2, 3ull << 30);
+                cv.notify_all();
             }
-            if (want_image && S->bytes && movi_host_bpf_append_image(fd_bpf, S->image.p, S->bytes)) {
-                std::lock_guard<std::mutex> lk(mu);
-                *err = movi_host_last_error(); status = -1; cv.notify_all();
-                return;
-            }
-            std::lock_guard<std::mutex> lk(mu);
-            S->full = false; write_seq += 1;
-            cv.notify_all();
+            rc = movi_gpu_file_chunk_query(ctx[g], zml ? 1 : 0, qflags, nullptr, 0, fd_bpf, my_off);
+            if (rc) { std::lock_guard<std::mutex> lk(mu); if (status == 0) { *err = movi_gpu_last_error(ctx[g]); status = -1; } cv.notify_all(); return; }
         }
     };
     std::vector<std::thread> th;
     for (int g = 0; g < G; g++) th.emplace_back(worker, g);
-    std::thread wt(writer);
     for (auto& t : th) t.join();
-    {   // workers are done: let the writer drain (or stop on failure)
-        std::lock_guard<std::mutex> lk(mu);
-        cv.notify_all();
-    }
-    wt.join();
-    return status;        // 1: the caller starts over with the host parser (and a fresh output file)
+    return status;
 }
 
 void die(const std::string& m) { fprintf(stderr, "\033[31m\n\n[ERROR] %s\n\033[0m", m.c_str()); exit(1); }
@@ -268,8 +233,10 @@ int main(int argc, char** argv) {
         die("This query type is not suppported by the sampled modes yet.");
     movi_host_reader* reader = nullptr;
     if (movi_host_reader_open(o.read_file.c_str(), o.reverse ? 1 : 0, &reader)) die(movi_host_last_error());
+    auto t_files = std::chrono::steady_clock::now();
 
     int n_dev = movi_gpu_device_count();
+    auto t_cuda = std::chrono::steady_clock::now();
     if (n_dev <= 0) die("no CUDA device: movi-b200 has no CPU path (use the reference binaries on CPU-only hosts)");
     const int gpus = std::max(1, std::min(o.gpus, n_dev));
 
@@ -312,6 +279,10 @@ int main(int argc, char** argv) {
         for (int g = 0; g < gpus; g++) if (res[g].rc) die("GPU " + std::to_string(o.device + g) + ": " + res[g].err);
     }
     auto t_q0 = std::chrono::steady_clock::now();
+    if (o.verbose)
+        fprintf(stderr, "[INFO] start-up: files opened in %.3f s, CUDA driver up in %.3f s, %d context(s) + index upload in %.3f s\n",
+                std::chrono::duration<double>(t_files - t_load0).count(), std::chrono::duration<double>(t_cuda - t_files).count(), gpus,
+                std::chrono::duration<double>(t_q0 - t_cuda).count());
 
     // With --classify / --filter the binning runs on the device (movi_gpu_query_classify); the matching lengths only come
     // back when something needs them (the .bpf file next to a --classify report; never for --filter or --no-output).

@@ -234,8 +234,8 @@ def test_blocked_compact_device_layout(index_dirs, read_sets, ref_seq, sep):
 
 @pytest.mark.parametrize("sep", [False, True])
 def test_sampled_compact_device_layout(index_dirs, read_sets, ref_seq, sep):
-    """MOVI_GPU_LAYOUT_COMPACT for sampled-thresholds: 3-byte rows + id checkpoints stay in HBM (4 bytes per row in all);
-    MoveStructure::get_id's checkpoint scan + walk-back runs per LF step on the device."""
+    """MOVI_GPU_LAYOUT_COMPACT for sampled-thresholds: 4 bytes per row (the 3-byte row + its walk-back distance from the id
+    checkpoint) + the checkpoints = 5 bytes per row against 8; MoveStructure::get_id is one checkpoint read per LF step."""
     from movi_b200 import MoveStructure, MoviGpuError
     from movi_b200.api import LAYOUT_COMPACT
     from oracle.port import OracleIndex, pack_reads
@@ -243,7 +243,7 @@ def test_sampled_compact_device_layout(index_dirs, read_sets, ref_seq, sep):
     ms = MoveStructure(d, layout=LAYOUT_COMPACT)
     try:
         assert ms.device_layout == LAYOUT_COMPACT
-        assert ms.index_device_bytes < 4.3 * ms.r + 4096
+        assert ms.index_device_bytes < 5.1 * ms.r + 4096
         for read_set in READ_SETS:
             rd = read_sets[read_set]
             assert ml_text(rd.ids(), rd.offsets, ms.query_pml(rd.bases, rd.offsets)) == expected_text(read_set, "pml", sep)

@@ -1,50 +1,121 @@
 #!/usr/bin/env python3
-"""File-to-file timing of `movi-b200 query` on the c2 workload (1 M x 150 bp FASTA) next to the reference binary on the host cores."""
-import json, os, subprocess, sys, tempfile, time
+"""File-to-file timing of `movi-b200 query` next to the reference binary on the host cores (same box, outputs on tmpfs).
+
+usage: cli_e2e.py [n_reads_millions=10] [long]
+  default: the c2 index, n x 150 bp reads in one FASTA file (10 M reads = 1.6 GB in, 3.2 GB of .bpf out);
+  long   : the c2 index, 400 k x 10 kbp reads (configs[3] / [4] shape): the long-read occupancy check.
+Writes gpurun_out/r02_cli_e2e.jsonl."""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import bench
-from movi_b200 import build
+OUT = os.path.join(ROOT, "gpurun_out")
+os.makedirs(OUT, exist_ok=True)
+
+
+def emit(rec):
+    print(json.dumps(rec), flush=True)
+    open(os.path.join(OUT, "r02_cli_e2e.jsonl"), "a").write(json.dumps(rec) + "\n")
 
 
 def timed(cmd, **kw):
     t0 = time.perf_counter()
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, **kw)
+    r = subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, **kw)
     return time.perf_counter() - t0, r
 
 
 def main():
-    index_dir, bases, offsets, cfg = bench.prepare_workload(0)
-    n_reads = len(offsets) - 1
+    import bench
+    from movi_b200 import build
+    from movi_b200.datagen import synth
+    millions = float(sys.argv[1]) if len(sys.argv) > 1 else 10.0
+    long_reads = "long" in sys.argv[2:]
+    gpus = [a for a in sys.argv[2:] if a.startswith("gpus=")]
+    gpus = int(gpus[0][5:]) if gpus else 1
+    d, haps = synth.prepare("c2", ("regular-thresholds",))
+    index_dir = os.path.join(d, "regular-thresholds")
+    n_reads, L = (int(millions * 1e6), 150) if not long_reads else (int(millions * 1e6), 10_000)
     cli = build.CLI
     ref = os.path.join(ROOT, "oracle", "_ref", "movi-regular-thresholds")
     with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
         fa = os.path.join(td, "reads.fasta")
-        bench.write_fasta(fa, bases, offsets, n_reads)
+        t0 = time.time()
+        per = min(n_reads, 1_000_000 if not long_reads else 50_000)
+        with open(fa, "wb") as f:
+            pass
+        done = 0
+        while done < n_reads:                       # the file is written a million reads at a time (bounded host memory)
+            m = min(per, n_reads - done)
+            bases, offsets = synth.make_reads(haps, m, L, seed=43 + done, **({"sub": 0.05, "frac_random": 0.0} if long_reads else {}))
+            tmp = fa + ".part"
+            bench.write_fasta(tmp, bases, offsets, m)
+            with open(fa, "ab") as f, open(tmp, "rb") as g:
+                while True:
+                    buf = g.read(1 << 26)
+                    if not buf:
+                        break
+                    f.write(buf)
+            os.remove(tmp)
+            done += m
+        n_bases = n_reads * L
         size = os.path.getsize(fa)
-        out = []
-        for name, args in (("pml -> .bpf", ["--pml"]), ("pml --no-output", ["--pml", "--no-output"]), ("pml --classify (report + .bpf)", ["--pml", "--classify"]),
-                           ("pml --filter > /dev/null", ["--pml", "--filter"]), ("count -> .matches", ["--count"])):
-            if "--classify" in args or "--filter" in args:
-                if not os.path.exists(os.path.join(index_dir, "movi.pml.nulldb")):
-                    continue
-            best = None
-            for rep in range(3):
-                t, r = timed([cli, "query", "-i", index_dir, "-r", fa, "--verbose"] + args)
-                if r.returncode != 0:
-                    print("FAILED", name, r.stderr.decode()[-300:]); break
-                best = t if best is None else min(best, t)
-                info = [l for l in r.stderr.decode().split("\n") if "[INFO]" in l]
-            if best is not None:
-                out.append({"cmd": "movi-b200 query " + " ".join(args), "what": name, "wall_s": round(best, 3), "bases_per_s_wall": round(len(bases) / best), "info": info[-1] if info else ""})
-                print(json.dumps(out[-1]), flush=True)
+        emit({"what": "input", "reads": n_reads, "read_len": L, "fasta_bytes": size, "made_in_s": round(time.time() - t0, 1), "gpus": gpus})
+        threads = os.cpu_count() or 1
+        bpf = fa + ".regular-thresholds.pml.bpf"
+        sums = {}
+        runs = [("movi-b200 --pml -> .bpf (device-side ingest + .bpf emission)", [cli, "query", "-i", index_dir, "-r", fa, "--pml", "--verbose", "--gpus", str(gpus)], bpf),
+                ("movi-b200 --pml --no-output (device-side ingest)", [cli, "query", "-i", index_dir, "-r", fa, "--pml", "--no-output", "--verbose", "--gpus", str(gpus)], None),
+                ("movi-b200 --pml -> .bpf --host-parse (host parser, device-side .bpf emission)", [cli, "query", "-i", index_dir, "-r", fa, "--pml", "--host-parse", "--verbose", "--gpus", str(gpus)], bpf),
+                ("movi-b200 --pml --classify --stdout > /dev/null (fused classify; host parser)", [cli, "query", "-i", index_dir, "-r", fa, "--pml", "--filter", "--verbose", "--gpus", str(gpus)], None)]
         if os.path.exists(ref):
-            threads = os.cpu_count() or 1
-            for name, args in (("reference pml -> .bpf", ["--pml"]), ("reference pml --no-output", ["--pml", "--no-output"])):
-                t, r = timed([ref, "query", "--index", index_dir, "--read", fa, "-t", str(threads)] + args, cwd=td)
-                out.append({"cmd": "reference query -t %d %s" % (threads, " ".join(args)), "what": name, "wall_s": round(t, 3), "bases_per_s_wall": round(len(bases) / t)})
-                print(json.dumps(out[-1]), flush=True)
-        print(json.dumps({"fasta_bytes": size, "n_reads": n_reads}))
+            runs += [("reference --pml -t %d -> .bpf" % threads, [ref, "query", "--index", index_dir, "--read", fa, "--pml", "-t", str(threads)], bpf),
+                     ("reference --pml -t %d --no-output" % threads, [ref, "query", "--index", index_dir, "--read", fa, "--pml", "--no-output", "-t", str(threads)], None)]
+        for name, cmd, outfile in runs:
+            if "--filter" in cmd and not os.path.exists(os.path.join(index_dir, "movi.pml.nulldb")):
+                import struct
+                with open(os.path.join(index_dir, "movi.pml.nulldb"), "wb") as f:
+                    f.write(struct.pack("<QdQ", 1, 1.0, 6) + struct.pack("<Q", 1))
+            best, info = None, ""
+            for rep in range(2 if "reference" in name else 3):
+                if outfile and os.path.exists(outfile):
+                    os.remove(outfile)
+                t, r = timed(cmd, cwd=td)
+                if r.returncode != 0:
+                    emit({"what": name, "failed": r.stderr.decode()[-400:]})
+                    best = None
+                    break
+                best = t if best is None else min(best, t)
+                lines = [l for l in r.stderr.decode().split("\n") if "[INFO]" in l or "processing the reads" in l]
+                info = lines[-1] if lines else ""
+            if best is None:
+                continue
+            rec = {"what": name, "wall_s": round(best, 3), "bases_per_s_wall": round(n_bases / best), "info": info.strip()}
+            m = __import__("re").search(r"written in ([0-9.]+) s", info)
+            if m:
+                rec["steady_state_s"] = float(m.group(1)); rec["bases_per_s_steady"] = round(n_bases / float(m.group(1)))
+            if outfile and os.path.exists(outfile):
+                rec["out_bytes"] = os.path.getsize(outfile)
+                if "reference" not in name:              # (the reference writes its records in completion order)
+                    import hashlib
+                    h = hashlib.md5()
+                    with open(outfile, "rb") as f:
+                        f.seek(12)
+                        while True:
+                            buf = f.read(1 << 26)
+                            if not buf:
+                                break
+                            h.update(buf)
+                    rec["md5_after_header"] = h.hexdigest(); sums[name] = rec["md5_after_header"]
+            emit(rec)
+        if len(sums) > 1:
+            emit({"what": "device-side ingest and host parser write the same .bpf", "same": len(set(sums.values())) == 1})
 
 
 if __name__ == "__main__":
