@@ -949,8 +949,11 @@ namespace {
 // ---- staged copies: pageable host memory (a memory-mapped file, a std::vector) and file descriptors on one side, HBM on the other.
 // cudaMemcpyAsync on pageable memory is staged by the driver through one thread at ~6 GB/s and blocks; here the pieces go through
 // a ring of four pinned buffers, filled / drained by a few host threads while the previous pieces are on the wire.
-constexpr size_t PIN_PIECE = 32u << 20;
-constexpr int PIN_THREADS = 4;
+constexpr size_t PIN_PIECE = 64u << 20;
+inline int pin_threads() {                           // host threads that fill / drain a piece (page-cache writes run at ~1 GB/s per thread)
+    static const int n = (int)std::min(12u, std::max(2u, std::thread::hardware_concurrency() > 3 ? std::thread::hardware_concurrency() - 2 : 2u));
+    return n;
+}
 
 int ensure_pin_ring(movi_gpu_ctx* ctx) {
     for (int k = 0; k < 4; k++) {
@@ -964,8 +967,8 @@ bool is_pinned(const void* p) {
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
 }
-template <typename F> void in_parts(size_t n, F f) {          // f(begin, end) on PIN_THREADS threads
-    const int t = (int)std::min<size_t>(PIN_THREADS, (n + (4u << 20) - 1) / (4u << 20));
+template <typename F> void in_parts(size_t n, F f) {          // f(begin, end) on pin_threads() threads
+    const int t = (int)std::min<size_t>((size_t)pin_threads(), (n + (4u << 20) - 1) / (4u << 20));
     if (t <= 1) { f((size_t)0, n); return; }
     std::vector<std::thread> th;
     for (int k = 0; k < t; k++) th.emplace_back(f, n * k / t, n * (k + 1) / t);

@@ -38,6 +38,7 @@ struct Options {
     uint64_t max_chunk_bases = 1ull << 31;   // ... but never more bases than this per batch (pinned results: 2 x 2 bytes per base)
     uint64_t chunk_bytes = 256ull << 20;     // device-side ingest: file bytes per chunk (grows by itself when reads are long)
     bool host_parse = false;                 // --host-parse: never use the device-side ingest
+    int layout = MOVI_GPU_LAYOUT_AUTO;       // --layout auto|expanded|compact: device form of blocked / sampled indexes
     bool write_output_allowed() const { return !no_output && !filter; }          // movi_options.hpp:70
     bool write_stdout_enabled() const { return to_stdout && !classify; }         // movi_options.hpp:71
 };
@@ -47,7 +48,7 @@ struct Options {
     fprintf(stderr, "usage: movi-b200 query -i <index dir> -r <reads.fa|fq|-> [--pml [--rpml]|--zml|--count] [--classify|--filter [-v]]\n"
                     "                       [--stdout] [-o prefix] [--no-output] [--reverse] [--ignore-illegal-chars 1|2]\n"
                     "                       [--bin-width N] [--gpus N] [--device D] [--chunk-bases N] [--chunk-reads N] [--max-chunk-bases N]\n"
-                    "                       [--chunk-bytes N] [--host-parse]\n"
+                    "                       [--chunk-bytes N] [--host-parse] [--layout auto|expanded|compact]\n"
                     "                       [-t N] [-s N] [-n]\n"
                     "       movi-b200 view --bpf <file.bpf>\n");
     exit(1);
@@ -92,6 +93,10 @@ Options parse(int argc, char** argv) {
         else if (take_value(argc, argv, i, nullptr, "--chunk-reads", v)) o.chunk_reads = strtoull(v.c_str(), nullptr, 10);
         else if (take_value(argc, argv, i, nullptr, "--chunk-bytes", v)) o.chunk_bytes = std::max<uint64_t>(4096, strtoull(v.c_str(), nullptr, 10));
         else if (a == "--host-parse") o.host_parse = true;
+        else if (take_value(argc, argv, i, nullptr, "--layout", v)) {
+            if (v == "auto") o.layout = MOVI_GPU_LAYOUT_AUTO; else if (v == "expanded") o.layout = MOVI_GPU_LAYOUT_EXPANDED8;
+            else if (v == "compact") o.layout = MOVI_GPU_LAYOUT_COMPACT; else usage_error("--layout: auto, expanded or compact");
+        }
         else if (take_value(argc, argv, i, nullptr, "--max-chunk-bases", v)) o.max_chunk_bases = std::max<uint64_t>(1, strtoull(v.c_str(), nullptr, 10));
         else if (a == "--pml") o.query = "pml";
         else if (a == "--rpml") o.rpml = true;                                  // movi_parser.cpp:149,357
@@ -272,7 +277,7 @@ int main(int argc, char** argv) {
         for (int g = 0; g < gpus; g++) th.emplace_back([&, g]() {
             int rc = movi_gpu_create(o.device + g, &ctx[g]);
             if (rc) { res[g] = {rc, movi_gpu_last_error(nullptr)}; return; }
-            rc = movi_gpu_upload_index(ctx[g], &desc, MOVI_GPU_LAYOUT_AUTO);
+            rc = movi_gpu_upload_index(ctx[g], &desc, o.layout);
             if (rc) res[g] = {rc, movi_gpu_last_error(ctx[g])};
         });
         for (auto& t : th) t.join();
