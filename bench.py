@@ -355,6 +355,29 @@ def sub_records(dev, peak):
             else:
                 want = getattr(orc, "query_" + W["query"])(bases, offsets, threads=0)
                 ok = np.array_equal(want, d_outs[0][:n_bases].cpu().numpy().view(np.uint16))
+            # the host-buffer entry point on this shape: pinned caller buffers against pageable ones (numpy arrays = what a
+            # std::vector is to the driver: cudaMemcpyAsync stages them and blocks)
+            host = None
+            if name == "c2":
+                hb = torch.from_numpy(np.concatenate([bases, np.zeros(64, np.uint8)])).pin_memory()
+                ho = torch.from_numpy(offsets.astype(np.int64)).pin_memory()
+                hout = torch.empty(n_bases + 16, dtype=torch.int16).pin_memory()
+                pb, po, pout = np.concatenate([bases, np.zeros(64, np.uint8)]), offsets.astype(np.uint64), np.empty(n_bases + 16, np.uint16)
+
+                def t_host(fn, reps=10):
+                    fn(); fn()
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for _ in range(reps):
+                        fn()
+                    return (time.perf_counter() - t0) * 1e3 / reps
+                t_pin = t_host(lambda: ms._check(ms._L.movi_gpu_query_pml(ms._ctx, hb.data_ptr(), ho.data_ptr(), n_reads, 0, hout.data_ptr())))
+                t_page = t_host(lambda: ms._check(ms._L.movi_gpu_query_pml(ms._ctx, pb.ctypes.data, po.ctypes.data, n_reads, 0, pout.ctypes.data)))
+                ok = ok and np.array_equal(pout[:n_bases], want) and np.array_equal(hout[:n_bases].numpy().view(np.uint16), want)
+                host = {"e2e": {"value": n_bases / (t_pin * 1e-3), "unit": "bases/s", "ms_per_step": t_pin, "buffers": "pinned (movi_gpu_host_alloc / cudaHostAlloc)"},
+                        "e2e_pageable": {"value": n_bases / (t_page * 1e-3), "unit": "bases/s", "ms_per_step": t_page,
+                                         "buffers": "pageable caller memory (numpy arrays; the driver stages every copy)"}}
+                del hb, hout
             achieved = W["algo"] * work / (ms_step * 1e-3) / 1e9
             traffic = None
             tp = os.path.join(ROOT, "profiles", {"c2": "pml_c2_traffic.json", "c3-zml": "zml_c3_traffic.json", "c3-count": "count_c3_traffic.json"}[name])
@@ -367,6 +390,8 @@ def sub_records(dev, peak):
                                 "measured_dram_bytes_per_base": None if not traffic else traffic / work,
                                 "frac_by_measured_dram_bytes": None if not traffic else traffic / (ms_step * 1e-3) / 1e9 / peak},
                    "parity_checked": bool(ok), "parity_reads_vs_oracle": int(n_reads)}
+            if host:
+                rec.update(host)
             out[name.replace("-", "_")] = rec
             log("[bench] sub-record %s: %.3g bases/s, parity %s" % (name, rec["value"], ok))
             ms.close()

@@ -189,7 +189,8 @@ int  movi_gpu_query_file_chunk(movi_gpu_ctx* ctx, int zml, const char* raw, uint
 /* The same in two steps, for callers that place the records of several chunks (and GPUs) in one file: _parse copies the chunk up
  * and parses it (res->image_bytes = the size of its records); _query walks the reads parsed last and delivers the records to
  * out_image (may be NULL) and / or straight into the file out_fd at file_offset (-1: no file), through a ring of pinned buffers
- * and positional writes -- no host buffer of the size of the image is needed. */
+ * -- no host buffer of the size of the image is needed.  A file that already extends to file_offset + image_bytes (ftruncate) is
+ * filled through a shared mapping by several threads; otherwise with positional writes. */
 int  movi_gpu_file_chunk_parse(movi_gpu_ctx* ctx, const char* raw, uint64_t n_bytes, int fastq, int final_chunk, MoviGpuChunkResult* res);
 int  movi_gpu_file_chunk_query(movi_gpu_ctx* ctx, int zml, uint32_t flags, uint8_t* out_image, uint64_t image_capacity, int out_fd,
                                uint64_t file_offset);

@@ -18,6 +18,21 @@ __global__ void relayout_regular_kernel(uint2* __restrict__ rows, unsigned long 
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (; i < r; i += stride) rows[i] = r8_from_file(rows[i], sep);
 }
+// undo of relayout_regular_kernel, in place (an adopted table is handed back to its owner the way it came when the upload fails)
+__global__ void relayout_regular_undo_kernel(uint2* __restrict__ rows, unsigned long long r, uint32_t sep) {
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (; i < r; i += stride) rows[i] = r8_to_file(rows[i], sep);
+}
+// every row's character must be one of the index's sigma characters (the side tables are indexed by it): counts the offenders
+__global__ void check_row_chars_kernel(const uint2* __restrict__ rows, unsigned long long r, unsigned long long end_idx, uint32_t sigma,
+                                       unsigned int* __restrict__ status) {
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (; i < r; i += stride) bad |= (i != end_idx) && (row_c(rows[i].y) >= sigma);
+    if (bad) atomicOr(status, 8u);
+}
 // ---- MODE 3 ("regular", no thresholds): the same, into the 12-bit form of R8
 __global__ void relayout_regular_nt_kernel(uint2* __restrict__ rows, unsigned long long r) {
     unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;

@@ -6,6 +6,7 @@
 #include "../../include/movi_gpu.h"
 
 #include <cuda.h>
+#include <sys/mman.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -648,9 +649,19 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
     // whatever path leaves this function before the index is complete: nothing stays allocated (adopted rows go back to
     // the caller), and the conversion scratch below frees itself
     struct Rollback {
-        movi_gpu_ctx* c; uint2* adopted; bool done = false;
-        ~Rollback() { if (!done) { if (adopted && c->d_rows == adopted) c->d_rows = nullptr; free_index(c); } }
-    } rollback{ctx, adopt_rows};
+        movi_gpu_ctx* c; uint2* adopted; unsigned long long r; uint32_t sep; bool permuted = false, done = false;
+        ~Rollback() {
+            if (done) return;
+            if (adopted && c->d_rows == adopted) {
+                if (permuted) {      // the caller gets its table back in the format it handed over
+                    relayout_regular_undo_kernel<<<c->num_sms * 8, 256, 0, c->st_k[0]>>>(adopted, r, sep);
+                    cudaStreamSynchronize(c->st_k[0]);
+                }
+                c->d_rows = nullptr;
+            }
+            free_index(c);
+        }
+    } rollback{ctx, adopt_rows, r, sep ? 1u : 0u};
     struct Scratch { void* p = nullptr; ~Scratch() { if (p) cudaFree(p); } };
     // Device layout: EXPANDED8 unless the caller asks for COMPACT, or AUTO finds that the expanded table (plus the raw
     // copy the conversion needs) does not fit in free HBM.  COMPACT exists for blocked-thresholds (its 6-byte rows are
@@ -722,7 +733,7 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
         // the 8-byte rows of the reference: copy (unless already resident), then permute the bit fields into R8 in place
         if (!adopt_rows) CU(cudaMemcpyAsync(ctx->d_rows, d->rows, r * sizeof(uint2), cudaMemcpyHostToDevice, st));
         if (nt) relayout_regular_nt_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(ctx->d_rows, r);
-        else relayout_regular_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(ctx->d_rows, r, sep ? 1u : 0u);
+        else { relayout_regular_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(ctx->d_rows, r, sep ? 1u : 0u); rollback.permuted = adopt_rows != nullptr; }
         ctx->launches += 1;
         CU(cudaGetLastError());
     } else if (blocked) {
@@ -792,6 +803,16 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
         ix.code_of[b] = (a < d->sigma && !(sep && b == '%')) ? (uint8_t)a : (uint8_t)CODE_ILLEGAL;
     }
     CU(cudaStreamSynchronize(st));   // the table copy / conversion ran on a non-blocking stream
+    if (!compact) {
+        // a corrupt file must not become out-of-range reads of the side tables: every row's character is below sigma
+        CU(cudaMemsetAsync(ctx->d_status, 0, sizeof(unsigned int), st));
+        check_row_chars_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(ctx->d_rows, r, d->end_bwt_idx, d->sigma, ctx->d_status);
+        ctx->launches += 1;
+        unsigned int status = 0;
+        CU(cudaMemcpyAsync(&status, ctx->d_status, sizeof(status), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (status) { CU(cudaMemset(ctx->d_status, 0, sizeof(unsigned int))); return fail(ctx, MOVI_GPU_ERR_INDEX, "corrupt index: a row holds a character outside the alphabet"); }
+    }
     {   // n(r-1) for the start state of query_pml
         uint2 last = make_uint2(0u, n_last_host);
         if (!compact) CU(cudaMemcpy(&last, ctx->d_rows + (r - 1), sizeof(last), cudaMemcpyDeviceToHost));
@@ -1000,6 +1021,8 @@ int staged_d2h(movi_gpu_ctx* ctx, uint8_t* dst, int fd, uint64_t file_off, const
     const size_t pieces = (n + PIN_PIECE - 1) / PIN_PIECE;
     size_t issued = 0;
     bool io_ok = true;
+    uint64_t file_len = 0;
+    if (fd >= 0) { const off_t e = lseek(fd, 0, SEEK_END); if (e > 0) file_len = (uint64_t)e; }
     for (size_t done = 0; done < pieces; done++) {
         for (; issued < pieces && issued - done < 4; issued++) {
             const size_t off = issued * PIN_PIECE, len = std::min(PIN_PIECE, n - off);
@@ -1009,10 +1032,22 @@ int staged_d2h(movi_gpu_ctx* ctx, uint8_t* dst, int fd, uint64_t file_off, const
         CU(cudaEventSynchronize(ctx->pin_ev[done & 3]));
         const size_t off = done * PIN_PIECE, len = std::min(PIN_PIECE, n - off);
         const uint8_t* buf = ctx->pin[done & 3];
-        if (fd >= 0)
+        if (fd >= 0) {
+            // Into the page cache through a shared mapping when the file already reaches that far (the caller extends it): positional
+            // writes of several threads to ONE file take turns on its inode lock (2.9 GB/s on tmpfs whatever the thread count),
+            // page faults on a mapping do not.  Otherwise pwrite.
+            const uint64_t at = file_off + off, page = 4096, m0 = at & ~(page - 1);
+            const size_t mlen = (size_t)(at + len - m0);
+            void* m = (file_len >= at + len) ? mmap(nullptr, mlen, PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)m0) : MAP_FAILED;
+            if (m != MAP_FAILED) {
+                uint8_t* to = static_cast<uint8_t*>(m) + (at - m0);
+                in_parts(len, [&](size_t b, size_t e) { std::memcpy(to + b, buf + b, e - b); });
+                munmap(m, mlen);
+            } else
             in_parts(len, [&](size_t b, size_t e) {
                 while (b < e) { const ssize_t w = pwrite(fd, buf + b, e - b, (off_t)(file_off + off + b)); if (w <= 0) { io_ok = false; return; } b += (size_t)w; }
             });
+        }
         if (dst) in_parts(len, [&](size_t b, size_t e) { std::memcpy(dst + off + b, buf + b, e - b); });
     }
     if (!io_ok) return fail(ctx, MOVI_GPU_ERR_ARG, "write failed: .bpf");

@@ -202,6 +202,7 @@ int run_device_ingest(const Options& o, const std::vector<movi_gpu_ctx*>& ctx, c
                 cv.wait(lk, [&] { return place_seq == seq || status != 0; });      // places in the file go out in chunk order
                 if (status != 0) return;
                 my_off = file_off; file_off += res.image_bytes; place_seq += 1;
+                if (fd_bpf >= 0 && res.image_bytes && ftruncate(fd_bpf, (off_t)file_off) != 0) { /* the library falls back to pwrite */ }
                 stats->reads += res.n_reads; stats->bases += res.n_bases; stats->chunks += 1;
                 // a chunk should hold a read per lane of its GPU: long reads get bigger chunks (the table rows are random gathers,
                 // only the number of walks in flight hides their latency)

@@ -58,6 +58,12 @@ struct Cursor {
     bool need(size_t n) { if (!ok || pos + n > size || pos + n < pos) { ok = false; return false; } return true; }
     template <typename T> T get() { T v{}; if (need(sizeof(T))) { std::memcpy(&v, p + pos, sizeof(T)); pos += sizeof(T); } return v; }
     const uint8_t* take(size_t n) { if (!need(n)) return nullptr; const uint8_t* q = p + pos; pos += n; return q; }
+    // a * b [* c] bytes, the product checked against overflow (sizes come from the file)
+    const uint8_t* take_n(uint64_t a, uint64_t b, uint64_t c = 1) {
+        unsigned __int128 n = (unsigned __int128)a * b * c;
+        if ((a && b && c && (n / a / b != c)) || n > size) { ok = false; return nullptr; }
+        return take((size_t)n);
+    }
 };
 
 }  // namespace
@@ -119,19 +125,20 @@ int movi_host_index_open(const char* path, movi_host_index** out) {
     std::memcpy(d.alphabet, al, sigma);
     c.take(3);                                           // u16 nt_splitting; u8 constant
     // read_main_table, io.cpp:361-397
-    d.rows = c.take(d.r * row_bytes);
+    d.rows = c.take_n(d.r, row_bytes);
     if (!d.rows) return bad("truncated row table");
     // read_tally_table, io.cpp:338-349
     if (d.mode == MOVI_MODE_SAMPLED_THRESHOLDS || d.mode == MOVI_MODE_SAMPLED) {
         d.tally_checkpoints = c.get<uint32_t>();
         d.tally_len = c.get<uint64_t>();
-        d.tally_ids = c.take((size_t)sigma * d.tally_len * 5);
+        d.tally_ids = c.take_n(sigma, d.tally_len, 5);
         if (!d.tally_ids) return bad("truncated id checkpoint table");
+        if (d.tally_checkpoints == 0 || d.tally_len < d.r / d.tally_checkpoints + 1) return bad("id checkpoint table inconsistent with the number of rows");
     }
     // read_overflow_tables, io.cpp:219-237
-    uint64_t sz = c.get<uint64_t>(); c.take(sz * 8);
-    sz = c.get<uint64_t>(); c.take(sz * 8);
-    sz = c.get<uint64_t>(); c.take(sz * 8 * (sigma - 1));
+    uint64_t sz = c.get<uint64_t>(); c.take_n(sz, 8);
+    sz = c.get<uint64_t>(); c.take_n(sz, 8);
+    sz = c.get<uint64_t>(); c.take_n(sz, 8, sigma - 1);
     // read_counts_data, io.cpp:269-287
     sz = c.get<uint64_t>();
     if (!c.ok || sz != sigma) return bad("unexpected counts size");
@@ -145,24 +152,25 @@ int movi_host_index_open(const char* path, movi_host_index** out) {
     // read_id_blocks, io.cpp:305-324
     if (d.mode == MOVI_MODE_BLOCKED_THRESHOLDS || d.mode == MOVI_MODE_BLOCKED) {
         d.id_blocks_size = c.get<uint64_t>();
-        const uint8_t* b = c.take((size_t)sigma * d.id_blocks_size * 4);
+        const uint8_t* b = c.take_n(sigma, d.id_blocks_size, 4);
         if (!b && d.id_blocks_size) return bad("truncated id_blocks");
         ix->id_blocks.resize((size_t)sigma * d.id_blocks_size);
         if (b) std::memcpy(ix->id_blocks.data(), b, ix->id_blocks.size() * 4);
         d.id_blocks = ix->id_blocks.data();
         d.block_size = c.get<uint64_t>();
+        if (c.ok && (d.block_size == 0 || d.id_blocks_size < (d.r + d.block_size - 1) / d.block_size)) return bad("id_blocks inconsistent with the number of rows");
     }
     if (!c.ok) return bad("truncated index file");
     // read_separators_thresholds, io.cpp:415-433 (present iff use_separator(), move_structure.cpp:547-552)
     const bool no_thresholds = d.mode == MOVI_MODE_REGULAR || d.mode == MOVI_MODE_BLOCKED || d.mode == MOVI_MODE_SAMPLED;
     if (sigma == 5 && d.alphabet[0] == '%' && !no_thresholds) {                    // (#if USE_THRESHOLDS, io.cpp:504-508)
         d.sep_count = c.get<uint64_t>();
-        const uint8_t* t = c.take(d.sep_count * 8);
+        const uint8_t* t = c.take_n(d.sep_count, 8);
         if (!c.ok) return bad("truncated separators thresholds");
         ix->sep_thr.resize(d.sep_count * 4);
         if (t) std::memcpy(ix->sep_thr.data(), t, d.sep_count * 8);
         d.sep_map_size = c.get<uint64_t>();
-        const uint8_t* mp = c.take(d.sep_map_size * 16);
+        const uint8_t* mp = c.take_n(d.sep_map_size, 16);
         if (!c.ok) return bad("truncated separators map");
         ix->sep_map.resize(d.sep_map_size * 2);
         if (mp) std::memcpy(ix->sep_map.data(), mp, d.sep_map_size * 16);
@@ -232,6 +240,9 @@ static bool gunzip_all(const char* in, size_t n, std::string& out) {
         out.append(buf.data(), buf.size() - zs.avail_out);
         if (rc == Z_STREAM_END) {                            // next member of a concatenated gzip file, if any
             if (zs.avail_in == 0 && left == 0) break;
+            // what follows a complete member is another member only if it starts with the gzip magic; padding or garbage ends the
+            // input (gzread stops there too: the reference reads its inputs through gzopen / gzread, src/utils.cpp:69-80)
+            if (zs.avail_in < 2 || zs.next_in[0] != 0x1f || zs.next_in[1] != 0x8b) break;
             if (inflateReset(&zs) != Z_OK) { inflateEnd(&zs); return false; }
         } else if (rc == Z_BUF_ERROR && zs.avail_in == 0 && left == 0) break;   // truncated stream: keep what inflated (gzread does)
     }
@@ -427,7 +438,7 @@ int movi_host_nulldb_threshold(const char* index_dir, const char* query_type, ui
 // output_base_stats (binary branch) + BPFHeader, reference src/utils.cpp:202-246, include/utils.hpp:64-86
 int movi_host_bpf_begin(const char* file) {
     if (!file) { fail("null argument"); return -1; }
-    const int fd = open(file, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    const int fd = open(file, O_RDWR | O_CREAT | O_TRUNC, 0644);      // (read-write: images may be written through a shared mapping)
     if (fd < 0) { fail(std::string("cannot open ") + file); return -1; }
     uint8_t header[12] = {0};
     std::memcpy(header, &BPF_MAGIC, 4);

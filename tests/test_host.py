@@ -267,3 +267,52 @@ def test_index_reader_opens_the_types_without_thresholds(nothr_index_dirs):
             assert hix.alphabet == (b"%ACGT" if sep else b"ACGT")
             size = os.path.getsize(os.path.join(nothr_index_dirs[(typ, sep)], "index.movi"))
             assert hix.r * row_bytes < size
+
+
+def test_index_reader_survives_corrupt_sizes(index_dirs, tmp_path):
+    """Sizes read from a file are not trusted: a row count / table length that would overflow or run past the file is a clean
+    error, not an out-of-range read."""
+    import struct
+    for typ in TYPES:
+        raw = bytearray(open(os.path.join(index_dirs[(typ, False)], "index.movi"), "rb").read())
+        for r_bad in (1 << 61, (1 << 64) - 1, len(raw)):
+            bad = bytearray(raw)
+            struct.pack_into("<Q", bad, 24, r_bad)            # MoviHeader.r
+            d = tmp_path / ("%s_%d" % (typ, r_bad % 1000))
+            d.mkdir(exist_ok=True)
+            (d / "index.movi").write_bytes(bad)
+            with pytest.raises(RuntimeError, match="truncated|inconsistent|unexpected"):
+                HostIndex(str(d))
+        cut = tmp_path / (typ + "_cut")
+        cut.mkdir()
+        (cut / "index.movi").write_bytes(raw[: len(raw) // 2])
+        with pytest.raises(RuntimeError, match="truncated|unexpected"):
+            HostIndex(str(cut))
+
+
+def test_gzip_with_trailing_garbage_is_read_like_gzread(tmp_path):
+    """Bytes after a complete gzip member that are not another member end the input (the reference's gzopen / gzread does the same)."""
+    import gzip
+    raw = open(reads_path("synth300.fasta"), "rb").read()
+    plain = Reads(reads_path("synth300.fasta"))
+    f = tmp_path / "padded.fa.gz"
+    f.write_bytes(gzip.compress(raw) + b"\0" * 512 + b"trailing junk")
+    z = Reads(str(f))
+    assert z.count == plain.count and np.array_equal(z.bases, plain.bases)
+
+
+def test_record_boundary_finder():
+    """movi_host_record_boundary: where the device-side ingest may cut a file (FASTA: a line starting with '>'; FASTQ: '@' line whose
+    next-but-one line starts with '+', so that a quality line starting with '@' is not taken for a header)."""
+    import ctypes as C
+    H = N.host_lib()
+    fa = b">a\nACGT\nAC\n>b x\nGG\n>c\nT\n"
+    starts = [0, 11, 19]
+    for frm in range(len(fa) + 1):
+        want = min([s for s in starts if s >= frm] + [len(fa)])
+        assert H.movi_host_record_boundary(fa, len(fa), frm, 0) == want, frm
+    fq = b"@r1\nACGT\n+\n@@II\n@r2\nAC\n+\n@I\n@r3\nA\n+\nI\n"
+    starts = [0, 16, 28]
+    for frm in range(len(fq) + 1):
+        want = min([s for s in starts if s >= frm] + [len(fq)])
+        assert H.movi_host_record_boundary(fq, len(fq), frm, 1) == want, frm

@@ -89,7 +89,7 @@ def main():
                 ("movi-b200 --pml --no-output (device-side ingest)", [cli, "query", "-i", index_dir, "-r", fa, "--pml", "--no-output", "--verbose", "--gpus", str(gpus)], None),
                 ("movi-b200 --pml -> .bpf --host-parse (host parser, device-side .bpf emission)", [cli, "query", "-i", index_dir, "-r", fa, "--pml", "--host-parse", "--verbose", "--gpus", str(gpus)], bpf),
                 ("movi-b200 --pml --classify --stdout > /dev/null (fused classify; host parser)", [cli, "query", "-i", index_dir, "-r", fa, "--pml", "--filter", "--verbose", "--gpus", str(gpus)], None)]
-        if os.path.exists(ref):
+        if os.path.exists(ref) and "noref" not in sys.argv[2:]:
             runs += [("reference --pml -t %d -> .bpf" % threads, [ref, "query", "--index", index_dir, "--read", fa, "--pml", "-t", str(threads)], bpf),
                      ("reference --pml -t %d --no-output" % threads, [ref, "query", "--index", index_dir, "--read", fa, "--pml", "--no-output", "-t", str(threads)], None)]
         if rep:                                    # the big input: the device-ingest runs and the reference only
