@@ -42,6 +42,9 @@ WORKLOADS = {
                    kernel="movi_bs_kernel<uint32_t,ZML,R8>"),
     "c3-count": dict(data="c2", index="blocked-thresholds", query="count", metric="count query bases/sec (all bases of the reads)", algo=64,
                      kernel="movi_bs_kernel<uint32_t,COUNT,R8>"),
+    # a suffix-sorted index beyond the L2 (1 Gbp of text, 5.3e7 rows = 423 MB, real LCP thresholds); sub-record only
+    "g1": dict(data="g1", index="regular-thresholds", query="pml", metric="PML query bases/sec", algo=32,
+               kernel="movi_pml_kernel<uint32_t,false,6,R8>"),
 }
 W = WORKLOADS["c4"]               # replaced in main() from --workload
 ARGS_WORKLOAD = "c4"
@@ -124,21 +127,23 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ workloads
 class C2Data:
-    """configs[1] / [2]: suffix-sorted 64 x 5 Mbp bacterial pangenome (n = 6.4e8, r = 1.55e7: 124 MB of rows), 1 M x 150 bp reads."""
+    """configs[1] / [2]: suffix-sorted 64 x 5 Mbp bacterial pangenome (n = 6.4e8, r = 1.55e7: 124 MB of rows), 1 M x 150 bp reads.
+    Also the "g1" data set: 20 x 25 Mbp (n = 1e9, r = 5.3e7: 423 MB of rows, beyond the L2)."""
 
-    _haps = None                     # the pangenome, kept across the c2 / c3 sub-records of one run
+    _haps = {}                       # the pangenomes, kept across the sub-records of one run
 
     def __init__(self, rank, device, need_device=True):
         from movi_b200.datagen import synth
-        self.cfg = synth.CONFIGS["c2"]
+        self.name = W["data"]
+        self.cfg = synth.CONFIGS[self.name]
         t0 = time.time()
-        d, haps = synth.prepare("c2", (W["index"],), want_reads=C2Data._haps is None, log=sys.stderr)
-        haps = C2Data._haps = haps if haps is not None else C2Data._haps
+        d, haps = synth.prepare(self.name, (W["index"],), want_reads=self.name not in C2Data._haps, log=sys.stderr)
+        haps = C2Data._haps[self.name] = haps if haps is not None else C2Data._haps[self.name]
         self.index_dir = os.path.join(d, W["index"])
         self.n_reads, self.read_len = self.cfg["n_reads"], self.cfg["read_len"]
         self.host_batches = [synth.make_reads(haps, self.n_reads, self.read_len, seed=43 + rank + 1000 * b) for b in range(N_BATCHES)]
         self.n_bases = int(self.host_batches[0][1][-1])
-        log("[bench] rank %d: c2 workload ready in %.1f s (%d batches of %d reads)" % (rank, time.time() - t0, N_BATCHES, self.n_reads))
+        log("[bench] rank %d: %s workload ready in %.1f s (%d batches of %d reads)" % (rank, self.name, time.time() - t0, N_BATCHES, self.n_reads))
         self.ms = None
         if need_device:
             import torch
@@ -149,6 +154,9 @@ class C2Data:
             self.d_off = torch.from_numpy(self.host_batches[0][1].astype(np.int64)).to(device)
 
     def describe(self):
+        if self.name == "g1":
+            return ("g1: 20-haplotype x 25 Mbp synthetic pangenome (0.1% divergence, +reverse complements; 1 Gbp of text), suffix-sorted with "
+                    "real LCP thresholds, regular-thresholds index (5.3e7 rows = 423 MB: 3.4x the L2), 1M x 150 bp reads PML per GPU per step")
         return ("%s: 64-haplotype x 5 Mbp synthetic bacterial pangenome (0.1%% divergence, +reverse complements), suffix-sorted, %s index "
                 "(124 MB of rows: L2-sized), 1M x 150 bp reads %s per GPU per step"
                 % (ARGS_WORKLOAD, W["index"], W["query"].upper() if W["query"] != "count" else "count"))
@@ -305,9 +313,15 @@ def sub_records(dev, peak):
     global W, ARGS_WORKLOAD
     keep = (W, ARGS_WORKLOAD)
     out = {}
-    for name in ("c2", "c3-zml", "c3-count"):
+    for name in ("c2", "c3-zml", "c3-count", "g1"):
         W, ARGS_WORKLOAD = WORKLOADS[name], name
         try:
+            if name == "g1":          # its suffix array takes minutes: only when the prepared index travelled with the snapshot
+                from movi_b200.datagen import synth
+                f = os.path.join(synth.cache_dir("g1"), "regular-thresholds", "index.movi")
+                if not (os.path.exists(f) or os.path.exists(f + ".xz")):
+                    out["g1"] = {"skipped": "the prepared g1 index (_cache/g1) is not on this box"}
+                    continue
             data = C2Data(0, dev)
             ms, n_reads, n_bases = data.ms, data.n_reads, data.n_bases
             is_count = W["query"] == "count"
@@ -328,7 +342,7 @@ def sub_records(dev, peak):
                 launch(i, cur.cuda_stream)
             torch.cuda.synchronize()
             side = [torch.cuda.Stream(device=dev) for _ in range(2)]
-            steps = 400
+            steps = 400 if name != "g1" else 200
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for s_ in side:
@@ -380,7 +394,8 @@ def sub_records(dev, peak):
                 del hb, hout
             achieved = W["algo"] * work / (ms_step * 1e-3) / 1e9
             traffic = None
-            tp = os.path.join(ROOT, "profiles", {"c2": "pml_c2_traffic.json", "c3-zml": "zml_c3_traffic.json", "c3-count": "count_c3_traffic.json"}[name])
+            tp = os.path.join(ROOT, "profiles", {"c2": "pml_c2_traffic.json", "c3-zml": "zml_c3_traffic.json", "c3-count": "count_c3_traffic.json",
+                                                 "g1": "pml_g1_traffic.json"}[name])
             if os.path.exists(tp):
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             rec = {"workload": data.describe(), "metric": W["metric"], "value": n_bases / (ms_step * 1e-3), "unit": "bases/s", "ms_per_step": ms_step,
@@ -666,7 +681,7 @@ def main():
         achieved = W["algo"] * work_bases / per_launch_s / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", {"c4": "pml_c4_traffic.json", "c2": "pml_c2_traffic.json", "c3-zml": "zml_c3_traffic.json",
-                                            "c3-count": "count_c3_traffic.json"}[args.workload])
+                                            "c3-count": "count_c3_traffic.json", "g1": "pml_g1_traffic.json"}[args.workload])
         if os.path.exists(tp):
             try:
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")

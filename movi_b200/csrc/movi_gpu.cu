@@ -78,6 +78,7 @@ struct movi_gpu_ctx {
     uint64_t launches = 0;
     bool always_rpml = false;         // non-threshold index type: every PML query repositions with the --rpml rule
     uint32_t call_flags = 0;          // MOVI_GPU_FLAG_* of the entry point that is running
+    uint64_t batch_reads = 0;         // host-buffer entry points: reads of the whole batch the slice being launched belongs to
     // options
     int64_t pml_sector = -1;          // sector-cached row fetch: -1 by table size (> 512 MB) and batch size, 0 off, 1 on
     int64_t smem_carveout = -1;       // >= 0: preferred shared-memory carve-out of the query kernels, percent of the maximum (exploration)
@@ -246,8 +247,11 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
     //  a batch of few long reads, which leaves most lanes empty and is latency bound, -10 %: those keep the plain fetch)
     const bool b6 = ctx->ix.layout == LAYOUT_B6, t3 = ctx->ix.layout == LAYOUT_T4;
     int sm_cap = 0;                     // resident blocks per SM at most (0 = what the registers allow)
+    // (a slice of a bigger batch walks next to its neighbours: what counts is the reads of the batch, not of the slice -- slices of
+    //  5.7e4 long reads ran the plain fetch until round 2's pipeline trace showed it: profiles/r02_e2e_pipeline_trace_before.txt)
+    const uint64_t in_flight = std::max<uint64_t>(qa.n_reads, ctx->batch_reads);
     const bool sector = !b6 && !t3 && !ctx->ix.nt && (ctx->pml_sector == 1 || (ctx->pml_sector < 0 &&
-                        ctx->ix.r * sizeof(uint2) > (512ull << 20) && qa.n_reads >= (1u << 17)));
+                        ctx->ix.r * sizeof(uint2) > (512ull << 20) && in_flight >= (1u << 17)));
     if (kind == Q_PML) {
         if (sector) sm_cap = 4;
         // 6 blocks/SM (40 registers) measured fastest on L2-sized tables (c2); the sector-cached kernel of HBM-resident tables runs
@@ -346,6 +350,7 @@ int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* 
     CU(cudaMemset(ctx->d_status, 0, sizeof(unsigned int)));
     if (kind == Q_COUNT) { rc = ensure_prefix(ctx, ctx->st_k[0]); if (rc) return rc; }
 
+    struct BatchReads { movi_gpu_ctx* c; BatchReads(movi_gpu_ctx* x, uint64_t n) : c(x) { c->batch_reads = n; } ~BatchReads() { c->batch_reads = 0; } } batch_reads(ctx, n_reads);
     const int n_slots = (int)std::min<int64_t>(std::max<int64_t>(ctx->pipeline_slots, 2), NBUF);
     const int n_ks = (int)std::min<int64_t>(std::max<int64_t>(ctx->kernel_streams, 1), NKS);
     // a slice holds batch_bases bases, or -- reads longer than ~200 bases -- as many reads as one of the n_ks concurrently

@@ -136,6 +136,8 @@ CONFIGS = {
     # name: genome_len, n_hap, n_reads, read_len
     "c2": dict(genome_len=5_000_000, n_hap=64, n_reads=1_000_000, read_len=150),
     "c2-small": dict(genome_len=100_000, n_hap=16, n_reads=20_000, read_len=150),   # CPU-sized twin used by tests
+    # a suffix-sorted index BEYOND the L2: 20 haplotypes x 25 Mbp (+ reverse complements) = 1 Gbp of text, real LCP thresholds
+    "g1": dict(genome_len=25_000_000, n_hap=20, n_reads=1_000_000, read_len=150),
 }
 
 
