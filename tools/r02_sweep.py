@@ -80,15 +80,16 @@ def main():
     dev = torch.device("cuda:0")
     what = sys.argv[1]
     settings = [(0, 0), (1, 0), (1, 6), (1, 4), (0, 5)]
-    if what in ("c2", "long"):
+    if what in ("c2", "g1", "long"):
         from movi_b200 import MoveStructure
         from movi_b200.datagen import synth
-        d, haps = synth.prepare("c2", ("regular-thresholds",))
+        name = "g1" if what == "g1" else "c2"
+        d, haps = synth.prepare(name, ("regular-thresholds",))
         ms = MoveStructure(os.path.join(d, "regular-thresholds"))
-        if what == "c2":
+        if what in ("c2", "g1"):
             bases, offsets = synth.make_reads(haps, 1_000_000, 150, seed=43)
             kinds = sys.argv[2:] or ["pml"]
-            tag = "c2 1Mx150"
+            tag = name + " 1Mx150"
         else:
             n = int(sys.argv[2])
             bases, offsets = synth.make_reads(haps, n, 10_000, seed=45, sub=0.05, frac_random=0.0)
