@@ -44,7 +44,7 @@ WORKLOADS = {
                      kernel="movi_bs_kernel<uint32_t,COUNT,R8>"),
     # a suffix-sorted index beyond the L2 (1 Gbp of text, 5.3e7 rows = 423 MB, real LCP thresholds); sub-record only
     "g1": dict(data="g1", index="regular-thresholds", query="pml", metric="PML query bases/sec", algo=32,
-               kernel="movi_pml_kernel<uint32_t,false,6,R8>"),
+               kernel="movi_pml_kernel<uint32_t,false,4,R8,SECTOR>"),
 }
 W = WORKLOADS["c4"]               # replaced in main() from --workload
 ARGS_WORKLOAD = "c4"

@@ -250,8 +250,11 @@ int launch_query(movi_gpu_ctx* ctx, Kind kind, const QueryArgs& qa, cudaStream_t
     // (a slice of a bigger batch walks next to its neighbours: what counts is the reads of the batch, not of the slice -- slices of
     //  5.7e4 long reads ran the plain fetch until round 2's pipeline trace showed it: profiles/r02_e2e_pipeline_trace_before.txt)
     const uint64_t in_flight = std::max<uint64_t>(qa.n_reads, ctx->batch_reads);
+    // crossover between the two fetch forms (profiles/r02_sweep_g1.jsonl, r02_sweep_1.jsonl): PML 124 MB table plain 2.11 / sector
+    // 2.57 ms, 423 MB table 3.82 / 3.50 ms; ZML and count still prefer the plain fetch at 423 MB (5.63 / 6.18, 2.81 / 3.32 ms)
+    const uint64_t sector_from = kind == Q_PML ? (256ull << 20) : (512ull << 20);
     const bool sector = !b6 && !t3 && !ctx->ix.nt && (ctx->pml_sector == 1 || (ctx->pml_sector < 0 &&
-                        ctx->ix.r * sizeof(uint2) > (512ull << 20) && in_flight >= (1u << 17)));
+                        ctx->ix.r * sizeof(uint2) > sector_from && in_flight >= (1u << 17)));
     if (kind == Q_PML) {
         if (sector) sm_cap = 4;
         // 6 blocks/SM (40 registers) measured fastest on L2-sized tables (c2); the sector-cached kernel of HBM-resident tables runs
@@ -356,7 +359,13 @@ int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* 
     // a slice holds batch_bases bases, or -- reads longer than ~200 bases -- as many reads as one of the n_ks concurrently
     // walking slices has lanes: a read is one dependent chain, so a slice of few long reads would take the full walk latency
     // of a read however small it is (12 M bases = 1200 reads of 10 kbp: 4.7 s per 4.1e9-base batch instead of 0.3 s)
-    const uint64_t lanes = (uint64_t)ctx->num_sms * 6u * (uint64_t)ctx->threads_per_block;
+    // (lanes of the kernel the slices will run: the sector-cached forms keep 4 / 3 blocks per SM resident, the plain ones 6 / 5;
+    //  slices sized for more lanes than there are spill into an extra round of walks: profiles/r02_e2e_pipeline_trace_after.txt)
+    const bool big_table = ctx->ix.layout == LAYOUT_R8 && !ctx->ix.nt && (ctx->pml_sector == 1 || (ctx->pml_sector < 0 &&
+                           ctx->ix.r * sizeof(uint2) > (kind == Q_PML ? (256ull << 20) : (512ull << 20)) && n_reads >= (1u << 17)));
+    const unsigned blocks_per_sm = ctx->blocks_per_sm > 0 ? (unsigned)ctx->blocks_per_sm
+                                 : kind == Q_PML ? (big_table ? 4u : 6u) : (big_table ? 3u : 5u);
+    const uint64_t lanes = (uint64_t)ctx->num_sms * blocks_per_sm * (uint64_t)ctx->threads_per_block;
     const uint64_t avg_len = std::max<uint64_t>(1, (offsets[n_reads] - offsets[0]) / n_reads);
     const uint64_t max_bases = std::min<uint64_t>(std::max<uint64_t>((uint64_t)std::max<int64_t>(ctx->batch_bases, 1 << 16),
                                                                      avg_len * (lanes / (uint64_t)n_ks)), 1ull << 30);
