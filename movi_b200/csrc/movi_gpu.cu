@@ -45,6 +45,12 @@ struct Staging {                              // one pipeline slot
     unsigned long long* d_id_offsets = nullptr; size_t id_offsets_cap = 0;   // their offsets,
     uint8_t* d_image = nullptr; size_t image_cap = 0;                   // and its .bpf records
     unsigned long long* d_counter = nullptr;
+    // pageable caller buffers: the slice's bases / results pass through these pinned arenas (a copy to or from pageable memory
+    // is staged by the driver and makes the call wait for the stream: the pipeline would run slice by slice)
+    uint8_t* h_in = nullptr; size_t h_in_cap = 0;
+    uint8_t* h_out = nullptr; size_t h_out_cap = 0;
+    struct Pending { void* dst; const void* src; size_t n; } pend[8];
+    int n_pend = 0;
     bool busy = false;
 };
 
@@ -333,6 +339,110 @@ int grow(movi_gpu_ctx* ctx, T*& p, size_t& cap, size_t need) {
     return MOVI_GPU_OK;
 }
 
+// ---- staged copies: pageable host memory (a memory-mapped file, a std::vector) and file descriptors on one side, HBM on the other.
+// cudaMemcpyAsync on pageable memory is staged by the driver through one thread at ~6 GB/s and blocks; here the pieces go through
+// a ring of four pinned buffers, filled / drained by a few host threads while the previous pieces are on the wire.
+constexpr size_t PIN_PIECE = 64u << 20;
+inline int pin_threads() {                           // host threads that fill / drain a piece (page-cache writes run at ~1 GB/s per thread)
+    static const int n = (int)std::min(12u, std::max(2u, std::thread::hardware_concurrency() > 3 ? std::thread::hardware_concurrency() - 2 : 2u));
+    return n;
+}
+
+int ensure_pin_ring(movi_gpu_ctx* ctx) {
+    for (int k = 0; k < 4; k++) {
+        if (!ctx->pin[k]) CU(cudaHostAlloc(reinterpret_cast<void**>(&ctx->pin[k]), PIN_PIECE, cudaHostAllocDefault));
+        if (!ctx->pin_ev[k]) CU(cudaEventCreateWithFlags(&ctx->pin_ev[k], cudaEventDisableTiming));
+    }
+    return MOVI_GPU_OK;
+}
+bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+template <typename F> void in_parts(size_t n, F f) {          // f(begin, end) on pin_threads() threads
+    const int t = (int)std::min<size_t>((size_t)pin_threads(), (n + (4u << 20) - 1) / (4u << 20));
+    if (t <= 1) { f((size_t)0, n); return; }
+    std::vector<std::thread> th;
+    for (int k = 0; k < t; k++) th.emplace_back(f, n * k / t, n * (k + 1) / t);
+    for (auto& x : th) x.join();
+}
+int staged_h2d(movi_gpu_ctx* ctx, void* d_dst, const char* src, size_t n, cudaStream_t st) {
+    if (n == 0) return MOVI_GPU_OK;
+    if (is_pinned(src)) { CU(cudaMemcpyAsync(d_dst, src, n, cudaMemcpyHostToDevice, st)); return MOVI_GPU_OK; }
+    int rc = ensure_pin_ring(ctx);
+    if (rc) return rc;
+    size_t k = 0;
+    for (size_t off = 0; off < n; off += PIN_PIECE, k++) {
+        const size_t len = std::min(PIN_PIECE, n - off);
+        const int slot = (int)(k & 3);
+        if (k >= 4) CU(cudaEventSynchronize(ctx->pin_ev[slot]));
+        uint8_t* buf = ctx->pin[slot];
+        in_parts(len, [&](size_t b, size_t e) { std::memcpy(buf + b, src + off + b, e - b); });
+        CU(cudaMemcpyAsync(static_cast<uint8_t*>(d_dst) + off, buf, len, cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(ctx->pin_ev[slot], st));
+    }
+    return MOVI_GPU_OK;
+}
+// device -> host memory (dst != NULL) or -> file (fd >= 0, positional writes at file_off); returns when everything has landed
+int staged_d2h(movi_gpu_ctx* ctx, uint8_t* dst, int fd, uint64_t file_off, const uint8_t* d_src, size_t n, cudaStream_t st) {
+    if (n == 0) return MOVI_GPU_OK;
+    if (dst && fd < 0 && is_pinned(dst)) { CU(cudaMemcpyAsync(dst, d_src, n, cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); return MOVI_GPU_OK; }
+    int rc = ensure_pin_ring(ctx);
+    if (rc) return rc;
+    const size_t pieces = (n + PIN_PIECE - 1) / PIN_PIECE;
+    size_t issued = 0;
+    bool io_ok = true;
+    uint64_t file_len = 0;
+    if (fd >= 0) { const off_t e = lseek(fd, 0, SEEK_END); if (e > 0) file_len = (uint64_t)e; }
+    for (size_t done = 0; done < pieces; done++) {
+        for (; issued < pieces && issued - done < 4; issued++) {
+            const size_t off = issued * PIN_PIECE, len = std::min(PIN_PIECE, n - off);
+            CU(cudaMemcpyAsync(ctx->pin[issued & 3], d_src + off, len, cudaMemcpyDeviceToHost, st));
+            CU(cudaEventRecord(ctx->pin_ev[issued & 3], st));
+        }
+        CU(cudaEventSynchronize(ctx->pin_ev[done & 3]));
+        const size_t off = done * PIN_PIECE, len = std::min(PIN_PIECE, n - off);
+        const uint8_t* buf = ctx->pin[done & 3];
+        if (fd >= 0) {
+            // Into the page cache through a shared mapping when the file already reaches that far (the caller extends it): positional
+            // writes of several threads to ONE file take turns on its inode lock (2.9 GB/s on tmpfs whatever the thread count),
+            // page faults on a mapping do not.  Otherwise pwrite.
+            const uint64_t at = file_off + off, page = 4096, m0 = at & ~(page - 1);
+            const size_t mlen = (size_t)(at + len - m0);
+            void* m = (file_len >= at + len) ? mmap(nullptr, mlen, PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)m0) : MAP_FAILED;
+            if (m != MAP_FAILED) {
+                uint8_t* to = static_cast<uint8_t*>(m) + (at - m0);
+                in_parts(len, [&](size_t b, size_t e) { std::memcpy(to + b, buf + b, e - b); });
+                munmap(m, mlen);
+            } else
+            in_parts(len, [&](size_t b, size_t e) {
+                while (b < e) { const ssize_t w = pwrite(fd, buf + b, e - b, (off_t)(file_off + off + b)); if (w <= 0) { io_ok = false; return; } b += (size_t)w; }
+            });
+        }
+        if (dst) in_parts(len, [&](size_t b, size_t e) { std::memcpy(dst + off + b, buf + b, e - b); });
+    }
+    if (!io_ok) return fail(ctx, MOVI_GPU_ERR_ARG, "write failed: .bpf");
+    return MOVI_GPU_OK;
+}
+
+int grow_pinned(movi_gpu_ctx* ctx, uint8_t*& p, size_t& cap, size_t need) {
+    if (need <= cap) return MOVI_GPU_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    const size_t want = need + need / 8 + 4096;
+    CU(cudaHostAlloc(reinterpret_cast<void**>(&p), want, cudaHostAllocDefault));
+    cap = want;
+    return MOVI_GPU_OK;
+}
+void flush_slot(Staging& S) {            // results of a finished slice: pinned arena -> the caller's (pageable) buffers
+    for (int k = 0; k < S.n_pend; k++) {
+        const Staging::Pending& q = S.pend[k];
+        in_parts(q.n, [&](size_t b, size_t e) { std::memcpy(static_cast<uint8_t*>(q.dst) + b, static_cast<const uint8_t*>(q.src) + b, e - b); });
+    }
+    S.n_pend = 0;
+}
+
 // Host-buffer entry point: split the batch into slices of ~batch_bases, run them through a 3-deep
 // pipeline (H2D on slot stream, kernel, D2H), results land directly in the caller's buffers.
 struct ClassifyOut { uint32_t bin_width = 0, thr = 0; uint32_t* above = nullptr; uint32_t* below = nullptr; uint64_t* sum = nullptr; };
@@ -356,6 +466,12 @@ int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* 
     struct BatchReads { movi_gpu_ctx* c; BatchReads(movi_gpu_ctx* x, uint64_t n) : c(x) { c->batch_reads = n; } ~BatchReads() { c->batch_reads = 0; } } batch_reads(ctx, n_reads);
     const int n_slots = (int)std::min<int64_t>(std::max<int64_t>(ctx->pipeline_slots, 2), NBUF);
     const int n_ks = (int)std::min<int64_t>(std::max<int64_t>(ctx->kernel_streams, 1), NKS);
+    // caller buffers in pageable memory (std::vector, numpy): stage through the slots' pinned arenas
+    const void* main_out = kind == Q_COUNT ? static_cast<const void*>(out_count) : out_ml ? static_cast<const void*>(out_ml)
+                         : out_ml8 ? static_cast<const void*>(out_ml8) : bpf ? static_cast<const void*>(bpf->image)
+                         : cls ? static_cast<const void*>(cls->above) : nullptr;
+    const bool stage_in = !is_pinned(bases), stage_out = main_out && !is_pinned(main_out);
+    for (int k = 0; k < NBUF; k++) ctx->slot[k].n_pend = 0;         // (a call that failed half way may have left some)
     // a slice holds batch_bases bases, or -- reads longer than ~200 bases -- as many reads as one of the n_ks concurrently
     // walking slices has lanes: a read is one dependent chain, so a slice of few long reads would take the full walk latency
     // of a read however small it is (12 M bases = 1200 reads of 10 kbp: 4.7 s per 4.1e9-base batch instead of 0.3 s)
@@ -393,7 +509,7 @@ int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* 
         if (nb >= 0xFFFFFFF0ull) return fail(ctx, MOVI_GPU_ERR_ARG, "a single read longer than 2^32 bases is not supported");
         Staging& S = ctx->slot[slice % n_slots];
         cudaStream_t kst = ctx->st_k[slice % n_ks];
-        if (S.busy) { CU(cudaEventSynchronize(S.out_done)); S.busy = false; }   // the slot's previous results have left
+        if (S.busy) { CU(cudaEventSynchronize(S.out_done)); flush_slot(S); S.busy = false; }   // the slot's previous results have left
         // keep the device copy congruent to the host offsets modulo 32: the kernels stage whole aligned 32-byte sectors
         const uint64_t shift = o0 & 31u;
         if ((rc = grow(ctx, S.d_bases, S.bases_cap, nb + shift + 64))) return rc;
@@ -423,7 +539,25 @@ int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* 
         }
         // in
         mark(ctx->st_in);
-        CU(cudaMemcpyAsync(S.d_bases + shift, bases + o0, nb, cudaMemcpyHostToDevice, ctx->st_in));
+        const bool staged_in = stage_in && nb <= (64ull << 20), staged = stage_out && nb <= (64ull << 20);
+        size_t out_at = 0;
+        if (staged_in) {
+            if ((rc = grow_pinned(ctx, S.h_in, S.h_in_cap, nb + 64))) return rc;
+            in_parts(nb, [&](size_t b, size_t e) { std::memcpy(S.h_in + b, bases + o0 + b, e - b); });
+        }
+        if (staged) {
+            const size_t need_out = (kind == Q_COUNT ? nr * 12 : 0) + (out_ml ? nb * 2 : 0) + (out_ml8 ? nb : 0) + (cls ? nr * 16 : 0) + (bpf ? img_bytes : 0) + 1024;
+            if ((rc = grow_pinned(ctx, S.h_out, S.h_out_cap, need_out))) return rc;
+        }
+        // a result: straight to the caller's pinned buffer, or into the slot's pinned arena with the last hop deferred
+        auto copy_back = [&](void* dst, const void* d_src, size_t n) -> cudaError_t {
+            if (!staged) return cudaMemcpyAsync(dst, d_src, n, cudaMemcpyDeviceToHost, ctx->st_out);
+            uint8_t* via = S.h_out + out_at;
+            out_at += (n + 63) & ~(size_t)63;
+            S.pend[S.n_pend++] = Staging::Pending{dst, via, n};
+            return cudaMemcpyAsync(via, d_src, n, cudaMemcpyDeviceToHost, ctx->st_out);
+        };
+        CU(cudaMemcpyAsync(S.d_bases + shift, staged_in ? reinterpret_cast<const char*>(S.h_in) : bases + o0, nb, cudaMemcpyHostToDevice, ctx->st_in));
         CU(cudaMemcpyAsync(S.d_offsets, offsets + i0, (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->st_in));
         if (bpf) {
             CU(cudaMemcpyAsync(S.d_ids, bpf->ids + bpf->id_offsets[i0], id_bytes, cudaMemcpyHostToDevice, ctx->st_in));
@@ -463,17 +597,17 @@ int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* 
         // out
         CU(cudaStreamWaitEvent(ctx->st_out, S.k_done, 0));
         if (kind == Q_COUNT) {
-            CU(cudaMemcpyAsync(out_count + i0, S.d_count, nr * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->st_out));
-            CU(cudaMemcpyAsync(out_pos + i0, S.d_pos, nr * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->st_out));
+            CU(copy_back(out_count + i0, S.d_count, nr * sizeof(uint64_t)));
+            CU(copy_back(out_pos + i0, S.d_pos, nr * sizeof(int32_t)));
         } else {
             if (cls) {
-                CU(cudaMemcpyAsync(cls->above + i0, S.d_above, nr * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->st_out));
-                CU(cudaMemcpyAsync(cls->below + i0, S.d_below, nr * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->st_out));
-                CU(cudaMemcpyAsync(cls->sum + i0, S.d_sum, nr * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->st_out));
+                CU(copy_back(cls->above + i0, S.d_above, nr * sizeof(uint32_t)));
+                CU(copy_back(cls->below + i0, S.d_below, nr * sizeof(uint32_t)));
+                CU(copy_back(cls->sum + i0, S.d_sum, nr * sizeof(uint64_t)));
             }
-            if (out_ml) CU(cudaMemcpyAsync(out_ml + o0, S.d_ml + shift, nb * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->st_out));
-            if (out_ml8) CU(cudaMemcpyAsync(out_ml8 + o0, S.d_ml8 + shift, nb, cudaMemcpyDeviceToHost, ctx->st_out));
-            if (bpf) CU(cudaMemcpyAsync(bpf->image + (img0 - bpf_record_at(offsets, bpf->id_offsets, 0)), S.d_image, img_bytes, cudaMemcpyDeviceToHost, ctx->st_out));
+            if (out_ml) CU(copy_back(out_ml + o0, S.d_ml + shift, nb * sizeof(uint16_t)));
+            if (out_ml8) CU(copy_back(out_ml8 + o0, S.d_ml8 + shift, nb));
+            if (bpf) CU(copy_back(bpf->image + (img0 - bpf_record_at(offsets, bpf->id_offsets, 0)), S.d_image, img_bytes));
         }
         CU(cudaEventRecord(S.out_done, ctx->st_out));
         mark(ctx->st_out);
@@ -482,7 +616,7 @@ int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* 
         i0 = i1;
     }
     CU(cudaStreamSynchronize(ctx->st_out));            // st_out runs in slice order: its end is the end of the batch
-    for (int k = 0; k < NBUF; k++) ctx->slot[k].busy = false;
+    for (int k = 0; k < NBUF; k++) { flush_slot(ctx->slot[k]); ctx->slot[k].busy = false; }
     if (trace) {
         for (size_t k = 0; k + 3 < tev.size(); k += 4) {
             float t[4];
@@ -556,6 +690,8 @@ int movi_gpu_destroy(movi_gpu_ctx* ctx) {
         cudaFree(S.d_bases); cudaFree(S.d_offsets); cudaFree(S.d_ml); cudaFree(S.d_ml8); cudaFree(S.d_count); cudaFree(S.d_pos); cudaFree(S.d_counter);
         cudaFree(S.d_above); cudaFree(S.d_below); cudaFree(S.d_sum);
         cudaFree(S.d_ids); cudaFree(S.d_id_offsets); cudaFree(S.d_image);
+        if (S.h_in) cudaFreeHost(S.h_in);
+        if (S.h_out) cudaFreeHost(S.h_out);
         if (S.in_done) cudaEventDestroy(S.in_done);
         if (S.k_done) cudaEventDestroy(S.k_done);
         if (S.out_done) cudaEventDestroy(S.out_done);
@@ -981,93 +1117,6 @@ static unsigned long long* next_counter(movi_gpu_ctx* ctx) {
 }  // extern "C" (the helpers below are C++)
 
 namespace {
-// ---- staged copies: pageable host memory (a memory-mapped file, a std::vector) and file descriptors on one side, HBM on the other.
-// cudaMemcpyAsync on pageable memory is staged by the driver through one thread at ~6 GB/s and blocks; here the pieces go through
-// a ring of four pinned buffers, filled / drained by a few host threads while the previous pieces are on the wire.
-constexpr size_t PIN_PIECE = 64u << 20;
-inline int pin_threads() {                           // host threads that fill / drain a piece (page-cache writes run at ~1 GB/s per thread)
-    static const int n = (int)std::min(12u, std::max(2u, std::thread::hardware_concurrency() > 3 ? std::thread::hardware_concurrency() - 2 : 2u));
-    return n;
-}
-
-int ensure_pin_ring(movi_gpu_ctx* ctx) {
-    for (int k = 0; k < 4; k++) {
-        if (!ctx->pin[k]) CU(cudaHostAlloc(reinterpret_cast<void**>(&ctx->pin[k]), PIN_PIECE, cudaHostAllocDefault));
-        if (!ctx->pin_ev[k]) CU(cudaEventCreateWithFlags(&ctx->pin_ev[k], cudaEventDisableTiming));
-    }
-    return MOVI_GPU_OK;
-}
-bool is_pinned(const void* p) {
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
-}
-template <typename F> void in_parts(size_t n, F f) {          // f(begin, end) on pin_threads() threads
-    const int t = (int)std::min<size_t>((size_t)pin_threads(), (n + (4u << 20) - 1) / (4u << 20));
-    if (t <= 1) { f((size_t)0, n); return; }
-    std::vector<std::thread> th;
-    for (int k = 0; k < t; k++) th.emplace_back(f, n * k / t, n * (k + 1) / t);
-    for (auto& x : th) x.join();
-}
-int staged_h2d(movi_gpu_ctx* ctx, void* d_dst, const char* src, size_t n, cudaStream_t st) {
-    if (n == 0) return MOVI_GPU_OK;
-    if (is_pinned(src)) { CU(cudaMemcpyAsync(d_dst, src, n, cudaMemcpyHostToDevice, st)); return MOVI_GPU_OK; }
-    int rc = ensure_pin_ring(ctx);
-    if (rc) return rc;
-    size_t k = 0;
-    for (size_t off = 0; off < n; off += PIN_PIECE, k++) {
-        const size_t len = std::min(PIN_PIECE, n - off);
-        const int slot = (int)(k & 3);
-        if (k >= 4) CU(cudaEventSynchronize(ctx->pin_ev[slot]));
-        uint8_t* buf = ctx->pin[slot];
-        in_parts(len, [&](size_t b, size_t e) { std::memcpy(buf + b, src + off + b, e - b); });
-        CU(cudaMemcpyAsync(static_cast<uint8_t*>(d_dst) + off, buf, len, cudaMemcpyHostToDevice, st));
-        CU(cudaEventRecord(ctx->pin_ev[slot], st));
-    }
-    return MOVI_GPU_OK;
-}
-// device -> host memory (dst != NULL) or -> file (fd >= 0, positional writes at file_off); returns when everything has landed
-int staged_d2h(movi_gpu_ctx* ctx, uint8_t* dst, int fd, uint64_t file_off, const uint8_t* d_src, size_t n, cudaStream_t st) {
-    if (n == 0) return MOVI_GPU_OK;
-    if (dst && fd < 0 && is_pinned(dst)) { CU(cudaMemcpyAsync(dst, d_src, n, cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); return MOVI_GPU_OK; }
-    int rc = ensure_pin_ring(ctx);
-    if (rc) return rc;
-    const size_t pieces = (n + PIN_PIECE - 1) / PIN_PIECE;
-    size_t issued = 0;
-    bool io_ok = true;
-    uint64_t file_len = 0;
-    if (fd >= 0) { const off_t e = lseek(fd, 0, SEEK_END); if (e > 0) file_len = (uint64_t)e; }
-    for (size_t done = 0; done < pieces; done++) {
-        for (; issued < pieces && issued - done < 4; issued++) {
-            const size_t off = issued * PIN_PIECE, len = std::min(PIN_PIECE, n - off);
-            CU(cudaMemcpyAsync(ctx->pin[issued & 3], d_src + off, len, cudaMemcpyDeviceToHost, st));
-            CU(cudaEventRecord(ctx->pin_ev[issued & 3], st));
-        }
-        CU(cudaEventSynchronize(ctx->pin_ev[done & 3]));
-        const size_t off = done * PIN_PIECE, len = std::min(PIN_PIECE, n - off);
-        const uint8_t* buf = ctx->pin[done & 3];
-        if (fd >= 0) {
-            // Into the page cache through a shared mapping when the file already reaches that far (the caller extends it): positional
-            // writes of several threads to ONE file take turns on its inode lock (2.9 GB/s on tmpfs whatever the thread count),
-            // page faults on a mapping do not.  Otherwise pwrite.
-            const uint64_t at = file_off + off, page = 4096, m0 = at & ~(page - 1);
-            const size_t mlen = (size_t)(at + len - m0);
-            void* m = (file_len >= at + len) ? mmap(nullptr, mlen, PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)m0) : MAP_FAILED;
-            if (m != MAP_FAILED) {
-                uint8_t* to = static_cast<uint8_t*>(m) + (at - m0);
-                in_parts(len, [&](size_t b, size_t e) { std::memcpy(to + b, buf + b, e - b); });
-                munmap(m, mlen);
-            } else
-            in_parts(len, [&](size_t b, size_t e) {
-                while (b < e) { const ssize_t w = pwrite(fd, buf + b, e - b, (off_t)(file_off + off + b)); if (w <= 0) { io_ok = false; return; } b += (size_t)w; }
-            });
-        }
-        if (dst) in_parts(len, [&](size_t b, size_t e) { std::memcpy(dst + off + b, buf + b, e - b); });
-    }
-    if (!io_ok) return fail(ctx, MOVI_GPU_ERR_ARG, "write failed: .bpf");
-    return MOVI_GPU_OK;
-}
-
 // ---- device-side ingest: a chunk of a FASTA / FASTQ file (starting at a record boundary) parsed in HBM (parse_kernels.cuh)
 
 // raw chunk (host memory) -> ctx->p_bases / p_offsets / p_ids / p_id_offsets on the device; synchronises `st`

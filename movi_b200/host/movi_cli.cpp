@@ -192,6 +192,12 @@ int run_device_ingest(const Options& o, const std::vector<movi_gpu_ctx*>& ctx, c
                 end = begin + chunk_bytes >= size ? size : movi_host_record_boundary(data, size, begin + chunk_bytes, fastq);
                 next_begin = end; seq = next_seq++;
             }
+            if (end - begin >= 0xFFFFFF00ull) {            // one record of 4 GiB or more: not a chunk the device parser takes
+                std::lock_guard<std::mutex> lk(mu);
+                if (status == 0) status = 1;
+                cv.notify_all();
+                return;
+            }
             MoviGpuChunkResult res{};
             int rc = movi_gpu_file_chunk_parse(ctx[g], data + begin, end - begin, fastq, 1, &res);
             uint64_t my_off = 0;
