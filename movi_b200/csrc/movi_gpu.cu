@@ -483,8 +483,11 @@ int host_query(movi_gpu_ctx* ctx, Kind kind, const char* bases, const uint64_t* 
                                  : kind == Q_PML ? (big_table ? 4u : 6u) : (big_table ? 3u : 5u);
     const uint64_t lanes = (uint64_t)ctx->num_sms * blocks_per_sm * (uint64_t)ctx->threads_per_block;
     const uint64_t avg_len = std::max<uint64_t>(1, (offsets[n_reads] - offsets[0]) / n_reads);
+    // n_ks slices walk at a time; with twice the lanes' worth of reads among them, blocks of the next slice move in as blocks of an
+    // earlier one drain (c4, 4.1e9 bases per call, profiles/r02_e2e_sweep.jsonl: 274 ms with slices of lanes / 2 reads, 329 ms with
+    // lanes / 4, 289 ms with lanes / 1.4; two or one slices at a time: 322 - 452 ms)
     const uint64_t max_bases = std::min<uint64_t>(std::max<uint64_t>((uint64_t)std::max<int64_t>(ctx->batch_bases, 1 << 16),
-                                                                     avg_len * (lanes / (uint64_t)n_ks)), 1ull << 30);
+                                                                     avg_len * (2 * lanes / (uint64_t)n_ks)), 1ull << 30);
     // MOVI_GPU_TRACE=1: per-slice device timeline (ms since the first copy was enqueued) on stderr -- a debugging aid for
     // the copy / kernel overlap of this pipeline, off the product path
     static const bool trace = getenv("MOVI_GPU_TRACE") != nullptr;
