@@ -420,6 +420,33 @@ def sub_records(dev, peak):
 
 
 
+def cli_file_to_file(index_dir, bases, offsets, n_reads, n_bases):
+    """The same boundary as the reference arm -- a FASTA file in, PML of every base, nothing written (`--no-output`), index load not
+    timed -- through the drop-in command line (`movi-b200 query`): one full step's reads, parsed, walked on the GPU from the file's
+    bytes (device-side ingest).  Timer: the command's own "queried ... in X s" line, like the reference's "processing the reads"."""
+    from movi_b200 import build
+    out = {"unit": "bases/s", "what": "movi-b200 query --pml --no-output on one step's reads as a FASTA file (device-side ingest), index load excluded "
+                                      "like in the reference arm"}
+    try:
+        with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
+            fa = os.path.join(td, "step.fa")
+            write_fasta(fa, bases, offsets, n_reads)
+            t0 = time.time()
+            r = subprocess.run([build.CLI, "query", "-i", index_dir, "-r", fa, "--pml", "--no-output", "--verbose"], stdout=subprocess.DEVNULL,
+                               stderr=subprocess.PIPE, text=True)
+            wall = time.time() - t0
+            m = re.search(r"written in ([0-9.]+) s: (\d+) reads / (\d+) bases", r.stderr)
+            if r.returncode != 0 or not m or int(m.group(3)) != n_bases:
+                out["error"] = (r.stderr or "")[-300:]
+                return out
+            sec = float(m.group(1))
+            out.update({"value": n_bases / sec, "seconds": sec, "process_wall_s": round(wall, 2), "fasta_bytes": os.path.getsize(fa)})
+            log("[bench] movi-b200 query on one step's FASTA: %.3f s (process wall %.1f s incl. CUDA start-up and index upload)" % (sec, wall))
+    except Exception as e:
+        out["error"] = "%s: %s" % (type(e).__name__, e)
+    return out
+
+
 def make_data(rank, device, need_device=True):
     return C4Data(rank, device, need_device) if W["data"] == "c4" else C2Data(rank, device, need_device)
 
@@ -749,6 +776,8 @@ def main():
             data.d_bases = None
             del d_outs, h_bases, h_out
             torch.cuda.empty_cache()
+            if not args.no_cpu_baseline and data.cpu_index_dir():
+                line["e2e_cli"] = cli_file_to_file(data.cpu_index_dir(), h_bases_np, h_off_np, n_reads, n_bases)
             line.update(sub_records(dev, peak))
         emit_line(line)
     ms.close()
