@@ -181,6 +181,12 @@ int run_device_ingest(const Options& o, const std::vector<movi_gpu_ctx*>& ctx, c
     std::condition_variable cv;
     uint64_t next_begin = 0, next_seq = 0, place_seq = 0, file_off = 12, chunk_bytes = o.chunk_bytes;     // 12: the BPFHeader
     int status = 0;                                // 0 running / ok, 1 fall back, -1 error (under mu)
+    // long reads: a chunk should hold a read per lane from the start (a chunk of few long reads costs a full walk however small
+    // it is, and runs the plain-fetch kernel): judge by the size of the first record
+    if (size > 1) {
+        const uint64_t rec = movi_host_record_boundary(data, size, 1, fastq);
+        if (rec > 4096) chunk_bytes = std::max<uint64_t>(chunk_bytes, std::min<uint64_t>(rec * 230000ull, 3ull << 30));
+    }
 
     auto worker = [&](int g) {
         for (;;) {
