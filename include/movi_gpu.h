@@ -115,6 +115,9 @@ int  movi_gpu_upload_index(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* desc, int 
  * the side tables are taken from desc, ownership of d_rows moves to the context when the call succeeds (on failure it stays
  * with the caller).  The rows are rewritten IN PLACE into the device row format (same fields, other bit positions). */
 int  movi_gpu_adopt_device_rows(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* desc, void* d_rows);
+/* A second context on the SAME GPU that queries the index another context has uploaded (no copy; the owner must outlive it):
+ * a context serves one host thread at a time, two contexts let two batches / file chunks overlap their copies and walks. */
+int  movi_gpu_share_index(movi_gpu_ctx* ctx, const movi_gpu_ctx* owner);
 /* device pointer of the resident 8-byte row table in the DEVICE row format (movi_b200/csrc/dev_index.cuh; read-only;
  * NULL without an index or with a compact layout) */
 const void* movi_gpu_index_device_rows(const movi_gpu_ctx* ctx);

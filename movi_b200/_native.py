@@ -41,6 +41,7 @@ GPU_SYMBOLS = {
     "movi_gpu_last_error": (C.c_char_p, [C.c_void_p]),
     "movi_gpu_upload_index": (C.c_int, [C.c_void_p, C.POINTER(MoviGpuIndexDesc), C.c_int]),
     "movi_gpu_adopt_device_rows": (C.c_int, [C.c_void_p, C.POINTER(MoviGpuIndexDesc), C.c_void_p]),
+    "movi_gpu_share_index": (C.c_int, [C.c_void_p, C.c_void_p]),
     "movi_gpu_index_device_rows": (C.c_void_p, [C.c_void_p]),
     "movi_gpu_index_device_layout": (C.c_int, [C.c_void_p]),
     "movi_gpu_index_export_rows": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),

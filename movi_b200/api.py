@@ -126,6 +126,20 @@ class MoveStructure:
         self.r = self.host_index.r
         self.mode = self.host_index.mode
 
+    @classmethod
+    def sharing(cls, owner):
+        """A second context on the owner's GPU that queries the owner's uploaded index (no copy): one context serves one host
+        thread at a time, two let two batches overlap.  The owner must outlive it."""
+        self = cls.__new__(cls)
+        self._L = owner._L
+        self._ctx = C.c_void_p()
+        rc = self._L.movi_gpu_create(owner.device, C.byref(self._ctx))
+        if rc != 0:
+            raise MoviGpuError(rc, self._L.movi_gpu_last_error(None).decode())
+        self.device, self.host_index, self.r, self.mode = owner.device, owner.host_index, owner.r, owner.mode
+        self._check(self._L.movi_gpu_share_index(self._ctx, owner._ctx))
+        return self
+
     def _check(self, rc):
         if rc != 0:
             raise MoviGpuError(rc, self._L.movi_gpu_last_error(self._ctx).decode())

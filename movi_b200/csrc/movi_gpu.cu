@@ -62,6 +62,7 @@ struct movi_gpu_ctx {
     std::string err;
     // index
     bool has_index = false;
+    bool borrowed_index = false;      // movi_gpu_share_index: the device tables belong to another context of the same GPU
     DevIndex ix{};
     uint2* d_rows = nullptr;
     uint32_t* d_rows6 = nullptr;      // LAYOUT_B6: packed blocked-thresholds rows
@@ -195,6 +196,13 @@ int blocks_for(movi_gpu_ctx* ctx, K kernel, int threads, int cap_per_sm = 0) {
 }
 
 void free_index(movi_gpu_ctx* ctx) {
+    if (ctx->borrowed_index) {           // nothing here is ours, except a prefix table built for the count query
+        ctx->d_rows = nullptr; ctx->d_rows6 = nullptr; ctx->d_id_blocks = nullptr; ctx->d_rows4 = nullptr; ctx->d_tally = nullptr;
+        ctx->d_sep_keys = nullptr; ctx->d_sep_vals = nullptr;
+        cudaFree(ctx->d_prefix); ctx->d_prefix = nullptr;
+        ctx->borrowed_index = false; ctx->has_index = false; ctx->index_bytes = 0;
+        return;
+    }
     cudaFree(ctx->d_rows); ctx->d_rows = nullptr;
     cudaFree(ctx->d_rows6); ctx->d_rows6 = nullptr;
     cudaFree(ctx->d_id_blocks); ctx->d_id_blocks = nullptr;
@@ -998,6 +1006,22 @@ static int upload_impl(movi_gpu_ctx* ctx, const MoviGpuIndexDesc* d, int layout,
     ctx->always_rpml = no_thr;
     ctx->has_index = true;
     rollback.done = true;
+    return MOVI_GPU_OK;
+}
+
+int movi_gpu_share_index(movi_gpu_ctx* ctx, const movi_gpu_ctx* owner) {
+    if (!ctx || !owner) return MOVI_GPU_ERR_ARG;
+    if (!owner->has_index) return fail(ctx, MOVI_GPU_ERR_INDEX, "the owning context has no index");
+    if (owner->device != ctx->device) return fail(ctx, MOVI_GPU_ERR_ARG, "an index can only be shared between contexts of the same GPU");
+    if (owner == ctx) return MOVI_GPU_OK;
+    CU(cudaSetDevice(ctx->device));
+    free_index(ctx);
+    ctx->ix = owner->ix;
+    ctx->ix.prefix = nullptr;            // (built on demand per context: ensure_prefix)
+    ctx->d_rows = owner->d_rows; ctx->d_rows6 = owner->d_rows6; ctx->d_id_blocks = owner->d_id_blocks; ctx->d_rows4 = owner->d_rows4;
+    ctx->d_tally = owner->d_tally; ctx->d_sep_keys = owner->d_sep_keys; ctx->d_sep_vals = owner->d_sep_vals;
+    ctx->mode = owner->mode; ctx->always_rpml = owner->always_rpml; ctx->index_bytes = 0;
+    ctx->borrowed_index = true; ctx->has_index = true;
     return MOVI_GPU_OK;
 }
 

@@ -188,7 +188,20 @@ int run_device_ingest(const Options& o, const std::vector<movi_gpu_ctx*>& ctx, c
         if (rec > 4096) chunk_bytes = std::max<uint64_t>(chunk_bytes, std::min<uint64_t>(rec * 230000ull, 3ull << 30));
     }
 
-    auto worker = [&](int g) {
+    // inputs of several chunks: a second context per GPU (sharing the uploaded index) so that the copy-in and parse of one chunk run
+    // under the walk and write-back of another
+    std::vector<movi_gpu_ctx*> lanes2(G, nullptr);
+    const int per_gpu = size > 2 * chunk_bytes ? 2 : 1;
+    if (per_gpu == 2) {
+        std::vector<std::thread> mk;
+        for (int g = 0; g < G; g++) mk.emplace_back([&, g]() {
+            movi_gpu_ctx* c = nullptr;
+            if (movi_gpu_create(o.device + g, &c) == MOVI_GPU_OK && movi_gpu_share_index(c, ctx[g]) == MOVI_GPU_OK) lanes2[g] = c;
+            else if (c) movi_gpu_destroy(c);
+        });
+        for (auto& t : mk) t.join();
+    }
+    auto worker = [&](int g, movi_gpu_ctx* my) {
         for (;;) {
             uint64_t begin, end, seq;
             {
@@ -205,11 +218,11 @@ int run_device_ingest(const Options& o, const std::vector<movi_gpu_ctx*>& ctx, c
                 return;
             }
             MoviGpuChunkResult res{};
-            int rc = movi_gpu_file_chunk_parse(ctx[g], data + begin, end - begin, fastq, 1, &res);
+            int rc = movi_gpu_file_chunk_parse(my, data + begin, end - begin, fastq, 1, &res);
             uint64_t my_off = 0;
             {
                 std::unique_lock<std::mutex> lk(mu);
-                if (rc) { if (status == 0) { *err = movi_gpu_last_error(ctx[g]); status = -1; } cv.notify_all(); return; }
+                if (rc) { if (status == 0) { *err = movi_gpu_last_error(my); status = -1; } cv.notify_all(); return; }
                 if (res.parse_flags || res.consumed_bytes != end - begin) { if (status == 0) status = 1; cv.notify_all(); return; }
                 cv.wait(lk, [&] { return place_seq == seq || status != 0; });      // places in the file go out in chunk order
                 if (status != 0) return;
@@ -221,13 +234,17 @@ int run_device_ingest(const Options& o, const std::vector<movi_gpu_ctx*>& ctx, c
                 if (res.n_reads < 230000 && chunk_bytes < (3ull << 30)) chunk_bytes = std::min<uint64_t>(chunk_bytes * 2, 3ull << 30);
                 cv.notify_all();
             }
-            rc = movi_gpu_file_chunk_query(ctx[g], zml ? 1 : 0, qflags, nullptr, 0, fd_bpf, my_off);
-            if (rc) { std::lock_guard<std::mutex> lk(mu); if (status == 0) { *err = movi_gpu_last_error(ctx[g]); status = -1; } cv.notify_all(); return; }
+            rc = movi_gpu_file_chunk_query(my, zml ? 1 : 0, qflags, nullptr, 0, fd_bpf, my_off);
+            if (rc) { std::lock_guard<std::mutex> lk(mu); if (status == 0) { *err = movi_gpu_last_error(my); status = -1; } cv.notify_all(); return; }
         }
     };
     std::vector<std::thread> th;
-    for (int g = 0; g < G; g++) th.emplace_back(worker, g);
+    for (int g = 0; g < G; g++) {
+        th.emplace_back(worker, g, ctx[g]);
+        if (lanes2[g]) th.emplace_back(worker, g, lanes2[g]);
+    }
     for (auto& t : th) t.join();
+    for (movi_gpu_ctx* c : lanes2) if (c) movi_gpu_destroy(c);
     return status;
 }
 

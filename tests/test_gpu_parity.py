@@ -580,3 +580,29 @@ def test_file_bytes_to_bpf_records_on_the_device(structures, read_sets, tmp_path
                 image1, r1 = ms.query_file_chunk(text[: len(text) // 2], text[:1] == b"@", final=False, zml=zml)
                 image2, r2 = ms.query_file_chunk(text[r1.consumed_bytes:], text[:1] == b"@", final=True, zml=zml)
                 assert image1.tobytes() + image2.tobytes() == want
+
+
+def test_two_contexts_share_one_uploaded_index(structures, read_sets, ref_seq):
+    """movi_gpu_share_index: a second context on the same GPU walks the table the first one uploaded (what lets the command line keep
+    two file chunks in flight per GPU); closing the borrower leaves the owner's index alone."""
+    import threading
+    from movi_b200 import MoveStructure
+    from oracle.port import pack_reads
+    for key in (("regular-thresholds", False), ("blocked-thresholds", True)):
+        owner = structures[key]
+        bases, offsets = pack_reads(_random_reads(29, 8000, 400, ref_seq))
+        want = owner.query_pml(bases, offsets)
+        want_c = owner.query_backward_search(bases, offsets)
+        other = MoveStructure.sharing(owner)
+        try:
+            assert other.index_device_bytes == 0
+            got = {}
+            t = threading.Thread(target=lambda: got.update(a=other.query_pml(bases, offsets), c=other.query_backward_search(bases, offsets)))
+            t.start()
+            mine = owner.query_pml(bases, offsets)          # both contexts at once
+            t.join()
+            assert np.array_equal(got["a"], want) and np.array_equal(mine, want)
+            assert np.array_equal(got["c"][0], want_c[0]) and np.array_equal(got["c"][1], want_c[1])
+        finally:
+            other.close()
+        assert np.array_equal(owner.query_pml(bases, offsets), want)
