@@ -53,6 +53,7 @@ C4_ROWS = int(float(os.environ.get("MOVI_C4_ROWS", "4.6e9")))       # > 2^32 row
 C4_READS = int(os.environ.get("MOVI_C4_READS", "409600"))           # per GPU per step; x 10 kbp = 4.096e9 bases (< 2^32: one device call)
 C4_READ_LEN = 10_000
 C4_SEED = 44
+C4_PROFILE = int(os.environ.get("MOVI_C4_PROFILE", "1"))             # run-length profile of the synthetic table (datagen/synth_gpu.cu)
 C4_SUB_PER_1024, C4_RAND_EVERY, C4_LEAD = 51, 10, 24                # 5 % substitutions, 1 read in 10 uniform random, 24 scattering bases
 C4_CPU_SAMPLE = int(os.environ.get("MOVI_C4_CPU_SAMPLE", "4096"))   # reads per step of the CPU arm (4.1e7 bases)
 N_BATCHES = 2                                                        # distinct read batches the steps cycle over
@@ -186,7 +187,7 @@ class C4Data:
         self.rank, self.device = rank, device
         self.n_reads, self.read_len = C4_READS, C4_READ_LEN
         self.n_bases = self.n_reads * self.read_len
-        self.ms = SyntheticStructure(C4_ROWS, seed=C4_SEED, device=device.index, profile=1)
+        self.ms = SyntheticStructure(C4_ROWS, seed=C4_SEED, device=device.index, profile=C4_PROFILE)
         torch.cuda.synchronize()
         t1 = time.time()
         self.d_off = torch.arange(self.n_reads + 1, dtype=torch.int64, device=device) * self.read_len
@@ -226,7 +227,7 @@ class C4Data:
         if self.index_dir:
             return self.index_dir
         need = C4_ROWS * 8 + (1 << 30)
-        name = "movi_bench_c4_r%d_s%d" % (C4_ROWS, C4_SEED)
+        name = "movi_bench_c4_r%d_s%d_p%d" % (C4_ROWS, C4_SEED, C4_PROFILE)
         for base in ("/dev/shm", tempfile.gettempdir()):
             d = os.path.join(base, name)
             if os.path.exists(os.path.join(d, "index.movi")) and os.path.getsize(os.path.join(d, "index.movi")) > C4_ROWS * 8:

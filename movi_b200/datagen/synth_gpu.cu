@@ -30,7 +30,7 @@ __host__ __device__ inline u64 mix(u64 x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
     return x;
 }
-struct Gen { u64 r, end_idx, seed; uint32_t profile; };   // profile 0: short runs (mean ~8), 1: pangenome-like runs (mean ~40)
+struct Gen { u64 r, end_idx, seed; uint32_t profile; };   // profile 0: short runs (mean ~8), 1: heavy-tailed runs (mean 55), 2: even runs (mean 56)
 
 __host__ __device__ inline uint32_t run_c(const Gen& g, u64 i) { return i == g.end_idx ? 0u : (uint32_t)(2 * (i & 1) + (mix(i ^ g.seed) & 1)); }
 __host__ __device__ inline uint32_t run_n(const Gen& g, u64 i) {
@@ -38,6 +38,8 @@ __host__ __device__ inline uint32_t run_n(const Gen& g, u64 i) {
     const u64 h = mix(i * 0x9E3779B97F4A7C15ULL + g.seed);
     // mixture: mostly short runs, a tail of long ones (mean ~ 8)
     const uint32_t k = (uint32_t)(h & 0xFF);
+    if (g.profile == 2)                                // n/r = 56, run lengths 48..64: the LF image of a run spans at most two rows, so a
+        return 48u + (uint32_t)((h >> 8) % 17);        // walk fast-forwards 0.5 rows per base (suffix-sorted indexes: 0.22 - 0.27; profile 1: 2.0)
     if (g.profile == 1) {                              // n/r ~ 40, like the c2 pangenome index (n/r = 41)
         uint32_t m = 1 + (uint32_t)((h >> 8) % 64);
         if (k < 32) m = 64 + (uint32_t)((h >> 20) % 192);
