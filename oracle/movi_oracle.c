@@ -610,3 +610,224 @@ int movi_oracle_trace_pml_rows(const movi_oracle_index* ix, const char* read, in
     }
     return 0;
 }
+
+/* ================================================================ Movi Color
+ * Multi-class classification with PMLs (`movi query --pml --multi-classify --no-prefetch`) on the default flat color table, and
+ * `--sa-entries`.  Files of the index directory, written by the reference's `color` / `build-SA` actions:
+ *   doc_sets_flat.bin   u64 size; u16 flat_colors[size]; MoveTally(5 B) doc_set_flat_inds[r]        move_structure_io.cpp:536-546, 587-607
+ *   ref.fa.doc_offsets  text, one cumulative length per document                                     prepare_ref.cpp:121-128
+ *   ref.fa.doc_ids      text, optional: taxon id per document                                        move_structure_io.cpp:643-700
+ *   ssa.movi            u64 rate; u64 k; u64 sampled_SA[k]; u64 r; u64 all_p[r]                       move_structure_io.cpp:702-735 */
+#include <math.h>
+
+struct movi_oracle_colors {
+    uint64_t flat_size; uint16_t* flat; uint8_t* inds; uint64_t r;
+    uint32_t num_docs, num_species;
+    uint32_t* to_taxon_id;            /* species -> taxon id (ascending: std::map order) */
+    double* log_lens;                 /* log(total length of the species' documents) */
+};
+
+static int cmp_u32(const void* a, const void* b) { uint32_t x = *(const uint32_t*)a, y = *(const uint32_t*)b; return x < y ? -1 : x > y; }
+
+void movi_oracle_colors_free(movi_oracle_colors* c) {
+    if (!c) return;
+    free(c->flat); free(c->inds); free(c->to_taxon_id); free(c->log_lens); free(c);
+}
+
+/* load_color_table -> deserialize_doc_sets_flat + load_document_info (movi.cpp:121-152) */
+int movi_oracle_colors_load(const char* index_dir, uint64_t r, movi_oracle_colors** out) {
+    char path[4096];
+    movi_oracle_colors* c = calloc(1, sizeof *c);
+    if (!c) return fail("out of memory");
+    c->r = r;
+    snprintf(path, sizeof path, "%s/doc_sets_flat.bin", index_dir);
+    FILE* f = fopen(path, "rb");
+    if (!f) { movi_oracle_colors_free(c); return fail("[deserialize doc sets flat] Failed to open document sets flat file"); }
+    if (rd(f, &c->flat_size, 8)) { fclose(f); movi_oracle_colors_free(c); return fail("doc_sets_flat.bin: truncated"); }
+    c->flat = malloc(c->flat_size * 2 + 2);
+    c->inds = malloc(r * 5 + 8);
+    if (!c->flat || !c->inds || rd(f, c->flat, c->flat_size * 2) || rd(f, c->inds, r * 5)) { fclose(f); movi_oracle_colors_free(c); return fail("doc_sets_flat.bin: truncated"); }
+    fclose(f);
+
+    snprintf(path, sizeof path, "%s/ref.fa.doc_offsets", index_dir);
+    f = fopen(path, "r");
+    if (!f) { movi_oracle_colors_free(c); return fail("[load document info] doc_offsets file not found"); }
+    uint64_t cap = 16, nd = 0, v;
+    uint64_t* offs = malloc(cap * 8);
+    while (fscanf(f, "%lu", &v) == 1) { if (nd == cap) { cap *= 2; offs = realloc(offs, cap * 8); } offs[nd++] = v; }
+    fclose(f);
+    c->num_docs = (uint32_t)nd;
+    uint32_t* ids = malloc((nd + 1) * 4);
+    uint64_t ni = 0;
+    snprintf(path, sizeof path, "%s/ref.fa.doc_ids", index_dir);
+    f = fopen(path, "r");
+    if (f) {                                              /* taxon id per document */
+        uint32_t* all = malloc(16 * 4); uint64_t acap = 16; unsigned t;
+        while (fscanf(f, "%u", &t) == 1) { if (ni == acap) { acap *= 2; all = realloc(all, acap * 4); } all[ni++] = t; }
+        fclose(f);
+        free(ids); ids = all;
+    } else {
+        for (uint64_t i = 0; i < nd; i++) ids[i] = (uint32_t)i + 1;
+        ni = nd;
+    }
+    /* "compress taxon id to 0 .. num_species - 1": ascending order of the distinct ids (a std::map) */
+    uint32_t* sorted = malloc((ni + 1) * 4);
+    memcpy(sorted, ids, ni * 4);
+    qsort(sorted, ni, 4, cmp_u32);
+    uint32_t ns = 0;
+    for (uint64_t i = 0; i < ni; i++) if (i == 0 || sorted[i] != sorted[i - 1]) sorted[ns++] = sorted[i];
+    c->num_species = ns;
+    c->to_taxon_id = sorted;
+    c->log_lens = calloc(ns + 1, sizeof(double));
+    for (uint64_t i = 0; i < nd && i < ni; i++) {
+        uint32_t* p = bsearch(&ids[i], sorted, ns, 4, cmp_u32);
+        uint64_t doc_len = offs[i] - (i == 0 ? 0 : offs[i - 1]);
+        c->log_lens[p - sorted] += (double)doc_len;
+    }
+    for (uint32_t i = 0; i < ns; i++) c->log_lens[i] = log(c->log_lens[i]);
+    free(ids); free(offs);
+    *out = c;
+    return 0;
+}
+
+uint32_t movi_oracle_colors_num_species(const movi_oracle_colors* c) { return c->num_species; }
+uint32_t movi_oracle_colors_taxon(const movi_oracle_colors* c, uint32_t species) { return species < c->num_species ? c->to_taxon_id[species] : 0; }
+
+/* query_pml with is_multi_classify() (move_structure_query.cpp:251-260, 351-437): after the LF step of every base whose
+ * match_len >= min_len, the documents of the color of the row the walk now stands on are counted; best / second best follow
+ * in the order the documents are met.  raw[] = {best_doc, second_best_doc (65535 = none), sum_matching_lengths (u32 arithmetic)};
+ * score[] = the two counters the final comparison reads (:452-462).  taxa[] = the two numbers of the output line (:439-470). */
+int movi_oracle_query_multi_classify(const movi_oracle_index* ix, const movi_oracle_colors* col, const char* read, int64_t len,
+                                     int min_len, int pvalue, uint16_t* out_ml, uint32_t raw[3], double score[2], uint32_t taxa[2]) {
+    const double log4 = log(4);                                   /* move_structure.hpp:315 */
+    uint32_t* cnts = calloc(col->num_species + 1, 4);
+    double* scores = calloc(col->num_species + 1, sizeof(double));
+    int64_t pos = len - 1;
+    uint64_t idx = ix->r - 1, offset = row_n(ix, idx) - 1, match_len = 0, k = 0;
+    uint16_t best = 65535, second = 65535;
+    uint32_t sum_ml = 0;
+    int rcode = 0;
+    while (pos > -1) {
+        unsigned char rc = (unsigned char)read[pos];
+        int row_ch = raw_char(ix, idx);
+        if (!check_alphabet(ix, rc)) {
+            match_len = 0;
+        } else if (row_ch == (int)rc) {
+            match_len += 1;
+        } else {
+            int up = reposition_thresholds(ix, &idx, offset, rc);
+            if (up < 0) { rcode = -1; break; }
+            match_len = 0;
+            offset = up ? row_n(ix, idx) - 1 : 0;
+        }
+        sum_ml += (uint32_t)match_len;
+        if (out_ml) out_ml[k] = clamp16(match_len);
+        k++;
+        pos -= 1;
+        if (lf_move(ix, &offset, &idx) < 0) { rcode = -1; break; }
+        if (match_len >= (uint64_t)min_len) {
+            const uint8_t* e = col->inds + idx * 5;               /* MoveTally::get, move_row.hpp:28-38 */
+            uint64_t color_id = (uint64_t)ld32(e) | ((uint64_t)e[4] << 32);
+            if (color_id >= col->flat_size) continue;             /* :395 */
+            uint32_t set_size = col->flat[color_id];
+            for (uint32_t j = 0; j < set_size; j++) {
+                int doc = col->flat[color_id + 1 + j];
+                if (!pvalue) {
+                    cnts[doc]++;
+                    if (doc != best) {
+                        if (best == 65535 || cnts[doc] > cnts[best]) { second = best; best = (uint16_t)doc; }
+                        else if (second == 65535 || cnts[doc] > cnts[second]) second = (uint16_t)doc;
+                    }
+                } else {
+                    double val = (double)match_len - (col->log_lens[doc] / log4);
+                    if (val >= 0) {
+                        scores[doc] += val < 1. ? val : 1.;
+                        if (doc != best) {
+                            if (best == 65535 || scores[doc] > scores[best]) { second = best; best = (uint16_t)doc; }
+                            else if (second == 65535 || scores[doc] > scores[second]) second = (uint16_t)doc;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    raw[0] = best; raw[1] = second; raw[2] = sum_ml;
+    score[0] = score[1] = 0;
+    taxa[0] = taxa[1] = 0;
+    float pml_mean = (float)sum_ml / (float)(uint64_t)len;        /* static_cast<float>(sum) / length() (:443) */
+    if (len == 0) pml_mean = NAN;                                  /* 0 / 0: the comparison below is false, best_doc decides */
+    if (!(pml_mean < 0.4) && best != 65535) {                      /* UNCLASSIFIED_THRESHOLD, utils.hpp:169 */
+        taxa[0] = col->to_taxon_id[best];
+        if (second != 65535) {
+            float best_cnt, second_cnt;
+            if (min_len > 0) { best_cnt = (float)cnts[best]; second_cnt = (float)cnts[second]; }
+            else             { best_cnt = (float)scores[best]; second_cnt = (float)scores[second]; }
+            float diff = best_cnt - second_cnt;
+            if (diff < 0.05 * best_cnt) taxa[1] = col->to_taxon_id[second];
+        }
+    }
+    if (best != 65535) score[0] = pvalue ? scores[best] : (double)cnts[best];
+    if (second != 65535) score[1] = pvalue ? scores[second] : (double)cnts[second];
+    free(cnts); free(scores);
+    return rcode;
+}
+
+/* --sa-entries: sampled suffix-array entries (build-SA) */
+struct movi_oracle_ssa { uint64_t rate, k, r; uint64_t* sampled; uint64_t* all_p; };
+
+void movi_oracle_ssa_free(movi_oracle_ssa* s) { if (s) { free(s->sampled); free(s->all_p); free(s); } }
+
+/* deserialize_sampled_SA, move_structure_io.cpp:716-735 */
+int movi_oracle_ssa_load(const char* index_dir, movi_oracle_ssa** out) {
+    char path[4096];
+    snprintf(path, sizeof path, "%s/ssa.movi", index_dir);
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail("[deserialize sampled SA] Failed to open sampled SA entries file");
+    movi_oracle_ssa* s = calloc(1, sizeof *s);
+    int bad = rd(f, &s->rate, 8) || rd(f, &s->k, 8);
+    if (!bad) { s->sampled = malloc(s->k * 8 + 8); bad = !s->sampled || rd(f, s->sampled, s->k * 8) || rd(f, &s->r, 8); }
+    if (!bad) { s->all_p = malloc(s->r * 8 + 8); bad = !s->all_p || rd(f, s->all_p, s->r * 8); }
+    fclose(f);
+    if (bad) { movi_oracle_ssa_free(s); return fail("ssa.movi: truncated"); }
+    *out = s;
+    return 0;
+}
+
+/* get_SA_entries, move_structure.cpp:35-48 */
+static int get_sa_entry(const movi_oracle_index* ix, const movi_oracle_ssa* s, uint64_t idx, uint64_t offset, uint64_t* out) {
+    uint64_t abs_offset = s->all_p[idx] + offset, distance = 0;
+    while (abs_offset % s->rate != 0) {
+        if (lf_move(ix, &offset, &idx) < 0) return -1;
+        abs_offset = s->all_p[idx] + offset;
+        distance += 1;
+    }
+    *out = s->sampled[abs_offset / s->rate] + distance;
+    return 0;
+}
+
+/* query_pml with is_get_sa_entries() (move_structure_query.cpp:353-357): one entry per base, same orientation as the lengths */
+int movi_oracle_query_pml_sa(const movi_oracle_index* ix, const movi_oracle_ssa* s, const char* read, int64_t len,
+                             uint16_t* out_ml, uint64_t* out_sa) {
+    int64_t pos = len - 1;
+    uint64_t idx = ix->r - 1, offset = row_n(ix, idx) - 1, match_len = 0, k = 0;
+    while (pos > -1) {
+        unsigned char rc = (unsigned char)read[pos];
+        int row_ch = raw_char(ix, idx);
+        if (!check_alphabet(ix, rc)) {
+            match_len = 0;
+        } else if (row_ch == (int)rc) {
+            match_len += 1;
+        } else {
+            int up = reposition_thresholds(ix, &idx, offset, rc);
+            if (up < 0) return -1;
+            match_len = 0;
+            offset = up ? row_n(ix, idx) - 1 : 0;
+        }
+        if (out_ml) out_ml[k] = clamp16(match_len);
+        if (get_sa_entry(ix, s, idx, offset, &out_sa[k])) return -1;
+        k++;
+        pos -= 1;
+        if (lf_move(ix, &offset, &idx) < 0) return -1;
+    }
+    return 0;
+}

@@ -69,6 +69,22 @@ int movi_oracle_query_count_batch(const movi_oracle_index* ix, const char* bases
 int movi_oracle_classify(const uint16_t* ml, uint64_t len, uint64_t bin_width, uint64_t max_value_thr,
                          uint64_t* bins_above, uint64_t* bins_below, uint64_t* sum_max, uint64_t* n_bins);
 
+/* ---- Movi Color: `--multi-classify` on the flat color table and `--sa-entries` (reference --no-prefetch path) */
+typedef struct movi_oracle_colors movi_oracle_colors;
+typedef struct movi_oracle_ssa movi_oracle_ssa;
+int  movi_oracle_colors_load(const char* index_dir, uint64_t r, movi_oracle_colors** out);   /* doc_sets_flat.bin, ref.fa.doc_offsets[, ref.fa.doc_ids] */
+void movi_oracle_colors_free(movi_oracle_colors* c);
+uint32_t movi_oracle_colors_num_species(const movi_oracle_colors* c);
+uint32_t movi_oracle_colors_taxon(const movi_oracle_colors* c, uint32_t species);
+/* raw = {best_doc, second_best_doc (65535: none), sum of matching lengths}; score = the two counters (or p-value scores);
+ * taxa = the two numbers of the reference's output line "<id>,<taxa[0]>,<taxa[1]>". */
+int movi_oracle_query_multi_classify(const movi_oracle_index* ix, const movi_oracle_colors* col, const char* read, int64_t len,
+                                     int min_len, int pvalue, uint16_t* out_ml, uint32_t raw[3], double score[2], uint32_t taxa[2]);
+int  movi_oracle_ssa_load(const char* index_dir, movi_oracle_ssa** out);                      /* ssa.movi */
+void movi_oracle_ssa_free(movi_oracle_ssa* s);
+int movi_oracle_query_pml_sa(const movi_oracle_index* ix, const movi_oracle_ssa* s, const char* read, int64_t len,
+                             uint16_t* out_ml, uint64_t* out_sa);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,17 @@ def lib():
         L.movi_oracle_query_count_batch.restype = C.c_int
         L.movi_oracle_classify.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64] + [C.POINTER(C.c_uint64)] * 4
         L.movi_oracle_classify.restype = C.c_int
+        L.movi_oracle_colors_load.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_void_p)]; L.movi_oracle_colors_load.restype = C.c_int
+        L.movi_oracle_colors_free.argtypes = [C.c_void_p]
+        L.movi_oracle_colors_num_species.argtypes = [C.c_void_p]; L.movi_oracle_colors_num_species.restype = C.c_uint32
+        L.movi_oracle_colors_taxon.argtypes = [C.c_void_p, C.c_uint32]; L.movi_oracle_colors_taxon.restype = C.c_uint32
+        L.movi_oracle_query_multi_classify.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p,
+                                                       C.c_void_p, C.c_void_p, C.c_void_p]
+        L.movi_oracle_query_multi_classify.restype = C.c_int
+        L.movi_oracle_ssa_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]; L.movi_oracle_ssa_load.restype = C.c_int
+        L.movi_oracle_ssa_free.argtypes = [C.c_void_p]
+        L.movi_oracle_query_pml_sa.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.movi_oracle_query_pml_sa.restype = C.c_int
         _lib = L
     return _lib
 
@@ -77,8 +88,17 @@ class OracleIndex:
         self.end_bwt_idx = L.movi_oracle_end_bwt_idx(self._h)
         self.sigma = L.movi_oracle_sigma(self._h)
         self.separators = bool(L.movi_oracle_has_separators(self._h))
+        self.index_dir = os.path.dirname(index_file)
+        self._colors = C.c_void_p()
+        self._ssa = C.c_void_p()
 
     def __del__(self):
+        if getattr(self, "_colors", None):
+            lib().movi_oracle_colors_free(self._colors)
+            self._colors = None
+        if getattr(self, "_ssa", None):
+            lib().movi_oracle_ssa_free(self._ssa)
+            self._ssa = None
         if getattr(self, "_h", None):
             lib().movi_oracle_free(self._h)
             self._h = None
@@ -128,6 +148,49 @@ class OracleIndex:
         if rc != 0:
             raise RuntimeError("oracle count failed: " + lib().movi_oracle_last_error().decode())
         return counts, pos
+
+    # ---- Movi Color (reference `--multi-classify` / `--sa-entries`, --no-prefetch path)
+    def load_colors(self):
+        """doc_sets_flat.bin + ref.fa.doc_offsets [+ ref.fa.doc_ids] of the index directory."""
+        if not self._colors:
+            if lib().movi_oracle_colors_load(self.index_dir.encode(), self.r, C.byref(self._colors)) != 0:
+                raise RuntimeError("oracle: " + lib().movi_oracle_last_error().decode())
+        return lib().movi_oracle_colors_num_species(self._colors)
+
+    def taxon(self, species):
+        self.load_colors()
+        return lib().movi_oracle_colors_taxon(self._colors, species)
+
+    def query_multi_classify(self, bases, offsets, min_len=1, pvalue=False):
+        """-> (taxa uint32[n, 2], raw uint32[n, 3] = best doc / second doc / sum of lengths, score float64[n, 2], ml uint16[total])."""
+        self.load_colors()
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        taxa = np.zeros((n, 2), np.uint32); raw = np.zeros((n, 3), np.uint32); score = np.zeros((n, 2), np.float64)
+        ml = np.zeros(int(offsets[-1]) + 1, dtype=np.uint16)
+        for i in range(n):
+            s, e = int(offsets[i]), int(offsets[i + 1])
+            rc = lib().movi_oracle_query_multi_classify(self._h, self._colors, bases.ctypes.data + s, e - s, int(min_len), int(bool(pvalue)),
+                                                        ml.ctypes.data + 2 * s, raw[i].ctypes.data, score[i].ctypes.data, taxa[i].ctypes.data)
+            if rc != 0:
+                raise RuntimeError("oracle multi-classify failed: " + lib().movi_oracle_last_error().decode())
+        return taxa, raw, score, ml[:-1]
+
+    def query_pml_sa(self, bases, offsets):
+        """-> (ml uint16[total], sa uint64[total]): `--pml --sa-entries`, same orientation as the lengths."""
+        if not self._ssa:
+            if lib().movi_oracle_ssa_load(self.index_dir.encode(), C.byref(self._ssa)) != 0:
+                raise RuntimeError("oracle: " + lib().movi_oracle_last_error().decode())
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        ml = np.zeros(int(offsets[-1]) + 1, dtype=np.uint16); sa = np.zeros(int(offsets[-1]) + 1, dtype=np.uint64)
+        for i in range(n):
+            s, e = int(offsets[i]), int(offsets[i + 1])
+            if lib().movi_oracle_query_pml_sa(self._h, self._ssa, bases.ctypes.data + s, e - s, ml.ctypes.data + 2 * s, sa.ctypes.data + 8 * s) != 0:
+                raise RuntimeError("oracle sa-entries failed: " + lib().movi_oracle_last_error().decode())
+        return ml[:-1], sa[:-1]
 
 
 def classify(ml, bin_width, max_value_thr):

@@ -83,3 +83,39 @@ def expected_text(read_set, query, sep=False):
 
 def reads_path(read_set):
     return os.path.join(GOLD, "reads", read_set)
+
+
+@pytest.fixture(scope="session")
+def color_index_dir(tmp_path_factory):
+    """Movi Color index directory (index.movi + doc_sets_flat.bin + ssa.movi + document info), built, coloured and sampled by the
+    unmodified reference (tests/golden/make_golden_color.py)."""
+    d = tmp_path_factory.mktemp("color")
+    src = os.path.join(GOLD, "color")
+    for f in ("index.movi", "doc_sets_flat.bin", "ssa.movi"):
+        with lzma.open(os.path.join(src, f + ".xz")) as g:
+            (d / f).write_bytes(g.read())
+    for f in ("ref.fa.doc_offsets", "ref.fa.doc_ids"):
+        (d / f).write_bytes(open(os.path.join(src, f), "rb").read())
+    return str(d)
+
+
+COLOR_VARIANTS = {"": dict(min_len=1, pvalue=False), ".minlen3": dict(min_len=3, pvalue=False), ".pvalue": dict(min_len=1, pvalue=True),
+                  ".minlen0": dict(min_len=0, pvalue=False), ".pvalue.minlen0": dict(min_len=0, pvalue=True)}
+
+
+def color_expected(tag):
+    return open(os.path.join(GOLD, "color", "expected.multi_classify%s.csv" % tag)).read()
+
+
+def parse_bpf_records(data, itemsize, header=True):
+    """[(name bytes, values)] of a .bpf stream (reference src/utils.cpp:202-246); the .sa_entries.bpf file has no header."""
+    import numpy as np
+    import struct
+    p = 12 if header else 0
+    out = []
+    while p < len(data):
+        (nl,) = struct.unpack_from("<H", data, p); p += 2
+        name = data[p:p + nl]; p += nl
+        (L,) = struct.unpack_from("<Q", data, p); p += 8
+        out.append((name, np.frombuffer(data[p:p + itemsize * L], dtype="<u%d" % itemsize))); p += itemsize * L
+    return out
