@@ -225,6 +225,41 @@ int  movi_gpu_classify_device(movi_gpu_ctx* ctx, const uint16_t* d_ml, const uin
                               uint32_t bin_width, uint32_t max_value_thr,
                               uint32_t* d_bins_above, uint32_t* d_bins_below, uint64_t* d_sum_max, void* cuda_stream);
 
+/* ---- Movi Color: multi-class classification with PMLs and suffix-array entries.  Threshold index types, expanded
+ * device layout.  Results follow the reference's --no-prefetch path (the deterministic one). */
+
+/* What load_color_table leaves in MoveStructure for the default flat colour table (src/movi.cpp:121-152,
+ * src/move_structure_io.cpp:587-607, 643-700): HOST pointers, needed during the call only. */
+typedef struct MoviGpuColorDesc {
+    const uint16_t* flat_colors;         /* flat_colors: {size, documents...} per colour, back to back */
+    uint64_t flat_size;                  /* flat_colors.size() */
+    const void* doc_set_flat_inds;       /* r MoveTally {u32 right; u8 left} (5 bytes each): the row's offset into flat_colors */
+    uint32_t num_species;                /* documents after the taxon-id compression of load_document_info */
+    uint32_t reserved;
+    const double* log_lens;              /* num_species: log(total length of the species' documents); NULL: no --pvalue-scoring */
+} MoviGpuColorDesc;
+/* Per read, what the end of query_pml reads to print "<id>,<taxon>,<taxon>" (src/move_structure_query.cpp:439-471):
+ * best_doc / second_best_doc = species indices (0xFFFF = none), their counters (uint32 counts, or the bits of the double scores
+ * under --pvalue-scoring) and the uint32 sum of the read's matching lengths (PML_mean = sum / length). */
+typedef struct MoviGpuColorResult {
+    uint32_t best_doc, second_best_doc;
+    uint32_t sum_matching_lengths, reserved;
+    uint64_t best_raw, second_raw;
+} MoviGpuColorResult;
+/* replaces: load_color_table (src/movi.cpp:121-152): the colour table goes to HBM next to the uploaded index */
+int  movi_gpu_upload_colors(movi_gpu_ctx* ctx, const MoviGpuColorDesc* desc);
+/* replaces: MoveStructure::query_pml with is_multi_classify() (src/move_structure_query.cpp:251-260, 373-437), per batch.
+ * min_len = --min-len (default 1), pvalue != 0 = --pvalue-scoring.  out_ml (may be NULL) also receives the matching lengths. */
+int  movi_gpu_query_multi_classify(movi_gpu_ctx* ctx, const char* bases, const uint64_t* read_offsets, uint64_t n_reads,
+                                   uint32_t flags, uint32_t min_len, int pvalue, MoviGpuColorResult* out, uint16_t* out_ml);
+/* replaces: deserialize_sampled_SA (src/move_structure_io.cpp:716-735): ssa.movi = sample rate, sampled_SA_entries, all_p (r) */
+int  movi_gpu_upload_sampled_sa(movi_gpu_ctx* ctx, uint64_t sample_rate, const uint64_t* sampled_sa, uint64_t n_sampled,
+                                const uint64_t* all_p);
+/* replaces: query_pml with is_get_sa_entries() (src/move_structure_query.cpp:353-357, get_SA_entries src/move_structure.cpp:35-48):
+ * one suffix-array entry per base at the same offsets and in the same order as the matching lengths (out_ml may be NULL). */
+int  movi_gpu_query_pml_sa(movi_gpu_ctx* ctx, const char* bases, const uint64_t* read_offsets, uint64_t n_reads,
+                           uint32_t flags, uint16_t* out_ml, uint64_t* out_sa);
+
 /* Introspection for benchmarks: kernels launched by this context so far, name and time of the last one. */
 uint64_t movi_gpu_launch_count(const movi_gpu_ctx* ctx);
 /* Tuning knobs (benchmarks / profiling / tests): "pml_sector" (-1 by table size / 0 / 1: sector-cached row fetch),

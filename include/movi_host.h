@@ -86,6 +86,31 @@ int  movi_host_classify(int fd, int mode, const movi_host_reads* rd, const uint1
 int  movi_host_classify_bins(int fd, int mode, const movi_host_reads* rd, uint64_t max_value_thr, const uint32_t* bins_above,
                              const uint32_t* bins_below, const uint64_t* sum_max, uint8_t* found_out);
 
+/* ---- Movi Color */
+typedef struct movi_host_colors movi_host_colors;
+typedef struct movi_host_ssa movi_host_ssa;
+/* load_color_table (reference src/movi.cpp:121-152) for the default flat colour table: <index_dir>/doc_sets_flat.bin (r = rows of
+ * the index), ref.fa.doc_offsets and, if present, ref.fa.doc_ids (taxon id per document; src/move_structure_io.cpp:587-607, 643-700) */
+int  movi_host_colors_open(const char* index_dir, uint64_t r, movi_host_colors** out);
+int  movi_host_colors_desc(const movi_host_colors* c, MoviGpuColorDesc* out);     /* pointers valid until _close */
+uint32_t movi_host_colors_num_species(const movi_host_colors* c);
+uint32_t movi_host_colors_taxon(const movi_host_colors* c, uint32_t species);     /* to_taxon_id */
+void movi_host_colors_close(movi_host_colors* c);
+/* the lines "<id>,<taxon>,<taxon>" query_pml writes to the -o file under --multi-classify (src/move_structure_query.cpp:439-471),
+ * from the per-read results of movi_gpu_query_multi_classify */
+int  movi_host_write_multi_classify(int fd, const movi_host_reads* rd, const movi_host_colors* c, const MoviGpuColorResult* res,
+                                    uint32_t min_len, int pvalue);
+/* <index_dir>/ssa.movi (deserialize_sampled_SA, src/move_structure_io.cpp:716-735): what movi_gpu_upload_sampled_sa takes */
+int  movi_host_ssa_open(const char* index_dir, movi_host_ssa** out);
+uint64_t movi_host_ssa_rate(const movi_host_ssa* s);
+uint64_t movi_host_ssa_rows(const movi_host_ssa* s);
+uint64_t movi_host_ssa_samples(const movi_host_ssa* s);
+const uint64_t* movi_host_ssa_sampled(const movi_host_ssa* s);
+const uint64_t* movi_host_ssa_all_p(const movi_host_ssa* s);
+void movi_host_ssa_close(movi_host_ssa* s);
+/* <prefix>.sa_entries.bpf records (output_base_stats, DataType::sa_entry; the file has no header: src/utils.cpp:371-375) */
+int  movi_host_sa_append(int fd, const movi_host_reads* rd, const uint64_t* sa);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,16 @@ class MoviGpuIndexDesc(C.Structure):
     ]
 
 
+class MoviGpuColorDesc(C.Structure):
+    _fields_ = [("flat_colors", C.c_void_p), ("flat_size", C.c_uint64), ("doc_set_flat_inds", C.c_void_p),
+                ("num_species", C.c_uint32), ("reserved", C.c_uint32), ("log_lens", C.c_void_p)]
+
+
+class MoviGpuColorResult(C.Structure):
+    _fields_ = [("best_doc", C.c_uint32), ("second_best_doc", C.c_uint32), ("sum_matching_lengths", C.c_uint32), ("reserved", C.c_uint32),
+                ("best_raw", C.c_uint64), ("second_raw", C.c_uint64)]
+
+
 GPU_SYMBOLS = {
     "movi_gpu_abi_version": (C.c_int, []),
     "movi_gpu_device_count": (C.c_int, []),
@@ -67,6 +77,10 @@ GPU_SYMBOLS = {
     "movi_gpu_check_device_status": (C.c_int, [C.c_void_p]),
     "movi_gpu_classify_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "movi_gpu_upload_colors": (C.c_int, [C.c_void_p, C.POINTER(MoviGpuColorDesc)]),
+    "movi_gpu_query_multi_classify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]),
+    "movi_gpu_upload_sampled_sa": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "movi_gpu_query_pml_sa": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
     "movi_gpu_launch_count": (C.c_uint64, [C.c_void_p]),
     "movi_gpu_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "movi_gpu_get_option": (C.c_int64, [C.c_void_p, C.c_char_p]),
@@ -107,6 +121,20 @@ HOST_SYMBOLS = {
     "movi_host_write_counts": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "movi_host_classify_bins": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "movi_host_classify": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "movi_host_colors_open": (C.c_int, [C.c_char_p, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "movi_host_colors_desc": (C.c_int, [C.c_void_p, C.POINTER(MoviGpuColorDesc)]),
+    "movi_host_colors_num_species": (C.c_uint32, [C.c_void_p]),
+    "movi_host_colors_taxon": (C.c_uint32, [C.c_void_p, C.c_uint32]),
+    "movi_host_colors_close": (None, [C.c_void_p]),
+    "movi_host_write_multi_classify": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int]),
+    "movi_host_ssa_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "movi_host_ssa_rate": (C.c_uint64, [C.c_void_p]),
+    "movi_host_ssa_rows": (C.c_uint64, [C.c_void_p]),
+    "movi_host_ssa_samples": (C.c_uint64, [C.c_void_p]),
+    "movi_host_ssa_sampled": (C.c_void_p, [C.c_void_p]),
+    "movi_host_ssa_all_p": (C.c_void_p, [C.c_void_p]),
+    "movi_host_ssa_close": (None, [C.c_void_p]),
+    "movi_host_sa_append": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
 }
 
 _gpu = None

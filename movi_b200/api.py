@@ -101,6 +101,10 @@ class Reads:
             pass
 
 
+COLOR_RESULT_DTYPE = np.dtype([("best_doc", "<u4"), ("second_best_doc", "<u4"), ("sum_matching_lengths", "<u4"), ("reserved", "<u4"),
+                               ("best_raw", "<u8"), ("second_raw", "<u8")])      # MoviGpuColorResult, include/movi_gpu.h
+
+
 def _ptr(a):
     return a.ctypes.data if isinstance(a, np.ndarray) else int(a)
 
@@ -145,6 +149,9 @@ class MoveStructure:
             raise MoviGpuError(rc, self._L.movi_gpu_last_error(self._ctx).decode())
 
     def close(self):
+        if getattr(self, "_colors", None):
+            N.host_lib().movi_host_colors_close(self._colors)
+            self._colors = None
         if getattr(self, "_ctx", None):
             self._L.movi_gpu_destroy(self._ctx)
             self._ctx = C.c_void_p()
@@ -199,6 +206,78 @@ class MoveStructure:
         self._check(self._L.movi_gpu_query_classify(self._ctx, int(zml), _ptr(bases), _ptr(offsets), n, FLAG_RPML if rpml else 0, bin_width, max_value_thr,
                                                     _ptr(above), _ptr(below), _ptr(total), _ptr(ml) if want_ml else None))
         return (above, below, total, ml) if want_ml else (above, below, total)
+
+    # ---- Movi Color (reference `movi query --multi-classify` / `--sa-entries`, --no-prefetch path)
+    def load_colors(self, index_dir=None):
+        """load_color_table (src/movi.cpp:121-152): doc_sets_flat.bin + document info of the index directory -> HBM."""
+        H = N.host_lib()
+        d = index_dir or self.host_index.path
+        if os.path.isfile(d):
+            d = os.path.dirname(d)
+        h = C.c_void_p()
+        if H.movi_host_colors_open(os.fsencode(d), self.r, C.byref(h)) != 0:
+            raise RuntimeError(H.movi_host_last_error().decode())
+        if getattr(self, "_colors", None):
+            H.movi_host_colors_close(self._colors)
+        self._colors = h
+        desc = N.MoviGpuColorDesc()
+        H.movi_host_colors_desc(h, C.byref(desc))
+        self._check(self._L.movi_gpu_upload_colors(self._ctx, C.byref(desc)))
+        self.num_species = H.movi_host_colors_num_species(h)
+        return self.num_species
+
+    def query_multi_classify(self, bases, offsets, min_len=1, pvalue=False, want_ml=False):
+        """-> numpy record array (best_doc, second_best_doc, sum_matching_lengths, best_raw, second_raw) per read [, ml]."""
+        bases, offsets, n = self._prep(bases, offsets)
+        n = max(n, 0)
+        res = np.zeros(n, dtype=COLOR_RESULT_DTYPE)
+        ml = np.empty(int(offsets[-1]) if len(offsets) else 0, dtype=np.uint16) if want_ml else None
+        self._check(self._L.movi_gpu_query_multi_classify(self._ctx, _ptr(bases), _ptr(offsets), n, 0, int(min_len), int(bool(pvalue)),
+                                                          _ptr(res), _ptr(ml) if want_ml else None))
+        return (res, ml) if want_ml else res
+
+    def multi_classify_text(self, reads, res, min_len=1, pvalue=False):
+        """The reference's -o file for these reads: "<id>,<taxon>,<taxon>" per line (src/move_structure_query.cpp:439-471)."""
+        H = N.host_lib()
+        rfd, wfd = os.pipe()
+        try:
+            import threading
+            buf = []
+            t = threading.Thread(target=lambda: buf.append(os.fdopen(rfd, "rb").read()))
+            t.start()
+            rc = H.movi_host_write_multi_classify(wfd, reads._h, self._colors, _ptr(res), int(min_len), int(bool(pvalue)))
+        finally:
+            os.close(wfd)
+            t.join()
+        if rc != 0:
+            raise RuntimeError(H.movi_host_last_error().decode())
+        return buf[0].decode()
+
+    def load_sampled_sa(self, index_dir=None):
+        """deserialize_sampled_SA (src/move_structure_io.cpp:716-735): ssa.movi -> HBM."""
+        H = N.host_lib()
+        d = index_dir or self.host_index.path
+        if os.path.isfile(d):
+            d = os.path.dirname(d)
+        h = C.c_void_p()
+        if H.movi_host_ssa_open(os.fsencode(d), C.byref(h)) != 0:
+            raise RuntimeError(H.movi_host_last_error().decode())
+        try:
+            if H.movi_host_ssa_rows(h) != self.r:
+                raise RuntimeError("ssa.movi belongs to another index (%d rows, the index has %d)" % (H.movi_host_ssa_rows(h), self.r))
+            self._check(self._L.movi_gpu_upload_sampled_sa(self._ctx, H.movi_host_ssa_rate(h), H.movi_host_ssa_sampled(h),
+                                                           H.movi_host_ssa_samples(h), H.movi_host_ssa_all_p(h)))
+            return H.movi_host_ssa_rate(h)
+        finally:
+            H.movi_host_ssa_close(h)
+
+    def query_pml_sa(self, bases, offsets):
+        """`--pml --sa-entries` -> (ml uint16[total], sa uint64[total]), same orientation."""
+        bases, offsets, n = self._prep(bases, offsets)
+        total = int(offsets[-1]) if len(offsets) else 0
+        ml, sa = np.empty(total, np.uint16), np.empty(total, np.uint64)
+        self._check(self._L.movi_gpu_query_pml_sa(self._ctx, _ptr(bases), _ptr(offsets), max(n, 0), 0, _ptr(ml), _ptr(sa)))
+        return ml, sa
 
     def export_rows(self, first=0, count=None):
         """Rows of the resident 8-byte table back in the reference's regular-thresholds MoveRow format -> uint32[count, 2]."""

@@ -83,7 +83,7 @@ __host__ __device__ __forceinline__ uint2 r8nt_to_file(uint2 v) {
 // alphamap_3 (src/utils.cpp:5-8): slot of read character b among the three thresholds of a row with character a
 __host__ __device__ __forceinline__ uint32_t thr_slot(uint32_t a, uint32_t b) { return b - (b > a ? 1u : 0u); }
 // threshold of a resident row against read character index ai (get_thresholds, move_structure.cpp:306-308): n or 0
-__device__ __forceinline__ uint32_t row_thr(uint32_t y, uint32_t ai, uint32_t n) { return ((y >> (ai & 3u)) & (1u << 25)) ? n : 0u; }
+__host__ __device__ __forceinline__ uint32_t row_thr(uint32_t y, uint32_t ai, uint32_t n) { return ((y >> (ai & 3u)) & (1u << 25)) ? n : 0u; }
 // the same for a row assembled on the fly from a packed layout (three reference bits in 25..27); a = c - sep
 __device__ __forceinline__ uint32_t row_thr_raw3(uint32_t y, uint32_t a, uint32_t ai, uint32_t n) {
     return ((y >> (25u + (thr_slot(a, ai) & 3u))) & 1u) ? n : 0u;
@@ -158,7 +158,7 @@ __device__ __forceinline__ uint2 fetch_row_b6(const uint32_t* __restrict__ w, Id
 
 // threshold value of a '%' row (separators_thresholds[separators_thresholds_map[idx]].values[ai],
 // src/move_structure_query.cpp:540-541); rows missing from the map read slot 0 like unordered_map::operator[]
-__device__ __forceinline__ uint32_t sep_threshold(const DevIndex& ix, unsigned long long idx, uint32_t ai) {
+__host__ __device__ __forceinline__ uint32_t sep_threshold(const DevIndex& ix, unsigned long long idx, uint32_t ai) {
     uint32_t lo = 0, hi = ix.sep_cnt;
     while (lo < hi) {
         uint32_t mid = (lo + hi) >> 1;

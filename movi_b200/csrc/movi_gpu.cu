@@ -10,6 +10,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -20,6 +21,7 @@
 #include "bs_kernel.cuh"
 #include "convert.cuh"
 #include "dev_index.cuh"
+#include "ext_kernel.cuh"
 #include "kernel_common.cuh"
 #include "misc_kernels.cuh"
 #include "parse_kernels.cuh"
@@ -115,6 +117,15 @@ struct movi_gpu_ctx {
     // pinned staging ring for copies from / to pageable memory and files (a file mapping is pageable by nature)
     uint8_t* pin[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t pin_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // Movi Color: the flat colour table, the sampled suffix array, scratch of the ext queries (ext_kernel.cuh)
+    uint8_t* c_inds = nullptr; uint16_t* c_flat = nullptr; double* c_lk = nullptr; uint64_t c_flat_size = 0; uint32_t c_species = 0; bool c_pvalue_ok = false;
+    unsigned long long* s_all_p = nullptr; unsigned long long* s_sampled = nullptr; uint64_t s_rate = 0, s_n = 0;
+    uint8_t* e_bases = nullptr; size_t e_bases_cap = 0;
+    unsigned long long* e_offsets = nullptr; size_t e_offsets_cap = 0;
+    uint16_t* e_ml = nullptr; size_t e_ml_cap = 0;
+    unsigned long long* e_sa = nullptr; size_t e_sa_cap = 0;
+    MoviGpuColorResult* e_res = nullptr; size_t e_res_cap = 0;
+    uint8_t* e_cnt = nullptr; size_t e_cnt_cap = 0;
     // gather probe scratch
     uint2* d_probe = nullptr; uint64_t probe_bytes = 0;
     int64_t probe_vmm_align_mb = 0;   // > 0: allocate the probe table through the VMM API at this alignment
@@ -714,6 +725,8 @@ int movi_gpu_destroy(movi_gpu_ctx* ctx) {
     cudaFree(ctx->p_raw); cudaFree(ctx->p_tile); cudaFree(ctx->p_nlpos); cudaFree(ctx->p_lines); cudaFree(ctx->p_ltile); cudaFree(ctx->p_res);
     cudaFree(ctx->p_bases); cudaFree(ctx->p_offsets); cudaFree(ctx->p_ids); cudaFree(ctx->p_id_offsets); cudaFree(ctx->p_ml); cudaFree(ctx->p_image);
     cudaFree(ctx->d_status); cudaFree(ctx->d_counters);
+    cudaFree(ctx->c_inds); cudaFree(ctx->c_flat); cudaFree(ctx->c_lk); cudaFree(ctx->s_all_p); cudaFree(ctx->s_sampled);
+    cudaFree(ctx->e_bases); cudaFree(ctx->e_offsets); cudaFree(ctx->e_ml); cudaFree(ctx->e_sa); cudaFree(ctx->e_res); cudaFree(ctx->e_cnt);
     if (ctx->probe_vmm[0]) { VmmBlock b; b.ptr = ctx->probe_vmm[0]; b.size = ctx->probe_vmm[1]; b.handle = ctx->probe_vmm[2]; vmm_free(&b); }
     else cudaFree(ctx->d_probe);
     delete ctx;
@@ -1403,6 +1416,165 @@ int movi_gpu_gather_probe(movi_gpu_ctx* ctx, uint64_t table_bytes, uint32_t load
     if (loads_done) *loads_done = (uint64_t)blocks * threads_per_block * steps;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_sink);
     return MOVI_GPU_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- Movi Color: --multi-classify, --sa-entries (ext_kernel.cuh)
+namespace {
+
+int ext_ready(movi_gpu_ctx* ctx, uint32_t flags) {
+    if (!ctx) return MOVI_GPU_ERR_ARG;
+    if (!ctx->has_index) return fail(ctx, MOVI_GPU_ERR_INDEX, "no index uploaded");
+    if (ctx->ix.layout != LAYOUT_R8 || ctx->ix.nt || ctx->always_rpml)
+        return fail(ctx, MOVI_GPU_ERR_INDEX, "multi-class classification and SA entries need a threshold index in the expanded device layout");
+    if (flags & MOVI_GPU_FLAG_RPML) return fail(ctx, MOVI_GPU_ERR_ARG, "--rpml is not available with multi-class classification / SA entries");
+    return MOVI_GPU_OK;
+}
+
+// one batch through movi_ext_kernel: slices of whole reads (a device call holds < 2^32 bases), copy in, walk, copy out
+int ext_query(movi_gpu_ctx* ctx, int ext, const char* bases, const uint64_t* offsets, uint64_t n_reads, uint32_t min_len,
+              MoviGpuColorResult* out_color, uint16_t* out_ml, uint64_t* out_sa) {
+    if (n_reads == 0) return MOVI_GPU_OK;
+    if (!bases || !offsets) return fail(ctx, MOVI_GPU_ERR_ARG, "null read batch");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->st_k[0];
+    const bool wide = ctx->ix.r > 0xFFFFFFF0ull || ctx->force_wide;
+    const bool sep = ctx->ix.sep != 0;
+    const uint64_t slice_bases = 1ull << 28, slice_reads = 1ull << 22;
+    const bool color = (ext & EXT_COLOR) != 0;
+    const size_t cnt_item = (ext & EXT_PVALUE) ? sizeof(double) : sizeof(uint32_t);
+    uint64_t i0 = 0;
+    while (i0 < n_reads) {
+        uint64_t i1 = i0 + 1;
+        while (i1 < n_reads && i1 - i0 < slice_reads && offsets[i1 + 1] - offsets[i0] <= slice_bases) i1++;
+        const uint64_t nr = i1 - i0, nb = offsets[i1] - offsets[i0];
+        if (nb >= 0xFFFFFFF0ull) return fail(ctx, MOVI_GPU_ERR_ARG, "a read of 2^32 bases or more");
+        int rc;
+        if ((rc = grow(ctx, ctx->e_bases, ctx->e_bases_cap, nb + 64))) return rc;
+        if ((rc = grow(ctx, ctx->e_offsets, ctx->e_offsets_cap, nr + 1))) return rc;
+        if (out_ml && (rc = grow(ctx, ctx->e_ml, ctx->e_ml_cap, nb + 32))) return rc;
+        if (out_sa && (rc = grow(ctx, ctx->e_sa, ctx->e_sa_cap, nb + 8))) return rc;
+        if (color && (rc = grow(ctx, ctx->e_res, ctx->e_res_cap, nr))) return rc;
+        // grid: one read per lane, at most what fits the machine; the per-lane counters bound it too (4 GiB of them at most)
+        uint64_t blocks = (nr + QUERY_THREADS - 1) / QUERY_THREADS;
+        blocks = std::min<uint64_t>(blocks, (uint64_t)ctx->num_sms * 6);
+        if (color) {
+            const uint64_t per_block = (uint64_t)QUERY_THREADS * ctx->c_species * cnt_item;
+            blocks = std::max<uint64_t>(1, std::min<uint64_t>(blocks, (4ull << 30) / std::max<uint64_t>(per_block, 1)));
+            if ((rc = grow(ctx, ctx->e_cnt, ctx->e_cnt_cap, blocks * per_block))) return rc;
+        }
+        CU(cudaMemcpyAsync(ctx->e_bases, bases + offsets[i0], nb, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->e_offsets, offsets + i0, (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        unsigned long long* counter = next_counter(ctx);
+        CU(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+        ExtArgs a{};
+        a.bases = ctx->e_bases; a.offsets = ctx->e_offsets; a.origin = offsets[i0]; a.n_reads = (uint32_t)nr;
+        a.out_ml = out_ml ? ctx->e_ml : nullptr;
+        a.counter = counter; a.status = ctx->d_status;
+        a.color_inds = ctx->c_inds; a.flat = ctx->c_flat; a.flat_size = ctx->c_flat_size; a.num_species = ctx->c_species; a.min_len = min_len;
+        a.lk = ctx->c_lk; a.cnt = ctx->e_cnt; a.cnt_stride = blocks * QUERY_THREADS; a.out_color = ctx->e_res;
+        a.all_p = ctx->s_all_p; a.sampled = ctx->s_sampled; a.rate = ctx->s_rate; a.out_sa = ctx->e_sa;
+#define EXT_LAUNCH(IDX, SEPV, EXTV) movi_ext_kernel<IDX, SEPV, EXTV><<<(unsigned)blocks, QUERY_THREADS, 0, st>>>(ctx->ix, a)
+#define EXT_PICK(EXTV) do { if (wide) { if (sep) EXT_LAUNCH(unsigned long long, true, EXTV); else EXT_LAUNCH(unsigned long long, false, EXTV); } \
+                            else      { if (sep) EXT_LAUNCH(uint32_t, true, EXTV); else EXT_LAUNCH(uint32_t, false, EXTV); } } while (0)
+        if (ext == EXT_COLOR) EXT_PICK(EXT_COLOR);
+        else if (ext == (EXT_COLOR | EXT_PVALUE)) EXT_PICK(EXT_COLOR | EXT_PVALUE);
+        else EXT_PICK(EXT_SA);
+#undef EXT_PICK
+#undef EXT_LAUNCH
+        ctx->launches += 1;
+        CU(cudaGetLastError());
+        if (out_ml) CU(cudaMemcpyAsync(out_ml + offsets[i0], ctx->e_ml, nb * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+        if (out_sa) CU(cudaMemcpyAsync(out_sa + offsets[i0], ctx->e_sa, nb * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        if (color) CU(cudaMemcpyAsync(out_color + i0, ctx->e_res, nr * sizeof(MoviGpuColorResult), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        int qs = movi_gpu_check_device_status(ctx);
+        if (qs) return qs;
+        i0 = i1;
+    }
+    return MOVI_GPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int movi_gpu_upload_colors(movi_gpu_ctx* ctx, const MoviGpuColorDesc* d) {
+    if (!ctx || !d) return MOVI_GPU_ERR_ARG;
+    if (!ctx->has_index) return fail(ctx, MOVI_GPU_ERR_INDEX, "upload the index before its colour table");
+    if (!d->flat_colors || !d->doc_set_flat_inds || d->num_species == 0 || d->num_species >= 0xFFFFu)
+        return fail(ctx, MOVI_GPU_ERR_INDEX, "empty colour table");
+    // every colour must lie inside the table and name documents below num_species (the kernels index per-lane counters with them)
+    for (uint64_t p = 0; p < d->flat_size;) {
+        const uint64_t k = d->flat_colors[p];
+        if (p + 1 + k > d->flat_size) return fail(ctx, MOVI_GPU_ERR_INDEX, "corrupt colour table: a colour runs past the end");
+        for (uint64_t j = 0; j < k; j++)
+            if (d->flat_colors[p + 1 + j] >= d->num_species) return fail(ctx, MOVI_GPU_ERR_INDEX, "corrupt colour table: document id out of range");
+        p += 1 + k;
+    }
+    const uint8_t* inds = static_cast<const uint8_t*>(d->doc_set_flat_inds);
+    for (uint64_t i = 0; i < ctx->ix.r; i++) {
+        const uint8_t* e = inds + 5 * i;
+        const uint64_t off = (uint64_t)e[0] | ((uint64_t)e[1] << 8) | ((uint64_t)e[2] << 16) | ((uint64_t)e[3] << 24) | ((uint64_t)e[4] << 32);
+        // (an offset at or beyond the end means "colour dropped by compression", move_structure_query.cpp:395; one inside must start a colour:
+        //  it does when it was written by flat_and_serialize_colors_vectors -- bounds are what protects the device)
+        if (off < d->flat_size && off + 1 + d->flat_colors[off] > d->flat_size) return fail(ctx, MOVI_GPU_ERR_INDEX, "corrupt colour table: a row points into the tail of the table");
+    }
+    CU(cudaSetDevice(ctx->device));
+    cudaFree(ctx->c_inds); cudaFree(ctx->c_flat); cudaFree(ctx->c_lk);
+    ctx->c_inds = nullptr; ctx->c_flat = nullptr; ctx->c_lk = nullptr; ctx->c_species = 0;
+    CU(cudaMalloc(&ctx->c_inds, ctx->ix.r * 5 + 16));
+    CU(cudaMalloc(&ctx->c_flat, (d->flat_size + 8) * sizeof(uint16_t)));
+    CU(cudaMemcpy(ctx->c_inds, inds, ctx->ix.r * 5, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->c_flat, d->flat_colors, d->flat_size * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    ctx->c_pvalue_ok = d->log_lens != nullptr;
+    if (d->log_lens) {
+        const double log4 = std::log(4.0);                                 // include/move_structure.hpp:315
+        std::vector<double> lk(d->num_species);
+        for (uint32_t i = 0; i < d->num_species; i++) lk[i] = d->log_lens[i] / log4;   // the quotient of move_structure_query.cpp:421
+        CU(cudaMalloc(&ctx->c_lk, lk.size() * sizeof(double)));
+        CU(cudaMemcpy(ctx->c_lk, lk.data(), lk.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    ctx->c_flat_size = d->flat_size; ctx->c_species = d->num_species;
+    return MOVI_GPU_OK;
+}
+
+int movi_gpu_query_multi_classify(movi_gpu_ctx* ctx, const char* bases, const uint64_t* read_offsets, uint64_t n_reads,
+                                  uint32_t flags, uint32_t min_len, int pvalue, MoviGpuColorResult* out, uint16_t* out_ml) {
+    int rc = ext_ready(ctx, flags);
+    if (rc) return rc;
+    if (!ctx->c_species) return fail(ctx, MOVI_GPU_ERR_INDEX, "no colour table uploaded (movi_gpu_upload_colors)");
+    if (pvalue && !ctx->c_pvalue_ok) return fail(ctx, MOVI_GPU_ERR_INDEX, "the colour table was uploaded without document lengths: no --pvalue-scoring");
+    if (n_reads && !out) return fail(ctx, MOVI_GPU_ERR_ARG, "null result buffer");
+    return ext_query(ctx, pvalue ? (EXT_COLOR | EXT_PVALUE) : EXT_COLOR, bases, read_offsets, n_reads, min_len, out, out_ml, nullptr);
+}
+
+int movi_gpu_upload_sampled_sa(movi_gpu_ctx* ctx, uint64_t rate, const uint64_t* sampled, uint64_t n_sampled, const uint64_t* all_p) {
+    if (!ctx || !sampled || !all_p) return MOVI_GPU_ERR_ARG;
+    if (!ctx->has_index) return fail(ctx, MOVI_GPU_ERR_INDEX, "upload the index before its sampled suffix array");
+    if (rate == 0 || n_sampled == 0) return fail(ctx, MOVI_GPU_ERR_INDEX, "empty sampled suffix array");
+    // all_p[i] = BWT offset of run i; every BWT offset / rate must have its sample
+    const uint64_t r = ctx->ix.r;
+    for (uint64_t i = 1; i < r; i++) if (all_p[i] <= all_p[i - 1]) return fail(ctx, MOVI_GPU_ERR_INDEX, "corrupt ssa.movi: run offsets must increase");
+    if ((all_p[r - 1] + ctx->ix.n_last - 1) / rate >= n_sampled) return fail(ctx, MOVI_GPU_ERR_INDEX, "corrupt ssa.movi: fewer samples than the BWT needs");
+    CU(cudaSetDevice(ctx->device));
+    cudaFree(ctx->s_all_p); cudaFree(ctx->s_sampled); ctx->s_all_p = nullptr; ctx->s_sampled = nullptr; ctx->s_rate = 0;
+    CU(cudaMalloc(&ctx->s_all_p, r * sizeof(uint64_t)));
+    CU(cudaMalloc(&ctx->s_sampled, n_sampled * sizeof(uint64_t)));
+    CU(cudaMemcpy(ctx->s_all_p, all_p, r * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->s_sampled, sampled, n_sampled * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    ctx->s_rate = rate; ctx->s_n = n_sampled;
+    return MOVI_GPU_OK;
+}
+
+int movi_gpu_query_pml_sa(movi_gpu_ctx* ctx, const char* bases, const uint64_t* read_offsets, uint64_t n_reads,
+                          uint32_t flags, uint16_t* out_ml, uint64_t* out_sa) {
+    int rc = ext_ready(ctx, flags);
+    if (rc) return rc;
+    if (!ctx->s_rate) return fail(ctx, MOVI_GPU_ERR_INDEX, "no sampled suffix array uploaded (movi_gpu_upload_sampled_sa)");
+    if (n_reads && !out_sa) return fail(ctx, MOVI_GPU_ERR_ARG, "null result buffer");
+    return ext_query(ctx, EXT_SA, bases, read_offsets, n_reads, 0, nullptr, out_ml, out_sa);
 }
 
 }  // extern "C"

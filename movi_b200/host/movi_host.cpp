@@ -9,6 +9,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -606,6 +607,152 @@ int movi_host_classify_bins(int fd, int mode, const movi_host_reads* rd, uint64_
                             const uint32_t* bins_below, const uint64_t* sum_max, uint8_t* found_out) {
     if (!rd || ((!bins_above || !bins_below || !sum_max) && rd->offsets.size() > 1)) return fail("bad argument");
     return classify_impl(fd, mode, rd, nullptr, 1, max_value_thr, bins_above, bins_below, sum_max, found_out);
+}
+
+// ---------------------------------------------------------------- Movi Color: colour table, sampled suffix array, their outputs
+struct movi_host_colors {
+    std::vector<uint16_t> flat;
+    std::vector<uint8_t> inds;                 // r x 5 bytes
+    std::vector<uint32_t> to_taxon_id;
+    std::vector<double> log_lens;
+    uint32_t num_docs = 0;
+};
+struct movi_host_ssa { uint64_t rate = 0; std::vector<uint64_t> sampled, all_p; };
+
+// load_color_table -> deserialize_doc_sets_flat + load_document_info (reference src/movi.cpp:121-152,
+// src/move_structure_io.cpp:587-607, 643-700)
+int movi_host_colors_open(const char* index_dir, uint64_t r, movi_host_colors** out) {
+    if (!index_dir || !out) return fail("null argument");
+    const std::string dir(index_dir);
+    std::unique_ptr<movi_host_colors> c(new movi_host_colors);
+    {
+        const std::string name = dir + "/doc_sets_flat.bin";
+        std::ifstream f(name, std::ios::binary);
+        if (!f) return fail("[deserialize doc sets flat] Failed to open document sets flat file at " + name);
+        f.seekg(0, std::ios::end); const uint64_t size = (uint64_t)f.tellg(); f.seekg(0);
+        uint64_t n = 0;
+        f.read(reinterpret_cast<char*>(&n), 8);
+        if (!f || n > size / 2 || r > size / 5 || 8 + n * 2 + r * 5 > size) return fail("truncated colour table " + name);
+        c->flat.resize(n); c->inds.resize(r * 5);
+        f.read(reinterpret_cast<char*>(c->flat.data()), (std::streamsize)(n * 2));
+        f.read(reinterpret_cast<char*>(c->inds.data()), (std::streamsize)(r * 5));
+        if (!f) return fail("truncated colour table " + name);
+    }
+    std::vector<uint64_t> doc_offsets;
+    {
+        const std::string name = dir + "/ref.fa.doc_offsets";
+        std::ifstream f(name);
+        if (!f) return fail("[load document info] doc_offsets file not found at \"" + name + "\"");
+        uint64_t v; while (f >> v) doc_offsets.push_back(v);
+    }
+    c->num_docs = (uint32_t)doc_offsets.size();
+    std::vector<uint32_t> doc_ids;
+    {
+        std::ifstream f(dir + "/ref.fa.doc_ids");
+        if (f) { uint32_t v; while (f >> v) doc_ids.push_back(v); }
+        else for (uint32_t i = 0; i < c->num_docs; i++) doc_ids.push_back(i + 1);       // "No doc ids information, setting doc ids to 1..."
+    }
+    // taxon ids compressed to 0 .. num_species - 1 in ascending order (a std::map in the reference)
+    c->to_taxon_id = doc_ids;
+    std::sort(c->to_taxon_id.begin(), c->to_taxon_id.end());
+    c->to_taxon_id.erase(std::unique(c->to_taxon_id.begin(), c->to_taxon_id.end()), c->to_taxon_id.end());
+    if (c->to_taxon_id.empty() || c->to_taxon_id.size() >= 0xFFFFu) return fail("the colour table needs between 1 and 65534 species");
+    c->log_lens.assign(c->to_taxon_id.size(), 0.0);
+    if (doc_ids.size() < doc_offsets.size()) return fail("ref.fa.doc_ids names fewer documents than ref.fa.doc_offsets");
+    for (size_t i = 0; i < doc_offsets.size(); i++) {
+        const size_t sp = (size_t)(std::lower_bound(c->to_taxon_id.begin(), c->to_taxon_id.end(), doc_ids[i]) - c->to_taxon_id.begin());
+        c->log_lens[sp] += (double)(doc_offsets[i] - (i == 0 ? 0 : doc_offsets[i - 1]));
+    }
+    for (double& v : c->log_lens) v = std::log(v);
+    *out = c.release();
+    return 0;
+}
+int movi_host_colors_desc(const movi_host_colors* c, MoviGpuColorDesc* out) {
+    if (!c || !out) return fail("null argument");
+    std::memset(out, 0, sizeof *out);
+    out->flat_colors = c->flat.data(); out->flat_size = c->flat.size(); out->doc_set_flat_inds = c->inds.data();
+    out->num_species = (uint32_t)c->to_taxon_id.size(); out->log_lens = c->log_lens.data();
+    return 0;
+}
+uint32_t movi_host_colors_num_species(const movi_host_colors* c) { return c ? (uint32_t)c->to_taxon_id.size() : 0; }
+uint32_t movi_host_colors_taxon(const movi_host_colors* c, uint32_t species) { return c && species < c->to_taxon_id.size() ? c->to_taxon_id[species] : 0; }
+void movi_host_colors_close(movi_host_colors* c) { delete c; }
+
+// the end of query_pml under is_multi_classify(): "<id>,<taxon>,<taxon>" (reference src/move_structure_query.cpp:439-471)
+int movi_host_write_multi_classify(int fd, const movi_host_reads* rd, const movi_host_colors* c, const MoviGpuColorResult* res,
+                                   uint32_t min_len, int pvalue) {
+    if (!rd || !c || (!res && rd->offsets.size() > 1)) return fail("null argument");
+    FdWriter w(fd);
+    const uint64_t n = rd->offsets.size() - 1;
+    for (uint64_t i = 0; i < n; i++) {
+        const MoviGpuColorResult& q = res[i];
+        const uint64_t len = rd->offsets[i + 1] - rd->offsets[i];
+        w.put(rd->ids.data() + rd->id_offsets[i], rd->id_offsets[i + 1] - rd->id_offsets[i]);
+        const float pml_mean = static_cast<float>(q.sum_matching_lengths) / len;                 // :443
+        const bool no_best = q.best_doc >= c->to_taxon_id.size();
+        if (pml_mean < 0.4 || no_best) { w.put(",0,0\n"); continue; }                            // UNCLASSIFIED_THRESHOLD, include/utils.hpp:169
+        std::string line = "," + std::to_string(c->to_taxon_id[q.best_doc]);
+        if (q.second_best_doc >= c->to_taxon_id.size()) line += ",0";
+        else {
+            // the comparison reads classify_cnts when --min-len > 0 and doc_scores otherwise (:452-461), whichever of the two the
+            // counting loop filled (:405-433): the other one is all zeros
+            float best_cnt = 0, second_cnt = 0;
+            if (min_len > 0 && !pvalue) { best_cnt = (float)(uint32_t)q.best_raw; second_cnt = (float)(uint32_t)q.second_raw; }
+            else if (min_len == 0 && pvalue) {
+                double b, s2; std::memcpy(&b, &q.best_raw, 8); std::memcpy(&s2, &q.second_raw, 8);
+                best_cnt = (float)b; second_cnt = (float)s2;
+            }
+            const float diff = best_cnt - second_cnt;
+            line += diff < 0.05 * best_cnt ? "," + std::to_string(c->to_taxon_id[q.second_best_doc]) : std::string(",0");
+        }
+        w.put(line + "\n");
+    }
+    return w.flush() ? 0 : fail("write failed");
+}
+
+// deserialize_sampled_SA (reference src/move_structure_io.cpp:716-735)
+int movi_host_ssa_open(const char* index_dir, movi_host_ssa** out) {
+    if (!index_dir || !out) return fail("null argument");
+    const std::string name = std::string(index_dir) + "/ssa.movi";
+    std::ifstream f(name, std::ios::binary);
+    if (!f) return fail("[deserialize sampled SA] Failed to open sampled SA entries file at " + name + "\nBuild the sampled SA by running the build-SA command.");
+    f.seekg(0, std::ios::end); const uint64_t size = (uint64_t)f.tellg(); f.seekg(0);
+    std::unique_ptr<movi_host_ssa> s(new movi_host_ssa);
+    uint64_t k = 0, r = 0;
+    f.read(reinterpret_cast<char*>(&s->rate), 8); f.read(reinterpret_cast<char*>(&k), 8);
+    if (!f || k > size / 8) return fail("truncated " + name);
+    s->sampled.resize(k);
+    f.read(reinterpret_cast<char*>(s->sampled.data()), (std::streamsize)(k * 8));
+    f.read(reinterpret_cast<char*>(&r), 8);
+    if (!f || r > size / 8) return fail("truncated " + name);
+    s->all_p.resize(r);
+    f.read(reinterpret_cast<char*>(s->all_p.data()), (std::streamsize)(r * 8));
+    if (!f) return fail("truncated " + name);
+    *out = s.release();
+    return 0;
+}
+uint64_t movi_host_ssa_rate(const movi_host_ssa* s) { return s ? s->rate : 0; }
+uint64_t movi_host_ssa_rows(const movi_host_ssa* s) { return s ? s->all_p.size() : 0; }
+uint64_t movi_host_ssa_samples(const movi_host_ssa* s) { return s ? s->sampled.size() : 0; }
+const uint64_t* movi_host_ssa_sampled(const movi_host_ssa* s) { return s ? s->sampled.data() : nullptr; }
+const uint64_t* movi_host_ssa_all_p(const movi_host_ssa* s) { return s ? s->all_p.data() : nullptr; }
+void movi_host_ssa_close(movi_host_ssa* s) { delete s; }
+
+// <prefix>.sa_entries.bpf: the records of output_base_stats(DataType::sa_entry) -- {u16 id_len; id; u64 L; u64 sa[L]} -- and NO
+// file header (the reference opens that file without writing one, src/utils.cpp:371-375)
+int movi_host_sa_append(int fd, const movi_host_reads* rd, const uint64_t* sa) {
+    if (fd < 0 || !rd || (!sa && !rd->bases.empty())) return fail("null argument");
+    FdWriter w(fd);
+    bool ok = true;
+    const uint64_t n = rd->offsets.size() - 1;
+    for (uint64_t i = 0; i < n && ok; i++) {
+        const uint16_t idl = (uint16_t)(rd->id_offsets[i + 1] - rd->id_offsets[i]);
+        const uint64_t len = rd->offsets[i + 1] - rd->offsets[i];
+        ok = w.put(reinterpret_cast<const char*>(&idl), 2) && w.put(rd->ids.data() + rd->id_offsets[i], idl) &&
+             w.put(reinterpret_cast<const char*>(&len), 8) && w.put(reinterpret_cast<const char*>(sa + rd->offsets[i]), len * 8);
+    }
+    ok = ok && w.flush();
+    return ok ? 0 : fail("write failed: .sa_entries.bpf");
 }
 
 }  // extern "C"

@@ -1,0 +1,90 @@
+"""Movi Color on the CPU side: the host loaders / writers of include/movi_host.h and the lane state machine of the device kernel
+(movi_b200/csrc/ext_kernel.cuh, compiled for the host by tests/native/ext_emulate.cu) against the reference's outputs and the oracle."""
+import lzma
+import os
+
+import numpy as np
+import pytest
+
+from _color import HostColors, HostSsa, emulate_color, emulate_sa, random_reads, result_scores
+from conftest import COLOR_VARIANTS, GOLD, color_expected, parse_bpf_records
+from movi_b200 import HostIndex, Reads
+from movi_b200 import _native as N
+from movi_b200.api import COLOR_RESULT_DTYPE
+from oracle.port import OracleIndex, pack_reads
+
+
+@pytest.fixture(scope="module")
+def case(color_index_dir):
+    hi = HostIndex(color_index_dir)
+    return dict(dir=color_index_dir, hi=hi, colors=HostColors(color_index_dir, hi.r), ssa=HostSsa(color_index_dir),
+                reads=Reads(os.path.join(GOLD, "color", "reads.fa")), orc=OracleIndex(color_index_dir))
+
+
+def test_host_loaders_match_the_oracle(case):
+    assert case["colors"].num_species == case["orc"].load_colors() == 5
+    assert [case["colors"].taxon(s) for s in range(5)] == [case["orc"].taxon(s) for s in range(5)] == [562, 1280, 9606, 10090, 28901]
+    assert case["ssa"].rate == 100 and case["ssa"].rows == case["hi"].r
+
+
+@pytest.mark.parametrize("tag", sorted(COLOR_VARIANTS))
+def test_host_writer_reproduces_the_reference_file_from_oracle_results(case, tag):
+    """movi_host_write_multi_classify: the oracle's per-read results in, the reference's -o file out."""
+    v = COLOR_VARIANTS[tag]
+    rd = case["reads"]
+    taxa, raw, score, _ = case["orc"].query_multi_classify(rd.bases, rd.offsets, **v)
+    res = np.zeros(rd.count, COLOR_RESULT_DTYPE)
+    res["best_doc"], res["second_best_doc"], res["sum_matching_lengths"] = raw[:, 0], raw[:, 1], raw[:, 2]
+    if v["pvalue"]:
+        res["best_raw"], res["second_raw"] = score[:, 0].view(np.uint64), score[:, 1].view(np.uint64)
+    else:
+        res["best_raw"], res["second_raw"] = score[:, 0].astype(np.uint64), score[:, 1].astype(np.uint64)
+    assert case["colors"].text(rd, res, **v) == color_expected(tag)
+
+
+@pytest.mark.parametrize("tag", sorted(COLOR_VARIANTS))
+@pytest.mark.parametrize("lanes,wide", [(1, False), (7, False), (64, True)])
+def test_kernel_lanes_on_the_cpu_multi_classify(case, tag, lanes, wide):
+    v = COLOR_VARIANTS[tag]
+    rd = case["reads"]
+    res, ml = emulate_color(case["hi"], case["colors"], rd.bases, rd.offsets, lanes=lanes, wide=wide, **v)
+    assert case["colors"].text(rd, res, **v) == color_expected(tag)
+    taxa, raw, score, oml = case["orc"].query_multi_classify(rd.bases, rd.offsets, **v)
+    assert np.array_equal(np.stack([res["best_doc"], res["second_best_doc"], res["sum_matching_lengths"]], axis=1), raw)
+    assert np.array_equal(result_scores(res, v["pvalue"]), score)
+    assert np.array_equal(ml, oml)
+
+
+@pytest.mark.parametrize("lanes,wide", [(1, False), (5, False), (33, True)])
+def test_kernel_lanes_on_the_cpu_sa_entries(case, lanes, wide):
+    rd = case["reads"]
+    ml, sa = emulate_sa(case["hi"], case["ssa"], rd.bases, rd.offsets, lanes=lanes, wide=wide)
+    want = parse_bpf_records(lzma.open(os.path.join(GOLD, "color", "expected.sa_entries.bpf.xz")).read(), 8, header=False)
+    for i, (_, v) in enumerate(want):
+        assert np.array_equal(v, sa[int(rd.offsets[i]):int(rd.offsets[i + 1])]), i
+    assert np.array_equal(ml, case["orc"].query_pml(rd.bases, rd.offsets))
+
+
+def test_kernel_lanes_on_the_cpu_ragged_reads(case):
+    """3000 ragged reads (empty, 1-base, with N, random) -- every lane slot is reused many times."""
+    b, o = pack_reads(random_reads(case["dir"], 3000, seed=5))
+    for v in (dict(min_len=1, pvalue=False), dict(min_len=0, pvalue=True)):
+        res, ml = emulate_color(case["hi"], case["colors"], b, o, lanes=48, **v)
+        taxa, raw, score, oml = case["orc"].query_multi_classify(b, o, **v)
+        assert np.array_equal(np.stack([res["best_doc"], res["second_best_doc"], res["sum_matching_lengths"]], axis=1), raw)
+        assert np.array_equal(result_scores(res, v["pvalue"]), score) and np.array_equal(ml, oml)
+    ml, sa = emulate_sa(case["hi"], case["ssa"], b, o, lanes=48)
+    oml, osa = case["orc"].query_pml_sa(b, o)
+    assert np.array_equal(ml, oml) and np.array_equal(sa, osa)
+
+
+def test_sa_writer_reproduces_the_reference_file(case, tmp_path):
+    rd = case["reads"]
+    _, sa = case["orc"].query_pml_sa(rd.bases, rd.offsets)
+    f = tmp_path / "x.sa_entries.bpf"
+    fd = os.open(f, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+    try:
+        assert N.host_lib().movi_host_sa_append(fd, rd._h, sa.ctypes.data) == 0
+    finally:
+        os.close(fd)
+    assert f.read_bytes() == lzma.open(os.path.join(GOLD, "color", "expected.sa_entries.bpf.xz")).read()
