@@ -6,6 +6,7 @@
 // GPUs walk the current one); each batch is sharded over --gpus GPUs (index replicated, one host thread + one context per
 // GPU) and its results are appended to the outputs in read order (= reference --no-prefetch -t1).
 // `movi-b200 view --bpf F` prints a .bpf file like the reference's view action (src/movi.cpp:402-503).
+#include <fcntl.h>
 #include <unistd.h>
 
 #include <atomic>
@@ -39,6 +40,9 @@ struct Options {
     uint64_t chunk_bytes = 256ull << 20;     // device-side ingest: file bytes per chunk (grows by itself when reads are long)
     bool host_parse = false;                 // --host-parse: never use the device-side ingest
     int layout = MOVI_GPU_LAYOUT_AUTO;       // --layout auto|expanded|compact: device form of blocked / sampled indexes
+    // Movi Color (movi_parser.cpp:155, 164-175)
+    bool multi_classify = false, pvalue_scoring = false, sa_entries = false;
+    uint32_t min_len = 1;                    // --min-len (uint8 in the reference, movi_options.hpp:291)
     bool write_output_allowed() const { return !no_output && !filter; }          // movi_options.hpp:70
     bool write_stdout_enabled() const { return to_stdout && !classify; }         // movi_options.hpp:71
 };
@@ -49,6 +53,7 @@ struct Options {
                     "                       [--stdout] [-o prefix] [--no-output] [--reverse] [--ignore-illegal-chars 1|2]\n"
                     "                       [--bin-width N] [--gpus N] [--device D] [--chunk-bases N] [--chunk-reads N] [--max-chunk-bases N]\n"
                     "                       [--chunk-bytes N] [--host-parse] [--layout auto|expanded|compact]\n"
+                    "                       [--multi-classify -o out.csv [--min-len N] [--pvalue-scoring]] [--sa-entries]\n"
                     "                       [-t N] [-s N] [-n]\n"
                     "       movi-b200 view --bpf <file.bpf>\n");
     exit(1);
@@ -98,6 +103,15 @@ Options parse(int argc, char** argv) {
             else if (v == "compact") o.layout = MOVI_GPU_LAYOUT_COMPACT; else usage_error("--layout: auto, expanded or compact");
         }
         else if (take_value(argc, argv, i, nullptr, "--max-chunk-bases", v)) o.max_chunk_bases = std::max<uint64_t>(1, strtoull(v.c_str(), nullptr, 10));
+        else if (a == "--multi-classify") o.multi_classify = true;
+        else if (a == "--pvalue-scoring") o.pvalue_scoring = true;
+        else if (a == "--sa-entries") o.sa_entries = true;
+        else if (take_value(argc, argv, i, nullptr, "--min-len", v)) o.min_len = (uint32_t)(uint8_t)strtoul(v.c_str(), nullptr, 10);
+        else if (a == "--early-stop" || a == "--report-all" || a == "--report-colors" || a == "--report-color-ids" || a == "--full" ||
+                 a == "--compress" || a == "--freq-compress" || a == "--tree-compress" || a == "--color-vectors" || a == "--color-move-rows" ||
+                 a == "--min-diff-frac" || a == "--min-score-frac")
+            usage_error(a + ": only the default flat colour table with the output of the --no-prefetch path is built here "
+                            "(--multi-classify [--min-len N] [--pvalue-scoring]); use the reference for " + a);
         else if (a == "--pml") o.query = "pml";
         else if (a == "--rpml") o.rpml = true;                                  // movi_parser.cpp:149,357
         else if (a == "--zml") o.query = "zml";
@@ -248,6 +262,98 @@ int run_device_ingest(const Options& o, const std::vector<movi_gpu_ctx*>& ctx, c
     return status;
 }
 
+// ---- Movi Color flows: `--multi-classify` writes "<id>,<taxon>,<taxon>" per read to the -o file
+// (src/move_structure_query.cpp:439-471) next to the usual <prefix>.pml.bpf; `--sa-entries` writes <prefix>.sa_entries.bpf
+// (src/utils.cpp:371-375, no header) next to it.  Batches are sharded over the GPUs like every other query.
+int run_color(const Options& o, const std::vector<movi_gpu_ctx*>& ctx, const MoviGpuIndexDesc& desc, movi_host_reader* reader,
+              const std::string& prefix, uint64_t min_reads, std::string* err) {
+    const int gpus = (int)ctx.size();
+    movi_host_colors* colors = nullptr; movi_host_ssa* ssa = nullptr;
+    if (o.multi_classify) {
+        if (movi_host_colors_open(o.index_dir.c_str(), desc.r, &colors)) { *err = movi_host_last_error(); return -1; }
+        MoviGpuColorDesc cd;
+        movi_host_colors_desc(colors, &cd);
+        for (int g = 0; g < gpus; g++) if (movi_gpu_upload_colors(ctx[g], &cd)) { *err = movi_gpu_last_error(ctx[g]); return -1; }
+    }
+    if (o.sa_entries) {
+        if (movi_host_ssa_open(o.index_dir.c_str(), &ssa)) { *err = movi_host_last_error(); return -1; }
+        if (movi_host_ssa_rows(ssa) != desc.r) { *err = "ssa.movi belongs to another index: run build-SA again"; return -1; }
+        for (int g = 0; g < gpus; g++)
+            if (movi_gpu_upload_sampled_sa(ctx[g], movi_host_ssa_rate(ssa), movi_host_ssa_sampled(ssa), movi_host_ssa_samples(ssa), movi_host_ssa_all_p(ssa))) {
+                *err = movi_gpu_last_error(ctx[g]); return -1;
+            }
+    }
+    int fd_csv = -1, fd_bpf = -1, fd_sa = -1;
+    if (o.multi_classify) {
+        fd_csv = open(o.out_file.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);                // open_output_files, src/utils.cpp:323-326
+        if (fd_csv < 0) { *err = "cannot open " + o.out_file; return -1; }
+    }
+    const bool want_files = o.write_output_allowed() && !o.write_stdout_enabled();
+    if (want_files) {
+        fd_bpf = movi_host_bpf_begin((prefix + ".bpf").c_str());
+        if (fd_bpf < 0) { *err = movi_host_last_error(); return -1; }
+        if (o.sa_entries) {
+            fd_sa = open((prefix + ".sa_entries.bpf").c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+            if (fd_sa < 0) { *err = "cannot open " + prefix + ".sa_entries.bpf"; return -1; }
+        }
+    }
+    const bool want_ml = o.write_output_allowed();
+    std::vector<uint16_t> ml; std::vector<uint64_t> sa; std::vector<MoviGpuColorResult> res;
+    for (;;) {
+        movi_host_reads* rd = nullptr;
+        if (movi_host_reader_next_reads(reader, o.chunk_bases, min_reads, std::max(o.max_chunk_bases, o.chunk_bases), &rd)) { *err = movi_host_last_error(); return -1; }
+        if (!rd) break;
+        const uint64_t n_reads = movi_host_reads_count(rd);
+        const uint64_t* offsets = movi_host_reads_offsets(rd);
+        const char* bases = movi_host_reads_bases(rd);
+        const uint64_t n_bases = n_reads ? offsets[n_reads] : 0;
+        if (want_ml) ml.resize(n_bases + 1);
+        if (o.sa_entries) sa.resize(n_bases + 1);
+        if (o.multi_classify) res.resize(n_reads + 1);
+        std::vector<uint64_t> cut(gpus + 1, n_reads);
+        cut[0] = 0;
+        for (int g = 1; g < gpus; g++) {
+            const uint64_t target = n_bases / gpus * g;
+            uint64_t i = cut[g - 1];
+            while (i < n_reads && offsets[i] < target) i++;
+            cut[g] = i;
+        }
+        std::vector<ShardResult> sr(gpus);
+        auto worker = [&](int g) {
+            if (cut[g + 1] <= cut[g]) return;
+            const uint64_t i0 = cut[g], nr = cut[g + 1] - cut[g];
+            int r = 0;
+            if (o.multi_classify)
+                r = movi_gpu_query_multi_classify(ctx[g], bases, offsets + i0, nr, 0, o.min_len, o.pvalue_scoring ? 1 : 0, res.data() + i0,
+                                                  (want_ml && !o.sa_entries) ? ml.data() : nullptr);
+            if (!r && o.sa_entries) r = movi_gpu_query_pml_sa(ctx[g], bases, offsets + i0, nr, 0, want_ml ? ml.data() : nullptr, sa.data());
+            if (r) sr[g] = {r, movi_gpu_last_error(ctx[g])};
+        };
+        if (gpus == 1) worker(0);
+        else {
+            std::vector<std::thread> th;
+            for (int g = 0; g < gpus; g++) th.emplace_back(worker, g);
+            for (auto& t : th) t.join();
+        }
+        for (int g = 0; g < gpus; g++) if (sr[g].rc) { *err = "GPU " + std::to_string(o.device + g) + ": " + sr[g].err; return -1; }
+        int rc = 0;
+        if (o.multi_classify) rc = movi_host_write_multi_classify(fd_csv, rd, colors, res.data(), o.min_len, o.pvalue_scoring ? 1 : 0);
+        if (!rc && o.write_output_allowed()) {
+            if (o.write_stdout_enabled()) rc = movi_host_write_ml_text(STDOUT_FILENO, rd, ml.data());
+            else {
+                rc = movi_host_bpf_append(fd_bpf, rd, ml.data());
+                if (!rc && o.sa_entries) rc = movi_host_sa_append(fd_sa, rd, sa.data());
+            }
+        }
+        movi_host_reads_free(rd);
+        if (rc) { *err = movi_host_last_error(); return -1; }
+    }
+    if (fd_csv >= 0) close(fd_csv);
+    if (fd_sa >= 0) close(fd_sa);
+    if (fd_bpf >= 0 && movi_host_bpf_end(fd_bpf)) { *err = movi_host_last_error(); return -1; }
+    return 0;
+}
+
 void die(const std::string& m) { fprintf(stderr, "\033[31m\n\n[ERROR] %s\n\033[0m", m.c_str()); exit(1); }
 
 }  // namespace
@@ -294,10 +400,16 @@ int main(int argc, char** argv) {
     };
     // Device-side ingest: when all that is wanted of a PML / ZML query is its .bpf file (or nothing: --no-output), the file
     // bytes go to the GPUs as they are and come back as .bpf records (run_device_ingest).
-    const bool ingest_on_device = !o.host_parse && (o.query == "pml" || o.query == "zml") && !o.classify && !o.reverse && o.ignore_illegal == 0 &&
+    if (o.multi_classify || o.sa_entries) {
+        if (o.query != "pml" || o.rpml) usage_error("--multi-classify / --sa-entries go with --pml");
+        if (o.classify) usage_error("--multi-classify / --sa-entries do not combine with --classify / --filter here");
+        if (o.multi_classify && o.out_file.empty()) usage_error("Please include the out file for multi-classify.");     // movi_parser.cpp:396-399
+    }
+    const bool color_flow = o.multi_classify || o.sa_entries;
+    const bool ingest_on_device = !color_flow && !o.host_parse && (o.query == "pml" || o.query == "zml") && !o.classify && !o.reverse && o.ignore_illegal == 0 &&
                                   !o.write_stdout_enabled() && !(o.to_stdout && o.write_output_allowed());
     std::future<Fetched> ahead;
-    if (!ingest_on_device) ahead = std::async(std::launch::async, fetch);
+    if (!ingest_on_device && !color_flow) ahead = std::async(std::launch::async, fetch);
 
     // one context per GPU, index replicated (uploaded while the first batch is being parsed)
     std::vector<movi_gpu_ctx*> ctx(gpus, nullptr);
@@ -318,6 +430,14 @@ int main(int argc, char** argv) {
         fprintf(stderr, "[INFO] start-up: files opened in %.3f s, CUDA driver up in %.3f s, %d context(s) + index upload in %.3f s\n",
                 std::chrono::duration<double>(t_files - t_load0).count(), std::chrono::duration<double>(t_cuda - t_files).count(), gpus,
                 std::chrono::duration<double>(t_q0 - t_cuda).count());
+
+    if (o.multi_classify || o.sa_entries) {
+        std::string err;
+        const std::string cprefix = (o.out_file.empty() ? o.read_file + "." + type : o.out_file) + "." + qname;
+        if (run_color(o, ctx, desc, reader, cprefix, min_reads, &err)) die(err);
+        fflush(stdout); fflush(stderr);
+        _exit(0);
+    }
 
     // With --classify / --filter the binning runs on the device (movi_gpu_query_classify); the matching lengths only come
     // back when something needs them (the .bpf file next to a --classify report; never for --filter or --no-output).

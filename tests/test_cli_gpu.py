@@ -207,3 +207,40 @@ def test_device_side_ingest_hands_odd_inputs_to_the_host_parser(cli, index_dirs,
         run(cli, "query", "-i", d, "-r", str(reads), "--pml", *extra)
         out[name] = open("%s.regular-thresholds.pml.bpf" % reads, "rb").read()
     assert out["device"][12:] == out["host"][12:] and len(out["host"]) > 12
+
+
+# ---- Movi Color flows: the command lines tests/golden/make_golden_color.py gave the unmodified reference
+@pytest.mark.parametrize("gpus", [1, 2])
+def test_multi_classify_and_sa_entries_files(cli, color_index_dir, tmp_path, gpus):
+    import torch
+    if gpus > torch.cuda.device_count():
+        pytest.skip("needs %d GPUs" % gpus)
+    from conftest import COLOR_VARIANTS, color_expected
+    reads = tmp_path / "reads.fa"
+    shutil.copy(os.path.join(GOLD, "color", "reads.fa"), reads)
+    flags = {"": [], ".minlen3": ["--min-len", "3"], ".pvalue": ["--pvalue-scoring"], ".minlen0": ["--min-len", "0"],
+             ".pvalue.minlen0": ["--pvalue-scoring", "--min-len", "0"]}
+    want_bpf = lzma.open(os.path.join(GOLD, "color", "expected.pml.bpf.xz")).read()
+    for tag in COLOR_VARIANTS:
+        o = str(tmp_path / ("mc%s.csv" % tag))
+        run(cli, "query", "--index", color_index_dir, "--read", str(reads), "--pml", "--multi-classify", "--no-prefetch", "-t1", "-o", o,
+            "--gpus", str(gpus), "--chunk-reads", "64", "--chunk-bases", "20000", *flags[tag])       # several batches
+        assert open(o).read() == color_expected(tag), tag
+        got = open(o + ".pml.bpf", "rb").read()
+        assert got[:10] == want_bpf[:10] and got[12:] == want_bpf[12:]
+    run(cli, "query", "--index", color_index_dir, "--read", str(reads), "--pml", "--sa-entries", "--no-prefetch", "-t1", "--gpus", str(gpus))
+    assert open(str(reads) + ".regular-thresholds.pml.sa_entries.bpf", "rb").read() == lzma.open(os.path.join(GOLD, "color", "expected.sa_entries.bpf.xz")).read()
+    got = open(str(reads) + ".regular-thresholds.pml.bpf", "rb").read()
+    assert got[12:] == want_bpf[12:]
+
+
+def test_multi_classify_argument_errors(cli, color_index_dir, index_dirs):
+    reads = os.path.join(GOLD, "color", "reads.fa")
+    r = subprocess.run([cli, "query", "-i", color_index_dir, "-r", reads, "--pml", "--multi-classify"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 1 and b"Please include the out file for multi-classify." in r.stderr
+    r = subprocess.run([cli, "query", "-i", index_dirs[("regular-thresholds", False)], "-r", reads, "--pml", "--multi-classify", "-o", "/tmp/x.csv"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 1 and b"doc_sets_flat.bin" in r.stderr
+    r = subprocess.run([cli, "query", "-i", index_dirs[("regular-thresholds", False)], "-r", reads, "--pml", "--sa-entries"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 1 and b"build-SA" in r.stderr
