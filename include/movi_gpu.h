@@ -197,6 +197,15 @@ int  movi_gpu_query_file_chunk(movi_gpu_ctx* ctx, int zml, const char* raw, uint
 int  movi_gpu_file_chunk_parse(movi_gpu_ctx* ctx, const char* raw, uint64_t n_bytes, int fastq, int final_chunk, MoviGpuChunkResult* res);
 int  movi_gpu_file_chunk_query(movi_gpu_ctx* ctx, int zml, uint32_t flags, uint8_t* out_image, uint64_t image_capacity, int out_fd,
                                uint64_t file_offset);
+/* The chunk parsed last, for the --classify / --filter workflows (handle_pml_zml, src/movi.cpp:23-60): walked, binned on the device
+ * (Classifier::classify, src/classifier.cpp:99-143; the three report columns per read come back, as from movi_gpu_query_classify) and,
+ * when a sink is given, also delivered as .bpf records like movi_gpu_file_chunk_query (the report of --classify comes with its .bpf). */
+int  movi_gpu_file_chunk_classify(movi_gpu_ctx* ctx, int zml, uint32_t flags, uint32_t bin_width, uint32_t max_value_thr,
+                                  uint32_t* out_bins_above, uint32_t* out_bins_below, uint64_t* out_sum_max,
+                                  uint8_t* out_image, uint64_t image_capacity, int out_fd, uint64_t file_offset);
+/* The reads of the chunk parsed last copied back to the host: n_bases bytes, n_reads + 1 offsets, id_bytes bytes, n_reads + 1 id
+ * offsets (sizes in the MoviGpuChunkResult of the parse; any pointer may be NULL) -- the ids a report prints, the sequences --filter echoes. */
+int  movi_gpu_file_chunk_fetch(movi_gpu_ctx* ctx, char* out_bases, uint64_t* out_offsets, char* out_ids, uint64_t* out_id_offsets);
 /* The parse alone, results copied back to the host (tests, tools). */
 int  movi_gpu_parse_chunk(movi_gpu_ctx* ctx, const char* raw, uint64_t n_bytes, int fastq, int final_chunk,
                           char* out_bases, uint64_t bases_capacity, uint64_t* out_offsets, char* out_ids, uint64_t ids_capacity,

@@ -51,7 +51,13 @@ int  movi_host_reader_raw(const movi_host_reader* r, const char** data, uint64_t
  * line starting with '>'; FASTQ = a line starting with '@' whose next-but-one line starts with '+' (a quality line may start
  * with '@' too, but then the line two further down is a sequence, never a '+' line). */
 uint64_t movi_host_record_boundary(const char* data, uint64_t size, uint64_t from, int fastq);
+/* Continue at byte `at` of the input (a record boundary found by movi_host_record_boundary / consumed by the device-side parser). */
+int  movi_host_reader_seek(movi_host_reader* r, uint64_t at);
 void movi_host_reader_close(movi_host_reader* r);
+/* A batch from parts (copies): what the device-side parser returns through movi_gpu_file_chunk_fetch.  bases may be NULL when only the
+ * ids and lengths are needed (a classification report); offsets and id_offsets start at 0. */
+int  movi_host_reads_adopt(const char* bases, const uint64_t* offsets, uint64_t n_reads, const char* ids, const uint64_t* id_offsets,
+                           movi_host_reads** out);
 uint64_t movi_host_reads_count(const movi_host_reads* rd);
 const char* movi_host_reads_bases(const movi_host_reads* rd);          /* concatenated */
 const uint64_t* movi_host_reads_offsets(const movi_host_reads* rd);    /* count + 1 */

@@ -67,6 +67,9 @@ GPU_SYMBOLS = {
                                             C.POINTER(MoviGpuChunkResult)]),
     "movi_gpu_file_chunk_parse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(MoviGpuChunkResult)]),
     "movi_gpu_file_chunk_query": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_uint64, C.c_int, C.c_uint64]),
+    "movi_gpu_file_chunk_classify": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_uint64, C.c_int, C.c_uint64]),
+    "movi_gpu_file_chunk_fetch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "movi_gpu_parse_chunk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
                                        C.c_void_p, C.c_uint64, C.POINTER(MoviGpuChunkResult)]),
     "movi_gpu_query_zml": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]),
@@ -121,6 +124,8 @@ HOST_SYMBOLS = {
     "movi_host_write_counts": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "movi_host_classify_bins": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "movi_host_classify": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "movi_host_reader_seek": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "movi_host_reads_adopt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "movi_host_colors_open": (C.c_int, [C.c_char_p, C.c_uint64, C.POINTER(C.c_void_p)]),
     "movi_host_colors_desc": (C.c_int, [C.c_void_p, C.POINTER(MoviGpuColorDesc)]),
     "movi_host_colors_num_species": (C.c_uint32, [C.c_void_p]),

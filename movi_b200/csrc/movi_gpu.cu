@@ -114,6 +114,7 @@ struct movi_gpu_ctx {
     uint16_t* p_ml = nullptr; size_t p_ml_cap = 0;
     uint8_t* p_image = nullptr; size_t p_image_cap = 0;
     ParseResult p_last{};                              // result of the last movi_gpu_file_chunk_parse (what _query works on)
+    uint32_t* p_above = nullptr; uint32_t* p_below = nullptr; unsigned long long* p_sum = nullptr; size_t p_cls_cap = 0;   // movi_gpu_file_chunk_classify
     // pinned staging ring for copies from / to pageable memory and files (a file mapping is pageable by nature)
     uint8_t* pin[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t pin_ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -724,6 +725,7 @@ int movi_gpu_destroy(movi_gpu_ctx* ctx) {
     for (int k = 0; k < 4; k++) { if (ctx->pin[k]) cudaFreeHost(ctx->pin[k]); if (ctx->pin_ev[k]) cudaEventDestroy(ctx->pin_ev[k]); }
     cudaFree(ctx->p_raw); cudaFree(ctx->p_tile); cudaFree(ctx->p_nlpos); cudaFree(ctx->p_lines); cudaFree(ctx->p_ltile); cudaFree(ctx->p_res);
     cudaFree(ctx->p_bases); cudaFree(ctx->p_offsets); cudaFree(ctx->p_ids); cudaFree(ctx->p_id_offsets); cudaFree(ctx->p_ml); cudaFree(ctx->p_image);
+    cudaFree(ctx->p_above); cudaFree(ctx->p_below); cudaFree(ctx->p_sum);
     cudaFree(ctx->d_status); cudaFree(ctx->d_counters);
     cudaFree(ctx->c_inds); cudaFree(ctx->c_flat); cudaFree(ctx->c_lk); cudaFree(ctx->s_all_p); cudaFree(ctx->s_sampled);
     cudaFree(ctx->e_bases); cudaFree(ctx->e_offsets); cudaFree(ctx->e_ml); cudaFree(ctx->e_sa); cudaFree(ctx->e_res); cudaFree(ctx->e_cnt);
@@ -1295,6 +1297,75 @@ extern "C" int movi_gpu_file_chunk_query(movi_gpu_ctx* ctx, int zml, uint32_t fl
     return movi_gpu_check_device_status(ctx);
 }
 
+// The chunk parsed last: walked, classified on the device (Classifier::classify's binning, src/classifier.cpp:99-143) and, when a sink is
+// given, delivered as .bpf records like movi_gpu_file_chunk_query does.  Only 16 bytes per read come back for the report.
+extern "C" int movi_gpu_file_chunk_classify(movi_gpu_ctx* ctx, int zml, uint32_t flags, uint32_t bin_width, uint32_t max_value_thr,
+                                            uint32_t* out_above, uint32_t* out_below, uint64_t* out_sum,
+                                            uint8_t* out_image, uint64_t image_capacity, int out_fd, uint64_t file_offset) {
+    if (!ctx) return MOVI_GPU_ERR_ARG;
+    if (bin_width == 0) return fail(ctx, MOVI_GPU_ERR_ARG, "bin_width must be positive");
+    CallFlags cf(ctx, flags);
+    const Kind kind = zml ? Q_ZML : Q_PML;
+    int rc = check_query_ready(ctx, kind, 0);
+    if (rc) return rc;
+    const ParseResult pr = ctx->p_last;
+    if (pr.n_reads == 0) return MOVI_GPU_OK;
+    if (!out_above || !out_below || !out_sum) return fail(ctx, MOVI_GPU_ERR_ARG, "null result buffer");
+    const uint64_t image_bytes = 10ull * pr.n_reads + pr.id_bytes + 2ull * pr.n_bases;
+    if (out_image && image_bytes > image_capacity) return fail(ctx, MOVI_GPU_ERR_NOMEM, "the .bpf image buffer is too small for this chunk");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->st_k[0];
+    if ((rc = grow(ctx, ctx->p_ml, ctx->p_ml_cap, (size_t)pr.n_bases + 96))) return rc;
+    if (pr.n_reads > ctx->p_cls_cap) {
+        cudaFree(ctx->p_above); cudaFree(ctx->p_below); cudaFree(ctx->p_sum);
+        ctx->p_above = nullptr; ctx->p_below = nullptr; ctx->p_sum = nullptr; ctx->p_cls_cap = 0;
+        const size_t want = (size_t)pr.n_reads + (size_t)pr.n_reads / 8 + 64;
+        CU(cudaMalloc(&ctx->p_above, want * sizeof(uint32_t))); CU(cudaMalloc(&ctx->p_below, want * sizeof(uint32_t)));
+        CU(cudaMalloc(&ctx->p_sum, want * sizeof(unsigned long long)));
+        ctx->p_cls_cap = want;
+    }
+    CU(cudaMemsetAsync(ctx->d_status, 0, sizeof(unsigned int), st));
+    CU(cudaMemsetAsync(ctx->p_bases + pr.n_bases, 0, 64, st));
+    rc = device_query(ctx, kind, reinterpret_cast<const char*>(ctx->p_bases), reinterpret_cast<const uint64_t*>(ctx->p_offsets), 0, pr.n_reads,
+                      ctx->p_ml, nullptr, nullptr, next_counter(ctx), st);
+    if (rc) return rc;
+    {
+        const unsigned blocks = (unsigned)std::min<uint64_t>((pr.n_reads * 32 + 255) / 256, (uint64_t)ctx->num_sms * 16);
+        classify_kernel<<<blocks, 256, 0, st>>>(ctx->p_ml, ctx->p_offsets, 0ull, pr.n_reads, bin_width, max_value_thr, ctx->p_above, ctx->p_below, ctx->p_sum);
+        ctx->launches += 1;
+        CU(cudaGetLastError());
+    }
+    if (out_image || out_fd >= 0) {
+        if ((rc = grow(ctx, ctx->p_image, ctx->p_image_cap, (size_t)image_bytes + 16))) return rc;
+        const unsigned blocks = (unsigned)std::min<uint64_t>((pr.n_reads * 32 + 255) / 256, (uint64_t)ctx->num_sms * 16);
+        bpf_assemble_kernel<<<blocks, 256, 0, st>>>(ctx->p_ml, ctx->p_offsets, 0ull, pr.n_reads, ctx->p_ids, ctx->p_id_offsets, ctx->p_image);
+        ctx->launches += 1;
+        CU(cudaGetLastError());
+        if ((rc = staged_d2h(ctx, out_image, out_fd, file_offset, ctx->p_image, image_bytes, st))) return rc;
+    }
+    CU(cudaMemcpyAsync(out_above, ctx->p_above, pr.n_reads * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out_below, ctx->p_below, pr.n_reads * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out_sum, ctx->p_sum, pr.n_reads * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return movi_gpu_check_device_status(ctx);
+}
+
+// The reads parsed last, copied back to the host (any pointer may be NULL): ids for a report, sequences for --filter.
+extern "C" int movi_gpu_file_chunk_fetch(movi_gpu_ctx* ctx, char* out_bases, uint64_t* out_offsets, char* out_ids, uint64_t* out_id_offsets) {
+    if (!ctx) return MOVI_GPU_ERR_ARG;
+    const ParseResult pr = ctx->p_last;
+    if (pr.n_reads == 0) return MOVI_GPU_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->st_k[0];
+    int rc;
+    if (out_bases && (rc = staged_d2h(ctx, reinterpret_cast<uint8_t*>(out_bases), -1, 0, ctx->p_bases, pr.n_bases, st))) return rc;
+    if (out_ids && (rc = staged_d2h(ctx, reinterpret_cast<uint8_t*>(out_ids), -1, 0, ctx->p_ids, pr.id_bytes, st))) return rc;
+    if (out_offsets) CU(cudaMemcpyAsync(out_offsets, ctx->p_offsets, (pr.n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (out_id_offsets) CU(cudaMemcpyAsync(out_id_offsets, ctx->p_id_offsets, (pr.n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return MOVI_GPU_OK;
+}
+
 extern "C" int movi_gpu_query_file_chunk(movi_gpu_ctx* ctx, int zml, const char* raw, uint64_t n_bytes, int fastq, int final_chunk, uint32_t flags,
                                          uint8_t* out_image, uint64_t image_capacity, MoviGpuChunkResult* res) {
     int rc = movi_gpu_file_chunk_parse(ctx, raw, n_bytes, fastq, final_chunk, res);
@@ -1464,8 +1535,9 @@ int ext_query(movi_gpu_ctx* ctx, int ext, const char* bases, const uint64_t* off
             blocks = std::max<uint64_t>(1, std::min<uint64_t>(blocks, (4ull << 30) / std::max<uint64_t>(per_block, 1)));
             if ((rc = grow(ctx, ctx->e_cnt, ctx->e_cnt_cap, blocks * per_block))) return rc;
         }
-        CU(cudaMemcpyAsync(ctx->e_bases, bases + offsets[i0], nb, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(ctx->e_offsets, offsets + i0, (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        // (pageable caller buffers pass through the ring of pinned pieces: staged_h2d / staged_d2h)
+        if ((rc = staged_h2d(ctx, ctx->e_bases, bases + offsets[i0], nb, st))) return rc;
+        if ((rc = staged_h2d(ctx, ctx->e_offsets, reinterpret_cast<const char*>(offsets + i0), (nr + 1) * sizeof(uint64_t), st))) return rc;
         unsigned long long* counter = next_counter(ctx);
         CU(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
         ExtArgs a{};
@@ -1485,9 +1557,9 @@ int ext_query(movi_gpu_ctx* ctx, int ext, const char* bases, const uint64_t* off
 #undef EXT_LAUNCH
         ctx->launches += 1;
         CU(cudaGetLastError());
-        if (out_ml) CU(cudaMemcpyAsync(out_ml + offsets[i0], ctx->e_ml, nb * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
-        if (out_sa) CU(cudaMemcpyAsync(out_sa + offsets[i0], ctx->e_sa, nb * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-        if (color) CU(cudaMemcpyAsync(out_color + i0, ctx->e_res, nr * sizeof(MoviGpuColorResult), cudaMemcpyDeviceToHost, st));
+        if (out_ml && (rc = staged_d2h(ctx, reinterpret_cast<uint8_t*>(out_ml + offsets[i0]), -1, 0, reinterpret_cast<const uint8_t*>(ctx->e_ml), nb * sizeof(uint16_t), st))) return rc;
+        if (out_sa && (rc = staged_d2h(ctx, reinterpret_cast<uint8_t*>(out_sa + offsets[i0]), -1, 0, reinterpret_cast<const uint8_t*>(ctx->e_sa), nb * sizeof(uint64_t), st))) return rc;
+        if (color && (rc = staged_d2h(ctx, reinterpret_cast<uint8_t*>(out_color + i0), -1, 0, reinterpret_cast<const uint8_t*>(ctx->e_res), nr * sizeof(MoviGpuColorResult), st))) return rc;
         CU(cudaStreamSynchronize(st));
         int qs = movi_gpu_check_device_status(ctx);
         if (qs) return qs;

@@ -179,22 +179,35 @@ struct Results {
     PinnedBuf<uint8_t> image; uint64_t image_bytes = 0;     // the batch's .bpf records, assembled on the GPUs
 };
 
-// ---- device-side ingest path: file bytes -> GPU (parse, walk, .bpf records) -> file.  The host only finds record boundaries
-// near the chunk ends; it copies nothing into buffers of its own and formats nothing.  Chunk k goes to GPU k mod G (one host
-// thread per GPU): the chunk is parsed there, which tells the size of its records, so the chunks' places in the output file are
-// handed out in chunk order while the walks and the writes (positional, straight from the copy-back ring of the library:
-// movi_gpu_file_chunk_query) run side by side.  Returns 0 when the whole input went through, 1 when the input holds something the
-// reference rejects or stops at (the caller starts over with the host parser, which reproduces the reference's behaviour, and a
-// fresh output file), -1 on errors (message in `err`).
+// ---- device-side ingest path: file bytes -> GPU (parse, walk, .bpf records / classification) -> file.  The host only finds record
+// boundaries near the chunk ends; it copies nothing into buffers of its own and formats nothing but report lines.  Chunk k goes to
+// GPU k mod G (one host thread per context): the chunk is parsed there, which tells the size of its records, so the chunks' places
+// in the output file are handed out in chunk order while the walks and the writes (positional, straight from the copy-back ring of
+// the library: movi_gpu_file_chunk_query) run side by side.  With --classify / --filter the chunk is binned on the device
+// (movi_gpu_file_chunk_classify), 16 bytes per read and the ids (--filter: the sequences too) come back, and the report rows are
+// written in chunk order.  Returns 0 when the whole input went through; 1 when a chunk holds something the reference rejects or
+// stops at: every chunk before it is complete in the outputs, and the caller continues from `end->resume_at` with the host parser,
+// which reproduces the reference's behaviour from there (the chunks before it ended exactly where it starts, so the host parser
+// sees what a parse of the whole file would see at that point); -1 on errors (message in `err`).
 struct IngestStats { uint64_t reads = 0, bases = 0, chunks = 0; };
+struct IngestSinks {
+    int fd_bpf = -1;                          // <prefix>.bpf (or -1)
+    bool classify = false;                    // --classify / --filter
+    int report_fd = -1, report_mode = 0;      // movi_host_classify_bins: 0 report rows, 1 --filter, 2 --filter --invert
+    uint32_t bin_width = 150, max_value_thr = 0;
+};
+struct IngestEnd { uint64_t resume_at = 0, file_off = 12; bool report_started = false; };
 
 int run_device_ingest(const Options& o, const std::vector<movi_gpu_ctx*>& ctx, const char* data, uint64_t size, int fastq, bool zml,
-                      uint32_t qflags, int fd_bpf, IngestStats* stats, std::string* err) {
+                      uint32_t qflags, const IngestSinks& sinks, IngestStats* stats, IngestEnd* fin, std::string* err) {
     const int G = (int)ctx.size();
+    const int fd_bpf = sinks.fd_bpf;
+    constexpr uint64_t NONE = ~0ull;
     std::mutex mu;
     std::condition_variable cv;
-    uint64_t next_begin = 0, next_seq = 0, place_seq = 0, file_off = 12, chunk_bytes = o.chunk_bytes;     // 12: the BPFHeader
-    int status = 0;                                // 0 running / ok, 1 fall back, -1 error (under mu)
+    uint64_t next_begin = 0, next_seq = 0, place_seq = 0, report_seq = 0, file_off = 12, chunk_bytes = o.chunk_bytes;     // 12: the BPFHeader
+    uint64_t fail_seq = NONE, fail_begin = 0;      // first chunk (in input order) the device parser does not take (under mu)
+    bool hard = false, report_started = false;     // hard: an error (message in *err)
     // long reads: a chunk should hold a read per lane from the start (a chunk of few long reads costs a full walk however small
     // it is, and runs the plain-fetch kernel): judge by the size of the first record
     if (size > 1) {
@@ -216,30 +229,37 @@ int run_device_ingest(const Options& o, const std::vector<movi_gpu_ctx*>& ctx, c
         for (auto& t : mk) t.join();
     }
     auto worker = [&](int g, movi_gpu_ctx* my) {
+        (void)g;
+        std::vector<uint32_t> above, below; std::vector<uint64_t> sum, offs, id_offs; std::vector<char> ids, bases;
         for (;;) {
             uint64_t begin, end, seq;
             {
                 std::lock_guard<std::mutex> lk(mu);
-                if (status != 0 || next_begin >= size) return;
+                if (hard || fail_seq != NONE || next_begin >= size) return;
                 begin = next_begin;
                 end = begin + chunk_bytes >= size ? size : movi_host_record_boundary(data, size, begin + chunk_bytes, fastq);
                 next_begin = end; seq = next_seq++;
             }
-            if (end - begin >= 0xFFFFFF00ull) {            // one record of 4 GiB or more: not a chunk the device parser takes
+            auto soft_fail = [&]() {               // this chunk goes to the host parser, and with it everything behind it
                 std::lock_guard<std::mutex> lk(mu);
-                if (status == 0) status = 1;
+                if (seq < fail_seq) { fail_seq = seq; fail_begin = begin; }
                 cv.notify_all();
-                return;
-            }
+            };
+            auto hard_fail = [&](const std::string& m) {
+                std::lock_guard<std::mutex> lk(mu);
+                if (!hard) { *err = m; hard = true; }
+                cv.notify_all();
+            };
+            if (end - begin >= 0xFFFFFF00ull) { soft_fail(); return; }     // one record of 4 GiB or more: not a chunk the device parser takes
             MoviGpuChunkResult res{};
             int rc = movi_gpu_file_chunk_parse(my, data + begin, end - begin, fastq, 1, &res);
+            if (rc) { hard_fail(movi_gpu_last_error(my)); return; }
+            if (res.parse_flags || res.consumed_bytes != end - begin) { soft_fail(); return; }
             uint64_t my_off = 0;
             {
                 std::unique_lock<std::mutex> lk(mu);
-                if (rc) { if (status == 0) { *err = movi_gpu_last_error(my); status = -1; } cv.notify_all(); return; }
-                if (res.parse_flags || res.consumed_bytes != end - begin) { if (status == 0) status = 1; cv.notify_all(); return; }
-                cv.wait(lk, [&] { return place_seq == seq || status != 0; });      // places in the file go out in chunk order
-                if (status != 0) return;
+                cv.wait(lk, [&] { return place_seq == seq || hard || seq > fail_seq; });      // places in the file go out in chunk order
+                if (hard || seq > fail_seq) return;
                 my_off = file_off; file_off += res.image_bytes; place_seq += 1;
                 if (fd_bpf >= 0 && res.image_bytes && ftruncate(fd_bpf, (off_t)file_off) != 0) { /* the library falls back to pwrite */ }
                 stats->reads += res.n_reads; stats->bases += res.n_bases; stats->chunks += 1;
@@ -248,8 +268,38 @@ int run_device_ingest(const Options& o, const std::vector<movi_gpu_ctx*>& ctx, c
                 if (res.n_reads < 230000 && chunk_bytes < (3ull << 30)) chunk_bytes = std::min<uint64_t>(chunk_bytes * 2, 3ull << 30);
                 cv.notify_all();
             }
-            rc = movi_gpu_file_chunk_query(my, zml ? 1 : 0, qflags, nullptr, 0, fd_bpf, my_off);
-            if (rc) { std::lock_guard<std::mutex> lk(mu); if (status == 0) { *err = movi_gpu_last_error(my); status = -1; } cv.notify_all(); return; }
+            movi_host_reads* rd = nullptr;
+            if (!sinks.classify) rc = movi_gpu_file_chunk_query(my, zml ? 1 : 0, qflags, nullptr, 0, fd_bpf, my_off);
+            else {
+                const bool want_seq = sinks.report_mode != 0;                  // --filter echoes the reads it keeps
+                above.resize(res.n_reads + 1); below.resize(res.n_reads + 1); sum.resize(res.n_reads + 1);
+                offs.resize(res.n_reads + 1); id_offs.resize(res.n_reads + 1); ids.resize(res.id_bytes + 1);
+                if (want_seq) bases.resize(res.n_bases + 1);
+                rc = movi_gpu_file_chunk_classify(my, zml ? 1 : 0, qflags, sinks.bin_width, sinks.max_value_thr, above.data(), below.data(), sum.data(),
+                                                  nullptr, 0, fd_bpf, my_off);
+                if (!rc && res.n_reads) rc = movi_gpu_file_chunk_fetch(my, want_seq ? bases.data() : nullptr, offs.data(), ids.data(), id_offs.data());
+                if (!rc && res.n_reads && movi_host_reads_adopt(want_seq ? bases.data() : nullptr, offs.data(), res.n_reads, ids.data(), id_offs.data(), &rd)) {
+                    hard_fail(movi_host_last_error()); return;
+                }
+            }
+            if (rc) { hard_fail(movi_gpu_last_error(my)); if (rd) movi_host_reads_free(rd); return; }
+            if (sinks.classify) {
+                {   // report rows / kept reads in chunk order: wait for the turn, write outside the lock (only the turn's holder writes)
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return report_seq == seq || hard; });
+                    if (hard) { if (rd) movi_host_reads_free(rd); return; }
+                }
+                int wrc = 0;
+                if (rd && sinks.report_fd >= 0)
+                    wrc = movi_host_classify_bins(sinks.report_fd, sinks.report_mode | (report_started ? MOVI_HOST_CLASSIFY_CONTINUE : 0), rd, sinks.max_value_thr,
+                                                  above.data(), below.data(), sum.data(), nullptr);
+                if (rd) movi_host_reads_free(rd);
+                if (wrc) { hard_fail(movi_host_last_error()); return; }
+                std::lock_guard<std::mutex> lk(mu);
+                if (res.n_reads && sinks.report_fd >= 0) report_started = true;
+                report_seq += 1;
+                cv.notify_all();
+            }
         }
     };
     std::vector<std::thread> th;
@@ -259,7 +309,9 @@ int run_device_ingest(const Options& o, const std::vector<movi_gpu_ctx*>& ctx, c
     }
     for (auto& t : th) t.join();
     for (movi_gpu_ctx* c : lanes2) if (c) movi_gpu_destroy(c);
-    return status;
+    fin->file_off = file_off; fin->report_started = report_started;
+    fin->resume_at = fail_seq != NONE ? fail_begin : size;
+    return hard ? -1 : (fail_seq != NONE ? 1 : 0);
 }
 
 // ---- Movi Color flows: `--multi-classify` writes "<id>,<taxon>,<taxon>" per read to the -o file
@@ -398,16 +450,22 @@ int main(int argc, char** argv) {
         if (f.rc) f.err = movi_host_last_error();
         return f;
     };
-    // Device-side ingest: when all that is wanted of a PML / ZML query is its .bpf file (or nothing: --no-output), the file
-    // bytes go to the GPUs as they are and come back as .bpf records (run_device_ingest).
     if (o.multi_classify || o.sa_entries) {
         if (o.query != "pml" || o.rpml) usage_error("--multi-classify / --sa-entries go with --pml");
         if (o.classify) usage_error("--multi-classify / --sa-entries do not combine with --classify / --filter here");
         if (o.multi_classify && o.out_file.empty()) usage_error("Please include the out file for multi-classify.");     // movi_parser.cpp:396-399
     }
+    // Device-side ingest: when all that is wanted of a PML / ZML query is its .bpf file (or nothing: --no-output), the file
+    // bytes go to the GPUs as they are and come back as .bpf records (run_device_ingest) ...
     const bool color_flow = o.multi_classify || o.sa_entries;
-    const bool ingest_on_device = !color_flow && !o.host_parse && (o.query == "pml" || o.query == "zml") && !o.classify && !o.reverse && o.ignore_illegal == 0 &&
-                                  !o.write_stdout_enabled() && !(o.to_stdout && o.write_output_allowed());
+    const char* raw_data = nullptr; uint64_t raw_size = 0; int raw_fastq = 0;
+    movi_host_reader_raw(reader, &raw_data, &raw_size, &raw_fastq);
+    // ... or its classification: --classify (report + .bpf) and --filter (the kept reads on stdout) bin the lengths on the device too
+    // (with --no-output the reference prints a report header and nothing else: left to the host path, like an empty input)
+    const bool plain_ingest = !o.classify && !o.write_stdout_enabled() && !(o.to_stdout && o.write_output_allowed());
+    const bool classify_ingest = o.classify && !o.no_output && raw_size > 0;
+    const bool ingest_on_device = !color_flow && !o.host_parse && (o.query == "pml" || o.query == "zml") && !o.reverse && o.ignore_illegal == 0 &&
+                                  (plain_ingest || classify_ingest);
     std::future<Fetched> ahead;
     if (!ingest_on_device && !color_flow) ahead = std::async(std::launch::async, fetch);
 
@@ -466,11 +524,16 @@ int main(int argc, char** argv) {
         }
     }
 
+    uint64_t total_reads = 0, total_bases = 0, batches = 0;
+    bool report_started = false;
     if (ingest_on_device) {
-        const char* data = nullptr; uint64_t size = 0; int fastq = 0;
-        movi_host_reader_raw(reader, &data, &size, &fastq);
-        IngestStats st; std::string err;
-        const int rc = run_device_ingest(o, ctx, data, size, fastq, o.query == "zml", qflags, fd_bpf, &st, &err);
+        IngestStats st; IngestEnd fin; std::string err;
+        IngestSinks sinks;
+        sinks.fd_bpf = fd_bpf; sinks.classify = o.classify;
+        sinks.report_mode = o.filter ? (o.invert ? 2 : 1) : 0;
+        sinks.report_fd = (!o.filter && f_report) ? fileno(f_report) : STDOUT_FILENO;
+        sinks.bin_width = (uint32_t)o.bin_width; sinks.max_value_thr = (uint32_t)max_value_thr;
+        const int rc = run_device_ingest(o, ctx, raw_data, raw_size, raw_fastq, o.query == "zml", qflags, sinks, &st, &fin, &err);
         if (rc < 0) die(err);
         if (rc == 0) {
             auto t_q1 = std::chrono::steady_clock::now();
@@ -478,16 +541,16 @@ int main(int argc, char** argv) {
                 fprintf(stderr, "[INFO] index loaded + uploaded in %.3f s; %llu chunk(s) ingested, queried on %d GPU(s) and written in %.3f s: %llu reads / %llu bases (device-side ingest)\n",
                         std::chrono::duration<double>(t_q0 - t_load0).count(), (unsigned long long)st.chunks, gpus,
                         std::chrono::duration<double>(t_q1 - t_q0).count(), (unsigned long long)st.reads, (unsigned long long)st.bases);
+            if (f_report) fclose(f_report);
             if (fd_bpf >= 0 && movi_host_bpf_end(fd_bpf)) die(movi_host_last_error());
             fflush(stdout); fflush(stderr);
             _exit(0);
         }
-        // the input holds something the reference rejects or stops at: start over with the host parser, which reproduces that
-        if (fd_bpf >= 0) {
-            movi_host_bpf_end(fd_bpf);
-            fd_bpf = movi_host_bpf_begin((prefix + ".bpf").c_str());
-            if (fd_bpf < 0) die(movi_host_last_error());
-        }
+        // a chunk holds something the reference rejects or stops at: everything before it is in the outputs; the host parser, which
+        // reproduces the reference's behaviour, carries on from that chunk's first byte
+        if (movi_host_reader_seek(reader, fin.resume_at)) die(movi_host_last_error());
+        if (fd_bpf >= 0 && (ftruncate(fd_bpf, (off_t)fin.file_off) != 0 || lseek(fd_bpf, (off_t)fin.file_off, SEEK_SET) < 0)) die("cannot reposition the .bpf file");
+        report_started = fin.report_started; batches = st.chunks; total_reads = st.reads; total_bases = st.bases;
         ahead = std::async(std::launch::async, fetch);
     }
 
@@ -496,8 +559,6 @@ int main(int argc, char** argv) {
     Results slot[2];
     std::mt19937 gen{std::random_device{}()};
     std::uniform_int_distribution<int> dist(1, 100);
-    uint64_t total_reads = 0, total_bases = 0, batches = 0;
-    bool report_started = false;
 
     auto write_batch = [&](Results& R) -> std::string {       // returns an error message, empty on success
         movi_host_reads* rd = R.rd;

@@ -395,6 +395,31 @@ int movi_host_reads_load(const char* path, int reverse, movi_host_reads** out) {
     return 0;
 }
 
+// A batch assembled elsewhere (the device-side parser): copies of its four arrays; bases may be NULL when only ids and lengths matter
+int movi_host_reads_adopt(const char* bases, const uint64_t* offsets, uint64_t n_reads, const char* ids, const uint64_t* id_offsets,
+                          movi_host_reads** out) {
+    if (!out || (n_reads && (!offsets || !ids || !id_offsets))) return fail("null argument");
+    std::unique_ptr<movi_host_reads> rd(new movi_host_reads());
+    if (n_reads) {
+        rd->offsets.assign(offsets, offsets + n_reads + 1);
+        rd->id_offsets.assign(id_offsets, id_offsets + n_reads + 1);
+        if (rd->offsets[0] != 0 || rd->id_offsets[0] != 0) return fail("offsets of an adopted batch must start at 0");
+        rd->ids.assign(ids, (size_t)id_offsets[n_reads]);
+        if (bases) rd->bases.assign(bases, (size_t)offsets[n_reads]);
+    }
+    *out = rd.release();
+    return 0;
+}
+
+// Continue parsing at byte `at` of the input (a record boundary): the device-side ingest hands over here when it meets something
+// the reference rejects or stops at
+int movi_host_reader_seek(movi_host_reader* r, uint64_t at) {
+    if (!r || at > r->size) return fail("seek beyond the input");
+    r->lc = LineCursor{r->data + at, r->data + r->size};
+    r->eof = (at >= r->size);
+    return 0;
+}
+
 uint64_t movi_host_reads_count(const movi_host_reads* rd) { return rd ? rd->offsets.size() - 1 : 0; }
 const char* movi_host_reads_bases(const movi_host_reads* rd) { return rd ? rd->bases.data() : nullptr; }
 const uint64_t* movi_host_reads_offsets(const movi_host_reads* rd) { return rd ? rd->offsets.data() : nullptr; }

@@ -244,3 +244,71 @@ def test_multi_classify_argument_errors(cli, color_index_dir, index_dirs):
     r = subprocess.run([cli, "query", "-i", index_dirs[("regular-thresholds", False)], "-r", reads, "--pml", "--sa-entries"],
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 1 and b"build-SA" in r.stderr
+
+
+# ---- device-side ingest for the classification flows, and the hand-over to the host parser in the middle of an input
+def _fastq_of(n, seed, read_len=120):
+    """n FASTQ records cut from the c1 reference (FOUND) or random (NOT_PRESENT), ids with and without descriptions."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    ref = "".join(l.strip() for l in lzma.open(os.path.join(GOLD, "ref.fasta.xz"), "rt") if not l.startswith(">")).upper()
+    out = []
+    for i in range(n):
+        L = int(rng.integers(30, read_len * 4))
+        if i % 3 == 2:
+            s = "".join(rng.choice(list("ACGT"), L))
+        else:
+            p = int(rng.integers(0, len(ref) - L))
+            s = ref[p:p + L]
+        out.append("@q%d%s\n%s\n+\n%s\n" % (i, " d" if i % 2 else "", s, "I" * L))
+    return out
+
+
+@pytest.mark.parametrize("chunk", [None, "4096"])
+def test_classify_flows_through_the_device_side_ingest(cli, index_dirs, tmp_path, chunk):
+    """--classify (report + .bpf), --classify --stdout, --filter, --filter -v: file bytes to the GPU, bins back; same outputs as the host
+    parser path (--host-parse), with one chunk and with many (several contexts take turns writing the report)."""
+    d = index_dirs[("regular-thresholds", False)]
+    recs = _fastq_of(400, seed=3)
+    extra = ["--chunk-bytes", chunk] if chunk else []
+    out = {}
+    for name, more in (("device", extra), ("host", ["--host-parse"])):
+        reads = tmp_path / (name + ".fastq")
+        reads.write_text("".join(recs))
+        run(cli, "query", "-i", d, "-r", str(reads), "--pml", "--classify", *more)
+        rep = open(str(reads) + ".regular-thresholds.pml.report").read()
+        bpf = open(str(reads) + ".regular-thresholds.pml.bpf", "rb").read()
+        os.remove(str(reads) + ".regular-thresholds.pml.bpf")
+        so = run(cli, "query", "-i", d, "-r", str(reads), "--pml", "--classify", "--stdout", *more)
+        bpf2 = open(str(reads) + ".regular-thresholds.pml.bpf", "rb").read()
+        flt = run(cli, "query", "-i", d, "-r", str(reads), "--pml", "--filter", *more)
+        inv = run(cli, "query", "-i", d, "-r", str(reads), "--pml", "--filter", "-v", *more)
+        zrep = run(cli, "query", "-i", d, "-r", str(reads), "--zml", "--classify", "--stdout", *more)
+        out[name] = (rep, bpf[12:], so, bpf2[12:], flt, inv, zrep)
+    assert out["device"] == out["host"]
+    rep, _, so, _, flt, inv, _ = out["device"]
+    assert rep == so and rep.count(" FOUND ") > 100 and rep.count("NOT_PRESENT") > 100
+    assert flt.count(">") + inv.count(">") == 400 and flt.count(">") == rep.count(" FOUND ")
+
+
+@pytest.mark.parametrize("flow", ["bpf", "classify", "filter"])
+def test_device_side_ingest_hands_over_in_the_middle_of_the_input(cli, index_dirs, tmp_path, flow):
+    """Several chunks go through the GPU parser, then one holds an empty line where a header is due (the reference stops reading
+    there): the host parser continues from that chunk's first byte, appending to the same outputs."""
+    d = index_dirs[("regular-thresholds", False)]
+    recs = _fastq_of(300, seed=4)
+    odd = "".join(recs[:220]) + "\n" + "".join(recs[220:])          # records 0..219 are read, then the input ends
+    flags = {"bpf": [], "classify": ["--classify", "--stdout"], "filter": ["--filter"]}[flow]
+    out = {}
+    for name, more in (("device", ["--chunk-bytes", "8192"]), ("host", ["--host-parse"])):
+        reads = tmp_path / (name + ".fastq")
+        reads.write_text(odd)
+        so = run(cli, "query", "-i", d, "-r", str(reads), "--pml", *flags, *more)
+        bpf = open(str(reads) + ".regular-thresholds.pml.bpf", "rb").read()[12:] if flow != "filter" else b""
+        out[name] = (so, bpf)
+    assert out["device"] == out["host"]
+    if flow == "bpf":
+        from conftest import parse_bpf_records
+        assert len(parse_bpf_records(b"\0" * 12 + out["device"][1], 2)) == 220
+    if flow == "classify":
+        assert out["device"][0].count("\n") == 221                     # header + 220 rows
