@@ -88,8 +88,16 @@ def main():
         runs = [("movi-b200 --pml -> .bpf (device-side ingest + .bpf emission)", [cli, "query", "-i", index_dir, "-r", fa, "--pml", "--verbose", "--gpus", str(gpus)], bpf),
                 ("movi-b200 --pml --no-output (device-side ingest)", [cli, "query", "-i", index_dir, "-r", fa, "--pml", "--no-output", "--verbose", "--gpus", str(gpus)], None),
                 ("movi-b200 --pml -> .bpf --host-parse (host parser, device-side .bpf emission)", [cli, "query", "-i", index_dir, "-r", fa, "--pml", "--host-parse", "--verbose", "--gpus", str(gpus)], bpf),
-                ("movi-b200 --pml --classify --stdout > /dev/null (fused classify; host parser)", [cli, "query", "-i", index_dir, "-r", fa, "--pml", "--filter", "--verbose", "--gpus", str(gpus)], None)]
-        if os.path.exists(ref) and "noref" not in sys.argv[2:]:
+                ("movi-b200 --pml --filter > /dev/null (device-side ingest, classification on the device)", [cli, "query", "-i", index_dir, "-r", fa, "--pml", "--filter", "--verbose", "--gpus", str(gpus)], None)]
+        if "classify" in sys.argv[2:]:             # the classification flows only: device-side ingest against the host parser (and the reference)
+            rpt = fa + ".regular-thresholds.pml.report"
+            runs = [runs[-1],
+                    ("movi-b200 --pml --filter --host-parse > /dev/null (host parser, fused classify)", [cli, "query", "-i", index_dir, "-r", fa, "--pml", "--filter", "--host-parse", "--verbose", "--gpus", str(gpus)], None),
+                    ("movi-b200 --pml --classify -> report + .bpf (device-side ingest)", [cli, "query", "-i", index_dir, "-r", fa, "--pml", "--classify", "--verbose", "--gpus", str(gpus)], bpf),
+                    ("movi-b200 --pml --classify --host-parse -> report + .bpf (host parser)", [cli, "query", "-i", index_dir, "-r", fa, "--pml", "--classify", "--host-parse", "--verbose", "--gpus", str(gpus)], bpf)]
+            if os.path.exists(ref) and "noref" not in sys.argv[2:]:
+                runs += [("reference --pml --filter -t %d > /dev/null" % threads, [ref, "query", "--index", index_dir, "--read", fa, "--pml", "--filter", "-t", str(threads)], None)]
+        if os.path.exists(ref) and "noref" not in sys.argv[2:] and "classify" not in sys.argv[2:]:
             runs += [("reference --pml -t %d -> .bpf" % threads, [ref, "query", "--index", index_dir, "--read", fa, "--pml", "-t", str(threads)], bpf),
                      ("reference --pml -t %d --no-output" % threads, [ref, "query", "--index", index_dir, "--read", fa, "--pml", "--no-output", "-t", str(threads)], None)]
         if rep:                                    # the big input: the device-ingest runs and the reference only
