@@ -396,7 +396,10 @@ int staged_h2d(movi_gpu_ctx* ctx, void* d_dst, const char* src, size_t n, cudaSt
     for (size_t off = 0; off < n; off += PIN_PIECE, k++) {
         const size_t len = std::min(PIN_PIECE, n - off);
         const int slot = (int)(k & 3);
-        if (k >= 4) CU(cudaEventSynchronize(ctx->pin_ev[slot]));
+        // the copy that last read this piece must be over before it is filled again -- also a copy of an EARLIER call (two staged
+        // uploads in a row: the second one's bytes would otherwise land in the first one's device buffer); an event never recorded
+        // is complete
+        CU(cudaEventSynchronize(ctx->pin_ev[slot]));
         uint8_t* buf = ctx->pin[slot];
         in_parts(len, [&](size_t b, size_t e) { std::memcpy(buf + b, src + off + b, e - b); });
         CU(cudaMemcpyAsync(static_cast<uint8_t*>(d_dst) + off, buf, len, cudaMemcpyHostToDevice, st));
@@ -1537,7 +1540,7 @@ int ext_query(movi_gpu_ctx* ctx, int ext, const char* bases, const uint64_t* off
         }
         // (pageable caller buffers pass through the ring of pinned pieces: staged_h2d / staged_d2h)
         if ((rc = staged_h2d(ctx, ctx->e_bases, bases + offsets[i0], nb, st))) return rc;
-        if ((rc = staged_h2d(ctx, ctx->e_offsets, reinterpret_cast<const char*>(offsets + i0), (nr + 1) * sizeof(uint64_t), st))) return rc;
+        CU(cudaMemcpyAsync(ctx->e_offsets, offsets + i0, (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
         unsigned long long* counter = next_counter(ctx);
         CU(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
         ExtArgs a{};

@@ -39,6 +39,7 @@ struct Options {
     uint64_t max_chunk_bases = 1ull << 31;   // ... but never more bases than this per batch (pinned results: 2 x 2 bytes per base)
     uint64_t chunk_bytes = 256ull << 20;     // device-side ingest: file bytes per chunk (grows by itself when reads are long)
     bool host_parse = false;                 // --host-parse: never use the device-side ingest
+    bool device_ingest = false;              // --device-ingest: use it wherever it exists (--filter too: measured slower than the host path on short reads)
     int layout = MOVI_GPU_LAYOUT_AUTO;       // --layout auto|expanded|compact: device form of blocked / sampled indexes
     // Movi Color (movi_parser.cpp:155, 164-175)
     bool multi_classify = false, pvalue_scoring = false, sa_entries = false;
@@ -52,7 +53,7 @@ struct Options {
     fprintf(stderr, "usage: movi-b200 query -i <index dir> -r <reads.fa|fq|-> [--pml [--rpml]|--zml|--count] [--classify|--filter [-v]]\n"
                     "                       [--stdout] [-o prefix] [--no-output] [--reverse] [--ignore-illegal-chars 1|2]\n"
                     "                       [--bin-width N] [--gpus N] [--device D] [--chunk-bases N] [--chunk-reads N] [--max-chunk-bases N]\n"
-                    "                       [--chunk-bytes N] [--host-parse] [--layout auto|expanded|compact]\n"
+                    "                       [--chunk-bytes N] [--host-parse|--device-ingest] [--layout auto|expanded|compact]\n"
                     "                       [--multi-classify -o out.csv [--min-len N] [--pvalue-scoring]] [--sa-entries]\n"
                     "                       [-t N] [-s N] [-n]\n"
                     "       movi-b200 view --bpf <file.bpf>\n");
@@ -98,6 +99,7 @@ Options parse(int argc, char** argv) {
         else if (take_value(argc, argv, i, nullptr, "--chunk-reads", v)) o.chunk_reads = strtoull(v.c_str(), nullptr, 10);
         else if (take_value(argc, argv, i, nullptr, "--chunk-bytes", v)) o.chunk_bytes = std::max<uint64_t>(4096, strtoull(v.c_str(), nullptr, 10));
         else if (a == "--host-parse") o.host_parse = true;
+        else if (a == "--device-ingest") o.device_ingest = true;
         else if (take_value(argc, argv, i, nullptr, "--layout", v)) {
             if (v == "auto") o.layout = MOVI_GPU_LAYOUT_AUTO; else if (v == "expanded") o.layout = MOVI_GPU_LAYOUT_EXPANDED8;
             else if (v == "compact") o.layout = MOVI_GPU_LAYOUT_COMPACT; else usage_error("--layout: auto, expanded or compact");
@@ -463,7 +465,9 @@ int main(int argc, char** argv) {
     // ... or its classification: --classify (report + .bpf) and --filter (the kept reads on stdout) bin the lengths on the device too
     // (with --no-output the reference prints a report header and nothing else: left to the host path, like an empty input)
     const bool plain_ingest = !o.classify && !o.write_stdout_enabled() && !(o.to_stdout && o.write_output_allowed());
-    const bool classify_ingest = o.classify && !o.no_output && raw_size > 0;
+    // --filter echoes the reads it keeps, so every base has to come back to the host anyway: on short reads the pipelined host path
+    // is faster (profiles/r02_cli_e2e_classify.jsonl: 0.45 s against 1.06 s for 6e8 bases) and stays the default there
+    const bool classify_ingest = o.classify && !o.no_output && raw_size > 0 && (!o.filter || o.device_ingest);
     const bool ingest_on_device = !color_flow && !o.host_parse && (o.query == "pml" || o.query == "zml") && !o.reverse && o.ignore_illegal == 0 &&
                                   (plain_ingest || classify_ingest);
     std::future<Fetched> ahead;

@@ -270,7 +270,7 @@ def test_classify_flows_through_the_device_side_ingest(cli, index_dirs, tmp_path
     parser path (--host-parse), with one chunk and with many (several contexts take turns writing the report)."""
     d = index_dirs[("regular-thresholds", False)]
     recs = _fastq_of(400, seed=3)
-    extra = ["--chunk-bytes", chunk] if chunk else []
+    extra = ["--device-ingest"] + (["--chunk-bytes", chunk] if chunk else [])      # (--filter takes the host path unless asked)
     out = {}
     for name, more in (("device", extra), ("host", ["--host-parse"])):
         reads = tmp_path / (name + ".fastq")
@@ -300,7 +300,7 @@ def test_device_side_ingest_hands_over_in_the_middle_of_the_input(cli, index_dir
     odd = "".join(recs[:220]) + "\n" + "".join(recs[220:])          # records 0..219 are read, then the input ends
     flags = {"bpf": [], "classify": ["--classify", "--stdout"], "filter": ["--filter"]}[flow]
     out = {}
-    for name, more in (("device", ["--chunk-bytes", "8192"]), ("host", ["--host-parse"])):
+    for name, more in (("device", ["--device-ingest", "--chunk-bytes", "8192"]), ("host", ["--host-parse"])):
         reads = tmp_path / (name + ".fastq")
         reads.write_text(odd)
         so = run(cli, "query", "-i", d, "-r", str(reads), "--pml", *flags, *more)
