@@ -203,6 +203,12 @@ int  movi_gpu_file_chunk_query(movi_gpu_ctx* ctx, int zml, uint32_t flags, uint8
 int  movi_gpu_file_chunk_classify(movi_gpu_ctx* ctx, int zml, uint32_t flags, uint32_t bin_width, uint32_t max_value_thr,
                                   uint32_t* out_bins_above, uint32_t* out_bins_below, uint64_t* out_sum_max,
                                   uint8_t* out_image, uint64_t image_capacity, int out_fd, uint64_t file_offset);
+/* The chunk parsed last, for --filter [-v] (src/movi.cpp:36-47): walked, binned, and the echo of the reads Classifier::classify keeps --
+ * ">" id "\n" sequence "\n" each (output_read, src/utils.cpp:291-294) -- assembled on the device; *text_bytes = its size.  _deliver
+ * fetches it into out_text (may be NULL) and / or writes it to out_fd with write() calls in order (stdout may be a pipe). */
+int  movi_gpu_file_chunk_filter(movi_gpu_ctx* ctx, int zml, uint32_t flags, uint32_t bin_width, uint32_t max_value_thr, int invert,
+                                uint64_t* text_bytes);
+int  movi_gpu_file_chunk_filter_deliver(movi_gpu_ctx* ctx, uint8_t* out_text, uint64_t capacity, int out_fd);
 /* The reads of the chunk parsed last copied back to the host: n_bases bytes, n_reads + 1 offsets, id_bytes bytes, n_reads + 1 id
  * offsets (sizes in the MoviGpuChunkResult of the parse; any pointer may be NULL) -- the ids a report prints, the sequences --filter echoes. */
 int  movi_gpu_file_chunk_fetch(movi_gpu_ctx* ctx, char* out_bases, uint64_t* out_offsets, char* out_ids, uint64_t* out_id_offsets);

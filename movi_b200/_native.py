@@ -69,6 +69,8 @@ GPU_SYMBOLS = {
     "movi_gpu_file_chunk_query": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_uint64, C.c_int, C.c_uint64]),
     "movi_gpu_file_chunk_classify": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_uint64, C.c_int, C.c_uint64]),
+    "movi_gpu_file_chunk_filter": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]),
+    "movi_gpu_file_chunk_filter_deliver": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]),
     "movi_gpu_file_chunk_fetch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "movi_gpu_parse_chunk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
                                        C.c_void_p, C.c_uint64, C.POINTER(MoviGpuChunkResult)]),

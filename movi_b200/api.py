@@ -332,6 +332,38 @@ class MoveStructure:
                                                       FLAG_RPML if rpml else 0, _ptr(image) if want_image else None, cap, C.byref(res)))
         return image[: int(res.image_bytes)] if want_image else None, res
 
+    def classify_file_chunk(self, raw, fastq, bin_width, max_value_thr, final=True, zml=False, want_reads=False):
+        """File bytes in, the three report columns per read out (movi_gpu_file_chunk_parse + _classify [+ _fetch]) ->
+        (above, below, sum_max, result struct[, (bases, offsets, ids, id_offsets)])."""
+        raw = np.frombuffer(raw, dtype=np.uint8) if not isinstance(raw, np.ndarray) else raw
+        res = N.MoviGpuChunkResult()
+        self._check(self._L.movi_gpu_file_chunk_parse(self._ctx, _ptr(raw) if len(raw) else None, len(raw), int(fastq), int(final), C.byref(res)))
+        n = int(res.n_reads)
+        above, below, total = np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.uint64)
+        if res.parse_flags == 0 and n:
+            self._check(self._L.movi_gpu_file_chunk_classify(self._ctx, int(zml), 0, bin_width, max_value_thr, _ptr(above), _ptr(below), _ptr(total),
+                                                             None, 0, -1, 0))
+        if not want_reads:
+            return above, below, total, res
+        bases, ids = np.zeros(int(res.n_bases), np.uint8), np.zeros(int(res.id_bytes), np.uint8)
+        off, id_off = np.zeros(n + 1, np.uint64), np.zeros(n + 1, np.uint64)
+        if res.parse_flags == 0 and n:
+            self._check(self._L.movi_gpu_file_chunk_fetch(self._ctx, _ptr(bases), _ptr(off), _ptr(ids), _ptr(id_off)))
+        return above, below, total, res, (bases, off, ids, id_off)
+
+    def filter_file_chunk(self, raw, fastq, bin_width, max_value_thr, invert=False, final=True, zml=False):
+        """File bytes in, the echo of the reads `--filter [-v]` keeps out (assembled on the device) -> (text bytes, result struct)."""
+        raw = np.frombuffer(raw, dtype=np.uint8) if not isinstance(raw, np.ndarray) else raw
+        res = N.MoviGpuChunkResult()
+        self._check(self._L.movi_gpu_file_chunk_parse(self._ctx, _ptr(raw) if len(raw) else None, len(raw), int(fastq), int(final), C.byref(res)))
+        if res.parse_flags or res.n_reads == 0:
+            return b"", res
+        nb = C.c_uint64()
+        self._check(self._L.movi_gpu_file_chunk_filter(self._ctx, int(zml), 0, bin_width, max_value_thr, int(invert), C.byref(nb)))
+        text = np.zeros(nb.value + 1, np.uint8)
+        self._check(self._L.movi_gpu_file_chunk_filter_deliver(self._ctx, _ptr(text), nb.value, -1))
+        return text[: nb.value].tobytes(), res
+
     def query_zml(self, bases, offsets, out=None):
         bases, offsets, n = self._prep(bases, offsets)
         if out is None:

@@ -22,6 +22,7 @@
 #include "convert.cuh"
 #include "dev_index.cuh"
 #include "ext_kernel.cuh"
+#include "filter_kernels.cuh"
 #include "kernel_common.cuh"
 #include "misc_kernels.cuh"
 #include "parse_kernels.cuh"
@@ -114,6 +115,7 @@ struct movi_gpu_ctx {
     uint16_t* p_ml = nullptr; size_t p_ml_cap = 0;
     uint8_t* p_image = nullptr; size_t p_image_cap = 0;
     ParseResult p_last{};                              // result of the last movi_gpu_file_chunk_parse (what _query works on)
+    unsigned long long* p_pos = nullptr; size_t p_pos_cap = 0; uint64_t p_text_bytes = 0;      // movi_gpu_file_chunk_filter: echo positions; the text sits in p_image
     uint32_t* p_above = nullptr; uint32_t* p_below = nullptr; unsigned long long* p_sum = nullptr; size_t p_cls_cap = 0;   // movi_gpu_file_chunk_classify
     // pinned staging ring for copies from / to pageable memory and files (a file mapping is pageable by nature)
     uint8_t* pin[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -407,7 +409,9 @@ int staged_h2d(movi_gpu_ctx* ctx, void* d_dst, const char* src, size_t n, cudaSt
     }
     return MOVI_GPU_OK;
 }
-// device -> host memory (dst != NULL) or -> file (fd >= 0, positional writes at file_off); returns when everything has landed
+// device -> host memory (dst != NULL) or -> file (fd >= 0, positional writes at file_off, or write() calls in order when file_off is
+// SEQUENTIAL_WRITES); returns when everything has landed
+constexpr uint64_t SEQUENTIAL_WRITES = ~0ull;
 int staged_d2h(movi_gpu_ctx* ctx, uint8_t* dst, int fd, uint64_t file_off, const uint8_t* d_src, size_t n, cudaStream_t st) {
     if (n == 0) return MOVI_GPU_OK;
     if (dst && fd < 0 && is_pinned(dst)) { CU(cudaMemcpyAsync(dst, d_src, n, cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); return MOVI_GPU_OK; }
@@ -417,7 +421,7 @@ int staged_d2h(movi_gpu_ctx* ctx, uint8_t* dst, int fd, uint64_t file_off, const
     size_t issued = 0;
     bool io_ok = true;
     uint64_t file_len = 0;
-    if (fd >= 0) { const off_t e = lseek(fd, 0, SEEK_END); if (e > 0) file_len = (uint64_t)e; }
+    if (fd >= 0 && file_off != SEQUENTIAL_WRITES) { const off_t e = lseek(fd, 0, SEEK_END); if (e > 0) file_len = (uint64_t)e; }
     for (size_t done = 0; done < pieces; done++) {
         for (; issued < pieces && issued - done < 4; issued++) {
             const size_t off = issued * PIN_PIECE, len = std::min(PIN_PIECE, n - off);
@@ -427,7 +431,11 @@ int staged_d2h(movi_gpu_ctx* ctx, uint8_t* dst, int fd, uint64_t file_off, const
         CU(cudaEventSynchronize(ctx->pin_ev[done & 3]));
         const size_t off = done * PIN_PIECE, len = std::min(PIN_PIECE, n - off);
         const uint8_t* buf = ctx->pin[done & 3];
-        if (fd >= 0) {
+        if (fd >= 0 && file_off == SEQUENTIAL_WRITES) {
+            // a stream (stdout may be a pipe): plain write() calls, piece after piece
+            size_t b = 0;
+            while (b < len && io_ok) { const ssize_t w = ::write(fd, buf + b, len - b); if (w <= 0) io_ok = false; else b += (size_t)w; }
+        } else if (fd >= 0) {
             // Into the page cache through a shared mapping when the file already reaches that far (the caller extends it): positional
             // writes of several threads to ONE file take turns on its inode lock (2.9 GB/s on tmpfs whatever the thread count),
             // page faults on a mapping do not.  Otherwise pwrite.
@@ -445,7 +453,7 @@ int staged_d2h(movi_gpu_ctx* ctx, uint8_t* dst, int fd, uint64_t file_off, const
         }
         if (dst) in_parts(len, [&](size_t b, size_t e) { std::memcpy(dst + off + b, buf + b, e - b); });
     }
-    if (!io_ok) return fail(ctx, MOVI_GPU_ERR_ARG, "write failed: .bpf");
+    if (!io_ok) return fail(ctx, MOVI_GPU_ERR_ARG, "write failed (output file / stream)");
     return MOVI_GPU_OK;
 }
 
@@ -728,7 +736,7 @@ int movi_gpu_destroy(movi_gpu_ctx* ctx) {
     for (int k = 0; k < 4; k++) { if (ctx->pin[k]) cudaFreeHost(ctx->pin[k]); if (ctx->pin_ev[k]) cudaEventDestroy(ctx->pin_ev[k]); }
     cudaFree(ctx->p_raw); cudaFree(ctx->p_tile); cudaFree(ctx->p_nlpos); cudaFree(ctx->p_lines); cudaFree(ctx->p_ltile); cudaFree(ctx->p_res);
     cudaFree(ctx->p_bases); cudaFree(ctx->p_offsets); cudaFree(ctx->p_ids); cudaFree(ctx->p_id_offsets); cudaFree(ctx->p_ml); cudaFree(ctx->p_image);
-    cudaFree(ctx->p_above); cudaFree(ctx->p_below); cudaFree(ctx->p_sum);
+    cudaFree(ctx->p_above); cudaFree(ctx->p_below); cudaFree(ctx->p_sum); cudaFree(ctx->p_pos);
     cudaFree(ctx->d_status); cudaFree(ctx->d_counters);
     cudaFree(ctx->c_inds); cudaFree(ctx->c_flat); cudaFree(ctx->c_lk); cudaFree(ctx->s_all_p); cudaFree(ctx->s_sampled);
     cudaFree(ctx->e_bases); cudaFree(ctx->e_offsets); cudaFree(ctx->e_ml); cudaFree(ctx->e_sa); cudaFree(ctx->e_res); cudaFree(ctx->e_cnt);
@@ -1320,7 +1328,7 @@ extern "C" int movi_gpu_file_chunk_classify(movi_gpu_ctx* ctx, int zml, uint32_t
     cudaStream_t st = ctx->st_k[0];
     if ((rc = grow(ctx, ctx->p_ml, ctx->p_ml_cap, (size_t)pr.n_bases + 96))) return rc;
     if (pr.n_reads > ctx->p_cls_cap) {
-        cudaFree(ctx->p_above); cudaFree(ctx->p_below); cudaFree(ctx->p_sum);
+        cudaFree(ctx->p_above); cudaFree(ctx->p_below); cudaFree(ctx->p_sum); cudaFree(ctx->p_pos);
         ctx->p_above = nullptr; ctx->p_below = nullptr; ctx->p_sum = nullptr; ctx->p_cls_cap = 0;
         const size_t want = (size_t)pr.n_reads + (size_t)pr.n_reads / 8 + 64;
         CU(cudaMalloc(&ctx->p_above, want * sizeof(uint32_t))); CU(cudaMalloc(&ctx->p_below, want * sizeof(uint32_t)));
@@ -1367,6 +1375,69 @@ extern "C" int movi_gpu_file_chunk_fetch(movi_gpu_ctx* ctx, char* out_bases, uin
     if (out_id_offsets) CU(cudaMemcpyAsync(out_id_offsets, ctx->p_id_offsets, (pr.n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return MOVI_GPU_OK;
+}
+
+// The chunk parsed last, for --filter: walked, binned, and the echo of the reads Classifier::classify keeps assembled on the device
+// (filter_kernels.cuh).  The text stays in HBM until movi_gpu_file_chunk_filter_deliver fetches it.
+extern "C" int movi_gpu_file_chunk_filter(movi_gpu_ctx* ctx, int zml, uint32_t flags, uint32_t bin_width, uint32_t max_value_thr, int invert,
+                                          uint64_t* text_bytes) {
+    if (!ctx || !text_bytes) return MOVI_GPU_ERR_ARG;
+    *text_bytes = 0; ctx->p_text_bytes = 0;
+    if (bin_width == 0) return fail(ctx, MOVI_GPU_ERR_ARG, "bin_width must be positive");
+    CallFlags cf(ctx, flags);
+    const Kind kind = zml ? Q_ZML : Q_PML;
+    int rc = check_query_ready(ctx, kind, 0);
+    if (rc) return rc;
+    const ParseResult pr = ctx->p_last;
+    if (pr.n_reads == 0) return MOVI_GPU_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->st_k[0];
+    if ((rc = grow(ctx, ctx->p_ml, ctx->p_ml_cap, (size_t)pr.n_bases + 96))) return rc;
+    if ((rc = grow(ctx, ctx->p_pos, ctx->p_pos_cap, (size_t)pr.n_reads + 2))) return rc;
+    if (pr.n_reads > ctx->p_cls_cap) {
+        cudaFree(ctx->p_above); cudaFree(ctx->p_below); cudaFree(ctx->p_sum);
+        ctx->p_above = nullptr; ctx->p_below = nullptr; ctx->p_sum = nullptr; ctx->p_cls_cap = 0;
+        const size_t want = (size_t)pr.n_reads + (size_t)pr.n_reads / 8 + 64;
+        CU(cudaMalloc(&ctx->p_above, want * sizeof(uint32_t))); CU(cudaMalloc(&ctx->p_below, want * sizeof(uint32_t)));
+        CU(cudaMalloc(&ctx->p_sum, want * sizeof(unsigned long long)));
+        ctx->p_cls_cap = want;
+    }
+    CU(cudaMemsetAsync(ctx->d_status, 0, sizeof(unsigned int), st));
+    CU(cudaMemsetAsync(ctx->p_bases + pr.n_bases, 0, 64, st));
+    rc = device_query(ctx, kind, reinterpret_cast<const char*>(ctx->p_bases), reinterpret_cast<const uint64_t*>(ctx->p_offsets), 0, pr.n_reads,
+                      ctx->p_ml, nullptr, nullptr, next_counter(ctx), st);
+    if (rc) return rc;
+    const unsigned wblocks = (unsigned)std::min<uint64_t>((pr.n_reads * 32 + 255) / 256, (uint64_t)ctx->num_sms * 16);
+    classify_kernel<<<wblocks, 256, 0, st>>>(ctx->p_ml, ctx->p_offsets, 0ull, pr.n_reads, bin_width, max_value_thr, ctx->p_above, ctx->p_below, ctx->p_sum);
+    filter_sizes_kernel<<<(unsigned)std::min<uint64_t>((pr.n_reads + 255) / 256, (uint64_t)ctx->num_sms * 8), 256, 0, st>>>(
+        ctx->p_above, ctx->p_below, invert ? 1 : 0, ctx->p_offsets, ctx->p_id_offsets, pr.n_reads, ctx->p_pos);
+    scan_u64_kernel<<<1, 1024, 0, st>>>(ctx->p_pos, pr.n_reads);
+    unsigned long long total = 0;
+    CU(cudaMemcpyAsync(&total, ctx->p_pos + pr.n_reads, sizeof total, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    ctx->launches += 3;
+    if ((rc = movi_gpu_check_device_status(ctx))) return rc;
+    if (total) {
+        if ((rc = grow(ctx, ctx->p_image, ctx->p_image_cap, (size_t)total + 16))) return rc;
+        filter_emit_kernel<<<wblocks, 256, 0, st>>>(ctx->p_pos, pr.n_reads, ctx->p_bases, ctx->p_offsets, ctx->p_ids, ctx->p_id_offsets, ctx->p_image);
+        ctx->launches += 1;
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(st));
+    }
+    ctx->p_text_bytes = total; *text_bytes = total;
+    return MOVI_GPU_OK;
+}
+
+// ... fetched: into out_text (may be NULL) and / or written to out_fd with write() calls in order (stdout may be a pipe)
+extern "C" int movi_gpu_file_chunk_filter_deliver(movi_gpu_ctx* ctx, uint8_t* out_text, uint64_t capacity, int out_fd) {
+    if (!ctx) return MOVI_GPU_ERR_ARG;
+    const uint64_t n = ctx->p_text_bytes;
+    if (n == 0) return MOVI_GPU_OK;
+    if (out_text && n > capacity) return fail(ctx, MOVI_GPU_ERR_NOMEM, "the text buffer is too small for this chunk's kept reads");
+    if (!out_text && out_fd < 0) return MOVI_GPU_OK;
+    CU(cudaSetDevice(ctx->device));
+    return staged_d2h(ctx, out_text, out_fd, SEQUENTIAL_WRITES, ctx->p_image, n, ctx->st_k[0]);
 }
 
 extern "C" int movi_gpu_query_file_chunk(movi_gpu_ctx* ctx, int zml, const char* raw, uint64_t n_bytes, int fastq, int final_chunk, uint32_t flags,

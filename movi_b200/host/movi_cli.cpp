@@ -39,7 +39,7 @@ struct Options {
     uint64_t max_chunk_bases = 1ull << 31;   // ... but never more bases than this per batch (pinned results: 2 x 2 bytes per base)
     uint64_t chunk_bytes = 256ull << 20;     // device-side ingest: file bytes per chunk (grows by itself when reads are long)
     bool host_parse = false;                 // --host-parse: never use the device-side ingest
-    bool device_ingest = false;              // --device-ingest: use it wherever it exists (--filter too: measured slower than the host path on short reads)
+    bool device_ingest = false;              // --device-ingest: accepted (the device-side ingest is the default wherever it exists)
     int layout = MOVI_GPU_LAYOUT_AUTO;       // --layout auto|expanded|compact: device form of blocked / sampled indexes
     // Movi Color (movi_parser.cpp:155, 164-175)
     bool multi_classify = false, pvalue_scoring = false, sa_entries = false;
@@ -232,7 +232,7 @@ int run_device_ingest(const Options& o, const std::vector<movi_gpu_ctx*>& ctx, c
     }
     auto worker = [&](int g, movi_gpu_ctx* my) {
         (void)g;
-        std::vector<uint32_t> above, below; std::vector<uint64_t> sum, offs, id_offs; std::vector<char> ids, bases;
+        std::vector<uint32_t> above, below; std::vector<uint64_t> sum, offs, id_offs; std::vector<char> ids;
         for (;;) {
             uint64_t begin, end, seq;
             {
@@ -271,16 +271,19 @@ int run_device_ingest(const Options& o, const std::vector<movi_gpu_ctx*>& ctx, c
                 cv.notify_all();
             }
             movi_host_reads* rd = nullptr;
+            const bool filter = sinks.classify && sinks.report_mode != 0;
             if (!sinks.classify) rc = movi_gpu_file_chunk_query(my, zml ? 1 : 0, qflags, nullptr, 0, fd_bpf, my_off);
-            else {
-                const bool want_seq = sinks.report_mode != 0;                  // --filter echoes the reads it keeps
+            else if (filter) {
+                // --filter: the echo of the kept reads is assembled on the device; it is fetched when this chunk's turn comes
+                uint64_t text_bytes = 0;
+                rc = movi_gpu_file_chunk_filter(my, zml ? 1 : 0, qflags, sinks.bin_width, sinks.max_value_thr, sinks.report_mode == 2 ? 1 : 0, &text_bytes);
+            } else {
                 above.resize(res.n_reads + 1); below.resize(res.n_reads + 1); sum.resize(res.n_reads + 1);
                 offs.resize(res.n_reads + 1); id_offs.resize(res.n_reads + 1); ids.resize(res.id_bytes + 1);
-                if (want_seq) bases.resize(res.n_bases + 1);
                 rc = movi_gpu_file_chunk_classify(my, zml ? 1 : 0, qflags, sinks.bin_width, sinks.max_value_thr, above.data(), below.data(), sum.data(),
                                                   nullptr, 0, fd_bpf, my_off);
-                if (!rc && res.n_reads) rc = movi_gpu_file_chunk_fetch(my, want_seq ? bases.data() : nullptr, offs.data(), ids.data(), id_offs.data());
-                if (!rc && res.n_reads && movi_host_reads_adopt(want_seq ? bases.data() : nullptr, offs.data(), res.n_reads, ids.data(), id_offs.data(), &rd)) {
+                if (!rc && res.n_reads) rc = movi_gpu_file_chunk_fetch(my, nullptr, offs.data(), ids.data(), id_offs.data());
+                if (!rc && res.n_reads && movi_host_reads_adopt(nullptr, offs.data(), res.n_reads, ids.data(), id_offs.data(), &rd)) {
                     hard_fail(movi_host_last_error()); return;
                 }
             }
@@ -292,11 +295,16 @@ int run_device_ingest(const Options& o, const std::vector<movi_gpu_ctx*>& ctx, c
                     if (hard) { if (rd) movi_host_reads_free(rd); return; }
                 }
                 int wrc = 0;
-                if (rd && sinks.report_fd >= 0)
+                std::string werr;
+                if (filter) {
+                    if (sinks.report_fd >= 0 && (wrc = movi_gpu_file_chunk_filter_deliver(my, nullptr, 0, sinks.report_fd))) werr = movi_gpu_last_error(my);
+                } else if (rd && sinks.report_fd >= 0) {
                     wrc = movi_host_classify_bins(sinks.report_fd, sinks.report_mode | (report_started ? MOVI_HOST_CLASSIFY_CONTINUE : 0), rd, sinks.max_value_thr,
                                                   above.data(), below.data(), sum.data(), nullptr);
+                    if (wrc) werr = movi_host_last_error();
+                }
                 if (rd) movi_host_reads_free(rd);
-                if (wrc) { hard_fail(movi_host_last_error()); return; }
+                if (wrc) { hard_fail(werr); return; }
                 std::lock_guard<std::mutex> lk(mu);
                 if (res.n_reads && sinks.report_fd >= 0) report_started = true;
                 report_seq += 1;
@@ -465,9 +473,8 @@ int main(int argc, char** argv) {
     // ... or its classification: --classify (report + .bpf) and --filter (the kept reads on stdout) bin the lengths on the device too
     // (with --no-output the reference prints a report header and nothing else: left to the host path, like an empty input)
     const bool plain_ingest = !o.classify && !o.write_stdout_enabled() && !(o.to_stdout && o.write_output_allowed());
-    // --filter echoes the reads it keeps, so every base has to come back to the host anyway: on short reads the pipelined host path
-    // is faster (profiles/r02_cli_e2e_classify.jsonl: 0.45 s against 1.06 s for 6e8 bases) and stays the default there
-    const bool classify_ingest = o.classify && !o.no_output && raw_size > 0 && (!o.filter || o.device_ingest);
+    // (--filter: the echo of the kept reads is assembled on the device, filter_kernels.cuh)
+    const bool classify_ingest = o.classify && !o.no_output && raw_size > 0;
     const bool ingest_on_device = !color_flow && !o.host_parse && (o.query == "pml" || o.query == "zml") && !o.reverse && o.ignore_illegal == 0 &&
                                   (plain_ingest || classify_ingest);
     std::future<Fetched> ahead;

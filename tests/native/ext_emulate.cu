@@ -92,3 +92,20 @@ extern "C" int movi_ext_emulate(const MoviGpuIndexDesc* d, int ext, const MoviGp
 #undef PICK
     return (int)status;
 }
+
+// ---- the --filter echo (movi_b200/csrc/filter_kernels.cuh): sizes, positions and the per-read copy, a read at a time
+#include "../../movi_b200/csrc/filter_kernels.cuh"
+extern "C" uint64_t movi_filter_emulate(const uint32_t* above, const uint32_t* below, int invert, const char* bases, const uint64_t* offsets,
+                                        const char* ids, const uint64_t* id_offsets, uint64_t n_reads, char* text, uint64_t capacity) {
+    std::vector<unsigned long long> pos(n_reads + 1, 0);
+    for (uint64_t i = 0; i < n_reads; i++)
+        pos[i + 1] = pos[i] + (filter_keeps(above[i], below[i], invert) ? filter_echo_bytes(id_offsets[i + 1] - id_offsets[i], offsets[i + 1] - offsets[i]) : 0ull);
+    if (pos[n_reads] > capacity) return ~0ull;
+    for (uint64_t i = 0; i < n_reads; i++) {
+        if (pos[i + 1] == pos[i]) continue;
+        for (unsigned lane = 0; lane < 3; lane++)                       // three "lanes" taking turns: the strided copy loops
+            filter_emit_read(reinterpret_cast<uint8_t*>(text) + pos[i], reinterpret_cast<const uint8_t*>(ids) + id_offsets[i], id_offsets[i + 1] - id_offsets[i],
+                             reinterpret_cast<const uint8_t*>(bases) + offsets[i], offsets[i + 1] - offsets[i], lane, 3u);
+    }
+    return pos[n_reads];
+}

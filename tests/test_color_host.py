@@ -88,3 +88,40 @@ def test_sa_writer_reproduces_the_reference_file(case, tmp_path):
     finally:
         os.close(fd)
     assert f.read_bytes() == lzma.open(os.path.join(GOLD, "color", "expected.sa_entries.bpf.xz")).read()
+
+
+def test_filter_echo_pieces_on_the_cpu(tmp_path):
+    """filter_kernels.cuh's per-read pieces (keep rule, sizes, the strided copy) against movi_host_classify_bins in filter mode,
+    which restates the reference's writer: same text, for --filter and --filter --invert."""
+    import ctypes as C
+    import threading
+    from _color import emulator
+    rng = np.random.default_rng(8)
+    n = 500
+    path = tmp_path / "r.fa"
+    with open(path, "w") as f:
+        for i in range(n):
+            L = int(rng.integers(0, 300)) if i % 9 else 0
+            f.write(">read%d%s\n%s\n" % (i, " x" if i % 2 else "", "".join(rng.choice(list("ACGTN"), L))))
+    rd = Reads(str(path))
+    assert rd.count == n
+    above = rng.integers(0, 5, n).astype(np.uint32); below = rng.integers(0, 5, n).astype(np.uint32)
+    above[::9] = 0; below[::9] = 0                                  # empty reads have no bins
+    total = np.zeros(n, np.uint64)
+    ids, id_off = rd.id_blob
+    H = N.host_lib()
+    L = emulator()
+    L.movi_filter_emulate.restype = C.c_uint64
+    L.movi_filter_emulate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    for invert in (0, 1):
+        rfd, wfd = os.pipe()
+        buf = []
+        t = threading.Thread(target=lambda: buf.append(os.fdopen(rfd, "rb").read()))
+        t.start()
+        assert H.movi_host_classify_bins(wfd, 2 if invert else 1, rd._h, 5, above.ctypes.data, below.ctypes.data, total.ctypes.data, None) == 0
+        os.close(wfd); t.join()
+        text = np.zeros(len(buf[0]) + 64, np.uint8)
+        got = L.movi_filter_emulate(above.ctypes.data, below.ctypes.data, invert, rd.bases.ctypes.data, rd.offsets.ctypes.data,
+                                    ids.ctypes.data, id_off.ctypes.data, n, text.ctypes.data, len(text))
+        assert got == len(buf[0]) and text[:got].tobytes() == buf[0]
+        assert 0 < got
