@@ -7,7 +7,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("profile", [0, 1])
+@pytest.mark.parametrize("profile", [0, 1, 2])
 def test_synthetic_table_matches_oracle(tmp_path, profile):
     import torch
     from movi_b200.datagen.synth_gpu import SyntheticStructure
