@@ -53,7 +53,13 @@ C4_ROWS = int(float(os.environ.get("MOVI_C4_ROWS", "4.6e9")))       # > 2^32 row
 C4_READS = int(os.environ.get("MOVI_C4_READS", "409600"))           # per GPU per step; x 10 kbp = 4.096e9 bases (< 2^32: one device call)
 C4_READ_LEN = 10_000
 C4_SEED = 44
-C4_PROFILE = int(os.environ.get("MOVI_C4_PROFILE", "1"))             # run-length profile of the synthetic table (datagen/synth_gpu.cu)
+# run-length profile of the synthetic table (datagen/synth_gpu.cu).  2 = run lengths 48..64: the LF image of a run spans at most two
+# rows and a walk fast-forwards 0.5 rows per base -- suffix-sorted indexes fast-forward 0.22 - 0.27 (c2, g1).  1 = heavy-tailed
+# lengths, the headline of the first half of round 2: a long run's image covers many short ones there, 2.0 fast-forward rows per
+# base, an artefact of arranging heavy-tailed runs at random (2.47e10 bases/s against 2.96e10: profiles/r02_bench_c4_profile1.json)
+C4_PROFILE = int(os.environ.get("MOVI_C4_PROFILE", "2"))
+C4_PROFILE_NOTE = {0: "geometric run lengths, mean 8", 1: "heavy-tailed run lengths: 2.0 fast-forward rows per base",
+                   2: "run lengths 48..64: 0.5 fast-forward rows per base (suffix-sorted indexes: 0.22 - 0.27)"}
 C4_SUB_PER_1024, C4_RAND_EVERY, C4_LEAD = 51, 10, 24                # 5 % substitutions, 1 read in 10 uniform random, 24 scattering bases
 C4_CPU_SAMPLE = int(os.environ.get("MOVI_C4_CPU_SAMPLE", "4096"))   # reads per step of the CPU arm (4.1e7 bases)
 N_BATCHES = 2                                                        # distinct read batches the steps cycle over
@@ -202,10 +208,11 @@ class C4Data:
             % (rank, C4_ROWS, C4_ROWS * 8 / 1e9, self.ms.n / C4_ROWS, t1 - t0, len(self.d_bases), self.n_reads, self.read_len, time.time() - t1))
 
     def describe(self):
-        return ("c4: synthetic human-scale move table resident in HBM (%.2e rows = %.1f GB per GPU, n/r = %.0f, row indices beyond 2^32), "
+        return ("c4: synthetic human-scale move table resident in HBM (%.2e rows = %.1f GB per GPU, n/r = %.0f, %s, row indices beyond 2^32), "
                 "regular-thresholds, %d x %d bp nanopore-like reads per GPU per step (%d %% substitutions, 1 read in %d uniform random; "
                 "reads written down by the query's own walk so that they re-synchronise after an error), PML"
-                % (C4_ROWS, C4_ROWS * 8 / 1e9, self.ms.n / C4_ROWS, self.n_reads, self.read_len, round(C4_SUB_PER_1024 / 10.24), C4_RAND_EVERY))
+                % (C4_ROWS, C4_ROWS * 8 / 1e9, self.ms.n / C4_ROWS, C4_PROFILE_NOTE.get(C4_PROFILE, "profile %d" % C4_PROFILE), self.n_reads, self.read_len,
+                   round(C4_SUB_PER_1024 / 10.24), C4_RAND_EVERY))
 
     def l2_note(self):
         return ("the 36.8 GB row table is 290x the 126 MB L2; each step streams 4.1 GB of reads in and 8.2 GB of lengths out and uses a "
@@ -706,7 +713,7 @@ def main():
             work_bases = int(np.minimum(L, L - h_pos.numpy().astype(np.int64) + 1).sum())
         achieved = W["algo"] * work_bases / per_launch_s / 1e9
         traffic = None
-        tp = os.path.join(ROOT, "profiles", {"c4": "pml_c4_traffic.json", "c2": "pml_c2_traffic.json", "c3-zml": "zml_c3_traffic.json",
+        tp = os.path.join(ROOT, "profiles", {"c4": "pml_c4_p%d_traffic.json" % C4_PROFILE, "c2": "pml_c2_traffic.json", "c3-zml": "zml_c3_traffic.json",
                                             "c3-count": "count_c3_traffic.json", "g1": "pml_g1_traffic.json"}[args.workload])
         if os.path.exists(tp):
             try:
