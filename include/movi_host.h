@@ -98,6 +98,9 @@ typedef struct movi_host_ssa movi_host_ssa;
 /* load_color_table (reference src/movi.cpp:121-152) for the default flat colour table: <index_dir>/doc_sets_flat.bin (r = rows of
  * the index), ref.fa.doc_offsets and, if present, ref.fa.doc_ids (taxon id per document; src/move_structure_io.cpp:587-607, 643-700) */
 int  movi_host_colors_open(const char* index_dir, uint64_t r, movi_host_colors** out);
+/* kind 0: the same; kind 1: <index_dir>/doc_sets.bin, the vectors-of-vectors table `--color-vectors` names (src/move_structure_io.cpp:571-641),
+ * flattened on load (the device takes one form) */
+int  movi_host_colors_open_kind(const char* index_dir, uint64_t r, int kind, movi_host_colors** out);
 int  movi_host_colors_desc(const movi_host_colors* c, MoviGpuColorDesc* out);     /* pointers valid until _close */
 uint32_t movi_host_colors_num_species(const movi_host_colors* c);
 uint32_t movi_host_colors_taxon(const movi_host_colors* c, uint32_t species);     /* to_taxon_id */

@@ -129,6 +129,7 @@ HOST_SYMBOLS = {
     "movi_host_reader_seek": (C.c_int, [C.c_void_p, C.c_uint64]),
     "movi_host_reads_adopt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "movi_host_colors_open": (C.c_int, [C.c_char_p, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "movi_host_colors_open_kind": (C.c_int, [C.c_char_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]),
     "movi_host_colors_desc": (C.c_int, [C.c_void_p, C.POINTER(MoviGpuColorDesc)]),
     "movi_host_colors_num_species": (C.c_uint32, [C.c_void_p]),
     "movi_host_colors_taxon": (C.c_uint32, [C.c_void_p, C.c_uint32]),

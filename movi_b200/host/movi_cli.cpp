@@ -42,7 +42,7 @@ struct Options {
     bool device_ingest = false;              // --device-ingest: accepted (the device-side ingest is the default wherever it exists)
     int layout = MOVI_GPU_LAYOUT_AUTO;       // --layout auto|expanded|compact: device form of blocked / sampled indexes
     // Movi Color (movi_parser.cpp:155, 164-175)
-    bool multi_classify = false, pvalue_scoring = false, sa_entries = false;
+    bool multi_classify = false, pvalue_scoring = false, sa_entries = false, color_vectors = false;
     uint32_t min_len = 1;                    // --min-len (uint8 in the reference, movi_options.hpp:291)
     bool write_output_allowed() const { return !no_output && !filter; }          // movi_options.hpp:70
     bool write_stdout_enabled() const { return to_stdout && !classify; }         // movi_options.hpp:71
@@ -54,7 +54,7 @@ struct Options {
                     "                       [--stdout] [-o prefix] [--no-output] [--reverse] [--ignore-illegal-chars 1|2]\n"
                     "                       [--bin-width N] [--gpus N] [--device D] [--chunk-bases N] [--chunk-reads N] [--max-chunk-bases N]\n"
                     "                       [--chunk-bytes N] [--host-parse|--device-ingest] [--layout auto|expanded|compact]\n"
-                    "                       [--multi-classify -o out.csv [--min-len N] [--pvalue-scoring]] [--sa-entries]\n"
+                    "                       [--multi-classify -o out.csv [--color-vectors] [--min-len N] [--pvalue-scoring]] [--sa-entries]\n"
                     "                       [-t N] [-s N] [-n]\n"
                     "       movi-b200 view --bpf <file.bpf>\n");
     exit(1);
@@ -107,13 +107,14 @@ Options parse(int argc, char** argv) {
         else if (take_value(argc, argv, i, nullptr, "--max-chunk-bases", v)) o.max_chunk_bases = std::max<uint64_t>(1, strtoull(v.c_str(), nullptr, 10));
         else if (a == "--multi-classify") o.multi_classify = true;
         else if (a == "--pvalue-scoring") o.pvalue_scoring = true;
+        else if (a == "--color-vectors") o.color_vectors = true;                // doc_sets.bin instead of doc_sets_flat.bin (movi_parser.cpp:369)
         else if (a == "--sa-entries") o.sa_entries = true;
         else if (take_value(argc, argv, i, nullptr, "--min-len", v)) o.min_len = (uint32_t)(uint8_t)strtoul(v.c_str(), nullptr, 10);
         else if (a == "--early-stop" || a == "--report-all" || a == "--report-colors" || a == "--report-color-ids" || a == "--full" ||
-                 a == "--compress" || a == "--freq-compress" || a == "--tree-compress" || a == "--color-vectors" || a == "--color-move-rows" ||
+                 a == "--compress" || a == "--freq-compress" || a == "--tree-compress" || a == "--color-move-rows" ||
                  a == "--min-diff-frac" || a == "--min-score-frac")
-            usage_error(a + ": only the default flat colour table with the output of the --no-prefetch path is built here "
-                            "(--multi-classify [--min-len N] [--pvalue-scoring]); use the reference for " + a);
+            usage_error(a + ": only the flat and the vectors-of-vectors colour tables with the output of the --no-prefetch path are built here "
+                            "(--multi-classify [--color-vectors] [--min-len N] [--pvalue-scoring]); use the reference for " + a);
         else if (a == "--pml") o.query = "pml";
         else if (a == "--rpml") o.rpml = true;                                  // movi_parser.cpp:149,357
         else if (a == "--zml") o.query = "zml";
@@ -332,7 +333,7 @@ int run_color(const Options& o, const std::vector<movi_gpu_ctx*>& ctx, const Mov
     const int gpus = (int)ctx.size();
     movi_host_colors* colors = nullptr; movi_host_ssa* ssa = nullptr;
     if (o.multi_classify) {
-        if (movi_host_colors_open(o.index_dir.c_str(), desc.r, &colors)) { *err = movi_host_last_error(); return -1; }
+        if (movi_host_colors_open_kind(o.index_dir.c_str(), desc.r, o.color_vectors ? 1 : 0, &colors)) { *err = movi_host_last_error(); return -1; }
         MoviGpuColorDesc cd;
         movi_host_colors_desc(colors, &cd);
         for (int g = 0; g < gpus; g++) if (movi_gpu_upload_colors(ctx[g], &cd)) { *err = movi_gpu_last_error(ctx[g]); return -1; }

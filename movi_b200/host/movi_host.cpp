@@ -646,11 +646,17 @@ struct movi_host_ssa { uint64_t rate = 0; std::vector<uint64_t> sampled, all_p; 
 
 // load_color_table -> deserialize_doc_sets_flat + load_document_info (reference src/movi.cpp:121-152,
 // src/move_structure_io.cpp:587-607, 643-700)
-int movi_host_colors_open(const char* index_dir, uint64_t r, movi_host_colors** out) {
+int movi_host_colors_open(const char* index_dir, uint64_t r, movi_host_colors** out) { return movi_host_colors_open_kind(index_dir, r, 0, out); }
+
+// kind 0: doc_sets_flat.bin (the default); kind 1: doc_sets.bin, the vectors-of-vectors form of `--color-vectors`
+// (serialize_doc_sets / deserialize_doc_sets, src/move_structure_io.cpp:571-641), brought into the flat form here the way
+// flat_and_serialize_colors_vectors does (:513-548) -- a row whose set index lies beyond the stored sets ("thrown away by
+// compression", src/move_structure_query.cpp:390-391) gets an offset beyond the table, which the query skips the same way (:395)
+int movi_host_colors_open_kind(const char* index_dir, uint64_t r, int kind, movi_host_colors** out) {
     if (!index_dir || !out) return fail("null argument");
     const std::string dir(index_dir);
     std::unique_ptr<movi_host_colors> c(new movi_host_colors);
-    {
+    if (kind == 0) {
         const std::string name = dir + "/doc_sets_flat.bin";
         std::ifstream f(name, std::ios::binary);
         if (!f) return fail("[deserialize doc sets flat] Failed to open document sets flat file at " + name);
@@ -662,7 +668,37 @@ int movi_host_colors_open(const char* index_dir, uint64_t r, movi_host_colors** 
         f.read(reinterpret_cast<char*>(c->flat.data()), (std::streamsize)(n * 2));
         f.read(reinterpret_cast<char*>(c->inds.data()), (std::streamsize)(r * 5));
         if (!f) return fail("truncated colour table " + name);
-    }
+    } else if (kind == 1) {
+        const std::string name = dir + "/doc_sets.bin";
+        std::ifstream f(name, std::ios::binary);
+        if (!f) return fail("[deserialize doc sets] Failed to open document sets file at " + name);
+        f.seekg(0, std::ios::end); const uint64_t size = (uint64_t)f.tellg(); f.seekg(0);
+        uint64_t n_sets = 0;
+        f.read(reinterpret_cast<char*>(&n_sets), 8);
+        if (!f || n_sets > size / 2) return fail("truncated colour table " + name);
+        std::vector<uint64_t> flat_index(n_sets);
+        std::vector<uint16_t> docs;
+        for (uint64_t i = 0; i < n_sets; i++) {
+            uint16_t k = 0;
+            f.read(reinterpret_cast<char*>(&k), 2);
+            docs.resize(k);
+            if (k) f.read(reinterpret_cast<char*>(docs.data()), (std::streamsize)k * 2);
+            if (!f) return fail("truncated colour table " + name);
+            flat_index[i] = c->flat.size();
+            c->flat.push_back(k);
+            c->flat.insert(c->flat.end(), docs.begin(), docs.end());
+        }
+        std::vector<uint32_t> set_of(r);
+        f.read(reinterpret_cast<char*>(set_of.data()), (std::streamsize)(r * 4));
+        if (!f) return fail("truncated colour table " + name);
+        if (c->flat.size() >= (1ull << 40) - 1) return fail("colour table too large for 40-bit offsets");
+        c->inds.resize(r * 5);
+        for (uint64_t i = 0; i < r; i++) {
+            const uint64_t off = set_of[i] < n_sets ? flat_index[set_of[i]] : (uint64_t)c->flat.size();
+            uint8_t* e = c->inds.data() + 5 * i;
+            e[0] = (uint8_t)off; e[1] = (uint8_t)(off >> 8); e[2] = (uint8_t)(off >> 16); e[3] = (uint8_t)(off >> 24); e[4] = (uint8_t)(off >> 32);
+        }
+    } else return fail("unknown colour table kind");
     std::vector<uint64_t> doc_offsets;
     {
         const std::string name = dir + "/ref.fa.doc_offsets";

@@ -41,10 +41,10 @@ def emulator():
 
 
 class HostColors:
-    def __init__(self, index_dir, r):
+    def __init__(self, index_dir, r, kind=0):
         H = N.host_lib()
         self._h = C.c_void_p()
-        if H.movi_host_colors_open(os.fsencode(index_dir), r, C.byref(self._h)) != 0:
+        if H.movi_host_colors_open_kind(os.fsencode(index_dir), r, kind, C.byref(self._h)) != 0:
             raise RuntimeError(H.movi_host_last_error().decode())
         self.desc = N.MoviGpuColorDesc()
         H.movi_host_colors_desc(self._h, C.byref(self.desc))

@@ -91,7 +91,7 @@ def color_index_dir(tmp_path_factory):
     unmodified reference (tests/golden/make_golden_color.py)."""
     d = tmp_path_factory.mktemp("color")
     src = os.path.join(GOLD, "color")
-    for f in ("index.movi", "doc_sets_flat.bin", "ssa.movi"):
+    for f in ("index.movi", "doc_sets_flat.bin", "doc_sets.bin", "ssa.movi"):
         with lzma.open(os.path.join(src, f + ".xz")) as g:
             (d / f).write_bytes(g.read())
     for f in ("ref.fa.doc_offsets", "ref.fa.doc_ids"):

@@ -6,9 +6,10 @@ reference's own `build`, coloured by its `color` action (flat color table, the d
 the reference then answers `query --pml --multi-classify --no-prefetch -t1` (default, `--min-len 3`, `--pvalue-scoring`,
 `--min-len 0`) and `query --pml --sa-entries --no-prefetch -t1`.  What is committed under tests/golden/color/:
 
-  index.movi.xz doc_sets_flat.bin.xz ssa.movi.xz ref.fa.doc_offsets ref.fa.doc_ids    the index directory
+  index.movi.xz doc_sets_flat.bin.xz doc_sets.bin.xz ssa.movi.xz ref.fa.doc_offsets ref.fa.doc_ids    the index directory
+                                                                                       (doc_sets.bin: `color --color-vectors`)
   reads.fa                                                                             220 reads (10 % random, some with N, one empty-ish)
-  expected.multi_classify[.minlen3|.pvalue|.minlen0].csv                               the reference's -o files
+  expected.multi_classify[.minlen3|.pvalue|.minlen0|.vectors].csv                      the reference's -o files (.vectors: --color-vectors)
   expected.pml.bpf.xz expected.sa_entries.bpf.xz                                       the reference's binary outputs
 """
 import lzma
@@ -94,7 +95,8 @@ def main():
     sh([MOVI, "build", "--index", idx, "--fasta", fa, "--verify"])
     sh([MOVI, "color", "--index", idx])
     sh([MOVI, "build-SA", "--index", idx])
-    for f in ("index.movi", "doc_sets_flat.bin", "ssa.movi"):
+    sh([MOVI, "color", "--index", idx, "--color-vectors"])                    # the same colours as vectors of vectors: doc_sets.bin
+    for f in ("index.movi", "doc_sets_flat.bin", "doc_sets.bin", "ssa.movi"):
         xz(os.path.join(idx, f), os.path.join(OUT, f + ".xz"))
     for f in ("ref.fa.doc_offsets", "ref.fa.doc_ids"):
         shutil.copy(os.path.join(idx, f), os.path.join(OUT, f))
@@ -109,6 +111,9 @@ def main():
         shutil.copy(o, os.path.join(OUT, "expected.multi_classify%s.csv" % tag))
         if tag == "":
             xz(o + ".pml.bpf", os.path.join(OUT, "expected.pml.bpf.xz"))
+    o = os.path.join(WORK, "mc.vectors.csv")
+    sh([MOVI, "query", "--index", idx, "--read", scratch, "--pml", "--multi-classify", "--color-vectors", "--no-prefetch", "-t1", "-o", o])
+    shutil.copy(o, os.path.join(OUT, "expected.multi_classify.vectors.csv"))
     sh([MOVI, "query", "--index", idx, "--read", scratch, "--pml", "--sa-entries", "--no-prefetch", "-t1"])
     xz(scratch + ".regular-thresholds.pml.sa_entries.bpf", os.path.join(OUT, "expected.sa_entries.bpf.xz"))
     assert open(scratch + ".regular-thresholds.pml.bpf", "rb").read() == lzma.open(os.path.join(OUT, "expected.pml.bpf.xz")).read()

@@ -228,6 +228,10 @@ def test_multi_classify_and_sa_entries_files(cli, color_index_dir, tmp_path, gpu
         assert open(o).read() == color_expected(tag), tag
         got = open(o + ".pml.bpf", "rb").read()
         assert got[:10] == want_bpf[:10] and got[12:] == want_bpf[12:]
+    o = str(tmp_path / "mc.vectors.csv")        # the vectors-of-vectors table (doc_sets.bin)
+    run(cli, "query", "--index", color_index_dir, "--read", str(reads), "--pml", "--multi-classify", "--color-vectors", "-o", o, "--gpus", str(gpus), "--no-output")
+    assert open(o).read() == open(os.path.join(GOLD, "color", "expected.multi_classify.vectors.csv")).read()
+    assert not os.path.exists(o + ".pml.bpf")
     run(cli, "query", "--index", color_index_dir, "--read", str(reads), "--pml", "--sa-entries", "--no-prefetch", "-t1", "--gpus", str(gpus))
     assert open(str(reads) + ".regular-thresholds.pml.sa_entries.bpf", "rb").read() == lzma.open(os.path.join(GOLD, "color", "expected.sa_entries.bpf.xz")).read()
     got = open(str(reads) + ".regular-thresholds.pml.bpf", "rb").read()

@@ -27,6 +27,21 @@ def test_host_loaders_match_the_oracle(case):
     assert case["ssa"].rate == 100 and case["ssa"].rows == case["hi"].r
 
 
+def test_vectors_of_vectors_table_flattens_to_the_reference_flat_table(case):
+    """doc_sets.bin (`color --color-vectors`) loaded and flattened on the host == doc_sets_flat.bin as the reference wrote it; the
+    kernel's lanes on it reproduce the reference's `--multi-classify --color-vectors` file."""
+    import ctypes as C
+    vec = HostColors(case["dir"], case["hi"].r, kind=1)
+    flat = case["colors"]
+    assert vec.num_species == flat.num_species and vec.desc.flat_size == flat.desc.flat_size
+    n = int(flat.desc.flat_size)
+    assert C.string_at(vec.desc.flat_colors, 2 * n) == C.string_at(flat.desc.flat_colors, 2 * n)
+    assert C.string_at(vec.desc.doc_set_flat_inds, 5 * case["hi"].r) == C.string_at(flat.desc.doc_set_flat_inds, 5 * case["hi"].r)
+    rd = case["reads"]
+    res, _ = emulate_color(case["hi"], vec, rd.bases, rd.offsets)
+    assert vec.text(rd, res) == open(os.path.join(GOLD, "color", "expected.multi_classify.vectors.csv")).read()
+
+
 @pytest.mark.parametrize("tag", sorted(COLOR_VARIANTS))
 def test_host_writer_reproduces_the_reference_file_from_oracle_results(case, tag):
     """movi_host_write_multi_classify: the oracle's per-read results in, the reference's -o file out."""
