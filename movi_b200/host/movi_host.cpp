@@ -16,6 +16,7 @@
 #include <iomanip>
 #include <iostream>
 #include <memory>
+#include <mutex>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -51,6 +52,32 @@ struct movi_host_reads {
     std::string ids;                      // concatenated ids
     std::vector<uint64_t> id_offsets{0};
 };
+
+namespace {
+// Batches are big (10 bytes per base and more) and short-lived: a freed one keeps its buffers and serves the next parse, so that
+// a streaming run touches fresh pages for its first few batches only (page faults on new allocations were half of the parser's
+// time: 1.0 -> 2.1 GB/s on a 322 MB FASTA).  At most three objects wait here, none holding more than 6 GB.
+std::mutex g_pool_mu;
+std::vector<movi_host_reads*> g_pool;
+movi_host_reads* pool_take() {
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (!g_pool.empty()) { movi_host_reads* rd = g_pool.back(); g_pool.pop_back(); return rd; }
+    }
+    return new movi_host_reads();
+}
+void pool_give(movi_host_reads* rd) {
+    if (!rd) return;
+    const size_t held = rd->bases.capacity() + rd->ids.capacity() + 8 * (rd->offsets.capacity() + rd->id_offsets.capacity());
+    if (held >= (64u << 10) && held <= (6ull << 30)) {
+        rd->bases.clear(); rd->ids.clear(); rd->offsets.assign(1, 0); rd->id_offsets.assign(1, 0);
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (g_pool.size() < 3) { g_pool.push_back(rd); return; }
+    }
+    delete rd;
+}
+struct PoolReturn { void operator()(movi_host_reads* rd) const { pool_give(rd); } };
+}  // namespace
 
 namespace {
 
@@ -340,7 +367,7 @@ int movi_host_reader_next_reads(movi_host_reader* r, uint64_t max_bases, uint64_
     if (r->eof) return 0;
     const bool fastq = r->fastq;
     LineCursor& lc = r->lc;
-    std::unique_ptr<movi_host_reads> rd(new movi_host_reads());
+    std::unique_ptr<movi_host_reads, PoolReturn> rd(pool_take());
     const size_t left = (size_t)(lc.end - lc.p);
     const size_t expect = (size_t)std::min<uint64_t>(left, max_bases + (max_bases >> 3) + 4096);
     rd->bases.reserve(fastq ? std::min(expect, left / 2 + 64) : expect);
@@ -430,7 +457,7 @@ const char* movi_host_reads_id(const movi_host_reads* rd, uint64_t i, uint32_t* 
 }
 const char* movi_host_reads_ids(const movi_host_reads* rd) { return rd ? rd->ids.data() : nullptr; }
 const uint64_t* movi_host_reads_id_offsets(const movi_host_reads* rd) { return rd ? rd->id_offsets.data() : nullptr; }
-void movi_host_reads_free(movi_host_reads* rd) { delete rd; }
+void movi_host_reads_free(movi_host_reads* rd) { pool_give(rd); }
 
 namespace {
 struct FdWriter {
