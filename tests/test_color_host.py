@@ -140,3 +140,46 @@ def test_filter_echo_pieces_on_the_cpu(tmp_path):
                                     ids.ctypes.data, id_off.ctypes.data, n, text.ctypes.data, len(text))
         assert got == len(buf[0]) and text[:got].tobytes() == buf[0]
         assert 0 < got
+
+
+@pytest.mark.parametrize("sep", [False, True])
+def test_kernel_lanes_on_the_cpu_separators_index(index_dirs, tmp_path, sep):
+    """The walk of the colour kernel on an index WITH separators ('%' rows, shifted threshold indices, the side table): a made-up
+    colour table (three documents spread over the rows) next to the reference-built c1 index; lengths == the oracle's PML, the
+    counters == the oracle's restatement, on the read sets that hold '%', N and lower-case characters."""
+    import shutil
+    import struct
+    src = index_dirs[("regular-thresholds", sep)]
+    d = tmp_path / "idx"
+    d.mkdir()
+    shutil.copy(os.path.join(src, "index.movi"), d / "index.movi")
+    hi = HostIndex(str(d))
+    r = hi.r
+    rng = np.random.default_rng(3)
+    colours = [[0], [1], [2], [0, 1], [1, 2], [0, 1, 2], [2, 0]]
+    flat, starts = [], []
+    for c in colours:
+        starts.append(len(flat)); flat += [len(c)] + c
+    flat = np.array(flat, dtype="<u2")
+    pick = rng.integers(0, len(colours) + 1, r)                       # some rows point beyond the table: "dropped by compression"
+    offs = np.array(starts + [len(flat) + 5], dtype=np.uint64)[pick]
+    inds = np.zeros((r, 5), np.uint8)
+    for k in range(5):
+        inds[:, k] = (offs >> np.uint64(8 * k)) & np.uint64(0xFF)
+    with open(d / "doc_sets_flat.bin", "wb") as f:
+        f.write(struct.pack("<Q", len(flat)) + flat.tobytes() + inds.tobytes())
+    (d / "ref.fa.doc_offsets").write_text("1000\n5000\n5600\n")
+    colors = HostColors(str(d), r)
+    orc = OracleIndex(str(d))
+    assert orc.load_colors() == colors.num_species == 3
+    for read_set in ("edge.fasta", "synth300.fasta", "sample.fastq"):
+        rd = Reads(os.path.join(GOLD, "reads", read_set))
+        for v in (dict(min_len=1, pvalue=False), dict(min_len=4, pvalue=False), dict(min_len=0, pvalue=True)):
+            res, ml = emulate_color(hi, colors, rd.bases, rd.offsets, lanes=9, **v)
+            taxa, raw, score, oml = orc.query_multi_classify(rd.bases, rd.offsets, **v)
+            assert np.array_equal(ml, orc.query_pml(rd.bases, rd.offsets)), (read_set, v)
+            assert np.array_equal(np.stack([res["best_doc"], res["second_best_doc"], res["sum_matching_lengths"]], axis=1), raw), (read_set, v)
+            assert np.array_equal(result_scores(res, v["pvalue"]), score), (read_set, v)
+            got = colors.text(rd, res, **v)
+            want = "".join("%s,%d,%d\n" % (name, t[0], t[1]) for name, t in zip(rd.ids(), taxa))
+            assert got == want, (read_set, v)
