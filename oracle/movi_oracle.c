@@ -831,3 +831,30 @@ int movi_oracle_query_pml_sa(const movi_oracle_index* ix, const movi_oracle_ssa*
     }
     return 0;
 }
+
+/* find_sampled_SA_entries (move_structure_build.cpp:1174-1212), the `build-SA` action: all_p = BWT offset of every run head; one LF
+ * walk over the whole BWT from row 0, offset 0, SA value n - 1 downwards, keeping the value at every rate-th BWT offset. */
+int movi_oracle_ssa_build(const movi_oracle_index* ix, uint64_t rate, movi_oracle_ssa** out) {
+    if (rate == 0) return fail("sample rate 0");
+    movi_oracle_ssa* s = calloc(1, sizeof *s);
+    s->rate = rate; s->r = ix->r;
+    s->all_p = malloc(ix->r * 8 + 8);
+    uint64_t tot = 0;
+    for (uint64_t i = 0; i < ix->r; i++) { s->all_p[i] = tot; tot += row_n(ix, i); }
+    s->k = tot / rate + 1;
+    s->sampled = calloc(s->k + 1, 8);
+    uint64_t offset = 0, index = 0, sa = tot;
+    for (uint64_t i = 0; i < tot; i++) {
+        sa--;
+        const uint64_t row_ind = s->all_p[index] + offset;
+        if (row_ind % rate == 0) s->sampled[row_ind / rate] = sa;
+        if (lf_move(ix, &offset, &index) < 0) { movi_oracle_ssa_free(s); return -1; }
+    }
+    *out = s;
+    return 0;
+}
+uint64_t movi_oracle_ssa_rate(const movi_oracle_ssa* s) { return s->rate; }
+uint64_t movi_oracle_ssa_samples(const movi_oracle_ssa* s) { return s->k; }
+uint64_t movi_oracle_ssa_rows(const movi_oracle_ssa* s) { return s->r; }
+const uint64_t* movi_oracle_ssa_sampled(const movi_oracle_ssa* s) { return s->sampled; }
+const uint64_t* movi_oracle_ssa_all_p(const movi_oracle_ssa* s) { return s->all_p; }

@@ -82,6 +82,13 @@ int movi_oracle_query_multi_classify(const movi_oracle_index* ix, const movi_ora
                                      int min_len, int pvalue, uint16_t* out_ml, uint32_t raw[3], double score[2], uint32_t taxa[2]);
 int  movi_oracle_ssa_load(const char* index_dir, movi_oracle_ssa** out);                      /* ssa.movi */
 void movi_oracle_ssa_free(movi_oracle_ssa* s);
+/* the `build-SA` action itself (find_sampled_SA_entries, move_structure_build.cpp:1174-1212) and what it yields */
+int  movi_oracle_ssa_build(const movi_oracle_index* ix, uint64_t rate, movi_oracle_ssa** out);
+uint64_t movi_oracle_ssa_rate(const movi_oracle_ssa* s);
+uint64_t movi_oracle_ssa_samples(const movi_oracle_ssa* s);
+uint64_t movi_oracle_ssa_rows(const movi_oracle_ssa* s);
+const uint64_t* movi_oracle_ssa_sampled(const movi_oracle_ssa* s);
+const uint64_t* movi_oracle_ssa_all_p(const movi_oracle_ssa* s);
 int movi_oracle_query_pml_sa(const movi_oracle_index* ix, const movi_oracle_ssa* s, const char* read, int64_t len,
                              uint16_t* out_ml, uint64_t* out_sa);
 

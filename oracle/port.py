@@ -56,6 +56,11 @@ def lib():
         L.movi_oracle_query_multi_classify.restype = C.c_int
         L.movi_oracle_ssa_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]; L.movi_oracle_ssa_load.restype = C.c_int
         L.movi_oracle_ssa_free.argtypes = [C.c_void_p]
+        L.movi_oracle_ssa_build.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]; L.movi_oracle_ssa_build.restype = C.c_int
+        for name in ("rate", "samples", "rows"):
+            f = getattr(L, "movi_oracle_ssa_" + name); f.argtypes = [C.c_void_p]; f.restype = C.c_uint64
+        for name in ("sampled", "all_p"):
+            f = getattr(L, "movi_oracle_ssa_" + name); f.argtypes = [C.c_void_p]; f.restype = C.c_void_p
         L.movi_oracle_query_pml_sa.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.movi_oracle_query_pml_sa.restype = C.c_int
         _lib = L
@@ -176,6 +181,18 @@ class OracleIndex:
             if rc != 0:
                 raise RuntimeError("oracle multi-classify failed: " + lib().movi_oracle_last_error().decode())
         return taxa, raw, score, ml[:-1]
+
+    def build_ssa(self, rate=100):
+        """The reference's `build-SA` action on this index -> (rate, sampled uint64[], all_p uint64[]); later query_pml_sa calls use it."""
+        L = lib()
+        if self._ssa:
+            L.movi_oracle_ssa_free(self._ssa); self._ssa = C.c_void_p()
+        if L.movi_oracle_ssa_build(self._h, rate, C.byref(self._ssa)) != 0:
+            raise RuntimeError("oracle: " + L.movi_oracle_last_error().decode())
+        k, r = L.movi_oracle_ssa_samples(self._ssa), L.movi_oracle_ssa_rows(self._ssa)
+        sampled = np.ctypeslib.as_array(C.cast(L.movi_oracle_ssa_sampled(self._ssa), C.POINTER(C.c_uint64)), shape=(k,)).copy()
+        all_p = np.ctypeslib.as_array(C.cast(L.movi_oracle_ssa_all_p(self._ssa), C.POINTER(C.c_uint64)), shape=(r,)).copy()
+        return L.movi_oracle_ssa_rate(self._ssa), sampled, all_p
 
     def query_pml_sa(self, bases, offsets):
         """-> (ml uint16[total], sa uint64[total]): `--pml --sa-entries`, same orientation as the lengths."""

@@ -183,3 +183,25 @@ def test_kernel_lanes_on_the_cpu_separators_index(index_dirs, tmp_path, sep):
             got = colors.text(rd, res, **v)
             want = "".join("%s,%d,%d\n" % (name, t[0], t[1]) for name, t in zip(rd.ids(), taxa))
             assert got == want, (read_set, v)
+
+
+@pytest.mark.parametrize("sep", [False, True])
+def test_kernel_lanes_on_the_cpu_sa_entries_separators_index(index_dirs, sep):
+    """SA entries on the reference-built c1 indexes (with and without separators), the sampled suffix array built by the oracle's
+    restatement of `build-SA` (pinned against the reference's ssa.movi in test_color_oracle.py), two sample rates."""
+    import ctypes as C
+    d = index_dirs[("regular-thresholds", sep)]
+    hi = HostIndex(d)
+    orc = OracleIndex(d)
+    for rate in (100, 7):
+        r_, sampled, all_p = orc.build_ssa(rate)
+
+        class S:                       # what emulate_sa takes (HostSsa's fields)
+            pass
+        s = S(); s.rate = rate; s.sampled = sampled.ctypes.data; s.all_p = all_p.ctypes.data
+        for read_set in ("edge.fasta", "synth300.fasta"):
+            rd = Reads(os.path.join(GOLD, "reads", read_set))
+            ml, sa = emulate_sa(hi, s, rd.bases, rd.offsets, lanes=6)
+            oml, osa = orc.query_pml_sa(rd.bases, rd.offsets)
+            assert np.array_equal(ml, oml) and np.array_equal(sa, osa), (read_set, rate)
+            assert np.array_equal(ml, orc.query_pml(rd.bases, rd.offsets))

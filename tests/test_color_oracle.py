@@ -37,3 +37,13 @@ def test_oracle_sa_entries_equal_reference(color_case):
         assert name.decode() == rd.id(i) and np.array_equal(v, sa[s:e]), i
     wml = parse_bpf_records(lzma.open(os.path.join(GOLD, "color", "expected.pml.bpf.xz")).read(), 2)
     assert all(np.array_equal(v, ml[int(rd.offsets[i]):int(rd.offsets[i + 1])]) for i, (_, v) in enumerate(wml))
+
+
+def test_oracle_build_sa_equals_reference_file(color_case, color_index_dir):
+    """find_sampled_SA_entries restated: the oracle's `build-SA` on the colour index == the ssa.movi the reference wrote."""
+    import struct
+    orc, _ = color_case
+    rate, sampled, all_p = OracleIndex(color_index_dir).build_ssa(100)
+    want = open(os.path.join(color_index_dir, "ssa.movi"), "rb").read()
+    got = struct.pack("<QQ", rate, len(sampled)) + sampled.tobytes() + struct.pack("<Q", len(all_p)) + all_p.tobytes()
+    assert got == want
