@@ -115,6 +115,8 @@ Options parse(int argc, char** argv) {
                  a == "--min-diff-frac" || a == "--min-score-frac")
             usage_error(a + ": only the flat and the vectors-of-vectors colour tables with the output of the --no-prefetch path are built here "
                             "(--multi-classify [--color-vectors] [--min-len N] [--pvalue-scoring]); use the reference for " + a);
+        else if (a == "--mem" || a == "--kmer" || a == "--kmer-count" || a == "-l" || a == "--min-mem-length" || a == "-k" || a == "--k-length")
+            usage_error(a + ": the MEM and k-mer queries are outside this build (PML / ZML / count, classification, Movi Color): use the reference");
         else if (a == "--pml") o.query = "pml";
         else if (a == "--rpml") o.rpml = true;                                  // movi_parser.cpp:149,357
         else if (a == "--zml") o.query = "zml";
